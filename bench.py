@@ -1,0 +1,419 @@
+#!/usr/bin/env python
+"""Benchmark of the GKGNet graph hot path on B200 (see DESIGN.md section "Measurement").
+
+    python bench.py --gpus N --steps K --warmup W            # our CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # reference algorithm on host cores
+
+A "step" is one pass of the hot path over one batch of synthetic input: the stage-1 Grapher
+layer of GKGNet-576 (BASELINE.json configs[1]: B=32 images per GPU, C=80, N=144x144 patches,
+M=1296 pooled keys, G=2 groups, k=9): kNN-graph construction (normalise + distance + top-k),
+max-relative aggregation forward and its backward.  Images are independent, so N GPUs each
+process their own batch (weak scaling, no data-path collective); value = images of all ranks
+/ max-over-ranks device time.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = "GKGNet-576 images/sec (fwd+bwd, 1/2/4/8 B200); Grapher kNN+agg us/layer, % roofline"
+WORKLOAD = dict(B=32, C=80, side=144, r=4, G=2, k=9, dilation=1)
+
+
+def make_inputs(B, device, dtype, seed):
+    """Synthetic stage-1 activations (unit-variance, like post-BN features), pooled keys and the
+    analytic relative-position bias of the reference's Grapher(80, n=20736, r=4)."""
+    from gkgnet_b200.pos_embed import relative_pos_table
+    w = WORKLOAD
+    N = w["side"] ** 2
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    x = torch.randn(B, N, w["C"], generator=g, dtype=torch.float32)
+    x4 = x.view(B, w["side"], w["side"], w["C"]).permute(0, 3, 1, 2)
+    y = torch.nn.functional.avg_pool2d(x4, w["r"], w["r"]).permute(0, 2, 3, 1).reshape(B, -1, w["C"])
+    rel = relative_pos_table(w["C"], N, w["r"])[0]
+    return x.to(dtype).contiguous(), y.to(dtype).contiguous(), rel.contiguous()
+
+
+# ----------------------------------------------------------------------------------------
+# clocks
+# ----------------------------------------------------------------------------------------
+_REASONS = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+
+
+class ClockSampler:
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.path = f"/tmp/gkg_clocks_{os.getpid()}.csv"
+
+    def start(self):
+        q = "index,clocks.sm,clocks.max.sm," + ",".join("clocks_event_reasons." + r for r in _REASONS)
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)],
+                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return None
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        try:
+            for line in open(self.path):
+                f = [s.strip() for s in line.split(",")]
+                if len(f) < 3 + len(_REASONS):
+                    continue
+                try:
+                    sm.append(float(f[1]))
+                    mx.append(float(f[2]))
+                except ValueError:
+                    continue
+                for name, val in zip(_REASONS, f[3:]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+            os.remove(self.path)
+        except Exception:
+            pass
+        if not sm:
+            return None
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------
+# our arm
+# ----------------------------------------------------------------------------------------
+class HotPath:
+    """Device-resident state + one step of the hot path through the C ABI."""
+
+    def __init__(self, x, y, rel, algo):
+        from gkgnet_b200 import _lib
+        self.lib = _lib.load()
+        self._lib = _lib
+        self.x, self.y, self.rel = x, y, rel
+        w = WORKLOAD
+        self.B, self.N, self.C = x.shape
+        self.M = y.shape[1]
+        self.G, self.k, self.d = w["G"], w["k"], w["dilation"]
+        self.D = self.C // self.G
+        self.algo = algo
+        dev = x.device
+        self.dt = _lib.GKG_BF16 if x.dtype == torch.bfloat16 else _lib.GKG_F32
+        self.ws_bytes = self.lib.gkg_knn_workspace_bytes(self.B, self.G, self.N, self.M, self.D, self.k,
+                                                         self.d, 0, algo)
+        self.ws = torch.empty(self.ws_bytes, dtype=torch.uint8, device=dev)
+        self.idx = torch.empty(self.B * self.G, self.N, self.k, dtype=torch.int32, device=dev)
+        self.out = torch.empty(self.B, self.N, 2 * self.C, dtype=x.dtype, device=dev)
+        self.amax = torch.empty(self.B, self.N, self.C, dtype=torch.uint8, device=dev)
+        self.gout = torch.randn(self.B, self.N, 2 * self.C, device=dev).to(x.dtype)
+        self.gx = torch.empty_like(x)
+        self.gy = torch.zeros(self.B, self.M, self.C, dtype=torch.float32, device=dev)
+        self.stream = torch.cuda.current_stream(dev)
+        self.ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+
+    def step(self, record=False):
+        lib, s = self.lib, self.stream.cuda_stream
+        x, y = self.x, self.y
+        a = (self.B, self.G, self.N, self.M, self.D, self.k, self.d)
+        if record:
+            self.ev[0].record(self.stream)
+        self._lib.check(lib.gkg_knn_prepare(x.data_ptr(), x.stride(0), x.stride(1), y.data_ptr(), y.stride(0),
+                                            y.stride(1), *a, self.dt, self.algo, self.ws.data_ptr(),
+                                            self.ws_bytes, s), "knn_prepare")
+        if record:
+            self.ev[1].record(self.stream)
+        self._lib.check(lib.gkg_knn_select(self.rel.data_ptr(), self.idx.data_ptr(), *a, 0, self.algo,
+                                           self.ws.data_ptr(), self.ws_bytes, s), "knn_select")
+        if record:
+            self.ev[2].record(self.stream)
+        self._lib.check(lib.gkg_mr_aggregate_fwd(x.data_ptr(), x.stride(0), x.stride(1), y.data_ptr(),
+                                                 y.stride(0), y.stride(1), self.idx.data_ptr(),
+                                                 self.out.data_ptr(), self.amax.data_ptr(), self.B, self.G,
+                                                 self.N, self.M, self.D, self.k, self.dt, s), "agg_fwd")
+        if record:
+            self.ev[3].record(self.stream)
+        self.gy.zero_()
+        self._lib.check(lib.gkg_mr_aggregate_bwd(self.gout.data_ptr(), self.idx.data_ptr(), self.amax.data_ptr(),
+                                                 self.gx.data_ptr(), self.gy.data_ptr(), self.B, self.G, self.N,
+                                                 self.M, self.D, self.k, self.dt, s), "agg_bwd")
+        if record:
+            self.ev[4].record(self.stream)
+
+    def phase_ms(self):
+        return [self.ev[i].elapsed_time(self.ev[i + 1]) for i in range(4)]
+
+
+def dist_setup(n_gpus):
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    return world, rank, local
+
+
+def barrier(world):
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+    torch.cuda.synchronize()
+
+
+def max_over_ranks(val, world, device):
+    if world == 1:
+        return val
+    import torch.distributed as dist
+    t = torch.tensor([val], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def load_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return p, "measured"
+    except Exception:
+        return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+def cpu_reference_step(x, y, rel, grad_out):
+    """One step of the same workload through the CPU oracle (the reference's algorithm)."""
+    from oracle import gkg_oracle as O
+    w = WORKLOAD
+    B, N, C = x.shape
+    G, D = w["G"], C // w["G"]
+
+    def ref_layout(t):
+        n = t.shape[1]
+        return t.reshape(B, n, G, D).permute(0, 2, 3, 1).reshape(B * G, D, n, 1)
+
+    xr = ref_layout(x).contiguous().requires_grad_(True)
+    yr = ref_layout(y).contiguous().requires_grad_(True)
+    ei = O.dense_dilated_knn_graph(xr, yr, w["k"], w["dilation"], rel.unsqueeze(0))
+    out = O.mr_aggregate(xr, ei, yr, in_channels=C)
+    out.backward(grad_out)
+    return out
+
+
+def time_cpu_reference(n_img, reps, seed=0):
+    x, y, rel = make_inputs(n_img, "cpu", torch.float32, seed)
+    grad_out = torch.randn(n_img, 2 * WORKLOAD["C"], x.shape[1], 1)
+    cpu_reference_step(x[:1], y[:1], rel, grad_out[:1])     # warm-up (thread pool, allocator)
+    best = float("inf")
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        cpu_reference_step(x, y, rel, grad_out)
+        best = min(best, time.perf_counter() - t0)
+    return n_img / best, best
+
+
+def run_reference(args):
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n_img = args.ref_images
+    x, y, rel = make_inputs(n_img, "cpu", torch.float32, 0)
+    grad_out = torch.randn(n_img, 2 * WORKLOAD["C"], x.shape[1], 1)
+    for _ in range(max(1, min(args.warmup, 2))):
+        cpu_reference_step(x, y, rel, grad_out)
+    steps = max(1, min(args.steps, args.ref_max_steps))
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        cpu_reference_step(x, y, rel, grad_out)
+    dt = (time.perf_counter() - t0) / steps
+    val = n_img / dt
+    cores = torch.get_num_threads()
+    sample = (f"{n_img} images per step (of the 32-image batch), fp32, stage-1 Grapher hot path "
+              f"(kNN graph + MR aggregate fwd+bwd), {steps} timed steps")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": "images/s", "n_gpus": args.gpus,
+        "steps": steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": config_dict(args.gpus, "reference algorithm (oracle port, PyTorch CPU ops) on host cores"),
+        "cpu_baseline": {"value": val, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def config_dict(n_gpus, note):
+    w = WORKLOAD
+    return {
+        "workload": ("BASELINE configs[1]: stage-1 Grapher layer hot path of GKGNet-576 -- kNN graph "
+                     "(normalise+distance+top-k) + max-relative aggregate fwd + bwd; "
+                     f"B={w['B']}/GPU, C={w['C']}, N={w['side']}x{w['side']}, M={(w['side'] // w['r']) ** 2}, "
+                     f"G={w['G']}, k={w['k']}, dilation={w['dilation']}, r={w['r']}"),
+        "images_per_gpu": w["B"], "global_batch": w["B"] * n_gpus, "parallelism": f"dp{n_gpus} (no collective)",
+        "l2": "inputs+outputs per step (>=370 MB) exceed the 126 MB L2; no explicit flush",
+        "note": note,
+    }
+
+
+def run_ours(args):
+    world, rank, local = dist_setup(args.gpus)
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    from gkgnet_b200 import _lib
+    algo = {"auto": _lib.KNN_AUTO, "exact": _lib.KNN_EXACT_FP32, "tc": _lib.KNN_TCGEN05}[args.algo]
+    dtype = torch.bfloat16 if args.dtype == "bf16" else torch.float32
+    B = WORKLOAD["B"]
+    xh, yh, relh = make_inputs(B, "cpu", dtype, seed=rank)
+    x, y, rel = xh.to(dev), yh.to(dev), relh.to(dev)
+    hp = HotPath(x, y, rel, algo)
+
+    for _ in range(max(args.warmup, 3)):
+        hp.step()
+    barrier(world)
+
+    sampler = ClockSampler(local)
+    sampler.start()
+    l0 = _lib.launch_count()
+    phases = [0.0] * 4
+    start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier(world)
+    start.record(hp.stream)
+    for _ in range(args.steps):
+        hp.step()
+    stop.record(hp.stream)
+    barrier(world)
+    total_ms = start.elapsed_time(stop)
+    launches = _lib.launch_count() - l0 + args.steps     # + the gy.zero_() memset per step
+    clocks = sampler.stop()
+
+    # per-phase durations: separate short loop (events inside the timed loop are overwritten)
+    reps = min(args.steps, 10)
+    for _ in range(reps):
+        hp.step(record=True)
+        torch.cuda.synchronize()
+        for i, v in enumerate(hp.phase_ms()):
+            phases[i] += v / reps
+
+    ms_per_step = max_over_ranks(total_ms / args.steps, world, dev)
+    value = world * B / (ms_per_step * 1e-3)
+
+    # ---- e2e: host buffers -> device -> hot path -> host, every step ------------------
+    xp, yp = xh.pin_memory(), yh.pin_memory()
+    out_host = torch.empty(hp.out.shape, dtype=hp.out.dtype).pin_memory()
+    e2e_steps = max(3, min(args.steps, 10))
+
+    def e2e_step():
+        hp.x.copy_(xp, non_blocking=True)
+        hp.y.copy_(yp, non_blocking=True)
+        hp.step()
+        out_host.copy_(hp.out, non_blocking=True)
+
+    for _ in range(2):
+        e2e_step()
+    barrier(world)
+    s2, t2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s2.record(hp.stream)
+    for _ in range(e2e_steps):
+        e2e_step()
+    t2.record(hp.stream)
+    barrier(world)
+    e2e_ms = max_over_ranks(s2.elapsed_time(t2) / e2e_steps, world, dev)
+    h2d = xp.numel() * xp.element_size() + yp.numel() * yp.element_size()
+    d2h = out_host.numel() * out_host.element_size()
+
+    if rank != 0:
+        return
+    peaks, peak_src = load_peaks()
+    w = WORKLOAD
+    N, M, C, G, k = hp.N, hp.M, hp.C, hp.G, hp.k
+    es = 2 if dtype == torch.bfloat16 else 4
+    flop_knn = 2.0 * B * N * M * C
+    bytes_agg = es * B * C * N + es * B * C * M + 4 * B * G * N * k + es * B * 2 * C * N
+    bytes_bwd = es * B * 2 * C * N + B * C * N + 4 * B * G * N * k + es * B * C * N + 4 * B * C * M
+    knn_ms = phases[1]
+    tf = flop_knn / (knn_ms * 1e-3) / 1e12
+    peak_tf = peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops"))
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "knn_select_traffic.json")
+    if os.path.isfile(tpath):
+        try:
+            traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    roofline = {"kernel": "gkg_knn_select (distance + fused top-k)", "bound": "tensor", "achieved": tf,
+                "peak": peak_tf, "unit": "TFLOP/s", "frac": tf / peak_tf, "traffic": traffic,
+                "peak_source": f"{peak_src} bf16_tflops_sustained (kernel timed inside the step)",
+                "algorithmic_flop": flop_knn, "ms": knn_ms}
+    agg_gbs = bytes_agg / (phases[2] * 1e-3) / 1e9
+    bwd_gbs = bytes_bwd / (phases[3] * 1e-3) / 1e9
+    extra = {
+        "phase_ms": {"knn_prepare": phases[0], "knn_select": phases[1], "agg_fwd": phases[2], "agg_bwd": phases[3]},
+        "roofline_agg_fwd": {"bound": "hbm", "achieved": agg_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                             "frac": agg_gbs / peaks["hbm_gbs"], "algorithmic_bytes": bytes_agg},
+        "roofline_agg_bwd": {"bound": "hbm", "achieved": bwd_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                             "frac": bwd_gbs / peaks["hbm_gbs"], "algorithmic_bytes": bytes_bwd},
+    }
+    cpu_val, cpu_s = time_cpu_reference(args.cpu_images, 2) if world == 1 and not args.no_cpu else (None, None)
+    line = {
+        "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+        "config": config_dict(world, f"knn algo={args.algo}"),
+        "clocks": clocks,
+        "e2e": {"value": world * B / (e2e_ms * 1e-3), "unit": "images/s", "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms},
+        "gpu_launches": int(launches),
+        "roofline": roofline,
+        "cpu_baseline": None if cpu_val is None else {
+            "value": cpu_val, "unit": "images/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{args.cpu_images} images, fp32, same hot path through oracle/gkg_oracle.py "
+                      f"(PyTorch CPU ops), best of 2: {cpu_s:.2f} s"},
+    }
+    line.update(extra)
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--algo", default="auto", choices=["auto", "exact", "tc"])
+    ap.add_argument("--dtype", default="bf16", choices=["bf16", "f32"])
+    ap.add_argument("--cpu-images", type=int, default=8)
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--ref-images", type=int, default=4)
+    ap.add_argument("--ref-max-steps", type=int, default=20)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        import torch.distributed as dist
+        if dist.is_initialized():
+            dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,121 @@
+// C-ABI glue: error reporting, launch accounting, gkg_knn_graph dispatch.
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+
+#include "common.cuh"
+#include "knn_tc.cuh"
+
+namespace gkg {
+
+static thread_local char g_err[512] = "";
+static std::atomic<uint64_t> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
+
+}  // namespace gkg
+
+using namespace gkg;
+
+extern "C" int gkg_abi_version(void) { return GKG_ABI_VERSION; }
+extern "C" const char* gkg_last_error(void) { return g_err; }
+extern "C" uint64_t gkg_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+static int resolve_algo(int algo, int N, int M, int D, int k, int dilation) {
+  if (algo == GKG_KNN_AUTO) return knn_tc_supported(N, M, D, k, dilation) ? GKG_KNN_TCGEN05 : GKG_KNN_EXACT_FP32;
+  return algo;
+}
+
+extern "C" size_t gkg_knn_workspace_bytes(int B, int G, int N, int M, int D, int k, int dilation,
+                                          int self_keys, int algo) {
+  if (B <= 0 || G <= 0 || N <= 0 || D <= 0) return 256;
+  if (self_keys) M = N;
+  const int P = B * G;
+  size_t bytes = carve_knn_workspace(nullptr, P, N, M, D, self_keys != 0).bytes;
+  if (resolve_algo(algo, N, M, D, k, dilation) == GKG_KNN_TCGEN05)
+    bytes += knn_tc_workspace_bytes(P, N, M, D, k, dilation, self_keys != 0);
+  return bytes + 256;
+}
+
+static int check_knn_common(int B, int G, int N, int M, int D, int k, int dilation, bool self_keys,
+                            int& algo, void* workspace, size_t workspace_bytes) {
+  GKG_CHECK_ARG(B >= 0 && G > 0 && N >= 0 && D > 0 && k > 0 && dilation > 0,
+                "knn_graph: bad shape B=%d G=%d N=%d D=%d k=%d dilation=%d", B, G, N, D, k, dilation);
+  GKG_CHECK_ARG(D <= 320, "knn_graph: D=%d > 320 channels per group is not supported", D);
+  if ((long long)B * N == 0) return GKG_OK;
+  // torch.topk raises when k*dilation exceeds the row length (reference: size < 192 fails)
+  GKG_CHECK_ARG(k * dilation <= M, "knn_graph: k*dilation=%d exceeds the %d keys", k * dilation, M);
+  GKG_CHECK_ARG(workspace != nullptr, "knn_graph: null workspace");
+  GKG_CHECK_ARG(((uintptr_t)workspace % 256) == 0, "knn_graph: workspace must be 256-byte aligned");
+  algo = resolve_algo(algo, N, M, D, k, dilation);
+  GKG_CHECK_ARG(algo == GKG_KNN_EXACT_FP32 || algo == GKG_KNN_TCGEN05, "knn_graph: bad algo %d", algo);
+  if (algo == GKG_KNN_TCGEN05)
+    GKG_CHECK_ARG(knn_tc_supported(N, M, D, k, dilation),
+                  "knn_graph: tcgen05 path does not support N=%d M=%d D=%d k*d=%d", N, M, D, k * dilation);
+  const size_t need = gkg_knn_workspace_bytes(B, G, N, M, D, k, dilation, self_keys, algo) - 256;
+  if (workspace_bytes < need) {
+    set_error("knn_graph: workspace %zu < %zu bytes", workspace_bytes, need);
+    return GKG_EWORKSPACE;
+  }
+  return GKG_OK;
+}
+
+extern "C" int gkg_knn_prepare(const void* x, int64_t x_sb, int64_t x_sn, const void* y, int64_t y_sb,
+                               int64_t y_sn, int B, int G, int N, int M, int D, int k, int dilation,
+                               int dtype, int algo, void* workspace, size_t workspace_bytes,
+                               gkg_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  GKG_CHECK_ARG(dtype == GKG_F32 || dtype == GKG_BF16, "knn_prepare: bad dtype %d", dtype);
+  const bool self_keys = (y == nullptr);
+  if (self_keys) M = N;
+  int rc = check_knn_common(B, G, N, M, D, k, dilation, self_keys, algo, workspace, workspace_bytes);
+  if (rc != GKG_OK || (long long)B * N == 0) return rc;
+  GKG_CHECK_ARG(x != nullptr, "knn_prepare: null pointer");
+  const int P = B * G;
+  KnnWorkspace w = carve_knn_workspace(workspace, P, N, M, D, self_keys);
+  rc = launch_knn_prepare(x, x_sb, x_sn, dtype, w.xhat, w.xsq, B, G, N, D, stream);
+  if (rc != GKG_OK) return rc;
+  if (!self_keys) {
+    rc = launch_knn_prepare(y, y_sb, y_sn, dtype, w.yhat, w.ysq, B, G, M, D, stream);
+    if (rc != GKG_OK) return rc;
+  }
+  if (algo == GKG_KNN_TCGEN05)
+    return launch_knn_tc_prepare(w, static_cast<char*>(workspace) + w.bytes, P, N, M, D, k, dilation,
+                                 self_keys, stream);
+  return GKG_OK;
+}
+
+extern "C" int gkg_knn_select(const float* relpos, int32_t* idx_out, int B, int G, int N, int M, int D,
+                              int k, int dilation, int self_keys_, int algo, void* workspace,
+                              size_t workspace_bytes, gkg_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const bool self_keys = self_keys_ != 0;
+  if (self_keys) M = N;
+  int rc = check_knn_common(B, G, N, M, D, k, dilation, self_keys, algo, workspace, workspace_bytes);
+  if (rc != GKG_OK || (long long)B * N == 0) return rc;
+  GKG_CHECK_ARG(idx_out != nullptr, "knn_select: null pointer");
+  const int P = B * G;
+  KnnWorkspace w = carve_knn_workspace(workspace, P, N, M, D, self_keys);
+  if (algo == GKG_KNN_TCGEN05)
+    return launch_knn_tc(w, static_cast<char*>(workspace) + w.bytes, relpos, idx_out, P, N, M, D, k,
+                         dilation, self_keys, stream);
+  return launch_knn_exact(w, relpos, idx_out, P, N, M, D, k, dilation, stream);
+}
+
+extern "C" int gkg_knn_graph(const void* x, int64_t x_sb, int64_t x_sn, const void* y, int64_t y_sb,
+                             int64_t y_sn, const float* relpos, int32_t* idx_out, int B, int G,
+                             int N, int M, int D, int k, int dilation, int dtype, int algo,
+                             void* workspace, size_t workspace_bytes, gkg_stream_t stream) {
+  int rc = gkg_knn_prepare(x, x_sb, x_sn, y, y_sb, y_sn, B, G, N, M, D, k, dilation, dtype, algo,
+                           workspace, workspace_bytes, stream);
+  if (rc != GKG_OK) return rc;
+  return gkg_knn_select(relpos, idx_out, B, G, N, M, D, k, dilation, y == nullptr, algo, workspace,
+                        workspace_bytes, stream);
+}

@@ -1,0 +1,140 @@
+"""Functional entry points of the graph hot path, backed by libgkg_b200.so.
+
+Tensors are token-major: features are ``(B, N, C)`` with the channel stride 1 (a
+``channels_last`` NCHW tensor viewed as ``(B, H*W, C)`` is exactly that, no copy).
+Channel group g of G owns channels ``[g*D, (g+1)*D)``; "problem" ``p = b*G + g`` as in the
+reference's ``(B*G, D, N, 1)`` regrouping (torch_vertex.py:197-202).
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+
+_DT = {torch.float32: _lib.GKG_F32, torch.bfloat16: _lib.GKG_BF16}
+
+
+def _stream(t: torch.Tensor) -> int:
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+def _token_major(t: torch.Tensor) -> torch.Tensor:
+    """(B, N, C) with stride(C) == 1 and 16-byte aligned rows; copies only if needed."""
+    assert t.dim() == 3
+    if t.stride(2) != 1 and t.shape[2] != 1:
+        t = t.contiguous()
+    return t
+
+
+def _require_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("gkgnet_b200 kernels need CUDA tensors (no CPU fallback)")
+
+
+def knn_graph(x, y=None, relative_pos=None, *, groups=1, k=9, dilation=1, algo=_lib.KNN_AUTO):
+    """Dilated group-kNN neighbour ids, int32 ``(B*G, N, k)``.
+
+    x: (B, N, C) queries; y: (B, M, C) keys or None (self); relative_pos: fp32 (N, M) /
+    (1, N, M) bias or None.  Equivalent to ``DenseDilatedKnnGraph(k, dilation)(x, y,
+    relative_pos)[0]`` of the reference (torch_edge.py:164-176) on the regrouped tensors.
+    """
+    _require_cuda(x, y, relative_pos)
+    lib = _lib.load()
+    x = _token_major(x)
+    B, N, C = x.shape
+    if C % groups:
+        raise ValueError(f"channels {C} not divisible by groups {groups}")
+    D = C // groups
+    if x.dtype not in _DT:
+        raise TypeError(f"unsupported dtype {x.dtype}")
+    if y is not None:
+        y = _token_major(y)
+        if y.dtype != x.dtype or y.shape[0] != B or y.shape[2] != C:
+            raise ValueError("keys must match queries in batch, channels and dtype")
+        M = y.shape[1]
+    else:
+        M = N
+    rel_ptr = None
+    if relative_pos is not None:
+        rel = relative_pos.reshape(relative_pos.shape[-2], relative_pos.shape[-1])
+        if rel.shape != (N, M):
+            raise ValueError(f"relative_pos {tuple(rel.shape)} != ({N}, {M})")
+        rel = rel.to(torch.float32).contiguous()
+        rel_ptr = rel.data_ptr()
+    idx = torch.empty((B * groups, N, k), dtype=torch.int32, device=x.device)
+    if B * N == 0:
+        return idx
+    ws_bytes = lib.gkg_knn_workspace_bytes(B, groups, N, M, D, k, dilation, int(y is None), algo)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
+    rc = lib.gkg_knn_graph(
+        x.data_ptr(), x.stride(0), x.stride(1),
+        y.data_ptr() if y is not None else None,
+        y.stride(0) if y is not None else 0, y.stride(1) if y is not None else 0,
+        rel_ptr, idx.data_ptr(), B, groups, N, M, D, k, dilation, _DT[x.dtype], algo,
+        ws.data_ptr(), ws_bytes, _stream(x))
+    _lib.check(rc, "gkg_knn_graph")
+    return idx
+
+
+class _MRAggregate(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, y, idx, groups):
+        lib = _lib.load()
+        x = _token_major(x)
+        B, N, C = x.shape
+        D = C // groups
+        k = idx.shape[-1]
+        self_keys = y is None
+        if not self_keys:
+            y = _token_major(y)
+        M = N if self_keys else y.shape[1]
+        out = torch.empty((B, N, 2 * C), dtype=x.dtype, device=x.device)
+        need_grad = x.requires_grad or (y is not None and y.requires_grad)
+        amax = torch.empty((B, N, C), dtype=torch.uint8, device=x.device) if need_grad else None
+        rc = lib.gkg_mr_aggregate_fwd(
+            x.data_ptr(), x.stride(0), x.stride(1),
+            None if self_keys else y.data_ptr(),
+            0 if self_keys else y.stride(0), 0 if self_keys else y.stride(1),
+            idx.data_ptr(), out.data_ptr(), amax.data_ptr() if amax is not None else None,
+            B, groups, N, M, D, k, _DT[x.dtype], _stream(x))
+        _lib.check(rc, "gkg_mr_aggregate_fwd")
+        ctx.save_for_backward(idx, amax)
+        ctx.meta = (B, groups, N, M, D, k, self_keys, x.dtype)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        idx, amax = ctx.saved_tensors
+        B, G, N, M, D, k, self_keys, dtype = ctx.meta
+        lib = _lib.load()
+        C = G * D
+        grad_out = grad_out.contiguous()
+        gx = torch.empty((B, N, C), dtype=dtype, device=grad_out.device)
+        gy = torch.zeros((B, M, C), dtype=torch.float32, device=grad_out.device)
+        rc = lib.gkg_mr_aggregate_bwd(grad_out.data_ptr(), idx.data_ptr(), amax.data_ptr(),
+                                      gx.data_ptr(), gy.data_ptr(), B, G, N, M, D, k, _DT[dtype],
+                                      _stream(grad_out))
+        _lib.check(rc, "gkg_mr_aggregate_bwd")
+        if self_keys:
+            return (gx.float() + gy).to(dtype), None, None, None
+        return gx, gy.to(dtype), None, None
+
+
+def mr_aggregate(x, idx, y=None, *, groups=1):
+    """Max-relative aggregation, ``(B, N, 2C)`` with channels ``[x_0, m_0, x_1, m_1, ...]``.
+
+    x: (B, N, C); idx: int32 (B*G, N, k) from :func:`knn_graph`; y: (B, M, C) or None.
+    Equivalent to MRConv2d.forward up to (not including) ``self.nn``
+    (torch_vertex.py:49-61).  Differentiable w.r.t. x and y.
+    """
+    _require_cuda(x, y, idx)
+    if idx.dtype != torch.int32:
+        idx = idx.to(torch.int32)
+    idx = idx.contiguous()
+    if x.dtype not in _DT:
+        raise TypeError(f"unsupported dtype {x.dtype}")
+    B, N, C = x.shape
+    if idx.shape[0] != B * groups or idx.shape[1] != N:
+        raise ValueError(f"idx shape {tuple(idx.shape)} does not match B*G={B * groups}, N={N}")
+    return _MRAggregate.apply(x, y, idx, groups)

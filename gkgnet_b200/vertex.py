@@ -1,0 +1,268 @@
+"""Graph convolution modules -- host-side mirror of vig_model/torch_vertex.py.
+
+Class names, constructor arguments, attribute names (hence state-dict keys) and forward
+signatures follow the reference so that configs and checkpoints drop in; the work is done
+by the CUDA kernels behind :mod:`gkgnet_b200.ops`.  Internally activations are handled
+token-major ``(B, N, C)`` (= ``channels_last`` NCHW), which makes the reference's
+transpose/contiguous copies (torch_nn.py:102-104) and the ``(B*G, D, N, 1)`` regrouping
+copies (torch_vertex.py:199-202) disappear: grouping is an index computation in the kernel.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+from . import ops
+from .graph import DenseDilatedKnnGraph, edge_index_from_neighbors
+from .layers import BasicConv, DropPath, act_layer, build_norm_layer, norm_cfg
+from .pos_embed import relative_pos_table
+
+
+def nchw_to_tokens(x):
+    """(B, C, H, W) -> (B, H*W, C) with channel stride 1 (a view for channels_last input)."""
+    B, C, H, W = x.shape
+    return x.permute(0, 2, 3, 1).reshape(B, H * W, C)
+
+
+def tokens_to_nchw(t, H, W):
+    """(B, H*W, C) token-major -> (B, C, H, W) view in channels_last memory format."""
+    B, _, C = t.shape
+    return t.view(B, H, W, C).permute(0, 3, 1, 2)
+
+
+class MRConv2d(nn.Module):
+    """Max-Relative graph convolution (reference: torch_vertex.py:38-62).
+
+    ``forward(x, edge_index, y=None)`` accepts the reference layout -- x (P, D, N, 1),
+    edge_index (2, P, N, k), y (P, D, M, 1) with P = B*G -- and returns
+    (B, 2*in_channels, N, 1).  ``forward_tokens`` is the copy-free entry used by the
+    DyGraph* wrappers."""
+
+    def __init__(self, in_channels, out_channels, act="relu", norm=None, bias=True):
+        super().__init__()
+        self.in_channels = in_channels
+        self.nn = BasicConv([in_channels * 2, out_channels], act, norm, bias)
+
+    def forward_tokens(self, xt, nn_idx, yt=None, groups=1, hw=None):
+        """xt (B, N, C), nn_idx int32 (B*G, N, k), yt (B, M, C) | None -> (B, 2C', H, W)
+        where (H, W) = hw or (N, 1)."""
+        agg = ops.mr_aggregate(xt, nn_idx, yt, groups=groups)          # (B, N, 2C) interleaved
+        H, W = hw if hw is not None else (xt.shape[1], 1)
+        return self.nn(tokens_to_nchw(agg, H, W))
+
+    def forward(self, x, edge_index, y=None):
+        P, D, N, _ = x.shape
+        if self.in_channels % D or (P * D) % self.in_channels:
+            raise ValueError(f"cannot regroup {tuple(x.shape)} into {self.in_channels} channels")
+        G = self.in_channels // D
+        B = P // G
+
+        def regroup(t):  # (B*G, D, n, 1) -> (B, n, G*D)
+            n = t.shape[2]
+            return t.reshape(B, G, D, n).permute(0, 3, 1, 2).reshape(B, n, G * D)
+
+        nn_idx = edge_index[0].to(torch.int32)
+        return self.forward_tokens(regroup(x), nn_idx, None if y is None else regroup(y), groups=G)
+
+
+class GraphConv2d(nn.Module):
+    """Static graph convolution selector (torch_vertex.py:153-173).  GKGNet fixes
+    ``conv='mr'`` (gkgnet.py:124,138,205,220); the other reference variants are outside the
+    accelerated path."""
+
+    def __init__(self, in_channels, out_channels, conv="edge", act="relu", norm=None, bias=True):
+        super().__init__()
+        if conv == "mr":
+            self.gconv = MRConv2d(in_channels, out_channels, act, norm, bias)
+        elif conv in ("edge", "gat", "sage", "gin"):
+            raise NotImplementedError(
+                f"conv:{conv} has no sm_100a kernel yet; GKGNet only instantiates conv='mr'")
+        else:
+            raise NotImplementedError("conv:{} is not supported".format(conv))
+
+    def forward(self, x, edge_index, y=None):
+        return self.gconv(x, edge_index, y)
+
+
+class _DynamicGraphBase(GraphConv2d):
+    #: when True, ``forward`` returns the compact int32 neighbour tensor (B*G, N, k) instead
+    #: of the reference's int64 ``edge_index`` (2, B*G, N, k) -- 191 MB per stage-1 layer at
+    #: B=32 that Grapher throws away immediately (torch_vertex.py:330).
+    compact_edge_index = False
+
+    def _edge_index(self, nn_idx):
+        return nn_idx if self.compact_edge_index else edge_index_from_neighbors(nn_idx)
+
+
+class DyGraphConv2dMultiGroup(_DynamicGraphBase):
+    """Dynamic grouped graph convolution over image patches (torch_vertex.py:175-205)."""
+
+    def __init__(self, in_channels, out_channels, kernel_size=9, dilation=1, conv="edge", act="relu",
+                 norm=None, bias=True, stochastic=False, epsilon=0.0, r=1, num_head=2):
+        super().__init__(in_channels, out_channels, conv, act, norm, bias)
+        self.k = kernel_size
+        self.d = dilation
+        self.r = r
+        self.num_head = num_head
+        self.dilated_knn_graph = DenseDilatedKnnGraph(kernel_size, dilation, stochastic, epsilon)
+
+    def forward(self, x, relative_pos=None):
+        B, C, H, W = x.shape
+        xt = nchw_to_tokens(x)
+        yt = None
+        if self.r > 1:
+            yt = nchw_to_tokens(F.avg_pool2d(x, self.r, self.r))
+        nn_idx = self.dilated_knn_graph.neighbors(xt, yt, relative_pos, groups=self.num_head)
+        out = self.gconv.forward_tokens(xt, nn_idx, yt, groups=self.num_head, hw=(H, W))
+        return out, self._edge_index(nn_idx)
+
+
+class DyGraphConv2d(DyGraphConv2dMultiGroup):
+    """Single-group variant (torch_vertex.py:206-228)."""
+
+    def __init__(self, in_channels, out_channels, kernel_size=9, dilation=1, conv="edge", act="relu",
+                 norm=None, bias=True, stochastic=False, epsilon=0.0, r=1):
+        super().__init__(in_channels, out_channels, kernel_size, dilation, conv, act, norm, bias,
+                         stochastic, epsilon, r, num_head=1)
+        del self.num_head
+        self.num_head = 1
+
+
+class DyGraphLabelMultiGroup(_DynamicGraphBase):
+    """Label-node <-> patch grouped graph convolution (torch_vertex.py:253-275): queries are
+    the label embeddings, keys all patches, dilation 1, no positional bias."""
+
+    def __init__(self, in_channels, out_channels, kernel_size=9, dilation=1, conv="edge", act="relu",
+                 norm=None, bias=True, stochastic=False, epsilon=0.0, r=1, num_head=2, bit_graph=True):
+        super().__init__(in_channels, out_channels, conv, act, norm, bias)
+        self.k = kernel_size
+        self.d = dilation
+        self.r = r
+        self.num_head = num_head
+        self.out_channels = out_channels
+        self.dilated_knn_graph = DenseDilatedKnnGraph(kernel_size, dilation, stochastic, epsilon)
+        self._multi_group_return = True
+
+    def forward_tokens(self, xt, yt):
+        nn_idx = self.dilated_knn_graph.neighbors(xt, yt, None, groups=self.num_head)
+        out = self.gconv.forward_tokens(xt, nn_idx, yt, groups=self.num_head)
+        if self._multi_group_return:
+            edge = nn_idx.long()                          # == edge_index[0], torch_vertex.py:275
+        else:
+            edge = edge_index_from_neighbors(nn_idx)      # DyGraphLabel returns the pair, :251
+        return out, edge
+
+    def forward(self, x, y=None):
+        B, C, N, _ = x.shape
+        xt = x.reshape(B, C, N).transpose(1, 2)
+        yt = None if y is None else y.reshape(B, C, -1).transpose(1, 2)
+        return self.forward_tokens(xt, yt)
+
+
+class DyGraphLabel(DyGraphLabelMultiGroup):
+    """Single-group variant (torch_vertex.py:229-251); returns the full edge_index."""
+
+    def __init__(self, in_channels, out_channels, kernel_size=9, dilation=1, conv="edge", act="relu",
+                 norm=None, bias=True, stochastic=False, epsilon=0.0, r=1):
+        super().__init__(in_channels, out_channels, kernel_size, dilation, conv, act, norm, bias,
+                         stochastic, epsilon, r, num_head=1)
+        self._multi_group_return = False
+
+
+def _conv_bn(cin, cout):
+    return nn.Sequential(nn.Conv2d(cin, cout, 1, stride=1, padding=0),
+                         build_norm_layer(norm_cfg, cout, postfix=1)[1])
+
+
+class Grapher(nn.Module):
+    """Grapher block: fc1 -> dynamic graph conv -> fc2 -> residual (torch_vertex.py:278-333)."""
+
+    def __init__(self, in_channels, kernel_size=9, dilation=1, conv="edge", act="relu", norm=None,
+                 bias=True, stochastic=False, epsilon=0.0, r=1, n=196, drop_path=0.0,
+                 relative_pos=False, use_multi_group=False, num_group=2):
+        super().__init__()
+        self.channels = in_channels
+        self.n = n
+        self.r = r
+        self.fc1 = _conv_bn(in_channels, in_channels)
+        if use_multi_group:
+            self.graph_conv = DyGraphConv2dMultiGroup(in_channels, in_channels * 2, kernel_size, dilation,
+                                                      conv, act, norm, bias, stochastic, epsilon, r,
+                                                      num_head=num_group)
+        else:
+            self.graph_conv = DyGraphConv2d(in_channels, in_channels * 2, kernel_size, dilation, conv,
+                                            act, norm, bias, stochastic, epsilon, r)
+        self.graph_conv.compact_edge_index = True
+        self.fc2 = _conv_bn(in_channels * 2, in_channels)
+        self.drop_path = DropPath(drop_path) if drop_path > 0.0 else nn.Identity()
+        self.relative_pos = None
+        if relative_pos:
+            self.relative_pos = nn.Parameter(relative_pos_table(in_channels, n, r), requires_grad=False)
+
+    def _get_relative_pos(self, relative_pos, H, W):
+        if relative_pos is None or H * W == self.n:
+            return relative_pos
+        N = H * W
+        return F.interpolate(relative_pos.unsqueeze(0), size=(N, N // (self.r * self.r)),
+                             mode="bicubic").squeeze(0)
+
+    def forward(self, x):
+        shortcut = x
+        x = self.fc1(x)
+        B, C, H, W = x.shape
+        x, _ = self.graph_conv(x, self._get_relative_pos(self.relative_pos, H, W))
+        x = self.fc2(x)
+        return self.drop_path(x) + shortcut
+
+
+class FFNLabel(nn.Module):
+    """Feed-forward block of the label branch (torch_vertex.py:334-360); returns (B, nodes, C)."""
+
+    def __init__(self, in_features, hidden_features=None, out_features=None, act="relu", drop_path=0.0):
+        super().__init__()
+        out_features = out_features or in_features
+        hidden_features = hidden_features or in_features
+        self.fc1 = _conv_bn(in_features, hidden_features)
+        self.act = act_layer(act)
+        self.fc2 = _conv_bn(hidden_features, out_features)
+        self.drop_path = DropPath(drop_path) if drop_path > 0.0 else nn.Identity()
+
+    def forward(self, x, y=None):
+        out = self.fc2(self.act(self.fc1(x)))
+        out = self.drop_path(out) + x
+        return out.transpose(2, 1).squeeze(-1)
+
+
+class GrapherLabel(nn.Module):
+    """Label-query Grapher: the group-kNN label head (torch_vertex.py:361-403).
+
+    forward(x (B, nodes, C), features (B, C, H, W)) -> (x (B, nodes, C), edge_index)."""
+
+    def __init__(self, in_channels, kernel_size=9, dilation=1, conv="edge", act="relu", norm=None,
+                 bias=True, stochastic=False, epsilon=0.0, r=1, n=196, drop_path=0.0,
+                 relative_pos=False, num_nodes=80, use_multi_group=False, num_group=2):
+        super().__init__()
+        self.channels = in_channels
+        self.fc1 = _conv_bn(in_channels, in_channels)
+        self.fc2 = _conv_bn(in_channels * 2, in_channels)
+        self.drop_path = DropPath(drop_path) if drop_path > 0.0 else nn.Identity()
+        if not use_multi_group:
+            self.graph_conv = DyGraphLabel(in_channels, in_channels * 2, kernel_size, dilation, conv,
+                                           act, norm, bias, stochastic, epsilon, r)
+        else:
+            self.graph_conv = DyGraphLabelMultiGroup(in_channels, in_channels * 2, kernel_size, dilation,
+                                                     conv, act, norm, bias, stochastic, epsilon, r,
+                                                     num_head=num_group)
+        self.ffn = FFNLabel(in_channels, in_channels * 4, act=act, drop_path=drop_path)
+
+    def forward(self, x, features):
+        feats = nchw_to_tokens(features)                       # (B, HW, C), no NCHW round trip
+        x = x.transpose(2, 1).unsqueeze(-1)                    # (B, C, nodes, 1)
+        shortcut = x
+        x = self.fc1(x)
+        B, C, N, _ = x.shape
+        x, edge_index = self.graph_conv.forward_tokens(x.permute(0, 2, 3, 1).reshape(B, N, C), feats)
+        x = self.fc2(x)
+        x = self.drop_path(x) + shortcut
+        return self.ffn(x), edge_index

@@ -1,0 +1,131 @@
+/*
+ * gkg_abi.h -- C ABI of libgkg_b200.so: the B200 (sm_100a) graph hot path of GKGNet.
+ *
+ * Drop-in boundary.  The reference (jin-s13/GKGNet) is pure Python; its hot path is the
+ * functional seam
+ *     DenseDilatedKnnGraph.forward(x, y=None, relative_pos=None) -> edge_index
+ *         (mmcls/models/backbones/vig_model/torch_edge.py:164-176)
+ *     MRConv2d.forward(x, edge_index, y=None)
+ *         (mmcls/models/backbones/vig_model/torch_vertex.py:47-62)
+ * A maintainer binds these entry points with ctypes; the host-side
+ * mirror of the reference classes lives in gkgnet_b200/.
+ *
+ * Conventions
+ *   - plain pointers + sizes, no torch types; every pointer is a DEVICE pointer unless
+ *     the function name ends in _host;
+ *   - all calls are asynchronous on `stream` (a cudaStream_t passed as void*);
+ *   - return 0 on success, a negative GKG_E* code otherwise; gkg_last_error() gives a
+ *     thread-local message; no exceptions cross the ABI;
+ *   - the caller owns every buffer (outputs and workspace included);
+ *   - node features are addressed as element (b, n, c) at
+ *         base + b*stride_b + n*stride_n + c        (element strides; channel stride 1)
+ *     i.e. channels-last / token-major.  A contiguous NCHW tensor must be permuted by
+ *     the caller (the Python mirror does it); `c = g*D + d` for channel group g of G.
+ *   - "problem" p = b*G + g, matching the reference's (B*G, D, N, 1) regrouping
+ *     (torch_vertex.py:197-202).
+ */
+#ifndef GKG_ABI_H_
+#define GKG_ABI_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GKG_ABI_VERSION 1
+
+/* feature dtypes */
+#define GKG_F32 0
+#define GKG_BF16 1
+
+/* kNN algorithms */
+#define GKG_KNN_AUTO 0       /* tcgen05 path when the shape allows it, else exact */
+#define GKG_KNN_EXACT_FP32 1 /* CUDA-core fp32 brute force, reference association order */
+#define GKG_KNN_TCGEN05 2    /* fp16x3 split GEMM on tcgen05/TMEM + fused top-k + exact re-rank */
+
+/* error codes */
+#define GKG_OK 0
+#define GKG_EINVAL (-1)   /* bad argument / unsupported shape */
+#define GKG_ECUDA (-2)    /* CUDA runtime error (message in gkg_last_error) */
+#define GKG_EWORKSPACE (-3) /* workspace too small */
+
+typedef void* gkg_stream_t; /* cudaStream_t */
+
+int gkg_abi_version(void);
+const char* gkg_last_error(void);
+
+/* Bytes of scratch gkg_knn_graph needs for this shape (normalised operands, norms,
+ * candidate lists).  self_keys != 0 when y == NULL (keys are the queries). */
+size_t gkg_knn_workspace_bytes(int B, int G, int N, int M, int D, int k, int dilation,
+                               int self_keys, int algo);
+
+/*
+ * Dilated (group) kNN graph.  Replaces DenseDilatedKnnGraph.forward
+ * (torch_edge.py:164-176 -> xy_dense_knn_matrix :89-106 / dense_knn_matrix :54-86 ->
+ * DenseDilated :139-149): L2-normalise queries and keys over the D channels of each
+ * group, rank keys by (|x|^2 - 2 x.y) + |y|^2 (+ relative_pos[n, m]), keep the
+ * k*dilation nearest in ascending order and emit ranks 0, d, 2d, ...
+ *
+ *   x        queries, (B, N, G*D) via strides, dtype `dtype`
+ *   y        keys, (B, M, G*D) via strides, or NULL -> keys are the queries (M == N)
+ *   relpos   fp32 (N, M) row-major bias shared by all problems, or NULL
+ *   idx_out  int32 (B*G, N, k): neighbour ids (edge_index[0]; edge_index[1][p,n,:] == n)
+ *
+ * Ties: the smaller key id wins (torch.topk leaves tie order unspecified).
+ */
+int gkg_knn_graph(const void* x, int64_t x_stride_b, int64_t x_stride_n,
+                  const void* y, int64_t y_stride_b, int64_t y_stride_n,
+                  const float* relpos, int32_t* idx_out,
+                  int B, int G, int N, int M, int D, int k, int dilation, int dtype,
+                  int algo, void* workspace, size_t workspace_bytes, gkg_stream_t stream);
+
+/*
+ * The two phases of gkg_knn_graph, exposed separately so a caller can time them or reuse
+ * the normalised operands.  gkg_knn_prepare fills the workspace (normalised fp32 rows,
+ * squared norms, tensor-core operands); gkg_knn_select ranks and writes idx_out.  Same
+ * arguments and workspace as gkg_knn_graph; gkg_knn_graph == prepare followed by select.
+ */
+int gkg_knn_prepare(const void* x, int64_t x_stride_b, int64_t x_stride_n,
+                    const void* y, int64_t y_stride_b, int64_t y_stride_n,
+                    int B, int G, int N, int M, int D, int k, int dilation, int dtype,
+                    int algo, void* workspace, size_t workspace_bytes, gkg_stream_t stream);
+int gkg_knn_select(const float* relpos, int32_t* idx_out,
+                   int B, int G, int N, int M, int D, int k, int dilation, int self_keys,
+                   int algo, void* workspace, size_t workspace_bytes, gkg_stream_t stream);
+
+/*
+ * Max-relative aggregation, forward.  Replaces the gather / subtract / max / interleave
+ * part of MRConv2d.forward (torch_vertex.py:49-61; batched_index_select torch_nn.py:84-105):
+ *     out[b, n, 2c]   = x[b, n, c]
+ *     out[b, n, 2c+1] = max_j y[b, idx[b*G+g, n, j], c] - x[b, n, c],   g = c / D
+ *   y == NULL gathers from x (M == N).  out is contiguous (B, N, 2*G*D), same dtype.
+ *   argmax (uint8 (B, N, G*D), nullable) records the winning j for the backward pass.
+ */
+int gkg_mr_aggregate_fwd(const void* x, int64_t x_stride_b, int64_t x_stride_n,
+                         const void* y, int64_t y_stride_b, int64_t y_stride_n,
+                         const int32_t* idx, void* out, uint8_t* argmax,
+                         int B, int G, int N, int M, int D, int k, int dtype,
+                         gkg_stream_t stream);
+
+/*
+ * Max-relative aggregation, backward (what autograd derives for torch_vertex.py:49-61:
+ * max-backward routes to the arg-max neighbour, index_put_(accumulate) into y).
+ *   grad_out      (B, N, 2*G*D) contiguous, dtype
+ *   grad_x        (B, N, G*D) contiguous, dtype:  g[2c] - g[2c+1]
+ *   grad_y_accum  fp32 (B, M, G*D) contiguous, MUST be zero-filled by the caller;
+ *                 receives sum over (n, j == argmax) of g[2c+1]   (atomic adds)
+ */
+int gkg_mr_aggregate_bwd(const void* grad_out, const int32_t* idx, const uint8_t* argmax,
+                         void* grad_x, float* grad_y_accum,
+                         int B, int G, int N, int M, int D, int k, int dtype,
+                         gkg_stream_t stream);
+
+/* Number of kernels this library has launched since load (for bench accounting). */
+uint64_t gkg_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GKG_ABI_H_ */

@@ -1,0 +1,85 @@
+"""CPU: the C-ABI library loads and exports every symbol include/gkg_abi.h declares; host
+logic of the Python mirror (state-dict layout, registry, error behaviour)."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "gkg_abi.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(gkg_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    from gkgnet_b200 import _lib
+    if not os.path.isfile(_lib.LIB_PATH):
+        _lib.build()
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    names = _declared_symbols()
+    assert "gkg_knn_graph" in names and "gkg_mr_aggregate_bwd" in names
+    for name in names:
+        assert hasattr(lib, name), name
+    assert set(names) == set(_lib.SIGNATURES), set(names) ^ set(_lib.SIGNATURES)
+    assert _lib.load().gkg_abi_version() == 1
+
+
+def test_workspace_query_is_host_only():
+    from gkgnet_b200 import _lib
+    lib = _lib.load()
+    small = lib.gkg_knn_workspace_bytes(1, 2, 64, 16, 8, 3, 1, 0, _lib.KNN_EXACT_FP32)
+    big = lib.gkg_knn_workspace_bytes(32, 2, 20736, 1296, 40, 9, 1, 0, _lib.KNN_EXACT_FP32)
+    assert 0 < small < big
+    # normalised operands + norms for queries and keys
+    assert big >= 4 * 64 * (20736 + 1296) * 41
+
+
+def test_kernels_refuse_cpu_tensors():
+    from gkgnet_b200 import ops
+    x = torch.randn(1, 8, 4)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        ops.knn_graph(x, None, None, groups=1, k=2)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        ops.mr_aggregate(x, torch.zeros(1, 8, 2, dtype=torch.int32), None, groups=1)
+
+
+def test_state_dict_layout_matches_reference():
+    import gkgnet_b200 as G
+    from tests._util import load_golden
+    g = load_golden("gkgnet_s192")
+    net = G.build_backbone(dict(type="GKGNet", choice="s", n_classes=7, size=192))
+    sd = net.state_dict()
+    assert [str(k) for k in g["keys"]] == list(sd.keys())
+    want = [tuple(int(s) for s in str(x).split(",") if s) for x in g["shapes"]]
+    assert want == [tuple(v.shape) for v in sd.values()]
+    rel = [k for k, p in net.named_parameters() if not p.requires_grad]
+    assert rel and all(k.endswith("relative_pos") for k in rel)
+
+
+def test_grapher_dilation_schedule_and_registry():
+    import gkgnet_b200 as G
+    net = G.GKGNet(choice="t", n_classes=5, size=192, k=18, k_label_gcn=18)
+    dil = [m.graph_conv.d for m in net.modules() if isinstance(m, G.Grapher)]
+    assert dil == [1, 1, 1, 1, 2, 2, 2, 2, 2, 2, 2, 2]      # max_dilation = 49 // 18 = 2
+    assert net.layer_index == [1, 4, 11, 14]
+    with pytest.raises(KeyError):
+        G.build_backbone(dict(type="NoSuchNet"))
+    with pytest.raises(NotImplementedError):
+        G.GraphConv2d(8, 16, conv="nope")
+    with pytest.raises(NotImplementedError):
+        G.act_layer("swishh")
+    head = G.build_head(dict(type="LabelQueryHead", num_classes=7, in_channels=16))
+    lab, gap = torch.randn(2, 7, 16), torch.randn(2, 16)
+    from oracle import gkg_oracle as O
+    want = O.label_query_score(head.state_dict(), lab, gap)
+    assert torch.allclose(head.get_score((lab, gap)), want, atol=1e-6)
+    tgt = (torch.rand(2, 7) < 0.3).float()
+    got = head.forward_train((lab, gap), tgt)
+    ref = O.head_losses(head.state_dict(), lab, gap, tgt)
+    for k in ("bce_loss", "asy_loss"):
+        assert torch.allclose(got[k], ref[k], atol=1e-5, rtol=1e-5)

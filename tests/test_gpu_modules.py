@@ -1,0 +1,108 @@
+"""GPU parity at module level: Grapher / GrapherLabel / GKGNet (reference class API,
+reference weights from the golden fixtures) against the reference outputs."""
+import pytest
+import torch
+
+from oracle import gkg_oracle as O
+from oracle.gen_golden import det_tensor
+from tests._util import load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+def _same_sets(a, b):
+    return (torch.sort(a, -1).values == torch.sort(b, -1).values).all(-1).float().mean().item()
+
+
+@pytest.mark.parametrize("name,mg", [("grapher_r2", True), ("grapher_r1", True), ("grapher_nogroup", False)])
+def test_grapher_eval(name, mg):
+    import gkgnet_b200 as G
+    g = load_golden(name)
+    m = G.Grapher(16, g["k"], g["dilation"], "mr", "gelu", "batch", True, False, 0.2, g["r"], 64, 0.0,
+                  True, mg, 2)
+    missing = m.load_state_dict(g["sd"], strict=True)
+    m = m.cuda().eval()
+    for fmt in (torch.contiguous_format, torch.channels_last):
+        out = m(g["x"].cuda().contiguous(memory_format=fmt))
+        assert torch.allclose(out.cpu(), g["out"], atol=1e-4, rtol=1e-4)
+    if "edge_index" in g:
+        m.graph_conv.compact_edge_index = False
+        _, ei = m.graph_conv(m.fc1(g["x"].cuda()), m.relative_pos)
+        assert ei.dtype == torch.int64 and torch.equal(ei.cpu(), g["edge_index"])
+
+
+def test_grapher_relative_pos_matches_reference_parameter():
+    import gkgnet_b200 as G
+    g = load_golden("grapher_r2")
+    m = G.Grapher(16, 3, 1, "mr", "gelu", "batch", True, False, 0.2, 2, 64, 0.0, True, True, 2)
+    assert torch.allclose(m.relative_pos.data, g["sd"]["relative_pos"], atol=1e-6, rtol=0)
+    assert not m.relative_pos.requires_grad
+
+
+@pytest.mark.parametrize("name,mg", [("grapher_label", True), ("grapher_label_nogroup", False)])
+def test_grapher_label_eval(name, mg):
+    import gkgnet_b200 as G
+    g = load_golden(name)
+    m = G.GrapherLabel(16, g["k"], 1, "mr", "gelu", "batch", True, False, 0.2, 1, 64, 0.0, False, 5, mg, 2)
+    m.load_state_dict(g["sd"], strict=True)
+    m = m.cuda().eval()
+    out, ei = m(g["labels"].cuda(), g["features"].cuda())
+    assert torch.allclose(out.cpu(), g["out"], atol=1e-4, rtol=1e-4)
+    assert ei.dtype == torch.int64 and torch.equal(ei.cpu(), g["edge_index"])
+
+
+def test_grapher_train_grads():
+    import gkgnet_b200 as G
+    g = load_golden("grapher_train")
+    m = G.Grapher(16, g["k"], g["dilation"], "mr", "gelu", "batch", True, False, 0.2, g["r"], 64, 0.0,
+                  True, True, 2)
+    m.load_state_dict(g["sd"], strict=True)
+    m = m.cuda().train()
+    x = g["x"].cuda().requires_grad_(True)
+    out = m(x)
+    assert torch.allclose(out.cpu(), g["out"], atol=1e-4, rtol=1e-4)
+    (out * g["w"].cuda()).sum().backward()
+    assert torch.allclose(x.grad.cpu(), g["grad_x"], atol=2e-4, rtol=1e-3)
+    params = dict(m.named_parameters())
+    for k, want in g["grads"].items():
+        assert torch.allclose(params[k].grad.cpu(), want, atol=5e-4, rtol=2e-3), k
+
+
+def test_gkgnet_s192_eval():
+    import gkgnet_b200 as G
+    g = load_golden("gkgnet_s192")
+    net = G.build_backbone(dict(type="GKGNet", choice="s", k=9, k_label_gcn=9, drop_path=0.0,
+                                n_classes=7, size=192))
+    sd = net.state_dict()
+    new = {k: (v if k.endswith("relative_pos") else det_tensor(k, v.shape, v.dtype)) for k, v in sd.items()}
+    net.load_state_dict(new, strict=True)
+    net = net.cuda().eval()
+    img = det_tensor("img", (2, 3, 192, 192)) * (3 * 192 * 192) ** 0.5
+    with torch.no_grad():
+        lab, gap, ei = net(img.cuda())
+    assert tuple(lab.shape) == (2, 7, 640) and tuple(gap.shape) == (2, 640) and tuple(ei.shape) == (4, 7, 9)
+    assert ei.dtype == torch.int64
+    assert torch.allclose(gap.cpu(), g["gap"], atol=1e-3, rtol=1e-2)
+    assert torch.allclose(lab.cpu(), g["label_emb"], atol=1e-3, rtol=1e-2)
+    assert _same_sets(ei.cpu(), g["edge_index"]) > 0.95
+
+
+def test_gkgnet_576_bf16_smoke():
+    """BASELINE config 3/4 plumbing at batch 2: GKGNet-576 fwd+bwd under bf16 autocast."""
+    import gkgnet_b200 as G
+    G.set_norm_type("BN")
+    try:
+        net = G.GKGNet(choice="s", n_classes=80, size=576, drop_path=0.1).cuda().train()
+        head = G.LabelQueryHead(80, 640).cuda()
+    finally:
+        G.set_norm_type("SyncBN")
+    img = torch.randn(2, 3, 576, 576, device="cuda")
+    tgt = (torch.rand(2, 80, device="cuda") < 0.04).float()
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        feats = net(img)
+        losses = head.forward_train(feats, tgt)
+    loss = sum(losses.values())
+    loss.backward()
+    assert torch.isfinite(loss)
+    missing = [n for n, p in net.named_parameters() if p.requires_grad and p.grad is None]
+    assert not missing, missing[:5]
