@@ -1,15 +1,746 @@
-// placeholder until the tcgen05 kernel lands
+// Fused pairwise-distance + top-k on the Blackwell tensor cores (tcgen05 / TMEM / TMA bulk).
+//
+// What it computes (reference: torch_edge.py:39-51, 89-106, 139-149): for every query row n
+// of problem p, the k*dilation keys with the smallest
+//     dist[n, m] = (|xh_n|^2 - 2 xh_n . yh_m) + |yh_m|^2 + relative_pos[n, m]
+// in ascending order, every `dilation`-th kept.  The N x M matrix never leaves the SM:
+//
+//   * operands: gkg_knn_prepare splits the normalised fp32 rows into fp16 hi/lo parts
+//     (scaled by 256 so the lo part stays normal) and writes them K-concatenated,
+//         A = [x_hi | x_hi | x_lo | S  S ],   B = [y_hi | y_lo | y_hi | c_hi c_lo]
+//     with c = -0.5*|yh|^2*S, so ONE fp16 GEMM with fp32 accumulation yields
+//     S^2 (xh.yh - |yh|^2/2) to ~2^-21 relative -- the "fp16x3" split.  Rows are stored
+//     in the UMMA no-swizzle K-major core-matrix order, tile by tile, so a whole operand
+//     tile is one contiguous TMA bulk copy (cp.async.bulk, mbarrier complete_tx);
+//   * warp 0 streams tiles (A: one 128-row query tile, all K; B: 128-key blocks through a
+//     ring), warp 1 issues tcgen05.mma (M=128, N=128, K=16 per instruction) into one of
+//     four 128-column TMEM accumulators, warps 2-5 drain accumulators with tcgen05.ld
+//     (thread == query row), add the bias and keep a per-row candidate list;
+//   * selection: threshold filter into a per-thread shared-memory buffer (branch-free),
+//     batched insertion into a sorted register list of T = k*d + 2 entries;
+//   * exactness: rows whose approximate gaps are below 2*delta are re-ranked with the
+//     exact fp32 formula (same arithmetic as knn_exact.cu); rows whose candidate set
+//     itself is in doubt go to a tiny exact fix-up kernel.
 #include "knn_tc.cuh"
+
 namespace gkg {
-bool knn_tc_supported(int, int, int, int, int) { return false; }
-size_t knn_tc_workspace_bytes(int, int, int, int, int, int, bool) { return 0; }
-int launch_knn_tc_prepare(const KnnWorkspace&, void*, int, int, int, int, int, int, bool, cudaStream_t) {
-  set_error("knn_tc: not built");
-  return GKG_EINVAL;
+
+namespace {
+
+constexpr int BM = 128;            // query rows per tile  (UMMA M)
+constexpr int BN = 128;            // keys per tile        (UMMA N)
+constexpr int NTHREADS = 192;      // warp 0 TMA, warp 1 MMA, warps 2..5 epilogue
+constexpr int NACC = 4;            // TMEM accumulators (4 x 128 columns = 512)
+constexpr int CAND_CAP = 40;       // per-row candidate buffer entries (>= max T for the id staging)
+constexpr float kScale = 256.f;    // operand scale S
+constexpr float kPadKey = -60000.f;  // B extra column of padded keys -> dist ~ +468
+constexpr float kDelta = 4e-6f;    // bound on |approx - exact| of the fp16x3 GEMM (dist units)
+constexpr int MAX_A_BUF = 2;
+constexpr int MAX_STAGES = 8;
+
+struct Plan {
+  int KP, KC, NKB, NA, NS, QT, KT;
+  uint32_t a_tile_bytes, b_block_bytes;
+  size_t smem_bytes;
+  size_t a_op_bytes, b_op_bytes;   // per launch operand buffers
+  bool ok;
+};
+
+constexpr size_t kSmemBudget = 227 * 1024;
+constexpr size_t kCandBytes = (size_t)BM * CAND_CAP * 8;
+constexpr size_t kBarBytes = 1024;
+
+Plan make_plan(int P, int N, int M, int D) {
+  Plan pl{};
+  pl.KP = (3 * D + 2 + 15) / 16 * 16;
+  pl.QT = (N + BM - 1) / BM;
+  pl.KT = (M + BN - 1) / BN;
+  pl.a_tile_bytes = (uint32_t)BM * pl.KP * 2;
+  pl.ok = false;
+  for (int na = MAX_A_BUF; na >= 1 && !pl.ok; --na) {
+    const size_t fixed = kCandBytes + kBarBytes + (size_t)na * pl.a_tile_bytes;
+    if (fixed >= kSmemBudget) continue;
+    const size_t room = kSmemBudget - fixed;
+    for (int kc = pl.KP; kc >= 16; kc -= 16) {
+      if (pl.KP % kc) continue;
+      const size_t blk = (size_t)BN * kc * 2;
+      int ns = (int)(room / blk);
+      if (ns > MAX_STAGES) ns = MAX_STAGES;
+      const int want = (na == 1) ? 2 : 3;
+      if (ns >= want || (ns >= 2 && kc == 16)) {
+        pl.NA = na; pl.KC = kc; pl.NKB = pl.KP / kc; pl.NS = ns;
+        pl.b_block_bytes = (uint32_t)blk;
+        pl.ok = true;
+        break;
+      }
+    }
+  }
+  if (!pl.ok) return pl;
+  pl.smem_bytes = kCandBytes + kBarBytes + (size_t)pl.NA * pl.a_tile_bytes + (size_t)pl.NS * pl.b_block_bytes;
+  pl.a_op_bytes = (size_t)P * pl.QT * pl.a_tile_bytes;
+  pl.b_op_bytes = (size_t)P * pl.KT * (size_t)BN * pl.KP * 2;
+  return pl;
 }
-int launch_knn_tc(const KnnWorkspace&, void*, const float*, int32_t*, int, int, int, int, int, int, bool,
-                  cudaStream_t) {
-  set_error("knn_tc: not built");
-  return GKG_EINVAL;
+
+// ------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
 }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok;
+}
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+// Bounded wait: a protocol bug must abort the kernel, never hang the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const unsigned long long t0 = globaltimer_ns();
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if ((++spins & 1023u) == 0 && globaltimer_ns() - t0 > 4000000000ull) __trap();
+  }
+}
+__device__ __forceinline__ void tma_bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                         uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+// The loaded registers are threaded through the wait so the compiler cannot hoist their uses.
+__device__ __forceinline__ void tmem_ld_wait(uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.wait::ld.sync.aligned;"
+      : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+        "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]),
+        "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]),
+        "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+      :
+      : "memory");
+}
+
+// UMMA shared-memory descriptor, no swizzle, K-major: core matrix = 8 rows x 16 bytes stored
+// contiguously; LBO = byte distance between core matrices adjacent in K, SBO = between 8-row
+// groups (cute::UMMA::SmemDescriptor: start[0,14) lbo[16,30) sbo[32,46) version[46,48)=1).
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) |
+         (1ull << 46);
+}
+// kind::f16 instruction descriptor: D=f32 (bit 4), A=B=f16 (0), K-major both, N>>3 at 17, M>>4 at 24.
+constexpr uint32_t kIdesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+
+// ------------------------------------------------------------------------------------
+// operand conversion (phase "prepare")
+// ------------------------------------------------------------------------------------
+// One thread writes one 16-byte core-matrix row (8 fp16 of one node).  Layout per problem:
+// [tile][k-block][row group (16)][k chunk (KC/8)][row (8)][elem (8)].
+template <bool IS_KEY>
+__global__ void __launch_bounds__(256)
+tc_operand_kernel(const float* __restrict__ hat, const float* __restrict__ sq, __half* __restrict__ op,
+                  int rows, int D, int KP, int KC, int tiles, long long total_chunks) {
+  const int chunks_per_row = KP >> 3;
+  const int kcs = KC >> 3;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total_chunks;
+       i += (long long)gridDim.x * blockDim.x) {
+    // decode destination index (fastest -> slowest): r(8), kc, rg(16), kb, tile, p
+    long long t = i;
+    const int r = (int)(t & 7); t >>= 3;
+    const int kc = (int)(t % kcs); t /= kcs;
+    const int rg = (int)(t & 15); t >>= 4;
+    const int nkb = KP / KC;
+    const int kb = (int)(t % nkb); t /= nkb;
+    const int tile = (int)(t % tiles);
+    const long long p = t / tiles;
+    const int row = tile * 128 + rg * 8 + r;
+    const int c0 = kb * KC + kc * 8;
+    (void)chunks_per_row;
+    __align__(16) __half out[8];
+    const bool valid = row < rows;
+    const float* src = hat + (p * rows + (valid ? row : 0)) * (long long)D;
+    float extra_hi = 0.f, extra_lo = 0.f;
+    if (IS_KEY) {
+      if (valid) {
+        const float c = -0.5f * sq[p * rows + row] * kScale;
+        const __half h = __float2half_rn(c);
+        extra_hi = __half2float(h);
+        extra_lo = c - extra_hi;
+      } else {
+        extra_hi = kPadKey;
+      }
+    } else {
+      extra_hi = valid ? kScale : 0.f;
+      extra_lo = valid ? kScale : 0.f;
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int c = c0 + e;
+      float v = 0.f;
+      if (c < 3 * D) {
+        if (valid) {
+          const int seg = c / D;
+          const float x = src[c - seg * D] * kScale;
+          const float hi = __half2float(__float2half_rn(x));
+          // A = [hi | hi | lo], B = [hi | lo | hi]
+          const bool want_lo = IS_KEY ? (seg == 1) : (seg == 2);
+          v = want_lo ? (x - hi) : hi;
+        }
+      } else if (c == 3 * D) {
+        v = extra_hi;
+      } else if (c == 3 * D + 1) {
+        v = extra_lo;
+      }
+      out[e] = __float2half_rn(v);
+    }
+    *reinterpret_cast<uint4*>(op + i * 8) = *reinterpret_cast<const uint4*>(out);
+  }
+}
+
+// ------------------------------------------------------------------------------------
+// sorted candidate list (registers)
+// ------------------------------------------------------------------------------------
+template <int T>
+struct TopList {
+  float v[T];
+  int id[T];
+  __device__ __forceinline__ void init() {
+#pragma unroll
+    for (int s = 0; s < T; ++s) { v[s] = INFINITY; id[s] = 0x7fffffff; }
+  }
+  // requires x < v[T-1]; equal values keep arrival order
+  __device__ __forceinline__ void insert(float x, int m) {
+#pragma unroll
+    for (int s = T - 1; s >= 1; --s) {
+      const bool up = x < v[s - 1];
+      const bool here = (!up) && (x < v[s]);
+      v[s] = up ? v[s - 1] : (here ? x : v[s]);
+      id[s] = up ? id[s - 1] : (here ? m : id[s]);
+    }
+    if (x < v[0]) { v[0] = x; id[0] = m; }
+  }
+};
+
+// Merge the buffered candidates of every lane into its sorted list (warp-uniform trip count).
+template <int T>
+__device__ __forceinline__ void compact_candidates(TopList<T>& top, float& tau, int& cnt, const float2* cbuf) {
+  const int mx = __reduce_max_sync(0xffffffffu, cnt);
+  for (int e = 0; e < mx; ++e) {
+    if (e < cnt) {
+      const float2 c = cbuf[e * BM];
+      if (c.x < tau) {
+        top.insert(c.x, __float_as_int(c.y));
+        tau = top.v[T - 1];
+      }
+    }
+  }
+  cnt = 0;
+}
+
+struct TcParams {
+  const __half* a_op;
+  const __half* b_op;
+  const float* xhat; const float* xsq; const float* yhat; const float* ysq;
+  const float* relpos;
+  int32_t* idx_out;
+  int* fix_count; int* fix_rows; unsigned int* stats;   // stats: [0] ambiguous rows, [1] max err bits
+  float* dbg_dist;
+  int P, N, M, D, k, dilation, kd;
+  int KP, KC, NKB, NA, NS, QT, KT;
+  uint32_t a_tile_bytes, b_block_bytes;
+  int force_rerank;
+};
+
+__device__ __forceinline__ float exact_dist(const float* __restrict__ xr, const float* __restrict__ yr, int D,
+                                            float xs, float ys, const float* relrow, int m) {
+  float acc = 0.f;
+  for (int d = 0; d < D; ++d) acc = fmaf(xr[d], yr[d], acc);
+  float v = (xs + (-2.f * acc)) + ys;
+  if (relrow != nullptr) v += relrow[m];
+  return v;
+}
+
+template <int T, bool HAS_REL>
+__global__ void __launch_bounds__(NTHREADS, 1) knn_tc_kernel(const TcParams prm) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  // carve-up: [A x NA][B ring x NS][candidates][barriers + tmem ptr]
+  uint8_t* sA = smem;
+  uint8_t* sB = sA + (size_t)prm.NA * prm.a_tile_bytes;
+  float2* cand = reinterpret_cast<float2*>(sB + (size_t)prm.NS * prm.b_block_bytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(cand) + kCandBytes);
+  uint64_t* a_full = bars;                    // [MAX_A_BUF]
+  uint64_t* a_empty = a_full + MAX_A_BUF;     // [MAX_A_BUF]
+  uint64_t* b_full = a_empty + MAX_A_BUF;     // [MAX_STAGES]
+  uint64_t* b_empty = b_full + MAX_STAGES;    // [MAX_STAGES]
+  uint64_t* t_full = b_empty + MAX_STAGES;    // [NACC]
+  uint64_t* t_empty = t_full + NACC;          // [NACC]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + NACC);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < MAX_A_BUF; ++i) { mbar_init(smem_u32(a_full + i), 1); mbar_init(smem_u32(a_empty + i), 1); }
+    for (int i = 0; i < MAX_STAGES; ++i) { mbar_init(smem_u32(b_full + i), 1); mbar_init(smem_u32(b_empty + i), 1); }
+    for (int i = 0; i < NACC; ++i) { mbar_init(smem_u32(t_full + i), 1); mbar_init(smem_u32(t_empty + i), 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "n"(512)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int total_items = prm.P * prm.QT;
+
+  if (warp == 0) {
+    // ================================ TMA producer ===================================
+    if (lane == 0) {
+      int ab = 0, aph = 0, bs = 0, bph = 0;
+      for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+        const int p = item / prm.QT, qt = item - p * prm.QT;
+        mbar_wait(smem_u32(a_empty + ab), aph ^ 1);
+        mbar_expect_tx(smem_u32(a_full + ab), prm.a_tile_bytes);
+        tma_bulk_g2s(smem_u32(sA + (size_t)ab * prm.a_tile_bytes),
+                     reinterpret_cast<const uint8_t*>(prm.a_op) + ((size_t)p * prm.QT + qt) * prm.a_tile_bytes,
+                     prm.a_tile_bytes, smem_u32(a_full + ab));
+        if (++ab == prm.NA) { ab = 0; aph ^= 1; }
+        const uint8_t* bsrc = reinterpret_cast<const uint8_t*>(prm.b_op) +
+                              (size_t)p * prm.KT * prm.NKB * prm.b_block_bytes;
+        const int nblk = prm.KT * prm.NKB;
+        for (int blk = 0; blk < nblk; ++blk) {
+          mbar_wait(smem_u32(b_empty + bs), bph ^ 1);
+          mbar_expect_tx(smem_u32(b_full + bs), prm.b_block_bytes);
+          tma_bulk_g2s(smem_u32(sB + (size_t)bs * prm.b_block_bytes), bsrc + (size_t)blk * prm.b_block_bytes,
+                       prm.b_block_bytes, smem_u32(b_full + bs));
+          if (++bs == prm.NS) { bs = 0; bph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer =====================================
+    if (lane == 0) {
+      int ab = 0, aph = 0, bs = 0, bph = 0, tb = 0, tph = 0;
+      const uint32_t lbo = 128, sbo = (uint32_t)(prm.KC >> 3) * 128;
+      const int ksteps = prm.KC >> 4;
+      for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+        mbar_wait(smem_u32(a_full + ab), aph);
+        tc_fence_after();
+        const uint32_t a_base = smem_u32(sA + (size_t)ab * prm.a_tile_bytes);
+        for (int kt = 0; kt < prm.KT; ++kt) {
+          mbar_wait(smem_u32(t_empty + tb), tph ^ 1);
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + (uint32_t)tb * BN;
+          for (int kb = 0; kb < prm.NKB; ++kb) {
+            mbar_wait(smem_u32(b_full + bs), bph);
+            tc_fence_after();
+            const uint32_t a_addr = a_base + (uint32_t)kb * (BM * prm.KC * 2);
+            const uint32_t b_addr = smem_u32(sB + (size_t)bs * prm.b_block_bytes);
+            for (int ks = 0; ks < ksteps; ++ks) {
+              const uint64_t ad = make_smem_desc(a_addr + ks * 256, lbo, sbo);
+              const uint64_t bd = make_smem_desc(b_addr + ks * 256, lbo, sbo);
+              umma_f16(d_tmem, ad, bd, kIdesc, (kb | ks) != 0 ? 1u : 0u);
+            }
+            umma_commit(smem_u32(b_empty + bs));       // frees the B block when the MMAs retire
+            if (++bs == prm.NS) { bs = 0; bph ^= 1; }
+          }
+          umma_commit(smem_u32(t_full + tb));           // accumulator ready for the epilogue
+          if (++tb == NACC) { tb = 0; tph ^= 1; }
+        }
+        umma_commit(smem_u32(a_empty + ab));            // A tile may be overwritten
+        if (++ab == prm.NA) { ab = 0; aph ^= 1; }
+      }
+    }
+  } else {
+    // ================================ epilogue / selection ===========================
+    const int q = warp & 3;                      // TMEM lane quarter this warp may read
+    const int row_t = q * 32 + lane;
+    float2* cbuf = cand + row_t;                 // entry e at cbuf[e * BM]
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+    const float c_scale = -2.f / (kScale * kScale);
+    int tb = 0, tph = 0;
+    TopList<T> top;
+    for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+      const int p = item / prm.QT, qt = item - p * prm.QT;
+      const int n = qt * BM + row_t;
+      const bool row_ok = n < prm.N;
+      const int n_c = row_ok ? n : prm.N - 1;
+      const float* relrow = HAS_REL ? prm.relpos + (size_t)n_c * prm.M : nullptr;
+      top.init();
+      float tau = INFINITY;
+      int cnt = 0;
+
+      for (int kt = 0; kt < prm.KT; ++kt) {
+        mbar_wait(smem_u32(t_full + tb), tph);
+        tc_fence_after();
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+          uint32_t r[32];
+          tmem_ld32(lane_addr + (uint32_t)(tb * BN + c * 32), r);
+          const int m0 = kt * BN + c * 32;
+          float bias[32];
+          if (HAS_REL) {
+            if ((prm.M & 3) == 0) {
+#pragma unroll
+              for (int j4 = 0; j4 < 8; ++j4) {
+                float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (m0 + j4 * 4 < prm.M) b4 = __ldg(reinterpret_cast<const float4*>(relrow + m0 + j4 * 4));
+                bias[j4 * 4 + 0] = b4.x; bias[j4 * 4 + 1] = b4.y; bias[j4 * 4 + 2] = b4.z; bias[j4 * 4 + 3] = b4.w;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) bias[j] = (m0 + j < prm.M) ? __ldg(relrow + m0 + j) : 0.f;
+            }
+          }
+          tmem_ld_wait(r);
+          if (prm.dbg_dist != nullptr && row_ok) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              if (m0 + j < prm.M) {
+                const float acc = __uint_as_float(r[j]);
+                prm.dbg_dist[((size_t)p * prm.N + n) * prm.M + m0 + j] =
+                    HAS_REL ? fmaf(acc, c_scale, bias[j]) : acc * c_scale;
+              }
+            }
+          }
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+#pragma unroll
+            for (int jj = 0; jj < 16; ++jj) {
+              const int j = half * 16 + jj;
+              const float acc = __uint_as_float(r[j]);
+              const float v = HAS_REL ? fmaf(acc, c_scale, bias[j]) : acc * c_scale;
+              if (v < tau) {
+                cbuf[cnt * BM] = make_float2(v, __int_as_float(m0 + j));
+                ++cnt;
+              }
+            }
+            // the buffer must always have room for the next 16 candidates
+            if (__any_sync(0xffffffffu, cnt > CAND_CAP - 16)) compact_candidates<T>(top, tau, cnt, cbuf);
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(t_empty + tb));
+        if (++tb == NACC) { tb = 0; tph ^= 1; }
+      }
+      compact_candidates<T>(top, tau, cnt, cbuf);
+
+      // ---------------- finalise the row -------------------------------------------
+      const int kd = prm.kd;
+      bool amb = prm.force_rerank != 0;
+#pragma unroll
+      for (int s = 0; s + 1 < T; ++s)
+        if (s < kd && (top.v[s + 1] - top.v[s]) < 2.f * kDelta) amb = true;
+      if (row_ok && amb) {
+        // exact fp32 re-rank of the T candidates (identical arithmetic to knn_exact.cu)
+        const float* xr = prm.xhat + ((size_t)p * prm.N + n) * prm.D;
+        const float xs = prm.xsq[(size_t)p * prm.N + n];
+        const float* yb = prm.yhat + (size_t)p * prm.M * prm.D;
+        const float* ysb = prm.ysq + (size_t)p * prm.M;
+        const float a_last = top.v[T - 1];
+        float maxerr = 0.f;
+#pragma unroll
+        for (int s = 0; s < T; ++s) {
+          const int m = top.id[s];
+          if (m < prm.M) {
+            const float e = exact_dist(xr, yb + (size_t)m * prm.D, prm.D, xs, ysb[m], relrow, m);
+            maxerr = fmaxf(maxerr, fabsf((e - xs) - top.v[s]));
+            top.v[s] = e;
+          } else {
+            top.v[s] = INFINITY;
+          }
+        }
+        // odd-even transposition sort by (dist, id)
+#pragma unroll
+        for (int pass = 0; pass < T; ++pass) {
+#pragma unroll
+          for (int s = pass & 1; s + 1 < T; s += 2) {
+            const bool sw = (top.v[s + 1] < top.v[s]) || (top.v[s + 1] == top.v[s] && top.id[s + 1] < top.id[s]);
+            const float tv = sw ? top.v[s] : top.v[s + 1];
+            const int ti = sw ? top.id[s] : top.id[s + 1];
+            top.v[s] = sw ? top.v[s + 1] : top.v[s];
+            top.id[s] = sw ? top.id[s + 1] : top.id[s];
+            top.v[s + 1] = tv;
+            top.id[s + 1] = ti;
+          }
+        }
+        atomicAdd(prm.stats + 0, 1u);
+        atomicMax(prm.stats + 1, __float_as_uint(maxerr));
+        // candidate set in doubt?  every non-candidate has approx >= a_last
+        float e_kd = -INFINITY;               // sorted ascending: kd-th value == max of the first kd
+#pragma unroll
+        for (int s = 0; s < T; ++s)
+          if (s < kd) e_kd = fmaxf(e_kd, top.v[s]);
+        if (a_last - kDelta <= (e_kd - xs) + kDelta && prm.M > T) {
+          const int slot = atomicAdd(prm.fix_count, 1);
+          prm.fix_rows[slot] = p * prm.N + n;
+        }
+      }
+      // stage the ids in this thread's (now idle) candidate slots so that the dilated pick is a
+      // shared-memory index, not a dynamic register index
+#pragma unroll
+      for (int s = 0; s < T; ++s) cbuf[s * BM].y = __int_as_float(top.id[s]);
+      if (row_ok) {
+        int32_t* out = prm.idx_out + ((size_t)p * prm.N + n) * prm.k;
+        for (int j = 0; j < prm.k; ++j) out[j] = __float_as_int(cbuf[j * prm.dilation * BM].y);
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------
+// exact fix-up for rows whose candidate set could not be certified (rare)
+// ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+knn_fixup_kernel(const int* __restrict__ count, const int* __restrict__ rows, const float* __restrict__ xhat,
+                 const float* __restrict__ xsq, const float* __restrict__ yhat, const float* __restrict__ ysq,
+                 const float* __restrict__ relpos, int32_t* __restrict__ idx_out, int N, int M, int D, int k,
+                 int dilation) {
+  extern __shared__ float dist_s[];            // [M]
+  __shared__ float red_v[8];
+  __shared__ int red_i[8];
+  __shared__ float sel_v;
+  __shared__ int sel_i;
+  const int total = *count;
+  const int kd = k * dilation;
+  for (int item = blockIdx.x; item < total; item += gridDim.x) {
+    const int id = rows[item];
+    const int p = id / N, n = id - p * N;
+    const float* xr = xhat + (size_t)id * D;
+    const float xs = xsq[id];
+    const float* relrow = relpos ? relpos + (size_t)n * M : nullptr;
+    for (int m = threadIdx.x; m < M; m += blockDim.x)
+      dist_s[m] = exact_dist(xr, yhat + ((size_t)p * M + m) * D, D, xs, ysq[(size_t)p * M + m], relrow, m);
+    __syncthreads();
+    float last_v = -INFINITY;
+    int last_i = -1;
+    for (int r = 0; r < kd; ++r) {
+      float bv = INFINITY;
+      int bi = 0x7fffffff;
+      for (int m = threadIdx.x; m < M; m += blockDim.x) {
+        const float v = dist_s[m];
+        const bool after = (v > last_v) || (v == last_v && m > last_i);
+        if (after && (v < bv || (v == bv && m < bi))) { bv = v; bi = m; }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ov < bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+      }
+      if ((threadIdx.x & 31) == 0) { red_v[threadIdx.x >> 5] = bv; red_i[threadIdx.x >> 5] = bi; }
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; ++w)
+          if (red_v[w] < bv || (red_v[w] == bv && red_i[w] < bi)) { bv = red_v[w]; bi = red_i[w]; }
+        sel_v = bv; sel_i = bi;
+        if (r % dilation == 0) idx_out[(size_t)id * k + r / dilation] = bi;
+      }
+      __syncthreads();
+      last_v = sel_v;
+      last_i = sel_i;
+    }
+    __syncthreads();
+  }
+}
+
+struct TcWorkspace {
+  __half* a_op; __half* b_op; int* fix_count; int* fix_rows; unsigned int* stats; size_t bytes;
+};
+
+TcWorkspace carve_tc(void* base, const Plan& pl, int P, int N) {
+  TcWorkspace w;
+  size_t off = 0;
+  char* b = static_cast<char*>(base);
+  auto take = [&](size_t n) { void* p = b ? b + off : nullptr; off += align_up(n, 256); return p; };
+  w.a_op = static_cast<__half*>(take(pl.a_op_bytes));
+  w.b_op = static_cast<__half*>(take(pl.b_op_bytes));
+  w.fix_count = static_cast<int*>(take(256));
+  w.stats = reinterpret_cast<unsigned int*>(w.fix_count ? w.fix_count + 4 : nullptr);
+  w.fix_rows = static_cast<int*>(take(sizeof(int) * (size_t)P * N));
+  w.bytes = off;
+  return w;
+}
+
+int g_force_rerank = 0;
+float* g_dbg_dist = nullptr;
+unsigned int g_last_stats[4] = {0, 0, 0, 0};
+
+template <int T>
+int launch_select_t(const TcParams& prm, const Plan& pl, bool has_rel, cudaStream_t stream) {
+  auto kern = has_rel ? knn_tc_kernel<T, true> : knn_tc_kernel<T, false>;
+  size_t smem = pl.smem_bytes < 120 * 1024 ? 120 * 1024 : pl.smem_bytes;   // 512 TMEM columns: 1 CTA / SM
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) {
+    set_error("knn_tc: cudaFuncSetAttribute(%zu): %s", smem, cudaGetErrorString(e));
+    return GKG_ECUDA;
+  }
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int items = prm.P * prm.QT;
+  const int grid = items < sms ? items : sms;
+  kern<<<grid, NTHREADS, smem, stream>>>(prm);
+  GKG_CHECK_LAUNCH("knn_tc_kernel");
+  return GKG_OK;
+}
+
+}  // namespace
+
+bool knn_tc_supported(int N, int M, int D, int k, int dilation) {
+  const int kd = k * dilation;
+  if (kd + 2 > 38 || kd > M) return false;
+  if (N < 1 || M < 1) return false;
+  Plan pl = make_plan(1, N, M, D);
+  return pl.ok;
+}
+
+size_t knn_tc_workspace_bytes(int P, int N, int M, int D, int k, int dilation, bool self_keys) {
+  (void)k; (void)dilation; (void)self_keys;
+  Plan pl = make_plan(P, N, M, D);
+  if (!pl.ok) return 0;
+  return carve_tc(nullptr, pl, P, N).bytes;
+}
+
+int launch_knn_tc_prepare(const KnnWorkspace& w, void* extra_ws, int P, int N, int M, int D, int k,
+                          int dilation, bool self_keys, cudaStream_t stream) {
+  (void)k; (void)dilation; (void)self_keys;
+  Plan pl = make_plan(P, N, M, D);
+  GKG_CHECK_ARG(pl.ok, "knn_tc: no tiling for D=%d", D);
+  TcWorkspace t = carve_tc(extra_ws, pl, P, N);
+  {
+    const long long chunks = (long long)P * pl.QT * BM * (pl.KP / 8);
+    const unsigned grid = (unsigned)((chunks + 255) / 256 < 148LL * 32 ? (chunks + 255) / 256 : 148LL * 32);
+    tc_operand_kernel<false><<<grid, 256, 0, stream>>>(w.xhat, w.xsq, t.a_op, N, D, pl.KP, pl.KC, pl.QT, chunks);
+    GKG_CHECK_LAUNCH("tc_operand_kernel<query>");
+  }
+  {
+    const long long chunks = (long long)P * pl.KT * BN * (pl.KP / 8);
+    const unsigned grid = (unsigned)((chunks + 255) / 256 < 148LL * 32 ? (chunks + 255) / 256 : 148LL * 32);
+    tc_operand_kernel<true><<<grid, 256, 0, stream>>>(w.yhat, w.ysq, t.b_op, M, D, pl.KP, pl.KC, pl.KT, chunks);
+    GKG_CHECK_LAUNCH("tc_operand_kernel<key>");
+  }
+  return GKG_OK;
+}
+
+int launch_knn_tc(const KnnWorkspace& w, void* extra_ws, const float* relpos, int32_t* idx_out, int P,
+                  int N, int M, int D, int k, int dilation, bool self_keys, cudaStream_t stream) {
+  (void)self_keys;
+  Plan pl = make_plan(P, N, M, D);
+  GKG_CHECK_ARG(pl.ok, "knn_tc: no tiling for D=%d", D);
+  TcWorkspace t = carve_tc(extra_ws, pl, P, N);
+  cudaError_t e = cudaMemsetAsync(t.fix_count, 0, 256, stream);
+  if (e != cudaSuccess) {
+    set_error("knn_tc: memset: %s", cudaGetErrorString(e));
+    return GKG_ECUDA;
+  }
+  count_launch();
+  TcParams prm{};
+  prm.a_op = t.a_op; prm.b_op = t.b_op;
+  prm.xhat = w.xhat; prm.xsq = w.xsq; prm.yhat = w.yhat; prm.ysq = w.ysq;
+  prm.relpos = relpos; prm.idx_out = idx_out;
+  prm.fix_count = t.fix_count; prm.fix_rows = t.fix_rows; prm.stats = t.stats;
+  prm.dbg_dist = g_dbg_dist;
+  prm.P = P; prm.N = N; prm.M = M; prm.D = D; prm.k = k; prm.dilation = dilation; prm.kd = k * dilation;
+  prm.KP = pl.KP; prm.KC = pl.KC; prm.NKB = pl.NKB; prm.NA = pl.NA; prm.NS = pl.NS; prm.QT = pl.QT; prm.KT = pl.KT;
+  prm.a_tile_bytes = pl.a_tile_bytes; prm.b_block_bytes = pl.b_block_bytes;
+  prm.force_rerank = g_force_rerank;
+  const int T = prm.kd + 2;
+  const bool has_rel = relpos != nullptr;
+  int rc;
+  if (T <= 11) rc = launch_select_t<11>(prm, pl, has_rel, stream);
+  else if (T <= 20) rc = launch_select_t<20>(prm, pl, has_rel, stream);
+  else if (T <= 29) rc = launch_select_t<29>(prm, pl, has_rel, stream);
+  else rc = launch_select_t<38>(prm, pl, has_rel, stream);
+  if (rc != GKG_OK) return rc;
+  const size_t fsmem = sizeof(float) * (size_t)M;
+  GKG_CHECK_ARG(fsmem <= 200 * 1024, "knn_tc: M=%d too large for the fix-up kernel", M);
+  static size_t fix_configured = 0;
+  if (fsmem > 48 * 1024 && fsmem > fix_configured) {
+    cudaFuncSetAttribute(knn_fixup_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem);
+    fix_configured = fsmem;
+  }
+  knn_fixup_kernel<<<148, 256, fsmem, stream>>>(t.fix_count, t.fix_rows, w.xhat, w.xsq, w.yhat, w.ysq, relpos,
+                                                idx_out, N, M, D, k, dilation);
+  GKG_CHECK_LAUNCH("knn_fixup_kernel");
+  if (g_dbg_dist != nullptr || g_force_rerank) {   // debug only: expose the counters
+    cudaStreamSynchronize(stream);
+    cudaMemcpy(g_last_stats, t.fix_count, sizeof(g_last_stats), cudaMemcpyDeviceToHost);
+    // layout: [0] fix_count, [4..] stats -> copy stats separately
+    unsigned int st[2];
+    cudaMemcpy(st, t.stats, sizeof(st), cudaMemcpyDeviceToHost);
+    g_last_stats[1] = st[0];
+    g_last_stats[2] = st[1];
+  }
+  return GKG_OK;
+}
+
 }  // namespace gkg
+
+// debug hooks (not part of the public header; used by tests through ctypes)
+extern "C" void gkg_debug_knn_tc(int force_rerank, float* dbg_dist) {
+  gkg::g_force_rerank = force_rerank;
+  gkg::g_dbg_dist = dbg_dist;
+}
+extern "C" void gkg_debug_knn_tc_stats(unsigned int* out3) {
+  out3[0] = gkg::g_last_stats[0];
+  out3[1] = gkg::g_last_stats[1];
+  out3[2] = gkg::g_last_stats[2];
+}

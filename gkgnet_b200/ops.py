@@ -90,7 +90,7 @@ class _MRAggregate(torch.autograd.Function):
             y = _token_major(y)
         M = N if self_keys else y.shape[1]
         out = torch.empty((B, N, 2 * C), dtype=x.dtype, device=x.device)
-        need_grad = x.requires_grad or (y is not None and y.requires_grad)
+        need_grad = any(ctx.needs_input_grad[:2])
         amax = torch.empty((B, N, C), dtype=torch.uint8, device=x.device) if need_grad else None
         rc = lib.gkg_mr_aggregate_fwd(
             x.data_ptr(), x.stride(0), x.stride(1),

@@ -1,0 +1,86 @@
+"""GPU: bring-up and accuracy checks specific to the tcgen05 kNN kernel (debug hooks of
+libgkg_b200.so: raw approximate distances out of TMEM, forced exact re-rank statistics)."""
+import ctypes
+
+import pytest
+import torch
+
+from oracle import gkg_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+KDELTA = 4e-6      # kDelta in csrc/knn_tc.cu
+
+
+def _ref_layout(t, G):
+    B, N, C = t.shape
+    D = C // G
+    return t.reshape(B, N, G, D).permute(0, 2, 3, 1).reshape(B * G, D, N, 1)
+
+
+def _debug(lib, force, buf):
+    lib.gkg_debug_knn_tc.argtypes = [ctypes.c_int, ctypes.c_void_p]
+    lib.gkg_debug_knn_tc.restype = None
+    lib.gkg_debug_knn_tc(int(force), None if buf is None else buf.data_ptr())
+
+
+def _stats(lib):
+    arr = (ctypes.c_uint * 3)()
+    lib.gkg_debug_knn_tc_stats.argtypes = [ctypes.c_void_p]
+    lib.gkg_debug_knn_tc_stats(arr)
+    import struct
+    return {"fixups": arr[0], "ambiguous": arr[1], "max_err": struct.unpack("f", struct.pack("I", arr[2]))[0]}
+
+
+@pytest.mark.parametrize("B,G,N,M,D,bias", [
+    (1, 2, 200, 300, 40, True),      # KP=128, one k-block
+    (2, 2, 128, 128, 40, False),     # exact tile multiples
+    (1, 2, 260, 140, 80, True),      # KP=256 -> 4 k-blocks of 64
+    (1, 2, 150, 270, 200, True),     # KP=608 -> 19 k-blocks of 32, single A buffer
+    (1, 8, 100, 90, 10, False),      # KP=32
+    (1, 1, 90, 2000, 40, False),     # label-head like: many key tiles
+])
+def test_tc_raw_distances(B, G, N, M, D, bias):
+    from gkgnet_b200 import _lib, ops
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(7)
+    C = G * D
+    x = torch.randn(B, N, C, generator=g)
+    y = torch.randn(B, M, C, generator=g)
+    rel = -(0.5 + 0.5 * torch.rand(1, N, M, generator=g)) if bias else None
+    dbg = torch.full((B * G, N, M), float("nan"), device="cuda")
+    _debug(lib, 1, dbg)
+    try:
+        idx = ops.knn_graph(x.cuda(), y.cuda(), None if rel is None else rel.cuda(), groups=G, k=9,
+                            dilation=1, algo=_lib.KNN_TCGEN05)
+        torch.cuda.synchronize()
+        st = _stats(lib)
+    finally:
+        _debug(lib, 0, None)
+    xr, yr = _ref_layout(x, G), _ref_layout(y, G)
+    dist = O.knn_distance_matrix(xr, yr, rel)
+    xn = O.l2_normalize(xr, 1).squeeze(-1)
+    xsq = (xn * xn).sum(1)                      # (P, N)
+    want = dist - xsq.unsqueeze(-1)             # the kernel ranks without the row constant
+    err = (dbg.cpu() - want).abs().max().item()
+    assert err < KDELTA / 2, err
+    assert st["max_err"] < KDELTA / 2, st
+    assert st["ambiguous"] == B * G * N          # forced re-rank touched every row
+    rep = O.check_knn_against_distances(idx.cpu(), dist, 9, 1, 1e-6)
+    assert rep["rows_bad"] == 0, rep
+
+
+def test_tc_matches_exact_bitwise_on_random_data():
+    """After the exact re-rank of ambiguous rows the tcgen05 path must agree with the
+    CUDA-core exact kernel except on true ties (random data: none)."""
+    from gkgnet_b200 import _lib, ops
+    g = torch.Generator(device="cuda").manual_seed(11)
+    x = torch.randn(4, 2304, 80, device="cuda", generator=g)
+    y = torch.randn(4, 576, 80, device="cuda", generator=g)
+    rel = -(0.5 + 0.5 * torch.rand(2304, 576, device="cuda", generator=g))
+    a = ops.knn_graph(x, y, rel, groups=2, k=9, dilation=1, algo=_lib.KNN_TCGEN05)
+    b = ops.knn_graph(x, y, rel, groups=2, k=9, dilation=1, algo=_lib.KNN_EXACT_FP32)
+    assert torch.equal(a, b)
+    a = ops.knn_graph(x[:, :1296], None, None, groups=2, k=9, dilation=3, algo=_lib.KNN_TCGEN05)
+    b = ops.knn_graph(x[:, :1296], None, None, groups=2, k=9, dilation=3, algo=_lib.KNN_EXACT_FP32)
+    assert torch.equal(a, b)
