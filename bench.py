@@ -104,7 +104,7 @@ class ClockSampler:
 class HotPath:
     """Device-resident state + one step of the hot path through the C ABI."""
 
-    def __init__(self, x, y, rel, algo):
+    def __init__(self, x, y, rel, algo, dense_bias=False):
         from gkgnet_b200 import _lib
         self.lib = _lib.load()
         self._lib = _lib
@@ -126,6 +126,10 @@ class HotPath:
         self.gout = torch.randn(self.B, self.N, 2 * self.C, device=dev).to(x.dtype)
         self.gx = torch.empty_like(x)
         self.gy = torch.zeros(self.B, self.M, self.C, dtype=torch.float32, device=dev)
+        from gkgnet_b200 import ops
+        fit = None if dense_bias else ops.fit_separable_bias(rel)
+        self._sep_keep = fit
+        self.sep = (None, None, 0, 0) if fit is None else (fit[0].data_ptr(), fit[1].data_ptr(), fit[2], fit[3])
         self.stream = torch.cuda.current_stream(dev)
         self.ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
 
@@ -140,7 +144,8 @@ class HotPath:
                                             self.ws_bytes, s), "knn_prepare")
         if record:
             self.ev[1].record(self.stream)
-        self._lib.check(lib.gkg_knn_select(self.rel.data_ptr(), self.idx.data_ptr(), *a, 0, self.algo,
+        sa, sb, sw, skw = self.sep
+        self._lib.check(lib.gkg_knn_select(self.rel.data_ptr(), sa, sb, sw, skw, self.idx.data_ptr(), *a, 0, self.algo,
                                            self.ws.data_ptr(), self.ws_bytes, s), "knn_select")
         if record:
             self.ev[2].record(self.stream)
@@ -284,7 +289,7 @@ def run_ours(args):
     B = WORKLOAD["B"]
     xh, yh, relh = make_inputs(B, "cpu", dtype, seed=rank)
     x, y, rel = xh.to(dev), yh.to(dev), relh.to(dev)
-    hp = HotPath(x, y, rel, algo)
+    hp = HotPath(x, y, rel, algo, dense_bias=args.dense_bias)
 
     for _ in range(max(args.warmup, 3)):
         hp.step()
@@ -402,6 +407,7 @@ def main():
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "f32"])
     ap.add_argument("--cpu-images", type=int, default=8)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--dense-bias", action="store_true", help="do not use the separable bias fast path")
     ap.add_argument("--ref-images", type=int, default=4)
     ap.add_argument("--ref-max-steps", type=int, default=20)
     args = ap.parse_args()

@@ -27,9 +27,10 @@ SIGNATURES = {
     "gkg_last_error": (_c.c_char_p, []),
     "gkg_launch_count": (_c.c_uint64, []),
     "gkg_knn_workspace_bytes": (_sz, [_i32] * 9),
-    "gkg_knn_graph": (_i32, [_vp, _i64, _i64, _vp, _i64, _i64, _vp, _vp] + [_i32] * 9 + [_vp, _sz, _vp]),
+    "gkg_knn_graph": (_i32, [_vp, _i64, _i64, _vp, _i64, _i64, _vp, _vp, _vp, _i32, _i32, _vp]
+                      + [_i32] * 9 + [_vp, _sz, _vp]),
     "gkg_knn_prepare": (_i32, [_vp, _i64, _i64, _vp, _i64, _i64] + [_i32] * 9 + [_vp, _sz, _vp]),
-    "gkg_knn_select": (_i32, [_vp, _vp] + [_i32] * 9 + [_vp, _sz, _vp]),
+    "gkg_knn_select": (_i32, [_vp, _vp, _vp, _i32, _i32, _vp] + [_i32] * 9 + [_vp, _sz, _vp]),
     "gkg_mr_aggregate_fwd": (_i32, [_vp, _i64, _i64, _vp, _i64, _i64, _vp, _vp, _vp] + [_i32] * 7 + [_vp]),
     "gkg_mr_aggregate_bwd": (_i32, [_vp, _vp, _vp, _vp, _vp] + [_i32] * 7 + [_vp]),
 }

@@ -92,8 +92,9 @@ extern "C" int gkg_knn_prepare(const void* x, int64_t x_sb, int64_t x_sn, const 
   return GKG_OK;
 }
 
-extern "C" int gkg_knn_select(const float* relpos, int32_t* idx_out, int B, int G, int N, int M, int D,
-                              int k, int dilation, int self_keys_, int algo, void* workspace,
+extern "C" int gkg_knn_select(const float* relpos, const float* relpos_sep_a, const float* relpos_sep_b,
+                              int sep_grid_w, int sep_kw, int32_t* idx_out, int B, int G, int N, int M,
+                              int D, int k, int dilation, int self_keys_, int algo, void* workspace,
                               size_t workspace_bytes, gkg_stream_t stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   const bool self_keys = self_keys_ != 0;
@@ -103,19 +104,22 @@ extern "C" int gkg_knn_select(const float* relpos, int32_t* idx_out, int B, int 
   GKG_CHECK_ARG(idx_out != nullptr, "knn_select: null pointer");
   const int P = B * G;
   KnnWorkspace w = carve_knn_workspace(workspace, P, N, M, D, self_keys);
-  if (algo == GKG_KNN_TCGEN05)
-    return launch_knn_tc(w, static_cast<char*>(workspace) + w.bytes, relpos, idx_out, P, N, M, D, k,
+  if (algo == GKG_KNN_TCGEN05) {
+    SepBias sep{relpos_sep_a, relpos_sep_b, sep_grid_w, sep_kw};
+    return launch_knn_tc(w, static_cast<char*>(workspace) + w.bytes, relpos, sep, idx_out, P, N, M, D, k,
                          dilation, self_keys, stream);
+  }
   return launch_knn_exact(w, relpos, idx_out, P, N, M, D, k, dilation, stream);
 }
 
 extern "C" int gkg_knn_graph(const void* x, int64_t x_sb, int64_t x_sn, const void* y, int64_t y_sb,
-                             int64_t y_sn, const float* relpos, int32_t* idx_out, int B, int G,
-                             int N, int M, int D, int k, int dilation, int dtype, int algo,
+                             int64_t y_sn, const float* relpos, const float* relpos_sep_a,
+                             const float* relpos_sep_b, int sep_grid_w, int sep_kw, int32_t* idx_out,
+                             int B, int G, int N, int M, int D, int k, int dilation, int dtype, int algo,
                              void* workspace, size_t workspace_bytes, gkg_stream_t stream) {
   int rc = gkg_knn_prepare(x, x_sb, x_sn, y, y_sb, y_sn, B, G, N, M, D, k, dilation, dtype, algo,
                            workspace, workspace_bytes, stream);
   if (rc != GKG_OK) return rc;
-  return gkg_knn_select(relpos, idx_out, B, G, N, M, D, k, dilation, y == nullptr, algo, workspace,
-                        workspace_bytes, stream);
+  return gkg_knn_select(relpos, relpos_sep_a, relpos_sep_b, sep_grid_w, sep_kw, idx_out, B, G, N, M, D, k,
+                        dilation, y == nullptr, algo, workspace, workspace_bytes, stream);
 }

@@ -28,9 +28,13 @@ namespace gkg {
 namespace {
 
 constexpr int BM = 128;            // query rows per tile  (UMMA M)
-constexpr int BN = 128;            // keys per tile        (UMMA N)
+constexpr int BN = 144;            // keys per tile        (UMMA N): 4 chunks of 36 = lcm of the
+                                   // key-grid widths 9/18/36 of the separable position bias
+constexpr int CH = 36;             // columns per epilogue chunk (tcgen05.ld x32 + x4)
 constexpr int NTHREADS = 192;      // warp 0 TMA, warp 1 MMA, warps 2..5 epilogue
-constexpr int NACC = 4;            // TMEM accumulators (4 x 128 columns = 512)
+constexpr int NACC = 3;            // TMEM accumulators
+constexpr int ACC_STRIDE = 160;    // TMEM columns between accumulators (3 x 160 <= 512)
+constexpr int SEP_B_FLOATS = 1024; // staged rows of the separable bias table B
 constexpr int CAND_CAP = 40;       // per-row candidate buffer entries (>= max T for the id staging)
 constexpr float kScale = 256.f;    // operand scale S
 constexpr float kPadKey = -60000.f;  // B extra column of padded keys -> dist ~ +468
@@ -48,7 +52,7 @@ struct Plan {
 
 constexpr size_t kSmemBudget = 227 * 1024;
 constexpr size_t kCandBytes = (size_t)BM * CAND_CAP * 8;
-constexpr size_t kBarBytes = 1024;
+constexpr size_t kBarBytes = 1024 + SEP_B_FLOATS * 4;
 
 Plan make_plan(int P, int N, int M, int D) {
   Plan pl{};
@@ -114,11 +118,15 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
   return t;
 }
 // Bounded wait: a protocol bug must abort the kernel, never hang the GPU.
+// BACKOFF: single-lane producer / MMA warps sleep between polls so that their spinning does not
+// take issue slots from the epilogue warp sharing the scheduler.
+template <bool BACKOFF>
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   const unsigned long long t0 = globaltimer_ns();
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
+    if (BACKOFF) __nanosleep(64);
     if ((++spins & 1023u) == 0 && globaltimer_ns() - t0 > 4000000000ull) __trap();
   }
 }
@@ -142,7 +150,8 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
                : "memory");
 }
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+// One epilogue chunk = 36 accumulator columns of this thread's row: x32 + x4 loads.
+__device__ __forceinline__ void tmem_ld36(uint32_t taddr, uint32_t (&r)[36]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
       "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -153,15 +162,20 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
         "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
       : "r"(taddr)
       : "memory");
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[32]), "=r"(r[33]), "=r"(r[34]), "=r"(r[35])
+               : "r"(taddr + 32)
+               : "memory");
 }
 // The loaded registers are threaded through the wait so the compiler cannot hoist their uses.
-__device__ __forceinline__ void tmem_ld_wait(uint32_t (&r)[32]) {
+__device__ __forceinline__ void tmem_ld_wait(uint32_t (&r)[36]) {
   asm volatile(
       "tcgen05.wait::ld.sync.aligned;"
       : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
         "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]),
         "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]),
-        "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+        "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31]),
+        "+r"(r[32]), "+r"(r[33]), "+r"(r[34]), "+r"(r[35])
       :
       : "memory");
 }
@@ -180,11 +194,11 @@ constexpr uint32_t kIdesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t
 // operand conversion (phase "prepare")
 // ------------------------------------------------------------------------------------
 // One thread writes one 16-byte core-matrix row (8 fp16 of one node).  Layout per problem:
-// [tile][k-block][row group (16)][k chunk (KC/8)][row (8)][elem (8)].
+// [tile][k-block][row group (tile_rows/8)][k chunk (KC/8)][row (8)][elem (8)].
 template <bool IS_KEY>
 __global__ void __launch_bounds__(256)
 tc_operand_kernel(const float* __restrict__ hat, const float* __restrict__ sq, __half* __restrict__ op,
-                  int rows, int D, int KP, int KC, int tiles, long long total_chunks) {
+                  int rows, int D, int KP, int KC, int tiles, int tile_rows, long long total_chunks) {
   const int chunks_per_row = KP >> 3;
   const int kcs = KC >> 3;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total_chunks;
@@ -193,12 +207,13 @@ tc_operand_kernel(const float* __restrict__ hat, const float* __restrict__ sq, _
     long long t = i;
     const int r = (int)(t & 7); t >>= 3;
     const int kc = (int)(t % kcs); t /= kcs;
-    const int rg = (int)(t & 15); t >>= 4;
+    const int rgs = tile_rows >> 3;
+    const int rg = (int)(t % rgs); t /= rgs;
     const int nkb = KP / KC;
     const int kb = (int)(t % nkb); t /= nkb;
     const int tile = (int)(t % tiles);
     const long long p = t / tiles;
-    const int row = tile * 128 + rg * 8 + r;
+    const int row = tile * tile_rows + rg * 8 + r;
     const int c0 = kb * KC + kc * 8;
     (void)chunks_per_row;
     __align__(16) __half out[8];
@@ -286,7 +301,10 @@ struct TcParams {
   const __half* a_op;
   const __half* b_op;
   const float* xhat; const float* xsq; const float* yhat; const float* ysq;
-  const float* relpos;
+  const float* relpos;             // dense (N, M) bias, or null
+  const float* sep_a;              // separable bias: A (grid_w, KW), B (N / grid_w, M / KW)
+  const float* sep_b;
+  int grid_w, sep_mh;
   int32_t* idx_out;
   int* fix_count; int* fix_rows; unsigned int* stats;   // stats: [0] ambiguous rows, [1] max err bits
   float* dbg_dist;
@@ -305,10 +323,17 @@ __device__ __forceinline__ float exact_dist(const float* __restrict__ xr, const 
   return v;
 }
 
-template <int T, bool HAS_REL>
+// BIAS: 0 = none, 1 = dense relative_pos read per element, KW (9 / 18 / 36) = separable
+// bias  relpos[n, m] = A[n % grid_w][m % KW] + B[n / grid_w][m / KW]  with the A row in registers
+// and the needed B rows staged in shared memory (the analytic table of the reference has this
+// form: pos_embed.py + the flattened bicubic resize, see gkgnet_b200/pos_embed.py).
+template <int T, int BIAS>
 __global__ void __launch_bounds__(NTHREADS, 1) knn_tc_kernel(const TcParams prm) {
+  constexpr bool HAS_REL = BIAS != 0;
+  constexpr bool DENSE = BIAS == 1;
+  constexpr int KW = BIAS > 1 ? BIAS : 36;
   extern __shared__ __align__(1024) uint8_t smem[];
-  // carve-up: [A x NA][B ring x NS][candidates][barriers + tmem ptr]
+  // carve-up: [A x NA][B ring x NS][candidates][barriers + tmem ptr][staged B rows]
   uint8_t* sA = smem;
   uint8_t* sB = sA + (size_t)prm.NA * prm.a_tile_bytes;
   float2* cand = reinterpret_cast<float2*>(sB + (size_t)prm.NS * prm.b_block_bytes);
@@ -320,6 +345,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) knn_tc_kernel(const TcParams prm)
   uint64_t* t_full = b_empty + MAX_STAGES;    // [NACC]
   uint64_t* t_empty = t_full + NACC;          // [NACC]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + NACC);
+  float* sepB_s = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 1024);   // [SEP_B_FLOATS]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -349,7 +375,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) knn_tc_kernel(const TcParams prm)
       int ab = 0, aph = 0, bs = 0, bph = 0;
       for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
         const int p = item / prm.QT, qt = item - p * prm.QT;
-        mbar_wait(smem_u32(a_empty + ab), aph ^ 1);
+        mbar_wait<true>(smem_u32(a_empty + ab), aph ^ 1);
         mbar_expect_tx(smem_u32(a_full + ab), prm.a_tile_bytes);
         tma_bulk_g2s(smem_u32(sA + (size_t)ab * prm.a_tile_bytes),
                      reinterpret_cast<const uint8_t*>(prm.a_op) + ((size_t)p * prm.QT + qt) * prm.a_tile_bytes,
@@ -359,7 +385,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) knn_tc_kernel(const TcParams prm)
                               (size_t)p * prm.KT * prm.NKB * prm.b_block_bytes;
         const int nblk = prm.KT * prm.NKB;
         for (int blk = 0; blk < nblk; ++blk) {
-          mbar_wait(smem_u32(b_empty + bs), bph ^ 1);
+          mbar_wait<true>(smem_u32(b_empty + bs), bph ^ 1);
           mbar_expect_tx(smem_u32(b_full + bs), prm.b_block_bytes);
           tma_bulk_g2s(smem_u32(sB + (size_t)bs * prm.b_block_bytes), bsrc + (size_t)blk * prm.b_block_bytes,
                        prm.b_block_bytes, smem_u32(b_full + bs));
@@ -374,15 +400,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) knn_tc_kernel(const TcParams prm)
       const uint32_t lbo = 128, sbo = (uint32_t)(prm.KC >> 3) * 128;
       const int ksteps = prm.KC >> 4;
       for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
-        mbar_wait(smem_u32(a_full + ab), aph);
+        mbar_wait<true>(smem_u32(a_full + ab), aph);
         tc_fence_after();
         const uint32_t a_base = smem_u32(sA + (size_t)ab * prm.a_tile_bytes);
         for (int kt = 0; kt < prm.KT; ++kt) {
-          mbar_wait(smem_u32(t_empty + tb), tph ^ 1);
+          mbar_wait<true>(smem_u32(t_empty + tb), tph ^ 1);
           tc_fence_after();
-          const uint32_t d_tmem = tmem_base + (uint32_t)tb * BN;
+          const uint32_t d_tmem = tmem_base + (uint32_t)tb * ACC_STRIDE;
           for (int kb = 0; kb < prm.NKB; ++kb) {
-            mbar_wait(smem_u32(b_full + bs), bph);
+            mbar_wait<true>(smem_u32(b_full + bs), bph);
             tc_fence_after();
             const uint32_t a_addr = a_base + (uint32_t)kb * (BM * prm.KC * 2);
             const uint32_t b_addr = smem_u32(sB + (size_t)bs * prm.b_block_bytes);
@@ -420,53 +446,84 @@ __global__ void __launch_bounds__(NTHREADS, 1) knn_tc_kernel(const TcParams prm)
       float tau = INFINITY;
       int cnt = 0;
 
+      // ---- separable bias: A row -> registers, B rows of this tile -> shared memory
+      float areg[KW];
+      const float* brow = sepB_s;
+      if (BIAS > 1) {
+        const int h0 = (qt * BM) / prm.grid_w;
+        const int last = min(prm.N - 1, qt * BM + BM - 1);
+        const int nh = last / prm.grid_w - h0 + 1;
+        asm volatile("bar.sync 1, 128;" ::: "memory");      // previous item done with sepB_s
+        for (int i = row_t; i < nh * prm.sep_mh; i += BM) sepB_s[i] = prm.sep_b[(size_t)h0 * prm.sep_mh + i];
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        const float* arow = prm.sep_a + (size_t)(n_c % prm.grid_w) * KW;
+#pragma unroll
+        for (int j = 0; j < KW; ++j) areg[j] = __ldg(arow + j);
+        brow = sepB_s + (n_c / prm.grid_w - h0) * prm.sep_mh;
+      }
+
+      float bias[DENSE ? CH : 1];
+      auto load_bias = [&](int m0) {
+        if (DENSE) {
+          if ((prm.M & 3) == 0) {
+#pragma unroll
+            for (int j4 = 0; j4 < CH / 4; ++j4) {
+              float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (m0 + j4 * 4 < prm.M) b4 = __ldg(reinterpret_cast<const float4*>(relrow + m0 + j4 * 4));
+              bias[j4 * 4 + 0] = b4.x; bias[j4 * 4 + 1] = b4.y; bias[j4 * 4 + 2] = b4.z; bias[j4 * 4 + 3] = b4.w;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < CH; ++j) bias[DENSE ? j : 0] = (m0 + j < prm.M) ? __ldg(relrow + m0 + j) : 0.f;
+          }
+        }
+      };
+
       for (int kt = 0; kt < prm.KT; ++kt) {
-        mbar_wait(smem_u32(t_full + tb), tph);
+        mbar_wait<false>(smem_u32(t_full + tb), tph);
         tc_fence_after();
 #pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
-          uint32_t r[32];
-          tmem_ld32(lane_addr + (uint32_t)(tb * BN + c * 32), r);
-          const int m0 = kt * BN + c * 32;
-          float bias[32];
-          if (HAS_REL) {
-            if ((prm.M & 3) == 0) {
-#pragma unroll
-              for (int j4 = 0; j4 < 8; ++j4) {
-                float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (m0 + j4 * 4 < prm.M) b4 = __ldg(reinterpret_cast<const float4*>(relrow + m0 + j4 * 4));
-                bias[j4 * 4 + 0] = b4.x; bias[j4 * 4 + 1] = b4.y; bias[j4 * 4 + 2] = b4.z; bias[j4 * 4 + 3] = b4.w;
-              }
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) bias[j] = (m0 + j < prm.M) ? __ldg(relrow + m0 + j) : 0.f;
-            }
-          }
+        for (int c = 0; c < BN / CH; ++c) {
+          uint32_t r[CH];
+          tmem_ld36(lane_addr + (uint32_t)(tb * ACC_STRIDE + c * CH), r);
+          const int m0 = kt * BN + c * CH;
+          load_bias(m0);
           tmem_ld_wait(r);
           if (prm.dbg_dist != nullptr && row_ok) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
+            for (int j = 0; j < CH; ++j) {
               if (m0 + j < prm.M) {
                 const float acc = __uint_as_float(r[j]);
-                prm.dbg_dist[((size_t)p * prm.N + n) * prm.M + m0 + j] =
-                    HAS_REL ? fmaf(acc, c_scale, bias[j]) : acc * c_scale;
+                float b = 0.f;
+                if (DENSE) b = bias[DENSE ? j : 0];
+                if (BIAS > 1) b = areg[j % KW] + brow[min(m0 / KW + j / KW, prm.sep_mh - 1)];
+                prm.dbg_dist[((size_t)p * prm.N + n) * prm.M + m0 + j] = fmaf(acc, c_scale, b);
               }
             }
           }
 #pragma unroll
-          for (int half = 0; half < 2; ++half) {
+          for (int g = 0; g < CH / KW; ++g) {
+            // per key group: fold the B term into the threshold, add it back on the rare pass
+            float bg = 0.f;
+            if (BIAS > 1) bg = brow[min(m0 / KW + g, prm.sep_mh - 1)];
+            const float taug = tau - bg;
 #pragma unroll
-            for (int jj = 0; jj < 16; ++jj) {
-              const int j = half * 16 + jj;
+            for (int jj = 0; jj < KW; ++jj) {
+              const int j = g * KW + jj;
               const float acc = __uint_as_float(r[j]);
-              const float v = HAS_REL ? fmaf(acc, c_scale, bias[j]) : acc * c_scale;
-              if (v < tau) {
-                cbuf[cnt * BM] = make_float2(v, __int_as_float(m0 + j));
+              float v;
+              if (DENSE) v = fmaf(acc, c_scale, bias[DENSE ? j : 0]);
+              else if (BIAS > 1) v = fmaf(acc, c_scale, areg[jj]);
+              else v = acc * c_scale;
+              if (v < taug) {
+                cbuf[cnt * BM] = make_float2(v + bg, __int_as_float(m0 + j));
                 ++cnt;
               }
+              // the buffer must always have room for the rest of the chunk
+              if ((j % 12) == 11 && __any_sync(0xffffffffu, cnt > CAND_CAP - 12)) {
+                compact_candidates<T>(top, tau, cnt, cbuf);
+              }
             }
-            // the buffer must always have room for the next 16 candidates
-            if (__any_sync(0xffffffffu, cnt > CAND_CAP - 16)) compact_candidates<T>(top, tau, cnt, cbuf);
           }
         }
         tc_fence_before();
@@ -623,9 +680,9 @@ int g_force_rerank = 0;
 float* g_dbg_dist = nullptr;
 unsigned int g_last_stats[4] = {0, 0, 0, 0};
 
-template <int T>
-int launch_select_t(const TcParams& prm, const Plan& pl, bool has_rel, cudaStream_t stream) {
-  auto kern = has_rel ? knn_tc_kernel<T, true> : knn_tc_kernel<T, false>;
+template <int T, int BIAS>
+int launch_select_tb(const TcParams& prm, const Plan& pl, cudaStream_t stream) {
+  auto kern = knn_tc_kernel<T, BIAS>;
   size_t smem = pl.smem_bytes < 120 * 1024 ? 120 * 1024 : pl.smem_bytes;   // 512 TMEM columns: 1 CTA / SM
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) {
@@ -668,20 +725,21 @@ int launch_knn_tc_prepare(const KnnWorkspace& w, void* extra_ws, int P, int N, i
   {
     const long long chunks = (long long)P * pl.QT * BM * (pl.KP / 8);
     const unsigned grid = (unsigned)((chunks + 255) / 256 < 148LL * 32 ? (chunks + 255) / 256 : 148LL * 32);
-    tc_operand_kernel<false><<<grid, 256, 0, stream>>>(w.xhat, w.xsq, t.a_op, N, D, pl.KP, pl.KC, pl.QT, chunks);
+    tc_operand_kernel<false><<<grid, 256, 0, stream>>>(w.xhat, w.xsq, t.a_op, N, D, pl.KP, pl.KC, pl.QT, BM, chunks);
     GKG_CHECK_LAUNCH("tc_operand_kernel<query>");
   }
   {
     const long long chunks = (long long)P * pl.KT * BN * (pl.KP / 8);
     const unsigned grid = (unsigned)((chunks + 255) / 256 < 148LL * 32 ? (chunks + 255) / 256 : 148LL * 32);
-    tc_operand_kernel<true><<<grid, 256, 0, stream>>>(w.yhat, w.ysq, t.b_op, M, D, pl.KP, pl.KC, pl.KT, chunks);
+    tc_operand_kernel<true><<<grid, 256, 0, stream>>>(w.yhat, w.ysq, t.b_op, M, D, pl.KP, pl.KC, pl.KT, BN, chunks);
     GKG_CHECK_LAUNCH("tc_operand_kernel<key>");
   }
   return GKG_OK;
 }
 
-int launch_knn_tc(const KnnWorkspace& w, void* extra_ws, const float* relpos, int32_t* idx_out, int P,
-                  int N, int M, int D, int k, int dilation, bool self_keys, cudaStream_t stream) {
+int launch_knn_tc(const KnnWorkspace& w, void* extra_ws, const float* relpos, const SepBias& sep,
+                  int32_t* idx_out, int P, int N, int M, int D, int k, int dilation, bool self_keys,
+                  cudaStream_t stream) {
   (void)self_keys;
   Plan pl = make_plan(P, N, M, D);
   GKG_CHECK_ARG(pl.ok, "knn_tc: no tiling for D=%d", D);
@@ -702,13 +760,28 @@ int launch_knn_tc(const KnnWorkspace& w, void* extra_ws, const float* relpos, in
   prm.KP = pl.KP; prm.KC = pl.KC; prm.NKB = pl.NKB; prm.NA = pl.NA; prm.NS = pl.NS; prm.QT = pl.QT; prm.KT = pl.KT;
   prm.a_tile_bytes = pl.a_tile_bytes; prm.b_block_bytes = pl.b_block_bytes;
   prm.force_rerank = g_force_rerank;
+  prm.sep_a = sep.a; prm.sep_b = sep.b; prm.grid_w = sep.grid_w > 0 ? sep.grid_w : 1;
+  prm.sep_mh = sep.kw > 0 ? M / sep.kw : 1;
   const int T = prm.kd + 2;
-  const bool has_rel = relpos != nullptr;
+  int bias = relpos != nullptr ? 1 : 0;
+  if (bias && sep.a != nullptr && sep.b != nullptr && (sep.kw == 9 || sep.kw == 18 || sep.kw == 36) &&
+      sep.grid_w > 0 && N % sep.grid_w == 0 && M % sep.kw == 0 &&
+      (BM / sep.grid_w + 2) * (M / sep.kw) <= SEP_B_FLOATS)
+    bias = sep.kw;
   int rc;
-  if (T <= 11) rc = launch_select_t<11>(prm, pl, has_rel, stream);
-  else if (T <= 20) rc = launch_select_t<20>(prm, pl, has_rel, stream);
-  else if (T <= 29) rc = launch_select_t<29>(prm, pl, has_rel, stream);
-  else rc = launch_select_t<38>(prm, pl, has_rel, stream);
+#define GKG_TC_DISPATCH_T(B)                                             \
+  (T <= 11 ? launch_select_tb<11, B>(prm, pl, stream)                    \
+   : T <= 20 ? launch_select_tb<20, B>(prm, pl, stream)                  \
+   : T <= 29 ? launch_select_tb<29, B>(prm, pl, stream)                  \
+             : launch_select_tb<38, B>(prm, pl, stream))
+  switch (bias) {
+    case 0: rc = GKG_TC_DISPATCH_T(0); break;
+    case 9: rc = GKG_TC_DISPATCH_T(9); break;
+    case 18: rc = GKG_TC_DISPATCH_T(18); break;
+    case 36: rc = GKG_TC_DISPATCH_T(36); break;
+    default: rc = GKG_TC_DISPATCH_T(1); break;
+  }
+#undef GKG_TC_DISPATCH_T
   if (rc != GKG_OK) return rc;
   const size_t fsmem = sizeof(float) * (size_t)M;
   GKG_CHECK_ARG(fsmem <= 200 * 1024, "knn_tc: M=%d too large for the fix-up kernel", M);

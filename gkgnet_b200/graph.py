@@ -60,7 +60,7 @@ class DenseDilatedKnnGraph(nn.Module):
         return self.stochastic and self.training and bool(torch.rand(1) < self.epsilon)
 
     @torch.no_grad()
-    def neighbors(self, x, y=None, relative_pos=None, groups=1):
+    def neighbors(self, x, y=None, relative_pos=None, groups=1, separable=None):
         if self._stochastic_now():
             # random k of the k*d nearest (torch_edge.py:141-144): needs the full sorted list
             full = ops.knn_graph(x, y, relative_pos, groups=groups, k=self.k * self.dilation,
@@ -68,7 +68,7 @@ class DenseDilatedKnnGraph(nn.Module):
             pick = torch.randperm(self.k * self.dilation, device=full.device)[:self.k]
             return full[:, :, pick].contiguous()
         return ops.knn_graph(x, y, relative_pos, groups=groups, k=self.k, dilation=self.dilation,
-                             algo=self.algo)
+                             algo=self.algo, separable=separable)
 
     def forward(self, x, y=None, relative_pos=None):
         nn_idx = self.neighbors(_to_tokens(x), None if y is None else _to_tokens(y), relative_pos)

@@ -32,7 +32,35 @@ def _require_cuda(*ts):
             raise RuntimeError("gkgnet_b200 kernels need CUDA tensors (no CPU fallback)")
 
 
-def knn_graph(x, y=None, relative_pos=None, *, groups=1, k=9, dilation=1, algo=_lib.KNN_AUTO):
+def fit_separable_bias(relative_pos, tol=5e-7):
+    """Try to write ``relative_pos[n, m] = A[n % W][m % Kw] + B[n // W][m // Kw]``.
+
+    The reference's table (2-D sin-cos embedding resized along the flattened key axis,
+    pos_embed.py:21-29 + torch_vertex.py:309-315) always has this form with ``W = sqrt(N)``
+    and ``Kw = W * M / N``; it lets the tensor-core kernel add the bias from registers
+    instead of streaming the dense (N, M) matrix for every problem.  Returns
+    ``(A, B, W, Kw)`` (fp32, on the table's device) or None when the table does not fit
+    within ``tol`` -- the dense matrix is then read (any stored parameter is honoured)."""
+    rel = relative_pos.reshape(relative_pos.shape[-2], relative_pos.shape[-1]).float()
+    N, M = rel.shape
+    W = int(round(N ** 0.5))
+    if W * W != N or (W * M) % N:
+        return None
+    kw = W * M // N
+    if kw < 1 or M % kw or M // kw < 1:
+        return None
+    mh = M // kw
+    r4 = rel.view(W, W, mh, kw)                       # [h_q, w_q, m_h, m_w]
+    a = r4[0, :, 0, :].contiguous()                   # (W, Kw)
+    b = (r4[:, 0, :, 0] - r4[0, 0, 0, 0]).contiguous()  # (W, Mh)
+    resid = (r4 - (a.view(1, W, 1, kw) + b.view(W, 1, mh, 1))).abs().max().item()
+    if not resid <= tol:
+        return None
+    return a, b, W, kw
+
+
+def knn_graph(x, y=None, relative_pos=None, *, groups=1, k=9, dilation=1, algo=_lib.KNN_AUTO,
+              separable=None):
     """Dilated group-kNN neighbour ids, int32 ``(B*G, N, k)``.
 
     x: (B, N, C) queries; y: (B, M, C) keys or None (self); relative_pos: fp32 (N, M) /
@@ -62,6 +90,13 @@ def knn_graph(x, y=None, relative_pos=None, *, groups=1, k=9, dilation=1, algo=_
             raise ValueError(f"relative_pos {tuple(rel.shape)} != ({N}, {M})")
         rel = rel.to(torch.float32).contiguous()
         rel_ptr = rel.data_ptr()
+    sep_a = sep_b = None
+    sep_w = sep_kw = 0
+    if separable is not None and relative_pos is not None:
+        sa, sb, sep_w, sep_kw = separable
+        if sa.shape != (sep_w, sep_kw) or sb.shape != (N // sep_w, M // sep_kw):
+            raise ValueError("separable bias tables do not match the problem shape")
+        sep_a, sep_b = sa.data_ptr(), sb.data_ptr()
     idx = torch.empty((B * groups, N, k), dtype=torch.int32, device=x.device)
     if B * N == 0:
         return idx
@@ -71,7 +106,8 @@ def knn_graph(x, y=None, relative_pos=None, *, groups=1, k=9, dilation=1, algo=_
         x.data_ptr(), x.stride(0), x.stride(1),
         y.data_ptr() if y is not None else None,
         y.stride(0) if y is not None else 0, y.stride(1) if y is not None else 0,
-        rel_ptr, idx.data_ptr(), B, groups, N, M, D, k, dilation, _DT[x.dtype], algo,
+        rel_ptr, sep_a, sep_b, sep_w, sep_kw, idx.data_ptr(), B, groups, N, M, D, k, dilation,
+        _DT[x.dtype], algo,
         ws.data_ptr(), ws_bytes, _stream(x))
     _lib.check(rc, "gkg_knn_graph")
     return idx

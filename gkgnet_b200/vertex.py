@@ -107,13 +107,14 @@ class DyGraphConv2dMultiGroup(_DynamicGraphBase):
         self.num_head = num_head
         self.dilated_knn_graph = DenseDilatedKnnGraph(kernel_size, dilation, stochastic, epsilon)
 
-    def forward(self, x, relative_pos=None):
+    def forward(self, x, relative_pos=None, separable=None):
         B, C, H, W = x.shape
         xt = nchw_to_tokens(x)
         yt = None
         if self.r > 1:
             yt = nchw_to_tokens(F.avg_pool2d(x, self.r, self.r))
-        nn_idx = self.dilated_knn_graph.neighbors(xt, yt, relative_pos, groups=self.num_head)
+        nn_idx = self.dilated_knn_graph.neighbors(xt, yt, relative_pos, groups=self.num_head,
+                                                  separable=separable)
         out = self.gconv.forward_tokens(xt, nn_idx, yt, groups=self.num_head, hw=(H, W))
         return out, self._edge_index(nn_idx)
 
@@ -197,6 +198,7 @@ class Grapher(nn.Module):
         self.fc2 = _conv_bn(in_channels * 2, in_channels)
         self.drop_path = DropPath(drop_path) if drop_path > 0.0 else nn.Identity()
         self.relative_pos = None
+        self._sep_cache = None
         if relative_pos:
             self.relative_pos = nn.Parameter(relative_pos_table(in_channels, n, r), requires_grad=False)
 
@@ -207,11 +209,22 @@ class Grapher(nn.Module):
         return F.interpolate(relative_pos.unsqueeze(0), size=(N, N // (self.r * self.r)),
                              mode="bicubic").squeeze(0)
 
+    def _separable(self, relative_pos):
+        """Separable factorisation of the bias, fitted once per parameter version (the table is
+        a frozen constant; a loaded checkpoint that does not factorise falls back to dense)."""
+        if relative_pos is None or relative_pos is not self.relative_pos or not relative_pos.is_cuda:
+            return None
+        key = (relative_pos.data_ptr(), relative_pos._version, relative_pos.device)
+        if self._sep_cache is None or self._sep_cache[0] != key:
+            self._sep_cache = (key, ops.fit_separable_bias(relative_pos.detach()))
+        return self._sep_cache[1]
+
     def forward(self, x):
         shortcut = x
         x = self.fc1(x)
         B, C, H, W = x.shape
-        x, _ = self.graph_conv(x, self._get_relative_pos(self.relative_pos, H, W))
+        rel = self._get_relative_pos(self.relative_pos, H, W)
+        x, _ = self.graph_conv(x, rel, self._separable(rel))
         x = self.fc2(x)
         return self.drop_path(x) + shortcut
 

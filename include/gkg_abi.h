@@ -74,10 +74,18 @@ size_t gkg_knn_workspace_bytes(int B, int G, int N, int M, int D, int k, int dil
  *   idx_out  int32 (B*G, N, k): neighbour ids (edge_index[0]; edge_index[1][p,n,:] == n)
  *
  * Ties: the smaller key id wins (torch.topk leaves tie order unspecified).
+ *
+ * Optional separable form of the bias (a hint that only accelerates the tensor-core path; the
+ * dense `relpos` stays authoritative and is what exact re-ranking reads):
+ *     relpos[n, m] == sep_a[n % sep_grid_w][m % sep_kw] + sep_b[n / sep_grid_w][m / sep_kw]
+ * sep_a is fp32 (sep_grid_w, sep_kw), sep_b fp32 (N / sep_grid_w, M / sep_kw); pass NULL / 0
+ * when unknown.  The analytic table of the reference (pos_embed.py:21-29 +
+ * torch_vertex.py:309-315) always has this form; the caller must have verified it.
  */
 int gkg_knn_graph(const void* x, int64_t x_stride_b, int64_t x_stride_n,
                   const void* y, int64_t y_stride_b, int64_t y_stride_n,
-                  const float* relpos, int32_t* idx_out,
+                  const float* relpos, const float* relpos_sep_a, const float* relpos_sep_b,
+                  int sep_grid_w, int sep_kw, int32_t* idx_out,
                   int B, int G, int N, int M, int D, int k, int dilation, int dtype,
                   int algo, void* workspace, size_t workspace_bytes, gkg_stream_t stream);
 
@@ -91,7 +99,8 @@ int gkg_knn_prepare(const void* x, int64_t x_stride_b, int64_t x_stride_n,
                     const void* y, int64_t y_stride_b, int64_t y_stride_n,
                     int B, int G, int N, int M, int D, int k, int dilation, int dtype,
                     int algo, void* workspace, size_t workspace_bytes, gkg_stream_t stream);
-int gkg_knn_select(const float* relpos, int32_t* idx_out,
+int gkg_knn_select(const float* relpos, const float* relpos_sep_a, const float* relpos_sep_b,
+                   int sep_grid_w, int sep_kw, int32_t* idx_out,
                    int B, int G, int N, int M, int D, int k, int dilation, int self_keys,
                    int algo, void* workspace, size_t workspace_bytes, gkg_stream_t stream);
 

@@ -263,9 +263,11 @@ def backbone_plan(choice="s", k=9):
 
 
 def gkgnet_forward(sd, img, choice="s", k=9, k_label_gcn=9, num_group=2, num_gcn=1,
-                   training=False):
+                   training=False, trace=None):
     """GKGNet.forward (gkgnet.py:263-284) in eval / drop_path=0 semantics.
-    Returns (label_emb (B, n_cls, C4), gap (B, C4), edge_index (B*G, n_cls, k))."""
+    Returns (label_emb (B, n_cls, C4), gap (B, C4), edge_index (B*G, n_cls, k)).
+    ``trace`` (a dict) receives the input/output of every backbone layer and label head so a
+    test can compare layer by layer without accumulating near-tie neighbour flips."""
     plan, layer_index, channels = backbone_plan(choice, k)
     B = img.shape[0]
     labels = sd["label_lt.weight"].unsqueeze(0).expand(B, -1, -1)
@@ -282,6 +284,8 @@ def gkgnet_forward(sd, img, choice="s", k=9, k_label_gcn=9, num_group=2, num_gcn
     edge_index = None
     for i, item in enumerate(plan):
         p = f"backbone.{i}."
+        if trace is not None:
+            trace[f"backbone.{i}.in"] = x
         if item[0] == "down":                                      # Downsample, gkgnet.py:107-118
             x = F.conv2d(x, sd[p + "conv.0.weight"], sd[p + "conv.0.bias"], stride=2, padding=1)
             x = batch_norm(sd, p + "conv.1.", x, training)
@@ -289,10 +293,16 @@ def gkgnet_forward(sd, img, choice="s", k=9, k_label_gcn=9, num_group=2, num_gcn
             _, C, kk, dil, r = item
             x = grapher(sd, p + "0.", x, kk, dil, r, num_group, True, training)
             x = ffn(sd, p + "1.", x, training)
+        if trace is not None:
+            trace[f"backbone.{i}.out"] = x
         if i in layer_index:                                       # gkgnet.py:272-277
             for g in range(num_gcn if j == 3 else 1):
+                if trace is not None:
+                    trace[f"gcn_label.{j}.{g}.in"] = labels
                 labels, edge_index = grapher_label(sd, f"gcn_label.{j}.{g}.", labels, x,
                                                    k_label_gcn, num_group, True, training)
+                if trace is not None:
+                    trace[f"gcn_label.{j}.{g}.out"] = labels
             if j < 3:
                 labels = F.linear(labels, sd[f"ffn_label.{j}.0.weight"], sd[f"ffn_label.{j}.0.bias"])
             j += 1

@@ -148,8 +148,13 @@ def test_knn_full_size_stage1_properties():
     x = torch.randn(B, N, G * D, device="cuda", generator=g)
     y = torch.nn.functional.avg_pool2d(x.view(B, 144, 144, G * D).permute(0, 3, 1, 2), 4, 4)
     y = y.permute(0, 2, 3, 1).reshape(B, M, G * D).contiguous()
-    rel = -(0.5 + 0.5 * torch.rand(N, M, device="cuda", generator=g))
-    ia = ops.knn_graph(x, y, rel, groups=G, k=k, dilation=1, algo=lib.KNN_AUTO)
+    from gkgnet_b200.pos_embed import relative_pos_table
+    rel = relative_pos_table(G * D, N, 4)[0].cuda()
+    sep = ops.fit_separable_bias(rel)
+    assert sep is not None and sep[2:] == (144, 9)
+    ia = ops.knn_graph(x, y, rel, groups=G, k=k, dilation=1, algo=lib.KNN_AUTO, separable=sep)
+    idn = ops.knn_graph(x, y, rel, groups=G, k=k, dilation=1, algo=lib.KNN_AUTO)
+    assert (ia != idn).any(-1).float().mean().item() < 1e-4
     ie = ops.knn_graph(x, y, rel, groups=G, k=k, dilation=1, algo=lib.KNN_EXACT_FP32)
     differ = (ia != ie).any(-1).float().mean().item()
     assert differ < 1e-3, differ

@@ -84,3 +84,60 @@ def test_tc_matches_exact_bitwise_on_random_data():
     a = ops.knn_graph(x[:, :1296], None, None, groups=2, k=9, dilation=3, algo=_lib.KNN_TCGEN05)
     b = ops.knn_graph(x[:, :1296], None, None, groups=2, k=9, dilation=3, algo=_lib.KNN_EXACT_FP32)
     assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("C,n,r,G,k,d", [
+    (16, 81, 1, 2, 4, 2),        # 9x9 grid, self keys  -> Kw = 9
+    (32, 324, 1, 2, 9, 3),       # 18x18 (stage-4 geometry) -> Kw = 18
+    (80, 1296, 1, 2, 9, 2),      # 36x36 (stage-3 geometry) -> Kw = 36
+    (80, 1296, 2, 2, 9, 1),      # 36x36 queries, 18x18 pooled keys -> M = 324, Kw = 9
+    (160, 5184, 2, 2, 9, 1),     # stage-2 geometry: M = 1296, Kw = 18
+])
+def test_tc_separable_bias(C, n, r, G, k, d):
+    """The analytic relative_pos table factorises; the register/shared-memory bias path must
+    give the same raw distances as the dense table and the same neighbours as the oracle."""
+    from gkgnet_b200 import _lib, ops
+    from gkgnet_b200.pos_embed import relative_pos_table
+    lib = _lib.load()
+    rel = relative_pos_table(C, n, r)
+    side = int(n ** 0.5)
+    g = torch.Generator().manual_seed(5)
+    B = 1
+    x = torch.randn(B, n, C, generator=g)
+    y = None
+    if r > 1:
+        x4 = x.view(B, side, side, C).permute(0, 3, 1, 2)
+        y = torch.nn.functional.avg_pool2d(x4, r, r).permute(0, 2, 3, 1).reshape(B, -1, C).contiguous()
+    M = n // (r * r)
+    sep = ops.fit_separable_bias(rel.cuda())
+    assert sep is not None and sep[3] in (9, 18, 36), None if sep is None else sep[2:]
+    dbg = torch.full((B * G, n, M), float("nan"), device="cuda")
+    _debug(lib, 1, dbg)
+    try:
+        idx = ops.knn_graph(x.cuda(), None if y is None else y.cuda(), rel.cuda(), groups=G, k=k, dilation=d,
+                            algo=_lib.KNN_TCGEN05, separable=sep)
+        torch.cuda.synchronize()
+        st = _stats(lib)
+    finally:
+        _debug(lib, 0, None)
+    xr = _ref_layout(x, G)
+    yr = None if y is None else _ref_layout(y, G)
+    dist = O.knn_distance_matrix(xr, yr, rel)
+    xn = O.l2_normalize(xr, 1).squeeze(-1)
+    want = dist - (xn * xn).sum(1).unsqueeze(-1)
+    assert (dbg.cpu() - want).abs().max().item() < KDELTA / 2
+    assert st["max_err"] < KDELTA / 2, st
+    rep = O.check_knn_against_distances(idx.cpu(), dist, k, d, 1e-6)
+    assert rep["rows_bad"] == 0, rep
+    # and without the debug hooks, against the dense-table run
+    a = ops.knn_graph(x.cuda(), None if y is None else y.cuda(), rel.cuda(), groups=G, k=k, dilation=d,
+                      algo=_lib.KNN_TCGEN05, separable=sep)
+    b = ops.knn_graph(x.cuda(), None if y is None else y.cuda(), rel.cuda(), groups=G, k=k, dilation=d,
+                      algo=_lib.KNN_TCGEN05)
+    assert torch.equal(a, b)
+
+
+def test_fit_separable_rejects_arbitrary_tables():
+    from gkgnet_b200 import ops
+    rel = torch.rand(1, 81, 81, device="cuda")
+    assert ops.fit_separable_bias(rel) is None
