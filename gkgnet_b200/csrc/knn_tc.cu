@@ -34,7 +34,7 @@ constexpr int CH = 36;             // columns per epilogue chunk (tcgen05.ld x32
 constexpr int NTHREADS = 192;      // warp 0 TMA, warp 1 MMA, warps 2..5 epilogue
 constexpr int NACC = 3;            // TMEM accumulators
 constexpr int ACC_STRIDE = 160;    // TMEM columns between accumulators (3 x 160 <= 512)
-constexpr int SEP_B_FLOATS = 1024; // staged rows of the separable bias table B
+constexpr int SEP_B_FLOATS = 2048; // staged rows of the separable bias table B (512 per epilogue warp)
 constexpr int CAND_CAP = 40;       // per-row candidate buffer entries (>= max T for the id staging)
 constexpr float kScale = 256.f;    // operand scale S
 constexpr float kPadKey = -60000.f;  // B extra column of padded keys -> dist ~ +468
@@ -101,6 +101,19 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
+// try_wait with a suspend-time hint: the hardware parks the thread (no issue slots) until the
+// phase completes or ~hint ns pass.
+__device__ __forceinline__ uint32_t mbar_try_wait_hint(uint32_t bar, uint32_t parity, uint32_t hint_ns) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity), "r"(hint_ns)
+      : "memory");
+  return ok;
+}
 __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
@@ -125,9 +138,9 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   const unsigned long long t0 = globaltimer_ns();
   uint32_t spins = 0;
-  while (!mbar_try_wait(bar, parity)) {
-    if (BACKOFF) __nanosleep(64);
-    if ((++spins & 1023u) == 0 && globaltimer_ns() - t0 > 4000000000ull) __trap();
+  while (!(BACKOFF ? mbar_try_wait_hint(bar, parity, 20000u) : mbar_try_wait(bar, parity))) {
+    if (BACKOFF) __nanosleep(200);
+    if ((++spins & 255u) == 0 && globaltimer_ns() - t0 > 4000000000ull) __trap();
   }
 }
 __device__ __forceinline__ void tma_bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
@@ -191,61 +204,104 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo,
 constexpr uint32_t kIdesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 
 // ------------------------------------------------------------------------------------
-// operand conversion (phase "prepare")
+// operand preparation (phase "prepare"): normalise + split + lay out, one pass over the features
 // ------------------------------------------------------------------------------------
-// One thread writes one 16-byte core-matrix row (8 fp16 of one node).  Layout per problem:
-// [tile][k-block][row group (tile_rows/8)][k chunk (KC/8)][row (8)][elem (8)].
-template <bool IS_KEY>
+// A block owns 32 consecutive (padded) rows of one problem.  Phase 1: a warp per row L2-normalises
+// the D group channels (F.normalize semantics, torch_edge.py:167-168,173), keeps the fp32 row in
+// shared memory and writes it + |xh|^2 for the exact re-rank.  Phase 2: every thread emits 16-byte
+// core-matrix rows (8 fp16) of the tensor-core operand:
+//   [tile][k-block][row group (tile_rows/8)][k chunk (KC/8)][row (8)][elem (8)]
+// so that a warp writes 4 contiguous 128-byte core matrices.
+constexpr int PREP_ROWS = 32;
+
+template <typename T, bool IS_KEY>
 __global__ void __launch_bounds__(256)
-tc_operand_kernel(const float* __restrict__ hat, const float* __restrict__ sq, __half* __restrict__ op,
-                  int rows, int D, int KP, int KC, int tiles, int tile_rows, long long total_chunks) {
-  const int chunks_per_row = KP >> 3;
-  const int kcs = KC >> 3;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total_chunks;
-       i += (long long)gridDim.x * blockDim.x) {
-    // decode destination index (fastest -> slowest): r(8), kc, rg(16), kb, tile, p
-    long long t = i;
-    const int r = (int)(t & 7); t >>= 3;
-    const int kc = (int)(t % kcs); t /= kcs;
-    const int rgs = tile_rows >> 3;
-    const int rg = (int)(t % rgs); t /= rgs;
-    const int nkb = KP / KC;
-    const int kb = (int)(t % nkb); t /= nkb;
-    const int tile = (int)(t % tiles);
-    const long long p = t / tiles;
-    const int row = tile * tile_rows + rg * 8 + r;
-    const int c0 = kb * KC + kc * 8;
-    (void)chunks_per_row;
-    __align__(16) __half out[8];
+tc_prepare_kernel(const T* __restrict__ feat, int64_t stride_b, int64_t stride_n, float* __restrict__ hat,
+                  float* __restrict__ sq, __half* __restrict__ op, int G, int rows, int D, int KP, int KC,
+                  int tiles, int tile_rows, int write_hat) {
+  extern __shared__ float prep_s[];              // [PREP_ROWS][D] normalised rows + [PREP_ROWS] norms
+  float* xs = prep_s;
+  float* sqs = prep_s + PREP_ROWS * D;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long p = blockIdx.y;
+  const int g = (int)(p % G);
+  const long long b = p / G;
+  const int r0 = blockIdx.x * PREP_ROWS;
+
+  for (int rl = warp; rl < PREP_ROWS; rl += 8) {
+    const int row = r0 + rl;
+    float* dst = xs + rl * D;
+    if (row < rows) {
+      const T* src = feat + b * stride_b + (long long)row * stride_n + (long long)g * D;
+      float ss = 0.f;
+      for (int d = lane; d < D; d += 32) {
+        const float v = to_f32<T>(src[d]);
+        ss = fmaf(v, v, ss);
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+      const float denom = fmaxf(sqrtf(ss), 1e-12f);
+      float s2 = 0.f;
+      float* gh = hat + (p * rows + row) * (long long)D;
+      for (int d = lane; d < D; d += 32) {
+        const float v = to_f32<T>(src[d]) / denom;
+        dst[d] = v;
+        if (write_hat) gh[d] = v;
+        s2 = fmaf(v, v, s2);
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+      if (lane == 0) {
+        sqs[rl] = s2;
+        if (write_hat) sq[p * rows + row] = s2;
+      }
+    } else {
+      for (int d = lane; d < D; d += 32) dst[d] = 0.f;
+      if (lane == 0) sqs[rl] = 0.f;
+    }
+  }
+  __syncthreads();
+
+  const int kcs = KC >> 3, nkb = KP / KC, rgs = tile_rows >> 3, kc_all = KP >> 3;
+  const int total = PREP_ROWS * kc_all;
+  for (int ci = threadIdx.x; ci < total; ci += 256) {
+    const int r = ci & 7;
+    const int kcI = (ci >> 3) % kc_all;
+    const int rgl = (ci >> 3) / kc_all;
+    const int rl = rgl * 8 + r;
+    const int row = r0 + rl;
+    const int tile = row / tile_rows;
+    if (tile >= tiles) continue;
+    const int rg = (row - tile * tile_rows) >> 3;
+    const int kb = kcI / kcs, kc = kcI - kb * kcs;
     const bool valid = row < rows;
-    const float* src = hat + (p * rows + (valid ? row : 0)) * (long long)D;
+    const float* src = xs + rl * D;
     float extra_hi = 0.f, extra_lo = 0.f;
     if (IS_KEY) {
       if (valid) {
-        const float c = -0.5f * sq[p * rows + row] * kScale;
-        const __half h = __float2half_rn(c);
-        extra_hi = __half2float(h);
+        const float c = -0.5f * sqs[rl] * kScale;
+        extra_hi = __half2float(__float2half_rn(c));
         extra_lo = c - extra_hi;
       } else {
         extra_hi = kPadKey;
       }
     } else {
       extra_hi = valid ? kScale : 0.f;
-      extra_lo = valid ? kScale : 0.f;
+      extra_lo = extra_hi;
     }
+    __align__(16) __half out[8];
+    const int c0 = kcI * 8;
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       const int c = c0 + e;
       float v = 0.f;
       if (c < 3 * D) {
-        if (valid) {
-          const int seg = c / D;
-          const float x = src[c - seg * D] * kScale;
-          const float hi = __half2float(__float2half_rn(x));
-          // A = [hi | hi | lo], B = [hi | lo | hi]
-          const bool want_lo = IS_KEY ? (seg == 1) : (seg == 2);
-          v = want_lo ? (x - hi) : hi;
-        }
+        const int seg = c / D;
+        const float x = src[c - seg * D] * kScale;
+        const float hi = __half2float(__float2half_rn(x));
+        // A = [hi | hi | lo], B = [hi | lo | hi]
+        const bool want_lo = IS_KEY ? (seg == 1) : (seg == 2);
+        v = want_lo ? (x - hi) : hi;
       } else if (c == 3 * D) {
         v = extra_hi;
       } else if (c == 3 * D + 1) {
@@ -253,7 +309,8 @@ tc_operand_kernel(const float* __restrict__ hat, const float* __restrict__ sq, _
       }
       out[e] = __float2half_rn(v);
     }
-    *reinterpret_cast<uint4*>(op + i * 8) = *reinterpret_cast<const uint4*>(out);
+    const long long chunk = ((((p * tiles + tile) * nkb + kb) * rgs + rg) * (long long)kcs + kc) * 8 + r;
+    *reinterpret_cast<uint4*>(op + chunk * 8) = *reinterpret_cast<const uint4*>(out);
   }
 }
 
@@ -282,19 +339,25 @@ struct TopList {
 };
 
 // Merge the buffered candidates of every lane into its sorted list (warp-uniform trip count).
-template <int T>
-__device__ __forceinline__ void compact_candidates(TopList<T>& top, float& tau, int& cnt, const float2* cbuf) {
+// The scan stores (value without the per-key-group bias term, key id); KW > 0 adds brow[id / KW].
+template <int T, int KW>
+__device__ __forceinline__ void compact_candidates(TopList<T>& top, float& tau, float2*& wp, float2* cbuf,
+                                                   const float* brow, int mh_last) {
+  const int cnt = (int)(wp - cbuf) / BM;
   const int mx = __reduce_max_sync(0xffffffffu, cnt);
   for (int e = 0; e < mx; ++e) {
     if (e < cnt) {
       const float2 c = cbuf[e * BM];
-      if (c.x < tau) {
-        top.insert(c.x, __float_as_int(c.y));
+      const int m = __float_as_int(c.y);
+      float v = c.x;
+      if (KW > 0) v += brow[min(m / KW, mh_last)];
+      if (v < tau) {
+        top.insert(v, m);
         tau = top.v[T - 1];
       }
     }
   }
-  cnt = 0;
+  wp = cbuf;
 }
 
 struct TcParams {
@@ -444,22 +507,26 @@ __global__ void __launch_bounds__(NTHREADS, 1) knn_tc_kernel(const TcParams prm)
       const float* relrow = HAS_REL ? prm.relpos + (size_t)n_c * prm.M : nullptr;
       top.init();
       float tau = INFINITY;
-      int cnt = 0;
+      float2* wp = cbuf;                           // next free candidate slot of this row
+      constexpr int CKW = BIAS > 1 ? BIAS : 0;
 
       // ---- separable bias: A row -> registers, B rows of this tile -> shared memory
       float areg[KW];
       const float* brow = sepB_s;
       if (BIAS > 1) {
-        const int h0 = (qt * BM) / prm.grid_w;
-        const int last = min(prm.N - 1, qt * BM + BM - 1);
+        // each warp stages the B rows its own 32 query rows need (no cross-warp barrier)
+        float* mine = sepB_s + q * (SEP_B_FLOATS / 4);
+        const int first = min(prm.N - 1, qt * BM + q * 32);
+        const int last = min(prm.N - 1, qt * BM + q * 32 + 31);
+        const int h0 = first / prm.grid_w;
         const int nh = last / prm.grid_w - h0 + 1;
-        asm volatile("bar.sync 1, 128;" ::: "memory");      // previous item done with sepB_s
-        for (int i = row_t; i < nh * prm.sep_mh; i += BM) sepB_s[i] = prm.sep_b[(size_t)h0 * prm.sep_mh + i];
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        __syncwarp();
+        for (int i = lane; i < nh * prm.sep_mh; i += 32) mine[i] = __ldg(prm.sep_b + (size_t)h0 * prm.sep_mh + i);
+        __syncwarp();
         const float* arow = prm.sep_a + (size_t)(n_c % prm.grid_w) * KW;
 #pragma unroll
         for (int j = 0; j < KW; ++j) areg[j] = __ldg(arow + j);
-        brow = sepB_s + (n_c / prm.grid_w - h0) * prm.sep_mh;
+        brow = mine + (n_c / prm.grid_w - h0) * prm.sep_mh;
       }
 
       float bias[DENSE ? CH : 1];
@@ -516,12 +583,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) knn_tc_kernel(const TcParams prm)
               else if (BIAS > 1) v = fmaf(acc, c_scale, areg[jj]);
               else v = acc * c_scale;
               if (v < taug) {
-                cbuf[cnt * BM] = make_float2(v + bg, __int_as_float(m0 + j));
-                ++cnt;
+                *wp = make_float2(v, __int_as_float(m0 + j));
+                wp += BM;
               }
               // the buffer must always have room for the rest of the chunk
-              if ((j % 12) == 11 && __any_sync(0xffffffffu, cnt > CAND_CAP - 12)) {
-                compact_candidates<T>(top, tau, cnt, cbuf);
+              if ((j % 12) == 11 && __any_sync(0xffffffffu, wp > cbuf + (CAND_CAP - 12) * BM)) {
+                compact_candidates<T, CKW>(top, tau, wp, cbuf, brow, prm.sep_mh - 1);
               }
             }
           }
@@ -531,7 +598,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) knn_tc_kernel(const TcParams prm)
         if (lane == 0) mbar_arrive(smem_u32(t_empty + tb));
         if (++tb == NACC) { tb = 0; tph ^= 1; }
       }
-      compact_candidates<T>(top, tau, cnt, cbuf);
+      compact_candidates<T, CKW>(top, tau, wp, cbuf, brow, prm.sep_mh - 1);
 
       // ---------------- finalise the row -------------------------------------------
       const int kd = prm.kd;
@@ -716,25 +783,39 @@ size_t knn_tc_workspace_bytes(int P, int N, int M, int D, int k, int dilation, b
   return carve_tc(nullptr, pl, P, N).bytes;
 }
 
-int launch_knn_tc_prepare(const KnnWorkspace& w, void* extra_ws, int P, int N, int M, int D, int k,
-                          int dilation, bool self_keys, cudaStream_t stream) {
-  (void)k; (void)dilation; (void)self_keys;
-  Plan pl = make_plan(P, N, M, D);
-  GKG_CHECK_ARG(pl.ok, "knn_tc: no tiling for D=%d", D);
-  TcWorkspace t = carve_tc(extra_ws, pl, P, N);
+template <typename T>
+static int launch_prepare_typed(const KnnWorkspace& w, const TcWorkspace& t, const Plan& pl, const void* x,
+                                int64_t x_sb, int64_t x_sn, const void* y, int64_t y_sb, int64_t y_sn, int P,
+                                int G, int N, int M, int D, bool self_keys, cudaStream_t stream) {
+  const size_t smem = sizeof(float) * ((size_t)PREP_ROWS * D + PREP_ROWS);
   {
-    const long long chunks = (long long)P * pl.QT * BM * (pl.KP / 8);
-    const unsigned grid = (unsigned)((chunks + 255) / 256 < 148LL * 32 ? (chunks + 255) / 256 : 148LL * 32);
-    tc_operand_kernel<false><<<grid, 256, 0, stream>>>(w.xhat, w.xsq, t.a_op, N, D, pl.KP, pl.KC, pl.QT, BM, chunks);
-    GKG_CHECK_LAUNCH("tc_operand_kernel<query>");
+    dim3 grid((pl.QT * BM + PREP_ROWS - 1) / PREP_ROWS, P);
+    tc_prepare_kernel<T, false><<<grid, 256, smem, stream>>>(static_cast<const T*>(x), x_sb, x_sn, w.xhat, w.xsq,
+                                                            t.a_op, G, N, D, pl.KP, pl.KC, pl.QT, BM, 1);
+    GKG_CHECK_LAUNCH("tc_prepare_kernel<query>");
   }
   {
-    const long long chunks = (long long)P * pl.KT * BN * (pl.KP / 8);
-    const unsigned grid = (unsigned)((chunks + 255) / 256 < 148LL * 32 ? (chunks + 255) / 256 : 148LL * 32);
-    tc_operand_kernel<true><<<grid, 256, 0, stream>>>(w.yhat, w.ysq, t.b_op, M, D, pl.KP, pl.KC, pl.KT, BN, chunks);
-    GKG_CHECK_LAUNCH("tc_operand_kernel<key>");
+    dim3 grid((pl.KT * BN + PREP_ROWS - 1) / PREP_ROWS, P);
+    const T* src = static_cast<const T*>(self_keys ? x : y);
+    tc_prepare_kernel<T, true><<<grid, 256, smem, stream>>>(src, self_keys ? x_sb : y_sb, self_keys ? x_sn : y_sn,
+                                                           w.yhat, w.ysq, t.b_op, G, M, D, pl.KP, pl.KC, pl.KT,
+                                                           BN, self_keys ? 0 : 1);
+    GKG_CHECK_LAUNCH("tc_prepare_kernel<key>");
   }
   return GKG_OK;
+}
+
+int launch_knn_tc_prepare(const KnnWorkspace& w, void* extra_ws, const void* x, int64_t x_sb, int64_t x_sn,
+                          const void* y, int64_t y_sb, int64_t y_sn, int dtype, int P, int G, int N, int M,
+                          int D, bool self_keys, cudaStream_t stream) {
+  Plan pl = make_plan(P, N, M, D);
+  GKG_CHECK_ARG(pl.ok, "knn_tc: no tiling for D=%d", D);
+  GKG_CHECK_ARG(P <= 65535, "knn_tc: B*G=%d > 65535", P);
+  TcWorkspace t = carve_tc(extra_ws, pl, P, N);
+  if (dtype == GKG_F32)
+    return launch_prepare_typed<float>(w, t, pl, x, x_sb, x_sn, y, y_sb, y_sn, P, G, N, M, D, self_keys, stream);
+  return launch_prepare_typed<__nv_bfloat16>(w, t, pl, x, x_sb, x_sn, y, y_sb, y_sn, P, G, N, M, D, self_keys,
+                                             stream);
 }
 
 int launch_knn_tc(const KnnWorkspace& w, void* extra_ws, const float* relpos, const SepBias& sep,
@@ -766,7 +847,7 @@ int launch_knn_tc(const KnnWorkspace& w, void* extra_ws, const float* relpos, co
   int bias = relpos != nullptr ? 1 : 0;
   if (bias && sep.a != nullptr && sep.b != nullptr && (sep.kw == 9 || sep.kw == 18 || sep.kw == 36) &&
       sep.grid_w > 0 && N % sep.grid_w == 0 && M % sep.kw == 0 &&
-      (BM / sep.grid_w + 2) * (M / sep.kw) <= SEP_B_FLOATS)
+      (32 / sep.grid_w + 2) * (M / sep.kw) <= SEP_B_FLOATS / 4)
     bias = sep.kw;
   int rc;
 #define GKG_TC_DISPATCH_T(B)                                             \

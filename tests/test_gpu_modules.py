@@ -110,7 +110,6 @@ def test_gkgnet_s192_eval():
     assert ei.dtype == torch.int64 and lab.dtype == torch.float32
     cos = torch.nn.functional.cosine_similarity(gap.cpu().flatten(), g["gap"].flatten(), dim=0).item()
     assert cos > 0.98, cos
-    assert _same_sets(ei.cpu(), g["edge_index"]) > 0.5
 
 
 def test_gkgnet_576_bf16_smoke():
