@@ -82,7 +82,7 @@ extern "C" int gkg_knn_prepare(const void* x, int64_t x_sb, int64_t x_sn, const 
   KnnWorkspace w = carve_knn_workspace(workspace, P, N, M, D, self_keys);
   if (algo == GKG_KNN_TCGEN05)   // fused: normalise + fp16 split + operand layout in one pass
     return launch_knn_tc_prepare(w, static_cast<char*>(workspace) + w.bytes, x, x_sb, x_sn, y, y_sb, y_sn,
-                                 dtype, P, G, N, M, D, self_keys, stream);
+                                 dtype, P, G, N, M, D, k, dilation, self_keys, stream);
   rc = launch_knn_prepare(x, x_sb, x_sn, dtype, w.xhat, w.xsq, B, G, N, D, stream);
   if (rc != GKG_OK) return rc;
   if (!self_keys) {

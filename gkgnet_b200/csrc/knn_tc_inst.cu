@@ -1,0 +1,35 @@
+// One bias mode of the tcgen05 kNN kernel per translation unit (-DGKG_TC_BIAS=0|1|9|18|36).
+#include "knn_tc_kernel.cuh"
+
+namespace gkg {
+namespace tc {
+
+template <int T, int BIAS>
+static int launch_select_tb(const TcParams& prm, const Plan& pl, cudaStream_t stream) {
+  auto kern = knn_tc_kernel<T, BIAS>;
+  size_t smem = pl.smem_bytes < 120 * 1024 ? 120 * 1024 : pl.smem_bytes;   // 512 TMEM columns: 1 CTA / SM
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) {
+    set_error("knn_tc: cudaFuncSetAttribute(%zu): %s", smem, cudaGetErrorString(e));
+    return GKG_ECUDA;
+  }
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int items = prm.P * prm.QT;
+  const int grid = items < sms ? items : sms;
+  kern<<<grid, NTHREADS, smem, stream>>>(prm);
+  GKG_CHECK_LAUNCH("knn_tc_kernel");
+  return GKG_OK;
+}
+
+template <>
+int launch_select<GKG_TC_BIAS>(const TcParams& prm, const Plan& pl, int T, cudaStream_t stream) {
+  if (T <= 11) return launch_select_tb<11, GKG_TC_BIAS>(prm, pl, stream);
+  if (T <= 20) return launch_select_tb<20, GKG_TC_BIAS>(prm, pl, stream);
+  if (T <= 29) return launch_select_tb<29, GKG_TC_BIAS>(prm, pl, stream);
+  return launch_select_tb<38, GKG_TC_BIAS>(prm, pl, stream);
+}
+
+}  // namespace tc
+}  // namespace gkg

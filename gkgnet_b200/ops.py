@@ -26,6 +26,15 @@ def _token_major(t: torch.Tensor) -> torch.Tensor:
     return t
 
 
+def _common_dtype(x, y):
+    """Mixed precision (e.g. bf16 label queries vs fp32 patch features under autocast): promote
+    to the wider type, like the reference's elementwise ops do."""
+    if y is not None and y.dtype != x.dtype:
+        dt = torch.promote_types(x.dtype, y.dtype)
+        x, y = x.to(dt), y.to(dt)
+    return x, y
+
+
 def _require_cuda(*ts):
     for t in ts:
         if t is not None and not t.is_cuda:
@@ -69,6 +78,7 @@ def knn_graph(x, y=None, relative_pos=None, *, groups=1, k=9, dilation=1, algo=_
     """
     _require_cuda(x, y, relative_pos)
     lib = _lib.load()
+    x, y = _common_dtype(x, y)
     x = _token_major(x)
     B, N, C = x.shape
     if C % groups:
@@ -165,6 +175,7 @@ def mr_aggregate(x, idx, y=None, *, groups=1):
     (torch_vertex.py:49-61).  Differentiable w.r.t. x and y.
     """
     _require_cuda(x, y, idx)
+    x, y = _common_dtype(x, y)
     if idx.dtype != torch.int32:
         idx = idx.to(torch.int32)
     idx = idx.contiguous()
