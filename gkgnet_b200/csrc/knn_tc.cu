@@ -295,16 +295,17 @@ int launch_knn_tc(const KnnWorkspace& w, void* extra_ws, const float* relpos, co
   prm.fix_count = t.fix_count; prm.fix_rows = t.fix_rows; prm.stats = t.stats;
   prm.dbg_dist = g_dbg_dist;
   prm.P = P; prm.N = N; prm.M = M; prm.D = D; prm.k = k; prm.dilation = dilation; prm.kd = k * dilation;
-  prm.KP = pl.KP; prm.KC = pl.KC; prm.NKB = pl.NKB; prm.NA = pl.NA; prm.NS = pl.NS; prm.QT = pl.QT; prm.KT = pl.KT;
+  prm.H = pl.H; prm.KP = pl.KP; prm.KC = pl.KC; prm.NKB = pl.NKB; prm.NA = pl.NA; prm.NS = pl.NS; prm.QT = pl.QT; prm.KT = pl.KT;
   prm.a_tile_bytes = pl.a_tile_bytes; prm.b_block_bytes = pl.b_block_bytes;
   prm.force_rerank = g_force_rerank;
   prm.sep_a = sep.a; prm.sep_b = sep.b; prm.grid_w = sep.grid_w > 0 ? sep.grid_w : 1;
   prm.sep_mh = sep.kw > 0 ? M / sep.kw : 1;
+  prm.sep_mhp = sep.kw > 0 ? pl.KT * BN / sep.kw : 1;
   const int T = prm.kd + 2;
   int bias = relpos != nullptr ? 1 : 0;
   if (bias && sep.a != nullptr && sep.b != nullptr && (sep.kw == 9 || sep.kw == 18 || sep.kw == 36) &&
       sep.grid_w > 0 && N % sep.grid_w == 0 && M % sep.kw == 0 &&
-      (32 / sep.grid_w + 2) * (M / sep.kw) <= SEP_B_FLOATS / 4)
+      (32 / sep.grid_w + 2) * (pl.KT * BN / sep.kw) <= SEP_B_FLOATS / 4)
     bias = sep.kw;
   int rc;
   switch (bias) {

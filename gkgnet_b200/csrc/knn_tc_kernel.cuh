@@ -16,16 +16,19 @@ constexpr int NTHREADS = 192;      // warp 0 TMA, warp 1 MMA, warps 2..5 epilogu
 constexpr int NACC = 3;            // TMEM accumulators
 constexpr int ACC_STRIDE = 160;    // TMEM columns between accumulators (3 x 160 <= 512)
 constexpr int SEP_B_FLOATS = 2048; // staged rows of the separable bias table B (512 per epilogue warp)
-constexpr int CAND_SLACK = 24;     // per-row candidate buffer = T survivors + CAND_SLACK new entries
+constexpr int LOG_SLACK = 12;      // triplets a 36-column chunk can add to a row's log (CH / 3)
 constexpr int MAX_T = 38;
 constexpr float kScale = 256.f;    // operand scale S
-constexpr float kPadKey = -60000.f;  // B extra column of padded keys -> dist ~ +468
+constexpr float kNegHalfS2 = -0.5f * 256.f * 256.f;   // beta = kNegHalfS2 * relative_pos (exact: power of two)
+constexpr float kScoreToDist = 1.f / kNegHalfS2;      // dist - |xh|^2 = score * kScoreToDist
+constexpr float kPadKey = -60000.f;  // B extra column of padded keys -> score ~ -1.5e7 (dist ~ +468)
+constexpr float kScoreFloor = -8e6f; // initial threshold: above every padded key, below every real one (dist < 244)
 constexpr float kDelta = 4e-6f;    // bound on |approx - exact| of the fp16x3 GEMM (dist units)
 constexpr int MAX_A_BUF = 2;
 constexpr int MAX_STAGES = 8;
 
 struct Plan {
-  int KP, KC, NKB, NA, NS, QT, KT;
+  int KP, KC, NKB, NA, NS, QT, KT, H;
   uint32_t a_tile_bytes, b_block_bytes;
   size_t smem_bytes;
   size_t a_op_bytes, b_op_bytes;   // per launch operand buffers
@@ -33,37 +36,81 @@ struct Plan {
 };
 
 constexpr size_t kSmemBudget = 227 * 1024;
-__host__ __device__ constexpr size_t cand_bytes(int T) { return (size_t)BM * (T + CAND_SLACK) * 8; }
+// Log capacity per row: T + 1 survivors (one tie) + H slots of headroom + the triplets of one chunk.
+// The compaction that reclaims dead entries runs when a row of the warp exceeds T + 1 + H entries;
+// more headroom means fewer compactions.  The slots from T + 1 on double as the (score, id) pair
+// list of the final selection (2 pairs per slot).
+__host__ __device__ constexpr int log_cap(int T, int H) {
+  return T + 1 + ((T + 4) / 2 > H + LOG_SLACK ? (T + 4) / 2 : H + LOG_SLACK);
+}
+__host__ __device__ constexpr size_t cand_bytes(int T, int H) { return (size_t)BM * log_cap(T, H) * 16; }
 constexpr size_t kBarBytes = 1024 + SEP_B_FLOATS * 4;
 
+// Two operand-staging modes:
+//   resident  (NA = 1 | 2): the whole 128-row A tile (all K) sits in shared memory for the item, B
+//             blocks (BN keys x KC) stream through the ring -- used while the A tile is small (D <= 80);
+//   streaming (NA = 0):     A and B blocks of one K slice travel together through the ring (the A
+//             tile would not leave room for the triplet log) -- A is re-read once per key tile.
 inline Plan make_plan(int P, int N, int M, int D, int T = MAX_T) {
-  const size_t kCandBytes = cand_bytes(T);
   Plan pl{};
   pl.KP = (3 * D + 2 + 15) / 16 * 16;
   pl.QT = (N + BM - 1) / BM;
   pl.KT = (M + BN - 1) / BN;
   pl.a_tile_bytes = (uint32_t)BM * pl.KP * 2;
   pl.ok = false;
-  for (int na = MAX_A_BUF; na >= 1 && !pl.ok; --na) {
-    const size_t fixed = kCandBytes + kBarBytes + (size_t)na * pl.a_tile_bytes;
-    if (fixed >= kSmemBudget) continue;
-    const size_t room = kSmemBudget - fixed;
-    for (int kc = pl.KP; kc >= 16; kc -= 16) {
-      if (pl.KP % kc) continue;
-      const size_t blk = (size_t)BN * kc * 2;
-      int ns = (int)(room / blk);
-      if (ns > MAX_STAGES) ns = MAX_STAGES;
-      const int want = (na == 1) ? 2 : 3;
-      if (ns >= want || (ns >= 2 && kc == 16)) {
-        pl.NA = na; pl.KC = kc; pl.NKB = pl.KP / kc; pl.NS = ns;
-        pl.b_block_bytes = (uint32_t)blk;
-        pl.ok = true;
-        break;
+  size_t cand = 0;
+  static const int kHeadroom[] = {12, 6, 2};
+  if (pl.KP <= 256) {
+    // preference order: a well fed pipeline first (A double-buffered, >= 3 B stages), then log headroom
+    for (int pass = 0; pass < 2 && !pl.ok; ++pass) {
+      for (int hi = 0; hi < 3 && !pl.ok; ++hi) {
+        const int H = kHeadroom[hi];
+        cand = cand_bytes(T, H);
+        for (int na = MAX_A_BUF; na >= 1 && !pl.ok; --na) {
+          const size_t fixed = cand + kBarBytes + (size_t)na * pl.a_tile_bytes;
+          if (fixed >= kSmemBudget) continue;
+          const size_t room = kSmemBudget - fixed;
+          for (int kc = pl.KP; kc >= 16; kc -= 16) {
+            if (pl.KP % kc) continue;
+            const size_t blk = (size_t)BN * kc * 2;
+            int ns = (int)(room / blk);
+            if (ns > MAX_STAGES) ns = MAX_STAGES;
+            const int want = (na == 1) ? 2 : 3;
+            const bool good = ns >= want && (size_t)ns * blk >= 48 * 1024;
+            const bool usable = ns >= want || (ns >= 2 && kc == 16);
+            if (pass == 0 ? good : usable) {
+              pl.NA = na; pl.KC = kc; pl.NKB = pl.KP / kc; pl.NS = ns; pl.H = H;
+              pl.b_block_bytes = (uint32_t)blk;
+              pl.ok = true;
+              break;
+            }
+          }
+        }
+      }
+    }
+  }
+  if (!pl.ok) {
+    for (int hi = 0; hi < 3 && !pl.ok; ++hi) {
+      const int H = kHeadroom[hi];
+      cand = cand_bytes(T, H);
+      if (cand + kBarBytes >= kSmemBudget) continue;
+      const size_t room = kSmemBudget - cand - kBarBytes;
+      for (int kc = 64; kc >= 16 && !pl.ok; kc -= 16) {
+        if (pl.KP % kc) continue;
+        const size_t blk = (size_t)(BM + BN) * kc * 2;
+        int ns = (int)(room / blk);
+        if (ns > MAX_STAGES) ns = MAX_STAGES;
+        if (ns >= 4 || (ns >= 2 && kc == 16)) {
+          pl.NA = 0; pl.KC = kc; pl.NKB = pl.KP / kc; pl.NS = ns; pl.H = H;
+          pl.b_block_bytes = (uint32_t)((size_t)BN * kc * 2);
+          pl.ok = true;
+        }
       }
     }
   }
   if (!pl.ok) return pl;
-  pl.smem_bytes = kCandBytes + kBarBytes + (size_t)pl.NA * pl.a_tile_bytes + (size_t)pl.NS * pl.b_block_bytes;
+  const size_t stage = pl.b_block_bytes + (pl.NA == 0 ? (size_t)BM * pl.KC * 2 : 0);
+  pl.smem_bytes = cand + kBarBytes + (size_t)pl.NA * pl.a_tile_bytes + (size_t)pl.NS * stage;
   pl.a_op_bytes = (size_t)P * pl.QT * pl.a_tile_bytes;
   pl.b_op_bytes = (size_t)P * pl.KT * (size_t)BN * pl.KP * 2;
   return pl;
@@ -186,55 +233,118 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo,
 // kind::f16 instruction descriptor: D=f32 (bit 4), A=B=f16 (0), K-major both, N>>3 at 17, M>>4 at 24.
 constexpr uint32_t kIdesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 
-// Sorted list of the T smallest VALUES seen so far (registers).  Branch-free insertion:
-// new[s] = min(max(x, old[s-1]), old[s]) -- two FMNMX per slot, independent across slots, a
-// no-op when x >= v[T-1].  The (value, id) pairs themselves live in the row's shared-memory
-// buffer: [0, ns) survivors (value <= tau at the last compaction), [ns, cnt) new candidates.
+// ------------------------------------------------------------------------------------
+// selection machinery (epilogue warps; one thread == one query row)
+// ------------------------------------------------------------------------------------
+// Everything is ranked in the SCALED SCORE domain  s = acc + beta,  acc = S^2 (xh.yh - |yh|^2/2)
+// straight out of TMEM and beta = -(S^2/2) * relative_pos, so that
+//     dist - |xh|^2 = s * (-2 / S^2)          (both factors are powers of two: exact)
+// and "nearest" == "largest score".  Keys are examined three at a time: a TRIPLET is logged
+// (its three scores + the id of its first key, one 16-byte shared-memory store) when its largest
+// score beats the running threshold tau = T-th largest triplet maximum seen so far.  Because
+// the T largest triplet maxima are T distinct keys, tau never exceeds the T-th largest score,
+// so every key that can still be among the T best lives in a logged triplet.
+__device__ __forceinline__ float fmax3(float a, float b, float c) { return fmaxf(fmaxf(a, b), c); }  // FMNMX3
+
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, float a, float b, float c, float d) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__device__ __forceinline__ float4 ld_shared_v4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_shared_v2(uint32_t addr, float a, float b) {
+  asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(addr), "f"(a), "f"(b) : "memory");
+}
+__device__ __forceinline__ float2 ld_shared_v2(uint32_t addr) {
+  float2 v;
+  asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr) : "memory");
+  return v;
+}
+
+// The T largest triplet maxima seen so far, sorted descending, in registers.  Branch-free
+// insertion: new[s] = max(old[s], min(x, old[s-1])) -- two FMNMX per slot, a no-op when x <= v[T-1].
 template <int T>
-struct ValList {
+struct TopList {
   float v[T];
   __device__ __forceinline__ void init() {
 #pragma unroll
-    for (int s = 0; s < T; ++s) v[s] = INFINITY;
+    for (int s = 0; s < T; ++s) v[s] = kScoreFloor;
   }
   __device__ __forceinline__ void insert(float x) {
 #pragma unroll
-    for (int s = T - 1; s >= 1; --s) v[s] = fminf(fmaxf(x, v[s - 1]), v[s]);
-    v[0] = fminf(x, v[0]);
+    for (int s = T - 1; s >= 1; --s) v[s] = fmaxf(fminf(x, v[s - 1]), v[s]);
+    v[0] = fmaxf(x, v[0]);
   }
 };
 
-// Fold the new candidates of every lane into its value list, then keep only the entries that can
-// still be among the T smallest.  Loop trip counts are warp-uniform; bodies are predicated.
-template <int T>
-__device__ __forceinline__ void compact_candidates(ValList<T>& top, float& tau, float2*& wp, int& ns,
-                                                   bool& overflow, float2* cbuf) {
-  const int cnt = (int)(wp - cbuf) / BM;
+// Per-row triplet log in shared memory: entry e of the row handled by thread t lives at
+// log_base(t) + e * LOG_STRIDE (16 bytes per thread, consecutive lanes adjacent -> conflict-free
+// 128-bit accesses).  [0, ns) survivors of the last compaction, [ns, cnt) entries logged since.
+constexpr uint32_t LOG_STRIDE = BM * 16;
+
+// True maximum of a logged triplet (B term of its key group added back); kScoreFloor if !valid.
+template <int BIAS, int KW>
+__device__ __forceinline__ float entry_max(const float4& c, bool valid, const float* brow) {
+  float x = fmax3(c.x, c.y, c.z);
+  if (BIAS > 1) x += brow[valid ? __float_as_int(c.w) / KW : 0];
+  return valid ? x : kScoreFloor;
+}
+
+// Fold the new entries into the threshold list, then keep only the entries whose triplet can still
+// hold one of the T best keys.  Loop trip counts are warp-uniform; bodies are predicated; entries
+// are fetched four at a time so that the shared-memory latency is paid once per batch.  (Reads may
+// run up to 3 slots past a row's last entry: still inside this CTA's shared memory, values unused.)
+template <int T, int BIAS, int KW>
+__device__ __forceinline__ void compact_log(TopList<T>& top, float& tau, uint32_t& wp, int& ns, bool& overflow,
+                                            uint32_t log_base, const float* brow) {
+  const int cnt = (int)((wp - log_base) / LOG_STRIDE);
   const int mx_new = __reduce_max_sync(0xffffffffu, cnt - ns);
-  for (int i = 0; i < mx_new; ++i) {
-    const int e = ns + i;
-    const float x = (e < cnt) ? cbuf[e * BM].x : INFINITY;
-    top.insert(x);
+  for (int i0 = 0; i0 < mx_new; i0 += 4) {
+    float4 c[4];
+    float x[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) c[u] = ld_shared_v4(log_base + (uint32_t)(ns + i0 + u) * LOG_STRIDE);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) x[u] = entry_max<BIAS, KW>(c[u], ns + i0 + u < cnt, brow);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) top.insert(x[u]);
   }
   tau = top.v[T - 1];
   const int mx_all = __reduce_max_sync(0xffffffffu, cnt);
-  int w = 0;
-  for (int e = 0; e < mx_all; ++e) {
-    if (e < cnt) {
-      const float2 c = cbuf[e * BM];
-      if (c.x <= tau) {
-        cbuf[w * BM] = c;
-        ++w;
+  uint32_t w = log_base;
+  for (int e0 = 0; e0 < mx_all; e0 += 4) {
+    float4 c[4];
+    bool keep[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) c[u] = ld_shared_v4(log_base + (uint32_t)(e0 + u) * LOG_STRIDE);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) keep[u] = (e0 + u < cnt) && entry_max<BIAS, KW>(c[u], e0 + u < cnt, brow) >= tau;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (keep[u]) {
+        st_shared_v4(w, c[u].x, c[u].y, c[u].z, c[u].w);
+        w += LOG_STRIDE;
       }
     }
   }
-  if (w > T + 4) {          // many exact ties at the threshold: keep room, certify later by fix-up
-    w = T + 4;
+  int nw = (int)((w - log_base) / LOG_STRIDE);
+  if (nw > T + 1) {   // a pile of exact ties at the threshold: certify by fix-up
+    nw = T + 1;
     overflow = true;
   }
-  ns = w;
-  wp = cbuf + w * BM;
+  ns = nw;
+  wp = log_base + (uint32_t)nw * LOG_STRIDE;
 }
+
+// One chunk of a query row in flight: CH accumulator columns and the bias terms that go with them.
+template <bool DENSE, int NG>
+struct Chunk {
+  uint32_t r[CH];
+  float bias[DENSE ? CH : 1];
+  float bg[NG];
+};
 
 struct TcParams {
   const __half* a_op;
@@ -243,12 +353,12 @@ struct TcParams {
   const float* relpos;             // dense (N, M) bias, or null
   const float* sep_a;              // separable bias: A (grid_w, KW), B (N / grid_w, M / KW)
   const float* sep_b;
-  int grid_w, sep_mh;
+  int grid_w, sep_mh, sep_mhp;
   int32_t* idx_out;
   int* fix_count; int* fix_rows; unsigned int* stats;   // stats: [0] ambiguous rows, [1] max err bits
   float* dbg_dist;
   int P, N, M, D, k, dilation, kd;
-  int KP, KC, NKB, NA, NS, QT, KT;
+  int KP, KC, NKB, NA, NS, QT, KT, H;
   uint32_t a_tile_bytes, b_block_bytes;
   int force_rerank;
 };
@@ -270,13 +380,20 @@ template <int T, int BIAS>
 __global__ void __launch_bounds__(NTHREADS, 1) knn_tc_kernel(const TcParams prm) {
   constexpr bool HAS_REL = BIAS != 0;
   constexpr bool DENSE = BIAS == 1;
-  constexpr int KW = BIAS > 1 ? BIAS : 36;
+  constexpr int KW = BIAS > 1 ? BIAS : CH;      // columns that share one B term (whole chunk if none)
+  constexpr int TL = T + 3;                     // (score, id) pairs sorted at the end of a row
+  constexpr int NCH = BN / CH;                  // chunks per accumulator
+  constexpr int NG = CH / KW;                   // key groups per chunk
+  static_assert(NCH == 4, "chunk index arithmetic assumes 4 chunks per accumulator");
+  static_assert(TL <= 2 * (log_cap(T, 2) - T - 1), "pair list must fit its slots");
   extern __shared__ __align__(1024) uint8_t smem[];
-  // carve-up: [A x NA][B ring x NS][candidates][barriers + tmem ptr][staged B rows]
+  // carve-up: [A x NA][B ring x NS][triplet log][barriers + tmem ptr][staged B rows]
+  const uint32_t a_blk_bytes = prm.NA == 0 ? (uint32_t)(BM * prm.KC * 2) : 0u;   // streaming mode: A slice per stage
+  const uint32_t stage_bytes = prm.b_block_bytes + a_blk_bytes;                // [B block][A slice]
   uint8_t* sA = smem;
   uint8_t* sB = sA + (size_t)prm.NA * prm.a_tile_bytes;
-  float2* cand = reinterpret_cast<float2*>(sB + (size_t)prm.NS * prm.b_block_bytes);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(cand) + cand_bytes(T));
+  uint8_t* cand = sB + (size_t)prm.NS * stage_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(cand + cand_bytes(T, prm.H));
   uint64_t* a_full = bars;                    // [MAX_A_BUF]
   uint64_t* a_empty = a_full + MAX_A_BUF;     // [MAX_A_BUF]
   uint64_t* b_full = a_empty + MAX_A_BUF;     // [MAX_STAGES]
@@ -314,21 +431,27 @@ __global__ void __launch_bounds__(NTHREADS, 1) knn_tc_kernel(const TcParams prm)
       int ab = 0, aph = 0, bs = 0, bph = 0;
       for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
         const int p = item / prm.QT, qt = item - p * prm.QT;
-        mbar_wait<true>(smem_u32(a_empty + ab), aph ^ 1);
-        mbar_expect_tx(smem_u32(a_full + ab), prm.a_tile_bytes);
-        tma_bulk_g2s(smem_u32(sA + (size_t)ab * prm.a_tile_bytes),
-                     reinterpret_cast<const uint8_t*>(prm.a_op) + ((size_t)p * prm.QT + qt) * prm.a_tile_bytes,
-                     prm.a_tile_bytes, smem_u32(a_full + ab));
-        if (++ab == prm.NA) { ab = 0; aph ^= 1; }
+        const uint8_t* asrc = reinterpret_cast<const uint8_t*>(prm.a_op) + ((size_t)p * prm.QT + qt) * prm.a_tile_bytes;
+        if (prm.NA > 0) {
+          mbar_wait<true>(smem_u32(a_empty + ab), aph ^ 1);
+          mbar_expect_tx(smem_u32(a_full + ab), prm.a_tile_bytes);
+          tma_bulk_g2s(smem_u32(sA + (size_t)ab * prm.a_tile_bytes), asrc, prm.a_tile_bytes, smem_u32(a_full + ab));
+          if (++ab == prm.NA) { ab = 0; aph ^= 1; }
+        }
         const uint8_t* bsrc = reinterpret_cast<const uint8_t*>(prm.b_op) +
                               (size_t)p * prm.KT * prm.NKB * prm.b_block_bytes;
-        const int nblk = prm.KT * prm.NKB;
-        for (int blk = 0; blk < nblk; ++blk) {
-          mbar_wait<true>(smem_u32(b_empty + bs), bph ^ 1);
-          mbar_expect_tx(smem_u32(b_full + bs), prm.b_block_bytes);
-          tma_bulk_g2s(smem_u32(sB + (size_t)bs * prm.b_block_bytes), bsrc + (size_t)blk * prm.b_block_bytes,
-                       prm.b_block_bytes, smem_u32(b_full + bs));
-          if (++bs == prm.NS) { bs = 0; bph ^= 1; }
+        for (int kt = 0; kt < prm.KT; ++kt) {
+          for (int kb = 0; kb < prm.NKB; ++kb) {
+            mbar_wait<true>(smem_u32(b_empty + bs), bph ^ 1);
+            mbar_expect_tx(smem_u32(b_full + bs), stage_bytes);
+            uint8_t* dst = sB + (size_t)bs * stage_bytes;
+            tma_bulk_g2s(smem_u32(dst), bsrc + (size_t)(kt * prm.NKB + kb) * prm.b_block_bytes, prm.b_block_bytes,
+                         smem_u32(b_full + bs));
+            if (prm.NA == 0)
+              tma_bulk_g2s(smem_u32(dst + prm.b_block_bytes), asrc + (size_t)kb * a_blk_bytes, a_blk_bytes,
+                           smem_u32(b_full + bs));
+            if (++bs == prm.NS) { bs = 0; bph ^= 1; }
+          }
         }
       }
     }
@@ -339,9 +462,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) knn_tc_kernel(const TcParams prm)
       const uint32_t lbo = 128, sbo = (uint32_t)(prm.KC >> 3) * 128;
       const int ksteps = prm.KC >> 4;
       for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
-        mbar_wait<true>(smem_u32(a_full + ab), aph);
-        tc_fence_after();
-        const uint32_t a_base = smem_u32(sA + (size_t)ab * prm.a_tile_bytes);
+        uint32_t a_base = 0;
+        if (prm.NA > 0) {
+          mbar_wait<true>(smem_u32(a_full + ab), aph);
+          tc_fence_after();
+          a_base = smem_u32(sA + (size_t)ab * prm.a_tile_bytes);
+        }
         for (int kt = 0; kt < prm.KT; ++kt) {
           mbar_wait<true>(smem_u32(t_empty + tb), tph ^ 1);
           tc_fence_after();
@@ -349,32 +475,35 @@ __global__ void __launch_bounds__(NTHREADS, 1) knn_tc_kernel(const TcParams prm)
           for (int kb = 0; kb < prm.NKB; ++kb) {
             mbar_wait<true>(smem_u32(b_full + bs), bph);
             tc_fence_after();
-            const uint32_t a_addr = a_base + (uint32_t)kb * (BM * prm.KC * 2);
-            const uint32_t b_addr = smem_u32(sB + (size_t)bs * prm.b_block_bytes);
+            const uint32_t b_addr = smem_u32(sB + (size_t)bs * stage_bytes);
+            const uint32_t a_addr = prm.NA > 0 ? a_base + (uint32_t)kb * (BM * prm.KC * 2) : b_addr + prm.b_block_bytes;
             for (int ks = 0; ks < ksteps; ++ks) {
               const uint64_t ad = make_smem_desc(a_addr + ks * 256, lbo, sbo);
               const uint64_t bd = make_smem_desc(b_addr + ks * 256, lbo, sbo);
               umma_f16(d_tmem, ad, bd, kIdesc, (kb | ks) != 0 ? 1u : 0u);
             }
-            umma_commit(smem_u32(b_empty + bs));       // frees the B block when the MMAs retire
+            umma_commit(smem_u32(b_empty + bs));       // frees the stage when the MMAs retire
             if (++bs == prm.NS) { bs = 0; bph ^= 1; }
           }
           umma_commit(smem_u32(t_full + tb));           // accumulator ready for the epilogue
           if (++tb == NACC) { tb = 0; tph ^= 1; }
         }
-        umma_commit(smem_u32(a_empty + ab));            // A tile may be overwritten
-        if (++ab == prm.NA) { ab = 0; aph ^= 1; }
+        if (prm.NA > 0) {
+          umma_commit(smem_u32(a_empty + ab));          // A tile may be overwritten
+          if (++ab == prm.NA) { ab = 0; aph ^= 1; }
+        }
       }
     }
   } else {
     // ================================ epilogue / selection ===========================
     const int q = warp & 3;                      // TMEM lane quarter this warp may read
     const int row_t = q * 32 + lane;
-    float2* cbuf = cand + row_t;                 // entry e at cbuf[e * BM]
+    const uint32_t log_base = smem_u32(cand) + (uint32_t)row_t * 16;
+    const uint32_t log_full = log_base + (uint32_t)(T + 1 + prm.H) * LOG_STRIDE;   // compaction trigger
+    const uint32_t pair_base = log_base + (uint32_t)(T + 1) * LOG_STRIDE;   // (score, id) pairs of the final selection: 2 per slot
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
-    const float c_scale = -2.f / (kScale * kScale);
-    int tb = 0, tph = 0;
-    ValList<T> top;
+    int ltb = 0, ltph = 0, rtb = 0;              // accumulator ring: load side (slot, phase), release side
+    TopList<T> top;
     for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
       const int p = item / prm.QT, qt = item - p * prm.QT;
       const int n = qt * BM + row_t;
@@ -382,13 +511,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) knn_tc_kernel(const TcParams prm)
       const int n_c = row_ok ? n : prm.N - 1;
       const float* relrow = HAS_REL ? prm.relpos + (size_t)n_c * prm.M : nullptr;
       top.init();
-      float tau = INFINITY;
-      float2* wp = cbuf;                           // next free candidate slot of this row
-      int ns = 0;                                  // survivors at the front of the buffer
+      float tau = kScoreFloor;                     // T-th largest triplet maximum so far
+      uint32_t wp = log_base;                      // next free log slot of this row
+      int ns = 0;                                  // survivors at the front of the log
       bool overflow = false;
 
       // ---- separable bias: A row -> registers, B rows of this warp's 32 rows -> shared memory
-      float areg[KW];
+      float areg[BIAS > 1 ? KW : 1];
       const float* brow = sepB_s;
       if (BIAS > 1) {
         float* mine = sepB_s + q * (SEP_B_FLOATS / 4);
@@ -397,101 +526,157 @@ __global__ void __launch_bounds__(NTHREADS, 1) knn_tc_kernel(const TcParams prm)
         const int h0 = first / prm.grid_w;
         const int nh = last / prm.grid_w - h0 + 1;
         __syncwarp();
-        for (int i = lane; i < nh * prm.sep_mh; i += 32) mine[i] = __ldg(prm.sep_b + (size_t)h0 * prm.sep_mh + i);
+        // rows are staged zero-padded to sep_mhp = KT * BN / KW entries: no clamping when indexed by key id
+        for (int i = lane; i < nh * prm.sep_mhp; i += 32) {
+          const int rr = i / prm.sep_mhp, cc = i - rr * prm.sep_mhp;
+          mine[i] = cc < prm.sep_mh ? kNegHalfS2 * __ldg(prm.sep_b + (size_t)(h0 + rr) * prm.sep_mh + cc) : 0.f;
+        }
         __syncwarp();
         const float* arow = prm.sep_a + (size_t)(n_c % prm.grid_w) * KW;
 #pragma unroll
-        for (int j = 0; j < KW; ++j) areg[j] = __ldg(arow + j);
-        brow = mine + (n_c / prm.grid_w - h0) * prm.sep_mh;
+        for (int j = 0; j < KW; ++j) areg[BIAS > 1 ? j : 0] = kNegHalfS2 * __ldg(arow + j);
+        brow = mine + (n_c / prm.grid_w - h0) * prm.sep_mhp;
       }
 
-      float bias[DENSE ? CH : 1];
-      auto load_bias = [&](int m0) {
+      // ---- sweep over the keys: chunks of CH accumulator columns, software pipelined (the TMEM
+      // load and the bias terms of chunk i+1 are in flight while chunk i is ranked)
+      const int total_chunks = prm.KT * NCH;
+      auto issue = [&](int ci, Chunk<DENSE, NG>& ch) {
+        const int c = ci & (NCH - 1);
+        const int m0 = (ci >> 2) * BN + c * CH;
+        if (c == 0) {
+          mbar_wait<false>(smem_u32(t_full + ltb), ltph);
+          tc_fence_after();
+        }
+        tmem_ld36(lane_addr + (uint32_t)(ltb * ACC_STRIDE + c * CH), ch.r);
         if (DENSE) {
           if ((prm.M & 3) == 0) {
 #pragma unroll
             for (int j4 = 0; j4 < CH / 4; ++j4) {
               float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
               if (m0 + j4 * 4 < prm.M) b4 = __ldg(reinterpret_cast<const float4*>(relrow + m0 + j4 * 4));
-              bias[j4 * 4 + 0] = b4.x; bias[j4 * 4 + 1] = b4.y; bias[j4 * 4 + 2] = b4.z; bias[j4 * 4 + 3] = b4.w;
+              ch.bias[DENSE ? j4 * 4 + 0 : 0] = b4.x; ch.bias[DENSE ? j4 * 4 + 1 : 0] = b4.y;
+              ch.bias[DENSE ? j4 * 4 + 2 : 0] = b4.z; ch.bias[DENSE ? j4 * 4 + 3 : 0] = b4.w;
             }
           } else {
 #pragma unroll
-            for (int j = 0; j < CH; ++j) bias[DENSE ? j : 0] = (m0 + j < prm.M) ? __ldg(relrow + m0 + j) : 0.f;
+            for (int j = 0; j < CH; ++j) ch.bias[DENSE ? j : 0] = (m0 + j < prm.M) ? __ldg(relrow + m0 + j) : 0.f;
           }
+        }
+        if (BIAS > 1) {
+          const float* brow_c = brow + ((ci >> 2) * (BN / KW) + c * (CH / KW));
+#pragma unroll
+          for (int g = 0; g < NG; ++g) ch.bg[g] = brow_c[g];
+        } else {
+          ch.bg[0] = 0.f;
+        }
+        if (c == NCH - 1 && ++ltb == NACC) { ltb = 0; ltph ^= 1; }
+      };
+      auto complete = [&](int ci, Chunk<DENSE, NG>& ch) {
+        tmem_ld_wait(ch.r);
+        if ((ci & (NCH - 1)) == NCH - 1) {           // whole accumulator is in registers: hand it back
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(smem_u32(t_empty + rtb));
+          if (++rtb == NACC) rtb = 0;
         }
       };
-
-      for (int kt = 0; kt < prm.KT; ++kt) {
-        mbar_wait<false>(smem_u32(t_full + tb), tph);
-        tc_fence_after();
-#pragma unroll 1
-        for (int c = 0; c < BN / CH; ++c) {
-          uint32_t r[CH];
-          tmem_ld36(lane_addr + (uint32_t)(tb * ACC_STRIDE + c * CH), r);
-          const int m0 = kt * BN + c * CH;
-          load_bias(m0);
-          tmem_ld_wait(r);
-          if (prm.dbg_dist != nullptr && row_ok) {
+      auto process = [&](int ci, Chunk<DENSE, NG>& ch) {
+        const int m0 = (ci >> 2) * BN + (ci & (NCH - 1)) * CH;
+        if (prm.dbg_dist != nullptr && row_ok) {
 #pragma unroll
-            for (int j = 0; j < CH; ++j) {
-              if (m0 + j < prm.M) {
-                const float acc = __uint_as_float(r[j]);
-                float b = 0.f;
-                if (DENSE) b = bias[DENSE ? j : 0];
-                if (BIAS > 1) b = areg[j % KW] + brow[min(m0 / KW + j / KW, prm.sep_mh - 1)];
-                prm.dbg_dist[((size_t)p * prm.N + n) * prm.M + m0 + j] = fmaf(acc, c_scale, b);
-              }
+          for (int j = 0; j < CH; ++j) {
+            if (m0 + j < prm.M) {
+              float s = __uint_as_float(ch.r[j]);
+              if (DENSE) s = fmaf(ch.bias[DENSE ? j : 0], kNegHalfS2, s);
+              if (BIAS > 1) s += areg[BIAS > 1 ? j % KW : 0] + ch.bg[j / KW];
+              prm.dbg_dist[((size_t)p * prm.N + n) * prm.M + m0 + j] = s * kScoreToDist;
             }
           }
+        }
 #pragma unroll
-          for (int g = 0; g < CH / KW; ++g) {
-            // per key group: fold the B term into the threshold, add it back on the rare pass
+        for (int g = 0; g < NG; ++g) {
+          // per key group: fold the B term into the threshold (added back when the log is read)
+          const float thr = tau - ch.bg[g];
+#pragma unroll
+          for (int t = 0; t < KW / 3; ++t) {
+            const int j = g * KW + 3 * t;
+            float s0 = __uint_as_float(ch.r[j]), s1 = __uint_as_float(ch.r[j + 1]), s2 = __uint_as_float(ch.r[j + 2]);
+            if (DENSE) {
+              s0 = fmaf(ch.bias[DENSE ? j : 0], kNegHalfS2, s0);
+              s1 = fmaf(ch.bias[DENSE ? j + 1 : 0], kNegHalfS2, s1);
+              s2 = fmaf(ch.bias[DENSE ? j + 2 : 0], kNegHalfS2, s2);
+            } else if (BIAS > 1) {
+              s0 += areg[BIAS > 1 ? 3 * t : 0];
+              s1 += areg[BIAS > 1 ? 3 * t + 1 : 0];
+              s2 += areg[BIAS > 1 ? 3 * t + 2 : 0];
+            }
+            if (fmax3(s0, s1, s2) > thr) {
+              st_shared_v4(wp, s0, s1, s2, __int_as_float(m0 + j));
+              wp += LOG_STRIDE;
+            }
+          }
+        }
+        // the log must always have room for the LOG_SLACK triplets of the next chunk
+        if (__any_sync(0xffffffffu, wp > log_full))
+          compact_log<T, BIAS, KW>(top, tau, wp, ns, overflow, log_base, brow);
+      };
+      {
+        Chunk<DENSE, NG> c0, c1;
+        issue(0, c0);
+#pragma unroll 1
+        for (int ci = 0; ci < total_chunks; ci += 2) {
+          complete(ci, c0);
+          if (ci + 1 < total_chunks) issue(ci + 1, c1);
+          process(ci, c0);
+          if (ci + 1 < total_chunks) {
+            complete(ci + 1, c1);
+            if (ci + 2 < total_chunks) issue(ci + 2, c0);
+            process(ci + 1, c1);
+          }
+        }
+      }
+      compact_log<T, BIAS, KW>(top, tau, wp, ns, overflow, log_base, brow);
+
+      // ---------------- finalise the row -------------------------------------------
+      // keys of the surviving triplets that reach the threshold -> (score, id) pair list
+      int np = 0;
+      {
+        const int mx_ns = __reduce_max_sync(0xffffffffu, ns);
+        for (int e = 0; e < mx_ns; ++e) {
+          if (e < ns) {
+            const float4 c = ld_shared_v4(log_base + (uint32_t)e * LOG_STRIDE);
+            const int id = __float_as_int(c.w);
             float bg = 0.f;
-            if (BIAS > 1) bg = brow[min(m0 / KW + g, prm.sep_mh - 1)];
-            const float taug = tau - bg;
+            if (BIAS > 1) bg = brow[id / KW];
+            const float sc[3] = {c.x + bg, c.y + bg, c.z + bg};
 #pragma unroll
-            for (int jj = 0; jj < KW; ++jj) {
-              const int j = g * KW + jj;
-              const float acc = __uint_as_float(r[j]);
-              float v;
-              if (DENSE) v = fmaf(acc, c_scale, bias[DENSE ? j : 0]);
-              else if (BIAS > 1) v = fmaf(acc, c_scale, areg[jj]);
-              else v = acc * c_scale;
-              if (v < taug) {
-                *wp = make_float2(v + bg, __int_as_float(m0 + j));
-                wp += BM;
-              }
-              // the buffer must always have room for the next 12 candidates
-              if ((j % 12) == 11 && __any_sync(0xffffffffu, wp > cbuf + (T + CAND_SLACK - 12) * BM)) {
-                compact_candidates<T>(top, tau, wp, ns, overflow, cbuf);
+            for (int i = 0; i < 3; ++i) {
+              if (sc[i] >= tau && id + i < prm.M) {
+                if (np < TL) st_shared_v2(pair_base + (uint32_t)(np >> 1) * LOG_STRIDE + (np & 1) * 8, sc[i],
+                                          __int_as_float(id + i));
+                ++np;
               }
             }
           }
         }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(smem_u32(t_empty + tb));
-        if (++tb == NACC) { tb = 0; tph ^= 1; }
       }
-      compact_candidates<T>(top, tau, wp, ns, overflow, cbuf);
-
-      // ---------------- finalise the row -------------------------------------------
-      // survivors -> registers, sorted by (value, id)
-      float cv[T];
-      int cid[T];
+      if (np > TL) overflow = true;
+      // pairs -> registers as (dist - |xh|^2, id), sorted ascending by (value, id)
+      float cv[TL];
+      int cid[TL];
 #pragma unroll
-      for (int s = 0; s < T; ++s) {
-        const float2 c = cbuf[s * BM];
-        const bool have = s < ns;
-        cv[s] = have ? c.x : INFINITY;
+      for (int s = 0; s < TL; ++s) {
+        const float2 c = ld_shared_v2(pair_base + (uint32_t)(s >> 1) * LOG_STRIDE + (s & 1) * 8);
+        const bool have = s < np;
+        cv[s] = have ? c.x * kScoreToDist : INFINITY;
         cid[s] = have ? __float_as_int(c.y) : 0x7fffffff;
       }
       auto sort_pairs = [&]() {
 #pragma unroll
-        for (int pass = 0; pass < T; ++pass) {
+        for (int pass = 0; pass < TL; ++pass) {
 #pragma unroll
-          for (int s = pass & 1; s + 1 < T; s += 2) {
+          for (int s = pass & 1; s + 1 < TL; s += 2) {
             const bool sw = (cv[s + 1] < cv[s]) || (cv[s + 1] == cv[s] && cid[s + 1] < cid[s]);
             const float tv = sw ? cv[s] : cv[s + 1];
             const int ti = sw ? cid[s] : cid[s + 1];
@@ -505,20 +690,20 @@ __global__ void __launch_bounds__(NTHREADS, 1) knn_tc_kernel(const TcParams prm)
       sort_pairs();
 
       const int kd = prm.kd;
-      bool amb = prm.force_rerank != 0 || overflow || ns > T;
+      bool amb = prm.force_rerank != 0 || overflow;
 #pragma unroll
-      for (int s = 0; s + 1 < T; ++s)
+      for (int s = 0; s + 1 < TL; ++s)
         if (s < kd && (cv[s + 1] - cv[s]) < 2.f * kDelta) amb = true;
       if (row_ok && amb) {
-        // exact fp32 re-rank of the T candidates (identical arithmetic to knn_exact.cu)
+        // exact fp32 re-rank of the candidates (identical arithmetic to knn_exact.cu)
         const float* xr = prm.xhat + ((size_t)p * prm.N + n) * prm.D;
         const float xs = prm.xsq[(size_t)p * prm.N + n];
         const float* yb = prm.yhat + (size_t)p * prm.M * prm.D;
         const float* ysb = prm.ysq + (size_t)p * prm.M;
-        const float a_last = tau;                  // every non-candidate has approx >= tau
+        const float a_last = tau * kScoreToDist;   // every key outside the pair list has approx >= a_last
         float maxerr = 0.f;
 #pragma unroll
-        for (int s = 0; s < T; ++s) {
+        for (int s = 0; s < TL; ++s) {
           const int m = cid[s];
           if (m < prm.M) {
             const float e = exact_dist(xr, yb + (size_t)m * prm.D, prm.D, xs, ysb[m], relrow, m);
@@ -533,21 +718,27 @@ __global__ void __launch_bounds__(NTHREADS, 1) knn_tc_kernel(const TcParams prm)
         atomicMax(prm.stats + 1, __float_as_uint(maxerr));
         float e_kd = -INFINITY;               // sorted ascending: kd-th value == max of the first kd
 #pragma unroll
-        for (int s = 0; s < T; ++s)
+        for (int s = 0; s < TL; ++s)
           if (s < kd) e_kd = fmaxf(e_kd, cv[s]);
-        const bool unsure = overflow || ns > T || (a_last - kDelta <= (e_kd - xs) + kDelta);
-        if (unsure && prm.M > T) {
+        // every key is in the pair list when np == M: nothing outside to worry about
+        const bool unsure = overflow || (np < prm.M && a_last - kDelta <= (e_kd - xs) + kDelta);
+        if (unsure) {
           const int slot = atomicAdd(prm.fix_count, 1);
           prm.fix_rows[slot] = p * prm.N + n;
         }
       }
-      // stage the ids in this thread's (now idle) candidate slots so that the dilated pick is a
-      // shared-memory index, not a dynamic register index
+      // stage the ids in this thread's pair slots so that the dilated pick is a shared-memory
+      // index, not a dynamic register index
+      __syncwarp();
 #pragma unroll
-      for (int s = 0; s < T; ++s) cbuf[s * BM].y = __int_as_float(cid[s]);
+      for (int s = 0; s < TL; ++s)
+        st_shared_v2(pair_base + (uint32_t)(s >> 1) * LOG_STRIDE + (s & 1) * 8, 0.f, __int_as_float(cid[s]));
       if (row_ok) {
         int32_t* out = prm.idx_out + ((size_t)p * prm.N + n) * prm.k;
-        for (int j = 0; j < prm.k; ++j) out[j] = __float_as_int(cbuf[j * prm.dilation * BM].y);
+        for (int j = 0; j < prm.k; ++j) {
+          const int s = j * prm.dilation;
+          out[j] = __float_as_int(ld_shared_v2(pair_base + (uint32_t)(s >> 1) * LOG_STRIDE + (s & 1) * 8).y);
+        }
       }
     }
   }
