@@ -228,7 +228,7 @@ static int t_bucket(int T) { return T <= 11 ? 11 : T <= 20 ? 20 : T <= 29 ? 29 :
 bool knn_tc_supported(int N, int M, int D, int k, int dilation) {
   const int kd = k * dilation;
   if (kd + 2 > MAX_T || kd > M) return false;
-  if (N < 1 || M < 1) return false;
+  if (N < 1 || M < 1 || M > 65000) return false;   // key ids travel in 16 bits of a log entry
   Plan pl = make_plan(1, N, M, D, t_bucket(kd + 2));
   return pl.ok;
 }

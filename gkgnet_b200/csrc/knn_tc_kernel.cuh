@@ -288,7 +288,7 @@ constexpr uint32_t LOG_STRIDE = BM * 16;
 template <int BIAS, int KW>
 __device__ __forceinline__ float entry_max(const float4& c, bool valid, const float* brow) {
   float x = fmax3(c.x, c.y, c.z);
-  if (BIAS > 1) x += brow[valid ? __float_as_int(c.w) / KW : 0];
+  if (BIAS > 1) x += brow[valid ? (__float_as_uint(c.w) >> 16) : 0u];   // .w = key id | key group << 16
   return valid ? x : kScoreFloor;
 }
 
@@ -297,9 +297,8 @@ __device__ __forceinline__ float entry_max(const float4& c, bool valid, const fl
 // are fetched four at a time so that the shared-memory latency is paid once per batch.  (Reads may
 // run up to 3 slots past a row's last entry: still inside this CTA's shared memory, values unused.)
 template <int T, int BIAS, int KW>
-__device__ __forceinline__ void compact_log(TopList<T>& top, float& tau, uint32_t& wp, int& ns, bool& overflow,
+__device__ __forceinline__ void compact_log(TopList<T>& top, float& tau, int& cnt, int& ns, bool& overflow,
                                             uint32_t log_base, const float* brow) {
-  const int cnt = (int)((wp - log_base) / LOG_STRIDE);
   const int mx_new = __reduce_max_sync(0xffffffffu, cnt - ns);
   for (int i0 = 0; i0 < mx_new; i0 += 4) {
     float4 c[4];
@@ -313,7 +312,7 @@ __device__ __forceinline__ void compact_log(TopList<T>& top, float& tau, uint32_
   }
   tau = top.v[T - 1];
   const int mx_all = __reduce_max_sync(0xffffffffu, cnt);
-  uint32_t w = log_base;
+  int nw = 0;
   for (int e0 = 0; e0 < mx_all; e0 += 4) {
     float4 c[4];
     bool keep[4];
@@ -324,18 +323,17 @@ __device__ __forceinline__ void compact_log(TopList<T>& top, float& tau, uint32_
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       if (keep[u]) {
-        st_shared_v4(w, c[u].x, c[u].y, c[u].z, c[u].w);
-        w += LOG_STRIDE;
+        st_shared_v4(log_base + (uint32_t)nw * LOG_STRIDE, c[u].x, c[u].y, c[u].z, c[u].w);
+        ++nw;
       }
     }
   }
-  int nw = (int)((w - log_base) / LOG_STRIDE);
   if (nw > T + 1) {   // a pile of exact ties at the threshold: certify by fix-up
     nw = T + 1;
     overflow = true;
   }
   ns = nw;
-  wp = log_base + (uint32_t)nw * LOG_STRIDE;
+  cnt = nw;
 }
 
 // One chunk of a query row in flight: CH accumulator columns and the bias terms that go with them.
@@ -499,7 +497,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) knn_tc_kernel(const TcParams prm)
     const int q = warp & 3;                      // TMEM lane quarter this warp may read
     const int row_t = q * 32 + lane;
     const uint32_t log_base = smem_u32(cand) + (uint32_t)row_t * 16;
-    const uint32_t log_full = log_base + (uint32_t)(T + 1 + prm.H) * LOG_STRIDE;   // compaction trigger
+    const int log_full = T + 1 + prm.H;           // compaction trigger (entries)
     const uint32_t pair_base = log_base + (uint32_t)(T + 1) * LOG_STRIDE;   // (score, id) pairs of the final selection: 2 per slot
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
     int ltb = 0, ltph = 0, rtb = 0;              // accumulator ring: load side (slot, phase), release side
@@ -512,7 +510,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) knn_tc_kernel(const TcParams prm)
       const float* relrow = HAS_REL ? prm.relpos + (size_t)n_c * prm.M : nullptr;
       top.init();
       float tau = kScoreFloor;                     // T-th largest triplet maximum so far
-      uint32_t wp = log_base;                      // next free log slot of this row
+      int cnt = 0;                                 // entries in this row's log
       int ns = 0;                                  // survivors at the front of the log
       bool overflow = false;
 
@@ -583,6 +581,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) knn_tc_kernel(const TcParams prm)
       };
       auto process = [&](int ci, Chunk<DENSE, NG>& ch) {
         const int m0 = (ci >> 2) * BN + (ci & (NCH - 1)) * CH;
+        // id word of a logged triplet: first key id | key group index << 16 (group = slot in brow)
+        const int idw = m0 | (BIAS > 1 ? (m0 / KW) << 16 : 0);
         if (prm.dbg_dist != nullptr && row_ok) {
 #pragma unroll
           for (int j = 0; j < CH; ++j) {
@@ -612,14 +612,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) knn_tc_kernel(const TcParams prm)
               s2 += areg[BIAS > 1 ? 3 * t + 2 : 0];
             }
             if (fmax3(s0, s1, s2) > thr) {
-              st_shared_v4(wp, s0, s1, s2, __int_as_float(m0 + j));
-              wp += LOG_STRIDE;
+              st_shared_v4(log_base + (uint32_t)cnt * LOG_STRIDE, s0, s1, s2,
+                           __int_as_float(idw + (j | (BIAS > 1 ? g << 16 : 0))));
+              ++cnt;
             }
           }
         }
         // the log must always have room for the LOG_SLACK triplets of the next chunk
-        if (__any_sync(0xffffffffu, wp > log_full))
-          compact_log<T, BIAS, KW>(top, tau, wp, ns, overflow, log_base, brow);
+        if (__any_sync(0xffffffffu, cnt > log_full))
+          compact_log<T, BIAS, KW>(top, tau, cnt, ns, overflow, log_base, brow);
       };
       {
         Chunk<DENSE, NG> c0, c1;
@@ -636,7 +637,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) knn_tc_kernel(const TcParams prm)
           }
         }
       }
-      compact_log<T, BIAS, KW>(top, tau, wp, ns, overflow, log_base, brow);
+      compact_log<T, BIAS, KW>(top, tau, cnt, ns, overflow, log_base, brow);
 
       // ---------------- finalise the row -------------------------------------------
       // keys of the surviving triplets that reach the threshold -> (score, id) pair list
@@ -646,9 +647,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) knn_tc_kernel(const TcParams prm)
         for (int e = 0; e < mx_ns; ++e) {
           if (e < ns) {
             const float4 c = ld_shared_v4(log_base + (uint32_t)e * LOG_STRIDE);
-            const int id = __float_as_int(c.w);
+            const int id = (int)(__float_as_uint(c.w) & 0xffffu);
             float bg = 0.f;
-            if (BIAS > 1) bg = brow[id / KW];
+            if (BIAS > 1) bg = brow[__float_as_uint(c.w) >> 16];
             const float sc[3] = {c.x + bg, c.y + bg, c.z + bg};
 #pragma unroll
             for (int i = 0; i < 3; ++i) {
@@ -672,12 +673,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) knn_tc_kernel(const TcParams prm)
         cv[s] = have ? c.x * kScoreToDist : INFINITY;
         cid[s] = have ? __float_as_int(c.y) : 0x7fffffff;
       }
-      auto sort_pairs = [&]() {
+      // odd-even transposition sort; the first (approximate) pass ignores ids: equal values are a
+      // zero gap, which sends the row through the exact re-rank below, sorted with ids as tie-break
+      auto sort_pairs = [&](bool by_id) {
 #pragma unroll
         for (int pass = 0; pass < TL; ++pass) {
 #pragma unroll
           for (int s = pass & 1; s + 1 < TL; s += 2) {
-            const bool sw = (cv[s + 1] < cv[s]) || (cv[s + 1] == cv[s] && cid[s + 1] < cid[s]);
+            const bool sw = (cv[s + 1] < cv[s]) || (by_id && cv[s + 1] == cv[s] && cid[s + 1] < cid[s]);
             const float tv = sw ? cv[s] : cv[s + 1];
             const int ti = sw ? cid[s] : cid[s + 1];
             cv[s] = sw ? cv[s + 1] : cv[s];
@@ -687,7 +690,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) knn_tc_kernel(const TcParams prm)
           }
         }
       };
-      sort_pairs();
+      sort_pairs(false);
 
       const int kd = prm.kd;
       bool amb = prm.force_rerank != 0 || overflow;
@@ -713,7 +716,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) knn_tc_kernel(const TcParams prm)
             cv[s] = INFINITY;
           }
         }
-        sort_pairs();
+        sort_pairs(true);
         atomicAdd(prm.stats + 0, 1u);
         atomicMax(prm.stats + 1, __float_as_uint(maxerr));
         float e_kd = -INFINITY;               // sorted ascending: kd-th value == max of the first kd
