@@ -32,7 +32,9 @@ namespace {
 // ------------------------------------------------------------------------------------
 // operand preparation (phase "prepare"): normalise + split + lay out, one pass over the features
 // ------------------------------------------------------------------------------------
-// A block owns 32 consecutive (padded) rows of one problem.  Phase 1: a warp per row L2-normalises
+// A block owns 32 consecutive padded rows of one problem (a tile has tile_rows row slots of which the
+// first tile_keys hold nodes: UMMA N must be a multiple of 16 while key tiles follow the bias period).
+// Phase 1: a warp per row L2-normalises
 // the D group channels (F.normalize semantics, torch_edge.py:167-168,173), keeps the fp32 row in
 // shared memory and writes it + |xh|^2 for the exact re-rank.  Phase 2: every thread emits 16-byte
 // core-matrix rows (8 fp16) of the tensor-core operand:
@@ -44,7 +46,7 @@ template <typename T, bool IS_KEY>
 __global__ void __launch_bounds__(256)
 tc_prepare_kernel(const T* __restrict__ feat, int64_t stride_b, int64_t stride_n, float* __restrict__ hat,
                   float* __restrict__ sq, __half* __restrict__ op, int G, int rows, int D, int KP, int KC,
-                  int tiles, int tile_rows, int write_hat) {
+                  int tiles, int tile_rows, int tile_keys, int write_hat) {
   extern __shared__ float prep_s[];              // [PREP_ROWS][D] normalised rows + [PREP_ROWS] norms
   float* xs = prep_s;
   float* sqs = prep_s + PREP_ROWS * D;
@@ -52,10 +54,14 @@ tc_prepare_kernel(const T* __restrict__ feat, int64_t stride_b, int64_t stride_n
   const long long p = blockIdx.y;
   const int g = (int)(p % G);
   const long long b = p / G;
-  const int r0 = blockIdx.x * PREP_ROWS;
+  const int r0 = blockIdx.x * PREP_ROWS;      // first PADDED row: tile_rows slots per tile, tile_keys of them real
+  auto key_of = [&](int prow) {
+    const int tile = prow / tile_rows, slot = prow - tile * tile_rows;
+    return slot < tile_keys ? tile * tile_keys + slot : rows;   // rows == "no such node"
+  };
 
   for (int rl = warp; rl < PREP_ROWS; rl += 8) {
-    const int row = r0 + rl;
+    const int row = key_of(r0 + rl);
     float* dst = xs + rl * D;
     if (row < rows) {
       const T* src = feat + b * stride_b + (long long)row * stride_n + (long long)g * D;
@@ -95,12 +101,12 @@ tc_prepare_kernel(const T* __restrict__ feat, int64_t stride_b, int64_t stride_n
     const int kcI = (ci >> 3) % kc_all;
     const int rgl = (ci >> 3) / kc_all;
     const int rl = rgl * 8 + r;
-    const int row = r0 + rl;
-    const int tile = row / tile_rows;
+    const int prow = r0 + rl;
+    const int tile = prow / tile_rows;
     if (tile >= tiles) continue;
-    const int rg = (row - tile * tile_rows) >> 3;
+    const int rg = (prow - tile * tile_rows) >> 3;
     const int kb = kcI / kcs, kc = kcI - kb * kcs;
-    const bool valid = row < rows;
+    const bool valid = key_of(prow) < rows;
     const float* src = xs + rl * D;
     float extra_hi = 0.f, extra_lo = 0.f;
     if (IS_KEY) {
@@ -219,6 +225,8 @@ TcWorkspace carve_tc(void* base, const Plan& pl, int P, int N) {
 
 int g_force_rerank = 0;
 float* g_dbg_dist = nullptr;
+long long* g_trace = nullptr;
+int g_trace_tiles = 0;
 unsigned int g_last_stats[4] = {0, 0, 0, 0};
 
 }  // namespace
@@ -245,18 +253,19 @@ static int launch_prepare_typed(const KnnWorkspace& w, const TcWorkspace& t, con
                                 int64_t x_sb, int64_t x_sn, const void* y, int64_t y_sb, int64_t y_sn, int P,
                                 int G, int N, int M, int D, bool self_keys, cudaStream_t stream) {
   const size_t smem = sizeof(float) * ((size_t)PREP_ROWS * D + PREP_ROWS);
+  const int bn = pl.geom == 1 ? GeomB::BN : GeomA::BN, bnp = pl.geom == 1 ? GeomB::BNP : GeomA::BNP;
   {
-    dim3 grid((pl.QT * BM + PREP_ROWS - 1) / PREP_ROWS, P);
+    dim3 grid((pl.QTP * BM + PREP_ROWS - 1) / PREP_ROWS, P);
     tc_prepare_kernel<T, false><<<grid, 256, smem, stream>>>(static_cast<const T*>(x), x_sb, x_sn, w.xhat, w.xsq,
-                                                            t.a_op, G, N, D, pl.KP, pl.KC, pl.QT, BM, 1);
+                                                            t.a_op, G, N, D, pl.KP, pl.KC, pl.QTP, BM, BM, 1);
     GKG_CHECK_LAUNCH("tc_prepare_kernel<query>");
   }
   {
-    dim3 grid((pl.KT * BN + PREP_ROWS - 1) / PREP_ROWS, P);
+    dim3 grid((pl.KT * bnp + PREP_ROWS - 1) / PREP_ROWS, P);
     const T* src = static_cast<const T*>(self_keys ? x : y);
     tc_prepare_kernel<T, true><<<grid, 256, smem, stream>>>(src, self_keys ? x_sb : y_sb, self_keys ? x_sn : y_sn,
                                                            w.yhat, w.ysq, t.b_op, G, M, D, pl.KP, pl.KC, pl.KT,
-                                                           BN, self_keys ? 0 : 1);
+                                                           bnp, bn, self_keys ? 0 : 1);
     GKG_CHECK_LAUNCH("tc_prepare_kernel<key>");
   }
   return GKG_OK;
@@ -294,18 +303,22 @@ int launch_knn_tc(const KnnWorkspace& w, void* extra_ws, const float* relpos, co
   prm.relpos = relpos; prm.idx_out = idx_out;
   prm.fix_count = t.fix_count; prm.fix_rows = t.fix_rows; prm.stats = t.stats;
   prm.dbg_dist = g_dbg_dist;
+  prm.trace = g_trace; prm.trace_tiles = g_trace_tiles;
   prm.P = P; prm.N = N; prm.M = M; prm.D = D; prm.k = k; prm.dilation = dilation; prm.kd = k * dilation;
-  prm.H = pl.H; prm.KP = pl.KP; prm.KC = pl.KC; prm.NKB = pl.NKB; prm.NA = pl.NA; prm.NS = pl.NS; prm.QT = pl.QT; prm.KT = pl.KT;
+  prm.H = pl.H; prm.KP = pl.KP; prm.KC = pl.KC; prm.NKB = pl.NKB; prm.NA = pl.NA; prm.NS = pl.NS; prm.QT = pl.QT;
+  prm.QI = pl.QI; prm.QTP = pl.QTP; prm.KT = pl.KT;
   prm.a_tile_bytes = pl.a_tile_bytes; prm.b_block_bytes = pl.b_block_bytes;
   prm.force_rerank = g_force_rerank;
   prm.sep_a = sep.a; prm.sep_b = sep.b; prm.grid_w = sep.grid_w > 0 ? sep.grid_w : 1;
   prm.sep_mh = sep.kw > 0 ? M / sep.kw : 1;
-  prm.sep_mhp = sep.kw > 0 ? pl.KT * BN / sep.kw : 1;
+  const int bn = pl.geom == 1 ? GeomB::BN : GeomA::BN;
+  const int sepw = pl.geom == 1 ? GeomB::SEPW : GeomA::SEPW;
+  prm.sep_mhp = sep.kw > 0 ? pl.KT * bn / sep.kw : 1;
   const int T = prm.kd + 2;
   int bias = relpos != nullptr ? 1 : 0;
   if (bias && sep.a != nullptr && sep.b != nullptr && (sep.kw == 9 || sep.kw == 18 || sep.kw == 36) &&
       sep.grid_w > 0 && N % sep.grid_w == 0 && M % sep.kw == 0 &&
-      (32 / sep.grid_w + 2) * (pl.KT * BN / sep.kw) <= SEP_B_FLOATS / 4)
+      (32 / sep.grid_w + 2) * (pl.KT * bn / sep.kw) <= sepw)
     bias = sep.kw;
   int rc;
   switch (bias) {
@@ -344,6 +357,10 @@ int launch_knn_tc(const KnnWorkspace& w, void* extra_ws, const float* relpos, co
 extern "C" void gkg_debug_knn_tc(int force_rerank, float* dbg_dist) {
   gkg::g_force_rerank = force_rerank;
   gkg::g_dbg_dist = dbg_dist;
+}
+extern "C" void gkg_debug_knn_tc_trace(long long* buf, int tiles) {
+  gkg::g_trace = buf;
+  gkg::g_trace_tiles = tiles;
 }
 extern "C" void gkg_debug_knn_tc_stats(unsigned int* out3) {
   out3[0] = gkg::g_last_stats[0];

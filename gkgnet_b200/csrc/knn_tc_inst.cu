@@ -4,9 +4,9 @@
 namespace gkg {
 namespace tc {
 
-template <int T, int BIAS>
+template <class G, int T, int BIAS>
 static int launch_select_tb(const TcParams& prm, const Plan& pl, cudaStream_t stream) {
-  auto kern = knn_tc_kernel<T, BIAS>;
+  auto kern = knn_tc_kernel<G, T, BIAS>;
   size_t smem = pl.smem_bytes < 120 * 1024 ? 120 * 1024 : pl.smem_bytes;   // 512 TMEM columns: 1 CTA / SM
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) {
@@ -16,19 +16,23 @@ static int launch_select_tb(const TcParams& prm, const Plan& pl, cudaStream_t st
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const int items = prm.P * prm.QT;
+  const int items = prm.P * prm.QI;
   const int grid = items < sms ? items : sms;
-  kern<<<grid, NTHREADS, smem, stream>>>(prm);
+  kern<<<grid, G::NTHREADS, smem, stream>>>(prm);
   GKG_CHECK_LAUNCH("knn_tc_kernel");
   return GKG_OK;
 }
 
 template <>
 int launch_select<GKG_TC_BIAS>(const TcParams& prm, const Plan& pl, int T, cudaStream_t stream) {
-  if (T <= 11) return launch_select_tb<11, GKG_TC_BIAS>(prm, pl, stream);
-  if (T <= 20) return launch_select_tb<20, GKG_TC_BIAS>(prm, pl, stream);
-  if (T <= 29) return launch_select_tb<29, GKG_TC_BIAS>(prm, pl, stream);
-  return launch_select_tb<38, GKG_TC_BIAS>(prm, pl, stream);
+  if (pl.geom == 1) {   // 256-row items: only planned for lists of <= 20
+    if (T <= 11) return launch_select_tb<GeomB, 11, GKG_TC_BIAS>(prm, pl, stream);
+    return launch_select_tb<GeomB, 20, GKG_TC_BIAS>(prm, pl, stream);
+  }
+  if (T <= 11) return launch_select_tb<GeomA, 11, GKG_TC_BIAS>(prm, pl, stream);
+  if (T <= 20) return launch_select_tb<GeomA, 20, GKG_TC_BIAS>(prm, pl, stream);
+  if (T <= 29) return launch_select_tb<GeomA, 29, GKG_TC_BIAS>(prm, pl, stream);
+  return launch_select_tb<GeomA, 38, GKG_TC_BIAS>(prm, pl, stream);
 }
 
 }  // namespace tc

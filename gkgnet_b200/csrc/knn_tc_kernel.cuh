@@ -7,16 +7,9 @@
 namespace gkg {
 namespace tc {
 
-
-constexpr int BM = 128;            // query rows per tile  (UMMA M)
-constexpr int BN = 144;            // keys per tile        (UMMA N): 4 chunks of 36 = lcm of the
-                                   // key-grid widths 9/18/36 of the separable position bias
-constexpr int CH = 36;             // columns per epilogue chunk (tcgen05.ld x32 + x4)
-constexpr int NTHREADS = 192;      // warp 0 TMA, warp 1 MMA, warps 2..5 epilogue
-constexpr int NACC = 3;            // TMEM accumulators
-constexpr int ACC_STRIDE = 160;    // TMEM columns between accumulators (3 x 160 <= 512)
-constexpr int SEP_B_FLOATS = 2048; // staged rows of the separable bias table B (512 per epilogue warp)
-constexpr int LOG_SLACK = 12;      // triplets a 36-column chunk can add to a row's log (CH / 3)
+constexpr int BM = 128;            // query rows per row set (UMMA M)
+constexpr int CH = 36;             // accumulator columns per epilogue chunk (tcgen05.ld x32 + x4) = lcm of
+                                   // the key-grid widths 9/18/36 of the separable position bias
 constexpr int MAX_T = 38;
 constexpr float kScale = 256.f;    // operand scale S
 constexpr float kNegHalfS2 = -0.5f * 256.f * 256.f;   // beta = kNegHalfS2 * relative_pos (exact: power of two)
@@ -24,59 +17,84 @@ constexpr float kScoreToDist = 1.f / kNegHalfS2;      // dist - |xh|^2 = score *
 constexpr float kPadKey = -60000.f;  // B extra column of padded keys -> score ~ -1.5e7 (dist ~ +468)
 constexpr float kScoreFloor = -8e6f; // initial threshold: above every padded key, below every real one (dist < 244)
 constexpr float kDelta = 4e-6f;    // bound on |approx - exact| of the fp16x3 GEMM (dist units)
-constexpr int MAX_A_BUF = 2;
 constexpr int MAX_STAGES = 8;
+constexpr size_t kSmemBudget = 227 * 1024;
+
+// Kernel geometry.  One work item = RS row sets of 128 queries of one problem against all its keys;
+// every B block that streams through shared memory feeds RS MMAs, so RS = 2 halves the operand
+// traffic per query and doubles the epilogue warps (latency hiding) at the price of a log per row.
+//   BN   real keys per key tile (multiple of CH)      BNP  UMMA N (BN rounded up to 16; pad rows never read)
+//   NACC accumulator slots per row set                CHK  log-capacity checks per chunk
+template <int RS_, int BN_, int BNP_, int NACC_, int ACC_STRIDE_, int CHK_, int SEPW_>
+struct Geom {
+  static constexpr int RS = RS_, BN = BN_, BNP = BNP_, NACC = NACC_, ACC_STRIDE = ACC_STRIDE_, CHK = CHK_;
+  static constexpr int NCH = BN / CH;             // chunks per accumulator
+  static constexpr int NEPI = 4 * RS;             // epilogue warps
+  static constexpr int NTHREADS = 64 + 32 * NEPI; // warp 0 TMA, warp 1 MMA, then the epilogue warps
+  static constexpr int ROWS = BM * RS;
+  static constexpr uint32_t LOG_STRIDE = ROWS * 16;   // bytes between consecutive log slots of a row
+  static constexpr int SLACK = 12 / CHK;          // triplets that can be logged between two checks
+  static constexpr int SEPW = SEPW_;              // staged floats of the separable bias table B per epilogue warp
+  static constexpr size_t kBarBytes = 1024 + (size_t)NEPI * SEPW * 4;
+  // kind::f16 instruction descriptor: D=f32 (bit 4), A=B=f16 (0), K-major both, N>>3 at 17, M>>4 at 24.
+  static constexpr uint32_t kIdesc = (1u << 4) | ((uint32_t)(BNP >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+  static_assert(BN % CH == 0 && BNP % 16 == 0 && BNP >= BN && RS * NACC * ACC_STRIDE <= 512 && ACC_STRIDE >= BNP, "geometry");
+  // Log capacity per row: T + 1 survivors (one tie) + H slots of headroom + the triplets logged between
+  // two checks.  The compaction that reclaims dead entries runs when a row of the warp exceeds
+  // T + 1 + H entries; more headroom means fewer compactions.  The slots from T + 1 on double as the
+  // (score, id) pair list of the final selection (2 pairs per slot).
+  __host__ __device__ static constexpr int log_cap(int T, int H) {
+    return T + 1 + ((T + 4) / 2 > H + SLACK ? (T + 4) / 2 : H + SLACK);
+  }
+  __host__ __device__ static constexpr size_t cand_bytes(int T, int H) { return (size_t)ROWS * log_cap(T, H) * 16; }
+};
+using GeomA = Geom<1, 144, 144, 3, 160, 1, 512>;   // 128 rows / item: any shape
+using GeomB = Geom<2, 108, 112, 2, 128, 2, 384>;   // 256 rows / item: small operands (D <= 80), short lists
 
 struct Plan {
-  int KP, KC, NKB, NA, NS, QT, KT, H;
+  int geom;                        // 0 = GeomA, 1 = GeomB
+  int KP, KC, NKB, NA, NS, QT, QI, QTP, KT, H;
   uint32_t a_tile_bytes, b_block_bytes;
   size_t smem_bytes;
   size_t a_op_bytes, b_op_bytes;   // per launch operand buffers
   bool ok;
 };
 
-constexpr size_t kSmemBudget = 227 * 1024;
-// Log capacity per row: T + 1 survivors (one tie) + H slots of headroom + the triplets of one chunk.
-// The compaction that reclaims dead entries runs when a row of the warp exceeds T + 1 + H entries;
-// more headroom means fewer compactions.  The slots from T + 1 on double as the (score, id) pair
-// list of the final selection (2 pairs per slot).
-__host__ __device__ constexpr int log_cap(int T, int H) {
-  return T + 1 + ((T + 4) / 2 > H + LOG_SLACK ? (T + 4) / 2 : H + LOG_SLACK);
-}
-__host__ __device__ constexpr size_t cand_bytes(int T, int H) { return (size_t)BM * log_cap(T, H) * 16; }
-constexpr size_t kBarBytes = 1024 + SEP_B_FLOATS * 4;
-
 // Two operand-staging modes:
-//   resident  (NA = 1 | 2): the whole 128-row A tile (all K) sits in shared memory for the item, B
-//             blocks (BN keys x KC) stream through the ring -- used while the A tile is small (D <= 80);
+//   resident  (NA = 1 | 2 buffers per row set): the whole 128-row A tiles (all K) sit in shared memory
+//             for the item, B blocks (BNP keys x KC) stream through the ring;
 //   streaming (NA = 0):     A and B blocks of one K slice travel together through the ring (the A
-//             tile would not leave room for the triplet log) -- A is re-read once per key tile.
-inline Plan make_plan(int P, int N, int M, int D, int T = MAX_T) {
+//             tiles would not leave room for the triplet log) -- A is re-read once per key tile.
+template <class G>
+inline Plan make_plan_g(int P, int N, int M, int D, int T, bool strict) {
   Plan pl{};
   pl.KP = (3 * D + 2 + 15) / 16 * 16;
   pl.QT = (N + BM - 1) / BM;
-  pl.KT = (M + BN - 1) / BN;
+  pl.QI = (pl.QT + G::RS - 1) / G::RS;
+  pl.QTP = pl.QI * G::RS;
+  pl.KT = (M + G::BN - 1) / G::BN;
   pl.a_tile_bytes = (uint32_t)BM * pl.KP * 2;
   pl.ok = false;
   size_t cand = 0;
-  static const int kHeadroom[] = {12, 6, 2};
+  static const int kHeadroom[] = {24, 12, 9, 6, 2};
   if (pl.KP <= 256) {
     // preference order: a well fed pipeline first (A double-buffered, >= 3 B stages), then log headroom
-    for (int pass = 0; pass < 2 && !pl.ok; ++pass) {
-      for (int hi = 0; hi < 3 && !pl.ok; ++hi) {
+    for (int pass = 0; pass < (strict ? 1 : 2) && !pl.ok; ++pass) {
+      for (int hi = 0; hi < 5 && !pl.ok; ++hi) {
         const int H = kHeadroom[hi];
-        cand = cand_bytes(T, H);
-        for (int na = MAX_A_BUF; na >= 1 && !pl.ok; --na) {
-          const size_t fixed = cand + kBarBytes + (size_t)na * pl.a_tile_bytes;
+        if (strict && H < 9) break;
+        cand = G::cand_bytes(T, H);
+        for (int na = 2; na >= 1 && !pl.ok; --na) {
+          const size_t fixed = cand + G::kBarBytes + (size_t)na * G::RS * pl.a_tile_bytes;
           if (fixed >= kSmemBudget) continue;
           const size_t room = kSmemBudget - fixed;
           for (int kc = pl.KP; kc >= 16; kc -= 16) {
             if (pl.KP % kc) continue;
-            const size_t blk = (size_t)BN * kc * 2;
+            const size_t blk = (size_t)G::BNP * kc * 2;
             int ns = (int)(room / blk);
             if (ns > MAX_STAGES) ns = MAX_STAGES;
             const int want = (na == 1) ? 2 : 3;
-            const bool good = ns >= want && (size_t)ns * blk >= 48 * 1024;
+            const bool good = ns >= 3 && (size_t)ns * blk >= 40 * 1024;
             const bool usable = ns >= want || (ns >= 2 && kc == 16);
             if (pass == 0 ? good : usable) {
               pl.NA = na; pl.KC = kc; pl.NKB = pl.KP / kc; pl.NS = ns; pl.H = H;
@@ -89,31 +107,43 @@ inline Plan make_plan(int P, int N, int M, int D, int T = MAX_T) {
       }
     }
   }
-  if (!pl.ok) {
-    for (int hi = 0; hi < 3 && !pl.ok; ++hi) {
+  if (!pl.ok && !strict) {
+    for (int hi = 0; hi < 5 && !pl.ok; ++hi) {
       const int H = kHeadroom[hi];
-      cand = cand_bytes(T, H);
-      if (cand + kBarBytes >= kSmemBudget) continue;
-      const size_t room = kSmemBudget - cand - kBarBytes;
+      cand = G::cand_bytes(T, H);
+      if (cand + G::kBarBytes >= kSmemBudget) continue;
+      const size_t room = kSmemBudget - cand - G::kBarBytes;
       for (int kc = 64; kc >= 16 && !pl.ok; kc -= 16) {
         if (pl.KP % kc) continue;
-        const size_t blk = (size_t)(BM + BN) * kc * 2;
+        const size_t blk = (size_t)(G::ROWS + G::BNP) * kc * 2;
         int ns = (int)(room / blk);
         if (ns > MAX_STAGES) ns = MAX_STAGES;
         if (ns >= 4 || (ns >= 2 && kc == 16)) {
           pl.NA = 0; pl.KC = kc; pl.NKB = pl.KP / kc; pl.NS = ns; pl.H = H;
-          pl.b_block_bytes = (uint32_t)((size_t)BN * kc * 2);
+          pl.b_block_bytes = (uint32_t)((size_t)G::BNP * kc * 2);
           pl.ok = true;
         }
       }
     }
   }
   if (!pl.ok) return pl;
-  const size_t stage = pl.b_block_bytes + (pl.NA == 0 ? (size_t)BM * pl.KC * 2 : 0);
-  pl.smem_bytes = cand + kBarBytes + (size_t)pl.NA * pl.a_tile_bytes + (size_t)pl.NS * stage;
-  pl.a_op_bytes = (size_t)P * pl.QT * pl.a_tile_bytes;
-  pl.b_op_bytes = (size_t)P * pl.KT * (size_t)BN * pl.KP * 2;
+  const size_t stage = pl.b_block_bytes + (pl.NA == 0 ? (size_t)G::ROWS * pl.KC * 2 : 0);
+  pl.smem_bytes = cand + G::kBarBytes + (size_t)pl.NA * G::RS * pl.a_tile_bytes + (size_t)pl.NS * stage;
+  pl.a_op_bytes = (size_t)P * pl.QTP * pl.a_tile_bytes;
+  pl.b_op_bytes = (size_t)P * pl.KT * (size_t)G::BNP * pl.KP * 2;
   return pl;
+}
+
+// GeomB when its resident plan is comfortable (small operands, list of <= 20, enough rows to fill the
+// row sets), GeomA otherwise.
+inline Plan make_plan(int P, int N, int M, int D, int T = MAX_T) {
+  if (T <= 20 && N > BM) {
+    Plan pb = make_plan_g<GeomB>(P, N, M, D, T, true);
+    if (pb.ok) { pb.geom = 1; return pb; }
+  }
+  Plan pa = make_plan_g<GeomA>(P, N, M, D, T, false);
+  pa.geom = 0;
+  return pa;
 }
 
 // ------------------------------------------------------------------------------------
@@ -161,16 +191,17 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
   return t;
 }
 // Bounded wait: a protocol bug must abort the kernel, never hang the GPU.
-// BACKOFF: single-lane producer / MMA warps sleep between polls so that their spinning does not
-// take issue slots from the epilogue warp sharing the scheduler.
+// BACKOFF: the single-lane producer / MMA warps nap briefly between polls so that their spinning
+// does not take issue slots from the epilogue warp sharing the scheduler.  (A long suspend-time
+// hint on try_wait was measured to wake up microseconds late; short naps are the better trade.)
 template <bool BACKOFF>
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   const unsigned long long t0 = globaltimer_ns();
   uint32_t spins = 0;
-  while (!(BACKOFF ? mbar_try_wait_hint(bar, parity, 20000u) : mbar_try_wait(bar, parity))) {
-    if (BACKOFF) __nanosleep(200);
-    if ((++spins & 255u) == 0 && globaltimer_ns() - t0 > 4000000000ull) __trap();
+  while (!mbar_try_wait(bar, parity)) {
+    if (BACKOFF) __nanosleep(32);
+    if ((++spins & 1023u) == 0 && globaltimer_ns() - t0 > 4000000000ull) __trap();
   }
 }
 __device__ __forceinline__ void tma_bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
@@ -230,8 +261,6 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo,
   return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) |
          (1ull << 46);
 }
-// kind::f16 instruction descriptor: D=f32 (bit 4), A=B=f16 (0), K-major both, N>>3 at 17, M>>4 at 24.
-constexpr uint32_t kIdesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 
 // ------------------------------------------------------------------------------------
 // selection machinery (epilogue warps; one thread == one query row)
@@ -282,21 +311,14 @@ struct TopList {
 // Per-row triplet log in shared memory: entry e of the row handled by thread t lives at
 // log_base(t) + e * LOG_STRIDE (16 bytes per thread, consecutive lanes adjacent -> conflict-free
 // 128-bit accesses).  [0, ns) survivors of the last compaction, [ns, cnt) entries logged since.
-constexpr uint32_t LOG_STRIDE = BM * 16;
-
-// True maximum of a logged triplet (B term of its key group added back); kScoreFloor if !valid.
-template <int BIAS, int KW>
-__device__ __forceinline__ float entry_max(const float4& c, bool valid, const float* brow) {
-  float x = fmax3(c.x, c.y, c.z);
-  if (BIAS > 1) x += brow[valid ? (__float_as_uint(c.w) >> 16) : 0u];   // .w = key id | key group << 16
-  return valid ? x : kScoreFloor;
-}
-
+//
 // Fold the new entries into the threshold list, then keep only the entries whose triplet can still
-// hold one of the T best keys.  Loop trip counts are warp-uniform; bodies are predicated; entries
-// are fetched four at a time so that the shared-memory latency is paid once per batch.  (Reads may
-// run up to 3 slots past a row's last entry: still inside this CTA's shared memory, values unused.)
-template <int T, int BIAS, int KW>
+// hold one of the T best keys.  New entries are "raw" (scores without the B term of their key group);
+// the first pass adds it back in place, so that survivors never pay for the lookup again.  Loop trip
+// counts are warp-uniform; bodies are predicated; entries are fetched four at a time so that the
+// shared-memory latency is paid once per batch.  (Reads may run up to 3 slots past a row's last
+// entry: still inside this CTA's shared memory, values unused.)
+template <uint32_t LOG_STRIDE, int T, int BIAS>
 __device__ __forceinline__ void compact_log(TopList<T>& top, float& tau, int& cnt, int& ns, bool& overflow,
                                             uint32_t log_base, const float* brow) {
   const int mx_new = __reduce_max_sync(0xffffffffu, cnt - ns);
@@ -306,7 +328,15 @@ __device__ __forceinline__ void compact_log(TopList<T>& top, float& tau, int& cn
 #pragma unroll
     for (int u = 0; u < 4; ++u) c[u] = ld_shared_v4(log_base + (uint32_t)(ns + i0 + u) * LOG_STRIDE);
 #pragma unroll
-    for (int u = 0; u < 4; ++u) x[u] = entry_max<BIAS, KW>(c[u], ns + i0 + u < cnt, brow);
+    for (int u = 0; u < 4; ++u) {
+      const bool valid = ns + i0 + u < cnt;
+      if (BIAS > 1) {
+        const float bg = brow[valid ? (__float_as_uint(c[u].w) >> 16) : 0u];   // .w = key id | key group << 16
+        c[u].x += bg; c[u].y += bg; c[u].z += bg;
+        if (valid) st_shared_v4(log_base + (uint32_t)(ns + i0 + u) * LOG_STRIDE, c[u].x, c[u].y, c[u].z, c[u].w);
+      }
+      x[u] = valid ? fmax3(c[u].x, c[u].y, c[u].z) : kScoreFloor;
+    }
 #pragma unroll
     for (int u = 0; u < 4; ++u) top.insert(x[u]);
   }
@@ -319,7 +349,7 @@ __device__ __forceinline__ void compact_log(TopList<T>& top, float& tau, int& cn
 #pragma unroll
     for (int u = 0; u < 4; ++u) c[u] = ld_shared_v4(log_base + (uint32_t)(e0 + u) * LOG_STRIDE);
 #pragma unroll
-    for (int u = 0; u < 4; ++u) keep[u] = (e0 + u < cnt) && entry_max<BIAS, KW>(c[u], e0 + u < cnt, brow) >= tau;
+    for (int u = 0; u < 4; ++u) keep[u] = (e0 + u < cnt) && fmax3(c[u].x, c[u].y, c[u].z) >= tau;
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       if (keep[u]) {
@@ -355,8 +385,10 @@ struct TcParams {
   int32_t* idx_out;
   int* fix_count; int* fix_rows; unsigned int* stats;   // stats: [0] ambiguous rows, [1] max err bits
   float* dbg_dist;
+  long long* trace;                // debug: clock64 stamps of CTA 0, 8 slots per key tile (see tools/knn_trace.py)
+  int trace_tiles;
   int P, N, M, D, k, dilation, kd;
-  int KP, KC, NKB, NA, NS, QT, KT, H;
+  int KP, KC, NKB, NA, NS, QT, QI, QTP, KT, H;
   uint32_t a_tile_bytes, b_block_bytes;
   int force_rerank;
 };
@@ -374,40 +406,41 @@ __device__ __forceinline__ float exact_dist(const float* __restrict__ xr, const 
 // bias  relpos[n, m] = A[n % grid_w][m % KW] + B[n / grid_w][m / KW]  with the A row in registers
 // and the needed B rows staged in shared memory (the analytic table of the reference has this
 // form: pos_embed.py + the flattened bicubic resize, see gkgnet_b200/pos_embed.py).
-template <int T, int BIAS>
-__global__ void __launch_bounds__(NTHREADS, 1) knn_tc_kernel(const TcParams prm) {
+template <class G, int T, int BIAS>
+__global__ void __launch_bounds__(G::NTHREADS, 1) knn_tc_kernel(const TcParams prm) {
   constexpr bool HAS_REL = BIAS != 0;
   constexpr bool DENSE = BIAS == 1;
   constexpr int KW = BIAS > 1 ? BIAS : CH;      // columns that share one B term (whole chunk if none)
   constexpr int TL = T + 3;                     // (score, id) pairs sorted at the end of a row
-  constexpr int NCH = BN / CH;                  // chunks per accumulator
+  constexpr int NCH = G::NCH;                   // chunks per accumulator
   constexpr int NG = CH / KW;                   // key groups per chunk
-  static_assert(NCH == 4, "chunk index arithmetic assumes 4 chunks per accumulator");
-  static_assert(TL <= 2 * (log_cap(T, 2) - T - 1), "pair list must fit its slots");
+  constexpr int RS = G::RS, NACC = G::NACC;
+  constexpr uint32_t LOG_STRIDE = G::LOG_STRIDE;
+  static_assert(TL <= 2 * (G::log_cap(T, 2) - T - 1), "pair list must fit its slots");
   extern __shared__ __align__(1024) uint8_t smem[];
-  // carve-up: [A x NA][B ring x NS][triplet log][barriers + tmem ptr][staged B rows]
-  const uint32_t a_blk_bytes = prm.NA == 0 ? (uint32_t)(BM * prm.KC * 2) : 0u;   // streaming mode: A slice per stage
-  const uint32_t stage_bytes = prm.b_block_bytes + a_blk_bytes;                // [B block][A slice]
+  // carve-up: [A tiles x NA x RS][ring x NS: B block (+ A slices when streaming)][triplet log][barriers + tmem ptr][staged B rows]
+  const uint32_t a_blk_bytes = (uint32_t)(BM * prm.KC * 2);                    // one K slice of one A tile
+  const uint32_t stage_bytes = prm.b_block_bytes + (prm.NA == 0 ? RS * a_blk_bytes : 0u);
   uint8_t* sA = smem;
-  uint8_t* sB = sA + (size_t)prm.NA * prm.a_tile_bytes;
+  uint8_t* sB = sA + (size_t)prm.NA * RS * prm.a_tile_bytes;
   uint8_t* cand = sB + (size_t)prm.NS * stage_bytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(cand + cand_bytes(T, prm.H));
-  uint64_t* a_full = bars;                    // [MAX_A_BUF]
-  uint64_t* a_empty = a_full + MAX_A_BUF;     // [MAX_A_BUF]
-  uint64_t* b_full = a_empty + MAX_A_BUF;     // [MAX_STAGES]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(cand + G::cand_bytes(T, prm.H));
+  uint64_t* a_full = bars;                    // [2 * RS]
+  uint64_t* a_empty = a_full + 4;             // [2 * RS]
+  uint64_t* b_full = a_empty + 4;             // [MAX_STAGES]
   uint64_t* b_empty = b_full + MAX_STAGES;    // [MAX_STAGES]
-  uint64_t* t_full = b_empty + MAX_STAGES;    // [NACC]
-  uint64_t* t_empty = t_full + NACC;          // [NACC]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + NACC);
-  float* sepB_s = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 1024);   // [SEP_B_FLOATS]
+  uint64_t* t_full = b_empty + MAX_STAGES;    // [RS * NACC]
+  uint64_t* t_empty = t_full + 8;             // [RS * NACC]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 8);
+  float* sepB_s = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 1024);   // [NEPI][SEPW]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < MAX_A_BUF; ++i) { mbar_init(smem_u32(a_full + i), 1); mbar_init(smem_u32(a_empty + i), 1); }
+    for (int i = 0; i < 4; ++i) { mbar_init(smem_u32(a_full + i), 1); mbar_init(smem_u32(a_empty + i), 1); }
     for (int i = 0; i < MAX_STAGES; ++i) { mbar_init(smem_u32(b_full + i), 1); mbar_init(smem_u32(b_empty + i), 1); }
-    for (int i = 0; i < NACC; ++i) { mbar_init(smem_u32(t_full + i), 1); mbar_init(smem_u32(t_empty + i), 4); }
+    for (int i = 0; i < 8; ++i) { mbar_init(smem_u32(t_full + i), 1); mbar_init(smem_u32(t_empty + i), 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -421,19 +454,25 @@ __global__ void __launch_bounds__(NTHREADS, 1) knn_tc_kernel(const TcParams prm)
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int total_items = prm.P * prm.QT;
+  const int total_items = prm.P * prm.QI;
 
   if (warp == 0) {
     // ================================ TMA producer ===================================
     if (lane == 0) {
-      int ab = 0, aph = 0, bs = 0, bph = 0;
+      int ab = 0, aph = 0, bs = 0, bph = 0, tseq = 0;
       for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
-        const int p = item / prm.QT, qt = item - p * prm.QT;
-        const uint8_t* asrc = reinterpret_cast<const uint8_t*>(prm.a_op) + ((size_t)p * prm.QT + qt) * prm.a_tile_bytes;
+        const int p = item / prm.QI, qi = item - p * prm.QI;
+        const uint8_t* asrc = reinterpret_cast<const uint8_t*>(prm.a_op) +
+                              ((size_t)p * prm.QTP + (size_t)qi * RS) * prm.a_tile_bytes;   // RS consecutive tiles
         if (prm.NA > 0) {
-          mbar_wait<true>(smem_u32(a_empty + ab), aph ^ 1);
-          mbar_expect_tx(smem_u32(a_full + ab), prm.a_tile_bytes);
-          tma_bulk_g2s(smem_u32(sA + (size_t)ab * prm.a_tile_bytes), asrc, prm.a_tile_bytes, smem_u32(a_full + ab));
+#pragma unroll
+          for (int r = 0; r < RS; ++r) {
+            const int slot = ab * RS + r;
+            mbar_wait<true>(smem_u32(a_empty + slot), aph ^ 1);
+            mbar_expect_tx(smem_u32(a_full + slot), prm.a_tile_bytes);
+            tma_bulk_g2s(smem_u32(sA + (size_t)slot * prm.a_tile_bytes), asrc + (size_t)r * prm.a_tile_bytes,
+                         prm.a_tile_bytes, smem_u32(a_full + slot));
+          }
           if (++ab == prm.NA) { ab = 0; aph ^= 1; }
         }
         const uint8_t* bsrc = reinterpret_cast<const uint8_t*>(prm.b_op) +
@@ -445,66 +484,93 @@ __global__ void __launch_bounds__(NTHREADS, 1) knn_tc_kernel(const TcParams prm)
             uint8_t* dst = sB + (size_t)bs * stage_bytes;
             tma_bulk_g2s(smem_u32(dst), bsrc + (size_t)(kt * prm.NKB + kb) * prm.b_block_bytes, prm.b_block_bytes,
                          smem_u32(b_full + bs));
-            if (prm.NA == 0)
-              tma_bulk_g2s(smem_u32(dst + prm.b_block_bytes), asrc + (size_t)kb * a_blk_bytes, a_blk_bytes,
-                           smem_u32(b_full + bs));
+            if (prm.NA == 0) {
+#pragma unroll
+              for (int r = 0; r < RS; ++r)
+                tma_bulk_g2s(smem_u32(dst + prm.b_block_bytes + r * a_blk_bytes),
+                             asrc + (size_t)r * prm.a_tile_bytes + (size_t)kb * a_blk_bytes, a_blk_bytes,
+                             smem_u32(b_full + bs));
+            }
             if (++bs == prm.NS) { bs = 0; bph ^= 1; }
           }
+          if (prm.trace != nullptr && blockIdx.x == 0 && tseq < prm.trace_tiles) prm.trace[tseq * 8 + 6] = clock64();
+          ++tseq;
         }
       }
     }
   } else if (warp == 1) {
     // ================================ MMA issuer =====================================
     if (lane == 0) {
-      int ab = 0, aph = 0, bs = 0, bph = 0, tb = 0, tph = 0;
+      int ab = 0, aph = 0, bs = 0, bph = 0, tb = 0, tph = 0, tseq = 0;
+      const bool tr = prm.trace != nullptr && blockIdx.x == 0;
       const uint32_t lbo = 128, sbo = (uint32_t)(prm.KC >> 3) * 128;
       const int ksteps = prm.KC >> 4;
       for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
-        uint32_t a_base = 0;
+        uint32_t a_base[RS];
         if (prm.NA > 0) {
-          mbar_wait<true>(smem_u32(a_full + ab), aph);
+#pragma unroll
+          for (int r = 0; r < RS; ++r) {
+            mbar_wait<true>(smem_u32(a_full + ab * RS + r), aph);
+            a_base[r] = smem_u32(sA + (size_t)(ab * RS + r) * prm.a_tile_bytes);
+          }
           tc_fence_after();
-          a_base = smem_u32(sA + (size_t)ab * prm.a_tile_bytes);
         }
         for (int kt = 0; kt < prm.KT; ++kt) {
-          mbar_wait<true>(smem_u32(t_empty + tb), tph ^ 1);
+          if (tr && tseq < prm.trace_tiles) prm.trace[tseq * 8 + 0] = clock64();
+#pragma unroll
+          for (int r = 0; r < RS; ++r) mbar_wait<true>(smem_u32(t_empty + r * NACC + tb), tph ^ 1);
           tc_fence_after();
-          const uint32_t d_tmem = tmem_base + (uint32_t)tb * ACC_STRIDE;
+          if (tr && tseq < prm.trace_tiles) prm.trace[tseq * 8 + 1] = clock64();
           for (int kb = 0; kb < prm.NKB; ++kb) {
             mbar_wait<true>(smem_u32(b_full + bs), bph);
             tc_fence_after();
             const uint32_t b_addr = smem_u32(sB + (size_t)bs * stage_bytes);
-            const uint32_t a_addr = prm.NA > 0 ? a_base + (uint32_t)kb * (BM * prm.KC * 2) : b_addr + prm.b_block_bytes;
-            for (int ks = 0; ks < ksteps; ++ks) {
-              const uint64_t ad = make_smem_desc(a_addr + ks * 256, lbo, sbo);
-              const uint64_t bd = make_smem_desc(b_addr + ks * 256, lbo, sbo);
-              umma_f16(d_tmem, ad, bd, kIdesc, (kb | ks) != 0 ? 1u : 0u);
+#pragma unroll
+            for (int r = 0; r < RS; ++r) {
+              const uint32_t d_tmem = tmem_base + (uint32_t)((r * NACC + tb) * G::ACC_STRIDE);
+              const uint32_t a_addr = prm.NA > 0 ? a_base[r] + (uint32_t)kb * a_blk_bytes
+                                                 : b_addr + prm.b_block_bytes + r * a_blk_bytes;
+              for (int ks = 0; ks < ksteps; ++ks) {
+                const uint64_t ad = make_smem_desc(a_addr + ks * 256, lbo, sbo);
+                const uint64_t bd = make_smem_desc(b_addr + ks * 256, lbo, sbo);
+                umma_f16(d_tmem, ad, bd, G::kIdesc, (kb | ks) != 0 ? 1u : 0u);
+              }
             }
             umma_commit(smem_u32(b_empty + bs));       // frees the stage when the MMAs retire
             if (++bs == prm.NS) { bs = 0; bph ^= 1; }
           }
-          umma_commit(smem_u32(t_full + tb));           // accumulator ready for the epilogue
+#pragma unroll
+          for (int r = 0; r < RS; ++r) umma_commit(smem_u32(t_full + r * NACC + tb));   // accumulators ready
+          if (tr && tseq < prm.trace_tiles) prm.trace[tseq * 8 + 2] = clock64();
+          ++tseq;
           if (++tb == NACC) { tb = 0; tph ^= 1; }
         }
         if (prm.NA > 0) {
-          umma_commit(smem_u32(a_empty + ab));          // A tile may be overwritten
+#pragma unroll
+          for (int r = 0; r < RS; ++r) umma_commit(smem_u32(a_empty + ab * RS + r));   // A tiles may be overwritten
           if (++ab == prm.NA) { ab = 0; aph ^= 1; }
         }
       }
     }
   } else {
     // ================================ epilogue / selection ===========================
+    const int ew = warp - 2;                     // epilogue warp index
+    const int rset = ew >> 2;                    // row set this warp works on
     const int q = warp & 3;                      // TMEM lane quarter this warp may read
     const int row_t = q * 32 + lane;
-    const uint32_t log_base = smem_u32(cand) + (uint32_t)row_t * 16;
+    const uint32_t log_base = smem_u32(cand) + (uint32_t)(rset * BM + row_t) * 16;
     const int log_full = T + 1 + prm.H;           // compaction trigger (entries)
     const uint32_t pair_base = log_base + (uint32_t)(T + 1) * LOG_STRIDE;   // (score, id) pairs of the final selection: 2 per slot
-    const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(rset * NACC * G::ACC_STRIDE);
+    uint64_t* my_full = t_full + rset * NACC;
+    uint64_t* my_empty = t_empty + rset * NACC;
+    const bool tracer = prm.trace != nullptr && blockIdx.x == 0 && threadIdx.x == 64;
     int ltb = 0, ltph = 0, rtb = 0;              // accumulator ring: load side (slot, phase), release side
+    int lseq = 0, rseq = 0;                      // running tile numbers for the debug trace
     TopList<T> top;
     for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
-      const int p = item / prm.QT, qt = item - p * prm.QT;
-      const int n = qt * BM + row_t;
+      const int p = item / prm.QI, qi = item - p * prm.QI;
+      const int n = (qi * RS + rset) * BM + row_t;
       const bool row_ok = n < prm.N;
       const int n_c = row_ok ? n : prm.N - 1;
       const float* relrow = HAS_REL ? prm.relpos + (size_t)n_c * prm.M : nullptr;
@@ -518,9 +584,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) knn_tc_kernel(const TcParams prm)
       float areg[BIAS > 1 ? KW : 1];
       const float* brow = sepB_s;
       if (BIAS > 1) {
-        float* mine = sepB_s + q * (SEP_B_FLOATS / 4);
-        const int first = min(prm.N - 1, qt * BM + q * 32);
-        const int last = min(prm.N - 1, qt * BM + q * 32 + 31);
+        float* mine = sepB_s + ew * G::SEPW;
+        const int first = min(prm.N - 1, (qi * RS + rset) * BM + q * 32);
+        const int last = min(prm.N - 1, (qi * RS + rset) * BM + q * 32 + 31);
         const int h0 = first / prm.grid_w;
         const int nh = last / prm.grid_w - h0 + 1;
         __syncwarp();
@@ -540,13 +606,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) knn_tc_kernel(const TcParams prm)
       // load and the bias terms of chunk i+1 are in flight while chunk i is ranked)
       const int total_chunks = prm.KT * NCH;
       auto issue = [&](int ci, Chunk<DENSE, NG>& ch) {
-        const int c = ci & (NCH - 1);
-        const int m0 = (ci >> 2) * BN + c * CH;
+        const int kt = ci / NCH, c = ci - kt * NCH;
+        const int m0 = kt * G::BN + c * CH;
         if (c == 0) {
-          mbar_wait<false>(smem_u32(t_full + ltb), ltph);
+          if (tracer && lseq < prm.trace_tiles) prm.trace[lseq * 8 + 3] = clock64();
+          mbar_wait<false>(smem_u32(my_full + ltb), ltph);
           tc_fence_after();
+          if (tracer && lseq < prm.trace_tiles) prm.trace[lseq * 8 + 4] = clock64();
+          ++lseq;
         }
-        tmem_ld36(lane_addr + (uint32_t)(ltb * ACC_STRIDE + c * CH), ch.r);
+        tmem_ld36(lane_addr + (uint32_t)(ltb * G::ACC_STRIDE + c * CH), ch.r);
         if (DENSE) {
           if ((prm.M & 3) == 0) {
 #pragma unroll
@@ -562,7 +631,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) knn_tc_kernel(const TcParams prm)
           }
         }
         if (BIAS > 1) {
-          const float* brow_c = brow + ((ci >> 2) * (BN / KW) + c * (CH / KW));
+          const float* brow_c = brow + m0 / KW;
 #pragma unroll
           for (int g = 0; g < NG; ++g) ch.bg[g] = brow_c[g];
         } else {
@@ -572,15 +641,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) knn_tc_kernel(const TcParams prm)
       };
       auto complete = [&](int ci, Chunk<DENSE, NG>& ch) {
         tmem_ld_wait(ch.r);
-        if ((ci & (NCH - 1)) == NCH - 1) {           // whole accumulator is in registers: hand it back
+        if (ci % NCH == NCH - 1) {                   // whole accumulator is in registers: hand it back
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(smem_u32(t_empty + rtb));
+          if (lane == 0) mbar_arrive(smem_u32(my_empty + rtb));
+          if (tracer && rseq < prm.trace_tiles) prm.trace[rseq * 8 + 5] = clock64();
+          ++rseq;
           if (++rtb == NACC) rtb = 0;
         }
       };
       auto process = [&](int ci, Chunk<DENSE, NG>& ch) {
-        const int m0 = (ci >> 2) * BN + (ci & (NCH - 1)) * CH;
+        const int kt = ci / NCH;
+        const int m0 = kt * G::BN + (ci - kt * NCH) * CH;
         // id word of a logged triplet: first key id | key group index << 16 (group = slot in brow)
         const int idw = m0 | (BIAS > 1 ? (m0 / KW) << 16 : 0);
         if (prm.dbg_dist != nullptr && row_ok) {
@@ -596,7 +668,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) knn_tc_kernel(const TcParams prm)
         }
 #pragma unroll
         for (int g = 0; g < NG; ++g) {
-          // per key group: fold the B term into the threshold (added back when the log is read)
+          // per key group: fold the B term into the threshold (added back when the log is compacted)
           const float thr = tau - ch.bg[g];
 #pragma unroll
           for (int t = 0; t < KW / 3; ++t) {
@@ -616,11 +688,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) knn_tc_kernel(const TcParams prm)
                            __int_as_float(idw + (j | (BIAS > 1 ? g << 16 : 0))));
               ++cnt;
             }
+            // the log must always have room for the SLACK triplets up to the next check
+            if ((j / 3 + 1) % G::SLACK == 0) {
+              if (__any_sync(0xffffffffu, cnt > log_full))
+                compact_log<LOG_STRIDE, T, BIAS>(top, tau, cnt, ns, overflow, log_base, brow);
+            }
           }
         }
-        // the log must always have room for the LOG_SLACK triplets of the next chunk
-        if (__any_sync(0xffffffffu, cnt > log_full))
-          compact_log<T, BIAS, KW>(top, tau, cnt, ns, overflow, log_base, brow);
       };
       {
         Chunk<DENSE, NG> c0, c1;
@@ -637,7 +711,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) knn_tc_kernel(const TcParams prm)
           }
         }
       }
-      compact_log<T, BIAS, KW>(top, tau, cnt, ns, overflow, log_base, brow);
+      compact_log<LOG_STRIDE, T, BIAS>(top, tau, cnt, ns, overflow, log_base, brow);
 
       // ---------------- finalise the row -------------------------------------------
       // keys of the surviving triplets that reach the threshold -> (score, id) pair list
@@ -648,9 +722,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) knn_tc_kernel(const TcParams prm)
           if (e < ns) {
             const float4 c = ld_shared_v4(log_base + (uint32_t)e * LOG_STRIDE);
             const int id = (int)(__float_as_uint(c.w) & 0xffffu);
-            float bg = 0.f;
-            if (BIAS > 1) bg = brow[__float_as_uint(c.w) >> 16];
-            const float sc[3] = {c.x + bg, c.y + bg, c.z + bg};
+            const float sc[3] = {c.x, c.y, c.z};       // B term already added by compact_log
 #pragma unroll
             for (int i = 0; i < 3; ++i) {
               if (sc[i] >= tau && id + i < prm.M) {
@@ -752,7 +824,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) knn_tc_kernel(const TcParams prm)
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512) : "memory");
   }
 }
-
 
 // launcher for one bias mode; instantiated in knn_tc_inst.cu
 template <int BIAS>
