@@ -3,6 +3,7 @@
 
     python bench.py --gpus N --steps K --warmup W            # our CUDA path
     python bench.py --impl reference --gpus N --steps K ...  # reference algorithm on host cores
+    python bench.py --workload train|infer ...               # whole GKGNet-576 (BASELINE configs[3] / [2])
 
 A "step" is one pass of the hot path over one batch of synthetic input: the stage-1 Grapher
 layer of GKGNet-576 (BASELINE.json configs[1]: B=32 images per GPU, C=80, N=144x144 patches,
@@ -397,6 +398,108 @@ def run_ours(args):
     print(json.dumps(line), flush=True)
 
 
+
+# ----------------------------------------------------------------------------------------
+# whole-model workloads (BASELINE configs[2] inference, configs[3] training) -- secondary lines
+# ----------------------------------------------------------------------------------------
+def run_model(args):
+    """GKGNet-576 (pvig_s, 80 labels, random init) + LabelQueryHead under bf16 autocast.
+    train: fwd + loss + bwd + grad clip + AdamW step, 16 images / GPU, DDP (NCCL gradient all-reduce
+    only: per-GPU BatchNorm unless --syncbn).  infer: eval forward + sigmoid scores, 64 images / GPU,
+    replicas only.  value = images of all ranks / max-over-ranks device time."""
+    from gkgnet_b200 import parallel as P
+    world, rank, local = P.init_distributed()
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    import gkgnet_b200 as G
+    from gkgnet_b200 import _lib
+    train = args.workload == "train"
+    B = args.batch or (16 if train else 64)
+    G.set_norm_type("SyncBN" if args.syncbn else "BN")
+    torch.manual_seed(0)
+    net = G.GKGNet(choice="s", n_classes=80, size=576, drop_path=0.1 if train else 0.0)
+    head = G.LabelQueryHead(80, 640)
+
+    class Model(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.backbone, self.head = net, head
+
+        def forward(self, img, tgt=None):
+            feats = self.backbone(img)
+            if tgt is None:
+                return torch.sigmoid(self.head.get_score(feats))
+            return sum(self.head.forward_train(feats, tgt).values())
+
+    model = Model().to(dev)
+    model.train(train)
+    params = [p for p in model.parameters() if p.requires_grad]
+    opt = torch.optim.AdamW(params, lr=1e-4, weight_decay=0.05) if train else None
+    ddp = P.data_parallel(model, dev) if train else model
+    g = torch.Generator().manual_seed(100 + rank)
+    img_h = torch.randn(B, 3, 576, 576, generator=g).pin_memory()
+    tgt_h = (torch.rand(B, 80, generator=g) < 0.04).float().pin_memory()
+    img, tgt = img_h.to(dev), tgt_h.to(dev)
+    stream = torch.cuda.current_stream(dev)
+
+    def step(from_host=False):
+        x, t = (img_h.to(dev, non_blocking=True), tgt_h.to(dev, non_blocking=True)) if from_host else (img, tgt)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            if train:
+                loss = ddp(x, t)
+            else:
+                with torch.no_grad():
+                    return ddp(x)
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(params, 5.0)
+        opt.step()
+        opt.zero_grad(set_to_none=True)
+        return loss
+
+    def timed(n, from_host):
+        P.barrier(dev)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        for _ in range(n):
+            out = step(from_host)
+            if from_host:
+                out.float().sum().item() if not train else out.item()     # device -> host read of the result
+        b.record(stream)
+        P.barrier(dev)
+        return P.max_over_ranks(a.elapsed_time(b) / n, dev)
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    sampler = ClockSampler(local)
+    sampler.start()
+    l0 = _lib.launch_count()
+    ms = timed(args.steps, False)
+    launches = _lib.launch_count() - l0
+    clocks = sampler.stop()
+    e2e_ms = timed(max(3, min(args.steps, 5)), True)
+    if rank != 0:
+        return
+    out_bytes = 4 if train else B * 80 * 4
+    line = {
+        "metric": METRIC, "value": world * B / (ms * 1e-3), "unit": "images/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": ("BASELINE configs[3]: GKGNet-576 training fwd+bwd+AdamW, bf16 autocast, DDP" if train else
+                                "BASELINE configs[2]: GKGNet-576 inference, bf16 autocast, replicas only"),
+                   "images_per_gpu": B, "global_batch": B * world,
+                   "parallelism": f"dp{world}" + (" (NCCL gradient all-reduce)" if train else " (replicas)"),
+                   "norm": "SyncBN" if args.syncbn else "per-GPU BN",
+                   "l2": "activations per step exceed the 126 MB L2; no explicit flush"},
+        "clocks": clocks,
+        "e2e": {"value": world * B / (e2e_ms * 1e-3), "unit": "images/s", "ms_per_step": e2e_ms,
+                "h2d_bytes_per_step": img_h.numel() * 4 + tgt_h.numel() * 4, "d2h_bytes_per_step": out_bytes},
+        "gpu_launches": int(launches),     # launches of libgkg_b200 kernels only (torch ops not counted)
+        "roofline": None, "cpu_baseline": None,
+    }
+    print(json.dumps(line), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -410,9 +513,15 @@ def main():
     ap.add_argument("--dense-bias", action="store_true", help="do not use the separable bias fast path")
     ap.add_argument("--ref-images", type=int, default=4)
     ap.add_argument("--ref-max-steps", type=int, default=20)
+    ap.add_argument("--workload", default="layer", choices=["layer", "train", "infer"],
+                    help="layer = stage-1 Grapher hot path (the headline line); train / infer = whole GKGNet-576")
+    ap.add_argument("--batch", type=int, default=0, help="images per GPU for --workload train / infer")
+    ap.add_argument("--syncbn", action="store_true", help="keep the reference's SyncBN (default: per-GPU BN)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload != "layer":
+        run_model(args)
     else:
         run_ours(args)
     if int(os.environ.get("WORLD_SIZE", "1")) > 1:

@@ -714,10 +714,28 @@ __global__ void __launch_bounds__(G::NTHREADS, 1) knn_tc_kernel(const TcParams p
       compact_log<LOG_STRIDE, T, BIAS>(top, tau, cnt, ns, overflow, log_base, brow);
 
       // ---------------- finalise the row -------------------------------------------
+      // tau is the T-th largest TRIPLET maximum; neighbouring keys are often similar, so the surviving
+      // triplets can hold far more than T keys above it.  Tighten to the T-th largest KEY: the list
+      // already holds the triplet maxima, add the other two keys of every survivor.
+      const int mx_ns = __reduce_max_sync(0xffffffffu, ns);
+      for (int e = 0; e < mx_ns; ++e) {
+        float x1 = kScoreFloor, x2 = kScoreFloor;
+        if (e < ns) {
+          const float4 c = ld_shared_v4(log_base + (uint32_t)e * LOG_STRIDE);
+          const float mx = fmax3(c.x, c.y, c.z);
+          const bool is0 = c.x == mx, is1 = !is0 && c.y == mx;      // the one copy of the maximum already listed
+          x1 = is0 ? c.y : c.x;
+          x2 = (is0 || is1) ? c.z : c.y;
+        }
+        if (__any_sync(0xffffffffu, fmaxf(x1, x2) > tau)) {
+          top.insert(x1);
+          top.insert(x2);
+        }
+      }
+      tau = top.v[T - 1];                          // T-th largest key score (approximate)
       // keys of the surviving triplets that reach the threshold -> (score, id) pair list
       int np = 0;
       {
-        const int mx_ns = __reduce_max_sync(0xffffffffu, ns);
         for (int e = 0; e < mx_ns; ++e) {
           if (e < ns) {
             const float4 c = ld_shared_v4(log_base + (uint32_t)e * LOG_STRIDE);

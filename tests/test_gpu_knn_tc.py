@@ -141,3 +141,31 @@ def test_fit_separable_rejects_arbitrary_tables():
     from gkgnet_b200 import ops
     rel = torch.rand(1, 81, 81, device="cuda")
     assert ops.fit_separable_bias(rel) is None
+
+
+@pytest.mark.parametrize("N,M,D,bias", [(512, 1296, 40, True), (300, 648, 80, False)])
+def test_tc_similar_neighbouring_keys_stay_on_fast_path(N, M, D, bias):
+    """Image features are spatially smooth: consecutive keys (one logged triplet) are often all
+    close to the query.  Such rows must be ranked by the kernel itself, not by the exact fix-up
+    kernel (regression: the pair list overflowed and every row took the slow path)."""
+    from gkgnet_b200 import _lib, ops
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(3)
+    G, B = 2, 1
+    C = G * D
+    base = torch.randn(B, M // 3, C, generator=g)
+    y = base.repeat_interleave(3, dim=1) + 2e-3 * torch.randn(B, M, C, generator=g)
+    x = torch.randn(B, N, C, generator=g)
+    rel = -(0.5 + 0.5 * torch.rand(1, N, M, generator=g)) if bias else None
+    _debug(lib, 1, None)
+    try:
+        idx = ops.knn_graph(x.cuda(), y.cuda(), None if rel is None else rel.cuda(), groups=G, k=9,
+                            dilation=1, algo=_lib.KNN_TCGEN05)
+        torch.cuda.synchronize()
+        st = _stats(lib)
+    finally:
+        _debug(lib, 0, None)
+    assert st["fixups"] <= 0.02 * B * G * N, st
+    dist = O.knn_distance_matrix(_ref_layout(x, G), _ref_layout(y, G), rel)
+    rep = O.check_knn_against_distances(idx.cpu(), dist, 9, 1, 1e-6)
+    assert rep["rows_bad"] == 0, rep

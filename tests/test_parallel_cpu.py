@@ -1,0 +1,93 @@
+"""CPU: the N > 1 host logic under gloo with world size 2 -- image sharding, max-over-ranks timing
+reduction and the DDP gradient all-reduce (the only collective of the path)."""
+import os
+import socket
+import sys
+
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, out_dir):
+    sys.path.insert(0, ROOT)
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank),
+                      MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    import gkgnet_b200 as G
+    from gkgnet_b200 import parallel as P
+
+    w, r, _ = P.init_distributed("gloo")
+    assert (w, r) == (world, rank)
+    # timing reduction: the slowest rank wins; sums add up
+    assert P.max_over_ranks(float(rank + 1)) == float(world)
+    assert P.sum_over_ranks(1.0) == float(world)
+    P.barrier()
+
+    # data-parallel training step on the label head (CPU-capable part of the model): the averaged
+    # gradients of the two half batches must equal the gradient of the full batch
+    torch.manual_seed(0)
+    head = G.LabelQueryHead(num_classes=6, in_channels=16)
+    full_lab, full_gap = torch.randn(8, 6, 16), torch.randn(8, 16)
+    tgt = (torch.rand(8, 6) < 0.3).float()
+    lo, hi = P.shard_range(8, rank, world)
+
+    class _Loss(torch.nn.Module):
+        def __init__(self, m):
+            super().__init__()
+            self.m = m
+
+        def forward(self, lab, gap, t):
+            out = self.m.forward_train((lab, gap), t)
+            return out["bce_loss"] + out["asy_loss"]
+
+    ddp = P.data_parallel(_Loss(head))
+    loss = ddp(full_lab[lo:hi], full_gap[lo:hi], tgt[lo:hi])
+    loss.backward()
+    grads = {k: p.grad.clone() for k, p in head.named_parameters()}
+    torch.save({"grads": grads, "range": (lo, hi)}, os.path.join(out_dir, f"rank{rank}.pt"))
+    torch.distributed.destroy_process_group()
+
+
+def test_shard_range_partitions_every_image_once():
+    from gkgnet_b200.parallel import shard_range
+    for total in (0, 1, 7, 16, 33):
+        for world in (1, 2, 3, 8):
+            spans = [shard_range(total, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == total
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            sizes = [b - a for a, b in spans]
+            assert max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        shard_range(4, 2, 2)
+
+
+def test_world2_gloo_gradient_allreduce(tmp_path):
+    world = 2
+    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    import gkgnet_b200 as G
+    r0 = torch.load(tmp_path / "rank0.pt")
+    r1 = torch.load(tmp_path / "rank1.pt")
+    assert r0["range"] == (0, 4) and r1["range"] == (4, 8)
+    # both ranks hold the same (averaged) gradients after the all-reduce
+    for k in r0["grads"]:
+        assert torch.equal(r0["grads"][k], r1["grads"][k]), k
+    # and they equal the single-process gradient of the mean of the two half-batch losses
+    torch.manual_seed(0)
+    head = G.LabelQueryHead(num_classes=6, in_channels=16)
+    lab, gap = torch.randn(8, 6, 16), torch.randn(8, 16)
+    tgt = (torch.rand(8, 6) < 0.3).float()
+    total = 0.0
+    for lo, hi in ((0, 4), (4, 8)):
+        out = head.forward_train((lab[lo:hi], gap[lo:hi]), tgt[lo:hi])
+        total = total + 0.5 * (out["bce_loss"] + out["asy_loss"])
+    total.backward()
+    for k, p in head.named_parameters():
+        assert torch.allclose(p.grad, r0["grads"][k], atol=1e-6, rtol=1e-5), k
