@@ -12,7 +12,7 @@ timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -5 | 
 echo "== bench"
 timeout 600 python bench.py --steps 10 --warmup 3 "$@" 2>&1 | tail -3 | tee gpurun_out/${TAG}_bench.json
 echo "== ncu launch list"
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv \
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:'gkg|knn|mr_aggregate|tc_prepare' -c 80 --csv \
     --log-file gpurun_out/${TAG}_launches.csv python bench.py --steps 2 --warmup 3 --no-cpu "$@" > gpurun_out/${TAG}_ncu_bench.log 2>&1
 tail -2 gpurun_out/${TAG}_ncu_bench.log
 echo "== ncu full (knn + aggregate kernels)"
