@@ -209,6 +209,12 @@ __device__ __forceinline__ void tma_bulk_g2s(uint32_t dst, const void* src, uint
                ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
                : "memory");
 }
+// One lane of the (converged) warp: the issuer of TMA / tcgen05 instructions.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.b32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
@@ -458,28 +464,32 @@ __global__ void __launch_bounds__(G::NTHREADS, 1) knn_tc_kernel(const TcParams p
 
   if (warp == 0) {
     // ================================ TMA producer ===================================
-    if (lane == 0) {
-      int ab = 0, aph = 0, bs = 0, bph = 0, tseq = 0;
-      for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
-        const int p = item / prm.QI, qi = item - p * prm.QI;
-        const uint8_t* asrc = reinterpret_cast<const uint8_t*>(prm.a_op) +
-                              ((size_t)p * prm.QTP + (size_t)qi * RS) * prm.a_tile_bytes;   // RS consecutive tiles
-        if (prm.NA > 0) {
+    // The whole warp walks the loops (converged control flow); one elected lane issues the copies.
+    int ab = 0, aph = 0, bs = 0, bph = 0, tseq = 0;
+    for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+      const int p = item / prm.QI, qi = item - p * prm.QI;
+      const uint8_t* asrc = reinterpret_cast<const uint8_t*>(prm.a_op) +
+                            ((size_t)p * prm.QTP + (size_t)qi * RS) * prm.a_tile_bytes;   // RS consecutive tiles
+      if (prm.NA > 0) {
 #pragma unroll
-          for (int r = 0; r < RS; ++r) {
-            const int slot = ab * RS + r;
-            mbar_wait<true>(smem_u32(a_empty + slot), aph ^ 1);
+        for (int r = 0; r < RS; ++r) {
+          const int slot = ab * RS + r;
+          mbar_wait<true>(smem_u32(a_empty + slot), aph ^ 1);
+          if (elect_one()) {
             mbar_expect_tx(smem_u32(a_full + slot), prm.a_tile_bytes);
             tma_bulk_g2s(smem_u32(sA + (size_t)slot * prm.a_tile_bytes), asrc + (size_t)r * prm.a_tile_bytes,
                          prm.a_tile_bytes, smem_u32(a_full + slot));
           }
-          if (++ab == prm.NA) { ab = 0; aph ^= 1; }
+          __syncwarp();
         }
-        const uint8_t* bsrc = reinterpret_cast<const uint8_t*>(prm.b_op) +
-                              (size_t)p * prm.KT * prm.NKB * prm.b_block_bytes;
-        for (int kt = 0; kt < prm.KT; ++kt) {
-          for (int kb = 0; kb < prm.NKB; ++kb) {
-            mbar_wait<true>(smem_u32(b_empty + bs), bph ^ 1);
+        if (++ab == prm.NA) { ab = 0; aph ^= 1; }
+      }
+      const uint8_t* bsrc = reinterpret_cast<const uint8_t*>(prm.b_op) +
+                            (size_t)p * prm.KT * prm.NKB * prm.b_block_bytes;
+      for (int kt = 0; kt < prm.KT; ++kt) {
+        for (int kb = 0; kb < prm.NKB; ++kb) {
+          mbar_wait<true>(smem_u32(b_empty + bs), bph ^ 1);
+          if (elect_one()) {
             mbar_expect_tx(smem_u32(b_full + bs), stage_bytes);
             uint8_t* dst = sB + (size_t)bs * stage_bytes;
             tma_bulk_g2s(smem_u32(dst), bsrc + (size_t)(kt * prm.NKB + kb) * prm.b_block_bytes, prm.b_block_bytes,
@@ -491,65 +501,85 @@ __global__ void __launch_bounds__(G::NTHREADS, 1) knn_tc_kernel(const TcParams p
                              asrc + (size_t)r * prm.a_tile_bytes + (size_t)kb * a_blk_bytes, a_blk_bytes,
                              smem_u32(b_full + bs));
             }
-            if (++bs == prm.NS) { bs = 0; bph ^= 1; }
           }
-          if (prm.trace != nullptr && blockIdx.x == 0 && tseq < prm.trace_tiles) prm.trace[tseq * 8 + 6] = clock64();
-          ++tseq;
+          __syncwarp();
+          if (++bs == prm.NS) { bs = 0; bph ^= 1; }
         }
+        if (prm.trace != nullptr && blockIdx.x == 0 && lane == 0 && tseq < prm.trace_tiles)
+          prm.trace[tseq * 8 + 6] = clock64();
+        ++tseq;
       }
     }
   } else if (warp == 1) {
     // ================================ MMA issuer =====================================
-    if (lane == 0) {
-      int ab = 0, aph = 0, bs = 0, bph = 0, tb = 0, tph = 0, tseq = 0;
-      const bool tr = prm.trace != nullptr && blockIdx.x == 0;
-      const uint32_t lbo = 128, sbo = (uint32_t)(prm.KC >> 3) * 128;
-      const int ksteps = prm.KC >> 4;
-      for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
-        uint32_t a_base[RS];
-        if (prm.NA > 0) {
+    // Converged warp, one elected lane issues tcgen05.mma / tcgen05.commit (the commits must come from
+    // the thread that issued the MMAs they track; elect.sync picks the same lane every time).
+    int ab = 0, aph = 0, bs = 0, bph = 0, tb = 0, tph = 0, tseq = 0;
+    const bool tr = prm.trace != nullptr && blockIdx.x == 0 && lane == 0;
+    // descriptor halves: hi = SBO | version, lo = start address | LBO (both in 16-byte units)
+    const uint32_t desc_hi = ((uint32_t)(prm.KC >> 3) * 128u >> 4) | (1u << 14);
+    const uint32_t lbo_field = (128u >> 4) << 16;
+    const int ksteps = prm.KC >> 4;
+    for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+      uint32_t a_base[RS];
 #pragma unroll
-          for (int r = 0; r < RS; ++r) {
-            mbar_wait<true>(smem_u32(a_full + ab * RS + r), aph);
-            a_base[r] = smem_u32(sA + (size_t)(ab * RS + r) * prm.a_tile_bytes);
-          }
-          tc_fence_after();
+      for (int r = 0; r < RS; ++r) a_base[r] = 0;
+      if (prm.NA > 0) {
+#pragma unroll
+        for (int r = 0; r < RS; ++r) {
+          mbar_wait<true>(smem_u32(a_full + ab * RS + r), aph);
+          a_base[r] = smem_u32(sA + (size_t)(ab * RS + r) * prm.a_tile_bytes);
         }
-        for (int kt = 0; kt < prm.KT; ++kt) {
-          if (tr && tseq < prm.trace_tiles) prm.trace[tseq * 8 + 0] = clock64();
+        tc_fence_after();
+      }
+      for (int kt = 0; kt < prm.KT; ++kt) {
+        if (tr && tseq < prm.trace_tiles) prm.trace[tseq * 8 + 0] = clock64();
 #pragma unroll
-          for (int r = 0; r < RS; ++r) mbar_wait<true>(smem_u32(t_empty + r * NACC + tb), tph ^ 1);
+        for (int r = 0; r < RS; ++r) mbar_wait<true>(smem_u32(t_empty + r * NACC + tb), tph ^ 1);
+        tc_fence_after();
+        if (tr && tseq < prm.trace_tiles) prm.trace[tseq * 8 + 1] = clock64();
+        long long bwait = 0;
+        for (int kb = 0; kb < prm.NKB; ++kb) {
+          const long long tw0 = tr ? clock64() : 0;
+          mbar_wait<true>(smem_u32(b_full + bs), bph);
           tc_fence_after();
-          if (tr && tseq < prm.trace_tiles) prm.trace[tseq * 8 + 1] = clock64();
-          for (int kb = 0; kb < prm.NKB; ++kb) {
-            mbar_wait<true>(smem_u32(b_full + bs), bph);
-            tc_fence_after();
-            const uint32_t b_addr = smem_u32(sB + (size_t)bs * stage_bytes);
+          if (tr) bwait += clock64() - tw0;
+          const uint32_t b_addr = smem_u32(sB + (size_t)bs * stage_bytes);
+          if (elect_one()) {
+            const uint32_t b_lo = ((b_addr & 0x3FFFFu) >> 4) | lbo_field;
 #pragma unroll
             for (int r = 0; r < RS; ++r) {
               const uint32_t d_tmem = tmem_base + (uint32_t)((r * NACC + tb) * G::ACC_STRIDE);
               const uint32_t a_addr = prm.NA > 0 ? a_base[r] + (uint32_t)kb * a_blk_bytes
                                                  : b_addr + prm.b_block_bytes + r * a_blk_bytes;
-              for (int ks = 0; ks < ksteps; ++ks) {
-                const uint64_t ad = make_smem_desc(a_addr + ks * 256, lbo, sbo);
-                const uint64_t bd = make_smem_desc(b_addr + ks * 256, lbo, sbo);
+              const uint32_t a_lo = ((a_addr & 0x3FFFFu) >> 4) | lbo_field;
+#pragma unroll 4
+              for (int ks = 0; ks < ksteps; ++ks) {   // one K=16 step = two core matrices = 256 bytes = 16 units
+                const uint64_t ad = ((uint64_t)desc_hi << 32) | (a_lo + (uint32_t)ks * 16u);
+                const uint64_t bd = ((uint64_t)desc_hi << 32) | (b_lo + (uint32_t)ks * 16u);
                 umma_f16(d_tmem, ad, bd, G::kIdesc, (kb | ks) != 0 ? 1u : 0u);
               }
             }
             umma_commit(smem_u32(b_empty + bs));       // frees the stage when the MMAs retire
-            if (++bs == prm.NS) { bs = 0; bph ^= 1; }
-          }
+            if (kb == prm.NKB - 1) {
 #pragma unroll
-          for (int r = 0; r < RS; ++r) umma_commit(smem_u32(t_full + r * NACC + tb));   // accumulators ready
-          if (tr && tseq < prm.trace_tiles) prm.trace[tseq * 8 + 2] = clock64();
-          ++tseq;
-          if (++tb == NACC) { tb = 0; tph ^= 1; }
+              for (int r = 0; r < RS; ++r) umma_commit(smem_u32(t_full + r * NACC + tb));   // accumulators ready
+            }
+          }
+          __syncwarp();
+          if (++bs == prm.NS) { bs = 0; bph ^= 1; }
         }
-        if (prm.NA > 0) {
+        if (tr && tseq < prm.trace_tiles) { prm.trace[tseq * 8 + 2] = clock64(); prm.trace[tseq * 8 + 7] = bwait; }
+        ++tseq;
+        if (++tb == NACC) { tb = 0; tph ^= 1; }
+      }
+      if (prm.NA > 0) {
+        if (elect_one()) {
 #pragma unroll
           for (int r = 0; r < RS; ++r) umma_commit(smem_u32(a_empty + ab * RS + r));   // A tiles may be overwritten
-          if (++ab == prm.NA) { ab = 0; aph ^= 1; }
         }
+        __syncwarp();
+        if (++ab == prm.NA) { ab = 0; aph ^= 1; }
       }
     }
   } else {

@@ -128,6 +128,190 @@ mr_aggregate_bwd_kernel(const T* __restrict__ gout, const int32_t* __restrict__ 
   }
 }
 
+// ---- bf16 fast path: 8 channels (16 bytes) per thread, packed bf16x2 arithmetic -------------------
+// The maximum over the K neighbours is taken with HMNMX2 (exact: max selects one of its inputs); the
+// arg-max is recovered afterwards from equality masks (smallest j wins, like the scalar kernel), so the
+// per-element convert / compare / select chain of the generic kernel disappears.  m = max - x is formed
+// in fp32 and rounded once, exactly as the generic kernel (and the reference under autocast) does.
+__device__ __forceinline__ uint32_t bf2_max(uint32_t a, uint32_t b) {
+  __nv_bfloat162 r = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&a), *reinterpret_cast<__nv_bfloat162*>(&b));
+  return *reinterpret_cast<uint32_t*>(&r);
+}
+__device__ __forceinline__ uint32_t bf2_eq_mask(uint32_t a, uint32_t b) {
+  return __heq2_mask(*reinterpret_cast<__nv_bfloat162*>(&a), *reinterpret_cast<__nv_bfloat162*>(&b));
+}
+// (x_lo, x_hi), (best_lo, best_hi) -> interleaved (x_lo, m_lo), (x_hi, m_hi)
+__device__ __forceinline__ void bf2_emit(uint32_t x, uint32_t best, uint32_t& o0, uint32_t& o1) {
+  const float xl = __uint_as_float(x << 16), xh = __uint_as_float(x & 0xffff0000u);
+  const float bl = __uint_as_float(best << 16), bh = __uint_as_float(best & 0xffff0000u);
+  __nv_bfloat162 m = __floats2bfloat162_rn(bl - xl, bh - xh);
+  const uint32_t mu = *reinterpret_cast<uint32_t*>(&m);
+  o0 = __byte_perm(x, mu, 0x5410);
+  o1 = __byte_perm(x, mu, 0x7632);
+}
+
+template <int K, bool ARG>
+__device__ __forceinline__ void mr_chunk_bf16(const uint4 xv, const uint4 (&yv)[K], __nv_bfloat16* __restrict__ op,
+                                              uint8_t* __restrict__ ap) {
+  uint32_t b0 = yv[0].x, b1 = yv[0].y, b2 = yv[0].z, b3 = yv[0].w;
+#pragma unroll
+  for (int j = 1; j < K; ++j) {
+    b0 = bf2_max(b0, yv[j].x); b1 = bf2_max(b1, yv[j].y); b2 = bf2_max(b2, yv[j].z); b3 = bf2_max(b3, yv[j].w);
+  }
+  uint4 o0, o1;
+  bf2_emit(xv.x, b0, o0.x, o0.y); bf2_emit(xv.y, b1, o0.z, o0.w);
+  bf2_emit(xv.z, b2, o1.x, o1.y); bf2_emit(xv.w, b3, o1.z, o1.w);
+  reinterpret_cast<uint4*>(op)[0] = o0;
+  reinterpret_cast<uint4*>(op)[1] = o1;
+  if (ARG) {
+    uint32_t a0 = 0, a1 = 0, a2 = 0, a3 = 0;       // two 16-bit neighbour slots per register
+#pragma unroll
+    for (int j = K - 1; j >= 0; --j) {
+      const uint32_t jj = (uint32_t)j * 0x00010001u;
+      uint32_t m;
+      m = bf2_eq_mask(yv[j].x, b0); a0 = (a0 & ~m) | (jj & m);
+      m = bf2_eq_mask(yv[j].y, b1); a1 = (a1 & ~m) | (jj & m);
+      m = bf2_eq_mask(yv[j].z, b2); a2 = (a2 & ~m) | (jj & m);
+      m = bf2_eq_mask(yv[j].w, b3); a3 = (a3 & ~m) | (jj & m);
+    }
+    uint2 a;
+    a.x = __byte_perm(a0, a1, 0x6420);
+    a.y = __byte_perm(a2, a3, 0x6420);
+    *reinterpret_cast<uint2*>(ap) = a;
+  }
+}
+
+template <int K, bool ARG>
+__global__ void __launch_bounds__(256)
+mr_aggregate_fwd_bf16_kernel(const __nv_bfloat16* __restrict__ x, int64_t x_sb, int64_t x_sn,
+                             const __nv_bfloat16* __restrict__ y, int64_t y_sb, int64_t y_sn,
+                             const int32_t* __restrict__ idx, __nv_bfloat16* __restrict__ out,
+                             uint8_t* __restrict__ argmax, int G, int N, int D, long long total_chunks) {
+  const int C = G * D;
+  const int chunks_per_node = C >> 3;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total_chunks;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int cc = (int)(i % chunks_per_node);
+    const long long bn = i / chunks_per_node;
+    const int n = (int)(bn % N);
+    const long long b = bn / N;
+    const int c0 = cc << 3;
+    const int g = c0 / D;
+    const int32_t* ip = idx + ((b * G + g) * N + n) * (long long)K;
+    const uint4 xv = *reinterpret_cast<const uint4*>(x + b * x_sb + (long long)n * x_sn + c0);
+    const __nv_bfloat16* ybase = y + b * y_sb + c0;
+    uint4 yv[K];
+#pragma unroll
+    for (int j = 0; j < K; ++j) yv[j] = *reinterpret_cast<const uint4*>(ybase + (long long)__ldg(ip + j) * y_sn);
+    mr_chunk_bf16<K, ARG>(xv, yv, out + (bn * C + c0) * 2, ARG ? argmax + bn * C + c0 : nullptr);
+  }
+}
+
+// ---- bf16 fast path with the key rows staged in shared memory ---------------------------------------
+// The gather reads every key row ~N*k/M times (144 at stage 1): served from L1/L2 it is the l1tex
+// pipe, not HBM, that bounds the kernel.  Here a CTA owns a contiguous range of (image, channel
+// slice, node) work, copies the slice's keys (M x CS bf16 <= 110 KB, two CTAs per SM) into shared
+// memory once per (image, slice) it touches and gathers from there; global memory then only sees
+// the streaming traffic (x, idx in; out, argmax out).
+constexpr int kAggSmemThreads = 512;
+constexpr size_t kAggSmemKeysMax = 102 * 1024;   // + 2 idx tiles (<= 10 KB) per CTA, two CTAs per SM
+
+template <int K, bool ARG>
+__global__ void __launch_bounds__(kAggSmemThreads, 2)
+mr_aggregate_fwd_bf16_smem_kernel(const __nv_bfloat16* __restrict__ x, int64_t x_sb, int64_t x_sn,
+                                  const __nv_bfloat16* __restrict__ y, int64_t y_sb, int64_t y_sn,
+                                  const int32_t* __restrict__ idx, __nv_bfloat16* __restrict__ out,
+                                  uint8_t* __restrict__ argmax, int B, int G, int N, int M, int D, int CS) {
+  extern __shared__ __align__(16) uint8_t agg_smem[];          // [M][CS] bf16 keys, then 2 idx tiles
+  const int C = G * D;
+  const int NSL = C / CS;                                       // channel slices per image
+  const int CPN = CS >> 3;                                      // 16-byte chunks per node slice
+  const int npp = kAggSmemThreads / CPN;                        // nodes per pass of the CTA
+  const int node_l = threadIdx.x / CPN, ch = threadIdx.x - node_l * CPN;
+  const bool active = node_l < npp;
+  // CTA c works on slice c % NSL of node-row range c / NSL: the CTAs that need the same x rows run
+  // side by side, so x comes from HBM once and from L2 afterwards
+  const int slice = blockIdx.x % NSL;
+  const int range = blockIdx.x / NSL, nranges = gridDim.x / NSL;
+  const long long R = (long long)B * N;                         // node rows in total
+  const long long per = (R + nranges - 1) / nranges;
+  long long r = (long long)range * per;
+  const long long r_end = r + per < R ? r + per : R;
+  const int c0 = slice * CS, g = c0 / D, cc = c0 + ch * 8;
+  const uint32_t keys_s = (uint32_t)__cvta_generic_to_shared(agg_smem);
+  const uint32_t row_bytes = (uint32_t)CS * 2;
+  const uint32_t tile_s = keys_s + (uint32_t)M * row_bytes;     // 2 x [npp][K] int32
+  const uint32_t tile_bytes = (uint32_t)npp * K * 4;
+  if (range >= nranges) return;
+  while (r < r_end) {
+    const long long b = r / N;
+    const int n_lo = (int)(r - b * N);
+    const int n_hi = (int)((long long)n_lo + (r_end - r) < (long long)N ? n_lo + (r_end - r) : N);
+    const int32_t* ibase = idx + ((b * G + g) * N) * (long long)K;
+    auto fetch_tile = [&](int node0, int buf) {                 // idx rows of nodes [node0, node0 + npp) -> smem
+      const int cnt = (min(n_hi, node0 + npp) - node0) * K;
+      const int32_t* src = ibase + (long long)node0 * K;
+      for (int q = threadIdx.x; q < cnt; q += kAggSmemThreads)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(tile_s + buf * tile_bytes + q * 4), "l"(src + q)
+                     : "memory");
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    auto load_x = [&](int node) {
+      return node < n_hi && active ? *reinterpret_cast<const uint4*>(x + b * x_sb + (long long)node * x_sn + cc)
+                                   : make_uint4(0, 0, 0, 0);
+    };
+    __syncthreads();                                            // gathers of the previous image are done
+    {
+      const __nv_bfloat16* src = y + b * y_sb + c0;
+      const int pieces = M * CPN;
+      for (int q = threadIdx.x; q < pieces; q += kAggSmemThreads) {
+        const int m = q / CPN, qc = q - m * CPN;
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(keys_s + (uint32_t)m * row_bytes + qc * 16),
+                     "l"(src + (long long)m * y_sn + qc * 8) : "memory");
+      }
+    }
+    fetch_tile(n_lo, 0);                                        // same group as the keys
+    uint4 xv = load_x(n_lo + node_l);
+    int buf = 0;
+    for (int node0 = n_lo; node0 < n_hi; node0 += npp, buf ^= 1) {
+      __syncthreads();                                          // everyone is done with tile buf ^ 1
+      if (node0 + npp < n_hi) fetch_tile(node0 + npp, buf ^ 1); else asm volatile("cp.async.commit_group;" ::: "memory");
+      const uint4 xn = load_x(node0 + npp + node_l);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");      // keys + tile `buf` have landed
+      __syncthreads();
+      const int node = node0 + node_l;
+      if (active && node < n_hi) {
+        const long long bn = b * N + node;
+        const uint32_t ip = tile_s + buf * tile_bytes + (uint32_t)node_l * K * 4;
+        uint4 yv[K];
+#pragma unroll
+        for (int j = 0; j < K; ++j) {
+          uint32_t m;
+          asm volatile("ld.shared.u32 %0, [%1];" : "=r"(m) : "r"(ip + j * 4));
+          const uint32_t a = keys_s + m * row_bytes + ch * 16;
+          asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                       : "=r"(yv[j].x), "=r"(yv[j].y), "=r"(yv[j].z), "=r"(yv[j].w) : "r"(a));
+        }
+        mr_chunk_bf16<K, ARG>(xv, yv, out + (bn * C + cc) * 2, ARG ? argmax + bn * C + cc : nullptr);
+      }
+      xv = xn;
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    r += n_hi - n_lo;
+  }
+}
+
+// Channel-slice width for the shared-memory path: the widest multiple of 8 that divides D (a slice
+// stays inside one channel group) whose keys fit; 0 = use the L2 gather kernel.
+static int agg_smem_slice(int N, int M, int D) {
+  if (N < 1024 || N < M) return 0;                  // label heads: few queries, nothing to amortise
+  for (int cs = D; cs >= 8; --cs) {
+    if (D % cs || cs % 8) continue;
+    if ((size_t)M * cs * 2 <= kAggSmemKeysMax) return cs;
+  }
+  return 0;
+}
+
 static int pick_vec(int dtype, int D, int C, const void* a, const void* b, int64_t s0, int64_t s1,
                     int64_t s2, int64_t s3) {
   const int es = dtype == GKG_F32 ? 4 : 2;
@@ -173,13 +357,44 @@ extern "C" int gkg_mr_aggregate_fwd(const void* x, int64_t x_sb, int64_t x_sn, c
   mr_aggregate_fwd_kernel<T, V><<<grid, 256, 0, stream>>>(                                    \
       static_cast<const T*>(x), x_sb, x_sn, static_cast<const T*>(y), y_sb, y_sn, idx,        \
       static_cast<T*>(out), argmax, G, N, D, k, chunks)
+#define LAUNCH_BF(KK, AA)                                                                       \
+  mr_aggregate_fwd_bf16_kernel<KK, AA><<<grid, 256, 0, stream>>>(                                 \
+      static_cast<const __nv_bfloat16*>(x), x_sb, x_sn, static_cast<const __nv_bfloat16*>(y), y_sb, \
+      y_sn, idx, static_cast<__nv_bfloat16*>(out), argmax, G, N, D, chunks)
   if (dtype == GKG_F32) {
     if (vec == 4) LAUNCH(float, 4); else if (vec == 2) LAUNCH(float, 2); else LAUNCH(float, 1);
+  } else if (vec == 8 && (k == 9 || k == 18)) {
+    const int cs = agg_smem_slice(N, M, D);
+    if (cs > 0) {
+      const int nsl = C / cs, npp = kAggSmemThreads / (cs / 8);
+      const size_t smem = (size_t)M * cs * 2 + 2 * (size_t)npp * k * 4;
+      int dev = 0, sms = 148;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+      int nranges = 2 * sms / nsl;
+      if (nranges < 1) nranges = 1;
+      if ((long long)nranges * npp > (long long)B * N) nranges = (int)(((long long)B * N + npp - 1) / npp);
+      const int sgrid = nranges * nsl;
+#define LAUNCH_SM(KK, AA)                                                                          \
+  do {                                                                                               \
+    auto kern = mr_aggregate_fwd_bf16_smem_kernel<KK, AA>;                                           \
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kAggSmemKeysMax + 16 * 1024)); \
+    if (e != cudaSuccess) { set_error("mr_aggregate_fwd: smem attribute: %s", cudaGetErrorString(e)); return GKG_ECUDA; } \
+    kern<<<sgrid, kAggSmemThreads, smem, stream>>>(static_cast<const __nv_bfloat16*>(x), x_sb, x_sn,  \
+        static_cast<const __nv_bfloat16*>(y), y_sb, y_sn, idx, static_cast<__nv_bfloat16*>(out), argmax, \
+        B, G, N, M, D, cs);                                                                          \
+  } while (0)
+      if (k == 9) { if (argmax) LAUNCH_SM(9, true); else LAUNCH_SM(9, false); }
+      else { if (argmax) LAUNCH_SM(18, true); else LAUNCH_SM(18, false); }
+#undef LAUNCH_SM
+    } else if (k == 9) { if (argmax) LAUNCH_BF(9, true); else LAUNCH_BF(9, false); }
+    else { if (argmax) LAUNCH_BF(18, true); else LAUNCH_BF(18, false); }
   } else {
     if (vec == 8) LAUNCH(__nv_bfloat16, 8); else if (vec == 4) LAUNCH(__nv_bfloat16, 4);
     else if (vec == 2) LAUNCH(__nv_bfloat16, 2); else LAUNCH(__nv_bfloat16, 1);
   }
 #undef LAUNCH
+#undef LAUNCH_BF
   GKG_CHECK_LAUNCH("mr_aggregate_fwd");
   return GKG_OK;
 }

@@ -32,6 +32,9 @@ def _oracle_agg(x, idx, y, G):
     (2, 8, 150, 60, 10, 9),      # D=10: 4-byte vector path for bf16
     (1, 1, 33, 17, 7, 3),        # odd D: scalar path
     (2, 2, 80, 500, 200, 18),
+    (3, 2, 1100, 300, 16, 9),    # bf16: keys staged in shared memory, CTA ranges crossing images
+    (2, 2, 1500, 400, 40, 18),   # bf16: shared-memory path, k = 18
+    (1, 2, 1296, 1296, 200, 9),  # stage-3 geometry: 10 channel slices of 40
 ])
 def test_aggregate_forward(dtype, B, G, N, M, D, k):
     from gkgnet_b200 import ops
