@@ -49,7 +49,7 @@ struct Geom {
   __host__ __device__ static constexpr size_t cand_bytes(int T, int H) { return (size_t)ROWS * log_cap(T, H) * 16; }
 };
 using GeomA = Geom<1, 144, 144, 3, 160, 1, 512>;   // 128 rows / item: any shape
-using GeomB = Geom<2, 108, 112, 2, 128, 2, 384>;   // 256 rows / item: small operands (D <= 80), short lists
+using GeomB = Geom<2, 72, 80, 3, 80, 2, 384>;     // 256 rows / item: small operands (D <= 80), short lists
 
 struct Plan {
   int geom;                        // 0 = GeomA, 1 = GeomB

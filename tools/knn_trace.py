@@ -17,7 +17,7 @@ sep = ops.fit_separable_bias(rel)
 for _ in range(2):
     ops.knn_graph(x, y, rel, groups=2, k=9, dilation=1, algo=_lib.KNN_TCGEN05, separable=sep)
 torch.cuda.synchronize()
-KT = int(sys.argv[2]) if len(sys.argv) > 2 else 12
+KT = int(sys.argv[2]) if len(sys.argv) > 2 else 18
 tiles = 36 * KT
 buf = torch.zeros(tiles * 8, dtype=torch.int64, device="cuda")
 lib.gkg_debug_knn_tc_trace.argtypes = [ctypes.c_void_p, ctypes.c_int]
