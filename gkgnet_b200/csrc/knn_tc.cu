@@ -146,6 +146,131 @@ tc_prepare_kernel(const T* __restrict__ feat, int64_t stride_b, int64_t stride_n
   }
 }
 
+// Row-per-thread variant for small compile-time D (the large layers: D = 20 / 40 / 80): the whole row
+// lives in registers, loads and stores are 128-bit, and every K column's (segment, element) is known at
+// compile time -- ~10x fewer instructions than the generic kernel above.  Bitwise identical results:
+// the squared sums replay the lane-strided partial sums + xor-shuffle tree of the warp-per-row kernels.
+template <int D>
+__device__ __forceinline__ float sumsq_warp_order(const float (&v)[D]) {
+  float part[32];
+#pragma unroll
+  for (int l = 0; l < 32; ++l) {
+    part[l] = 0.f;
+#pragma unroll
+    for (int d = l; d < D; d += 32) part[l] = fmaf(v[d], v[d], part[l]);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+    for (int l = 0; l < o; ++l) part[l] += part[l + o];
+  }
+  return part[0];
+}
+
+template <typename T, int D> struct RowLoad;
+template <int D> struct RowLoad<__nv_bfloat16, D> {
+  static constexpr int kAlignElems = 8;
+  static __device__ __forceinline__ void load(const __nv_bfloat16* src, float (&v)[D]) {
+#pragma unroll
+    for (int c = 0; c < D / 8; ++c) {
+      const uint4 q = __ldg(reinterpret_cast<const uint4*>(src) + c);
+      const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        v[c * 8 + 2 * e] = __uint_as_float(w[e] << 16);
+        v[c * 8 + 2 * e + 1] = __uint_as_float(w[e] & 0xffff0000u);
+      }
+    }
+  }
+};
+template <int D> struct RowLoad<float, D> {
+  static constexpr int kAlignElems = 4;
+  static __device__ __forceinline__ void load(const float* src, float (&v)[D]) {
+#pragma unroll
+    for (int c = 0; c < D / 4; ++c) {
+      const float4 q = __ldg(reinterpret_cast<const float4*>(src) + c);
+      v[c * 4] = q.x; v[c * 4 + 1] = q.y; v[c * 4 + 2] = q.z; v[c * 4 + 3] = q.w;
+    }
+  }
+};
+
+constexpr int PREP_THREADS = 128;
+
+template <typename T, int D, bool IS_KEY>
+__global__ void __launch_bounds__(PREP_THREADS)
+tc_prepare_rows_kernel(const T* __restrict__ feat, int64_t stride_b, int64_t stride_n, float* __restrict__ hat,
+                       float* __restrict__ sq, __half* __restrict__ op, int G, int rows, int KC, int tiles,
+                       int tile_rows, int tile_keys, int write_hat) {
+  constexpr int KP = (3 * D + 2 + 15) / 16 * 16;
+  const long long p = blockIdx.y;
+  const int g = (int)(p % G);
+  const long long b = p / G;
+  const int prow = blockIdx.x * PREP_THREADS + threadIdx.x;
+  const int tile = prow / tile_rows, slot = prow - tile * tile_rows;
+  if (tile >= tiles) return;
+  const int row = slot < tile_keys ? tile * tile_keys + slot : rows;
+  const bool valid = row < rows;
+
+  float v[D];
+  float s2 = 0.f;
+  if (valid) {
+    RowLoad<T, D>::load(feat + b * stride_b + (long long)row * stride_n + (long long)g * D, v);
+    const float denom = fmaxf(sqrtf(sumsq_warp_order<D>(v)), 1e-12f);
+#pragma unroll
+    for (int d = 0; d < D; ++d) v[d] = v[d] / denom;     // true division, like aten::div
+    s2 = sumsq_warp_order<D>(v);
+    if (write_hat) {
+      float4* gh = reinterpret_cast<float4*>(hat + (p * rows + row) * (long long)D);
+#pragma unroll
+      for (int c = 0; c < D / 4; ++c) gh[c] = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+      sq[p * rows + row] = s2;
+    }
+  } else {
+#pragma unroll
+    for (int d = 0; d < D; ++d) v[d] = 0.f;
+  }
+  float extra_hi, extra_lo;
+  if (IS_KEY) {
+    if (valid) {
+      const float c = -0.5f * s2 * kScale;
+      extra_hi = __half2float(__float2half_rn(c));
+      extra_lo = c - extra_hi;
+    } else {
+      extra_hi = kPadKey;
+      extra_lo = 0.f;
+    }
+  } else {
+    extra_hi = valid ? kScale : 0.f;
+    extra_lo = extra_hi;
+  }
+  const int kcs = KC >> 3, nkb = KP / KC, rgs = tile_rows >> 3;
+  const int rg = slot >> 3, r = slot & 7;
+  uint4* base = reinterpret_cast<uint4*>(op) + ((p * tiles + tile) * nkb * (long long)rgs) * kcs * 8;
+#pragma unroll
+  for (int kcI = 0; kcI < KP / 8; ++kcI) {
+    __align__(16) __half out[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int c = kcI * 8 + e;                  // compile-time after unrolling
+      float val = 0.f;
+      if (c < 3 * D) {
+        const int seg = c / D;
+        const float x = v[c - seg * D] * kScale;
+        const float hi = __half2float(__float2half_rn(x));
+        const bool want_lo = IS_KEY ? (seg == 1) : (seg == 2);   // A = [hi | hi | lo], B = [hi | lo | hi]
+        val = want_lo ? (x - hi) : hi;
+      } else if (c == 3 * D) {
+        val = extra_hi;
+      } else if (c == 3 * D + 1) {
+        val = extra_lo;
+      }
+      out[e] = __float2half_rn(val);
+    }
+    const int kb = kcI / kcs, kc = kcI - kb * kcs;
+    base[(((long long)kb * rgs + rg) * kcs + kc) * 8 + r] = *reinterpret_cast<const uint4*>(out);
+  }
+}
+
 // ------------------------------------------------------------------------------------
 // sorted candidate list (registers)
 // ------------------------------------------------------------------------------------
@@ -248,10 +373,53 @@ size_t knn_tc_workspace_bytes(int P, int N, int M, int D, int k, int dilation, b
   return carve_tc(nullptr, pl, P, N).bytes;
 }
 
+// row-per-thread path: D in {20, 40, 80}, rows 16-byte aligned
+template <typename T, int D>
+static int launch_prepare_rows(const KnnWorkspace& w, const TcWorkspace& t, const Plan& pl, const T* x, int64_t x_sb,
+                               int64_t x_sn, const T* y, int64_t y_sb, int64_t y_sn, int P, int G, int N, int M,
+                               bool self_keys, cudaStream_t stream) {
+  const int bn = pl.geom == 1 ? GeomB::BN : GeomA::BN, bnp = pl.geom == 1 ? GeomB::BNP : GeomA::BNP;
+  {
+    dim3 grid((pl.QTP * BM + PREP_THREADS - 1) / PREP_THREADS, P);
+    tc_prepare_rows_kernel<T, D, false><<<grid, PREP_THREADS, 0, stream>>>(x, x_sb, x_sn, w.xhat, w.xsq, t.a_op, G, N,
+                                                                           pl.KC, pl.QTP, BM, BM, 1);
+    GKG_CHECK_LAUNCH("tc_prepare_rows_kernel<query>");
+  }
+  {
+    dim3 grid((pl.KT * bnp + PREP_THREADS - 1) / PREP_THREADS, P);
+    const T* src = self_keys ? x : y;
+    tc_prepare_rows_kernel<T, D, true><<<grid, PREP_THREADS, 0, stream>>>(
+        src, self_keys ? x_sb : y_sb, self_keys ? x_sn : y_sn, w.yhat, w.ysq, t.b_op, G, M, pl.KC, pl.KT, bnp, bn,
+        self_keys ? 0 : 1);
+    GKG_CHECK_LAUNCH("tc_prepare_rows_kernel<key>");
+  }
+  return GKG_OK;
+}
+
+template <typename T>
+static bool rows_path_ok(const void* x, int64_t x_sb, int64_t x_sn, const void* y, int64_t y_sb, int64_t y_sn,
+                         int D, bool self_keys) {
+  const int ae = (int)(16 / sizeof(T));
+  auto ok = [&](const void* p, int64_t sb, int64_t sn) {
+    return ((uintptr_t)p % 16) == 0 && sb % ae == 0 && sn % ae == 0;
+  };
+  return D % ae == 0 && ok(x, x_sb, x_sn) && (self_keys || ok(y, y_sb, y_sn));
+}
+
 template <typename T>
 static int launch_prepare_typed(const KnnWorkspace& w, const TcWorkspace& t, const Plan& pl, const void* x,
                                 int64_t x_sb, int64_t x_sn, const void* y, int64_t y_sb, int64_t y_sn, int P,
                                 int G, int N, int M, int D, bool self_keys, cudaStream_t stream) {
+  if (rows_path_ok<T>(x, x_sb, x_sn, y, y_sb, y_sn, D, self_keys)) {
+    const T* xt = static_cast<const T*>(x);
+    const T* yt = static_cast<const T*>(y);
+    switch (D) {
+      case 20: return launch_prepare_rows<T, 20>(w, t, pl, xt, x_sb, x_sn, yt, y_sb, y_sn, P, G, N, M, self_keys, stream);
+      case 40: return launch_prepare_rows<T, 40>(w, t, pl, xt, x_sb, x_sn, yt, y_sb, y_sn, P, G, N, M, self_keys, stream);
+      case 80: return launch_prepare_rows<T, 80>(w, t, pl, xt, x_sb, x_sn, yt, y_sb, y_sn, P, G, N, M, self_keys, stream);
+      default: break;
+    }
+  }
   const size_t smem = sizeof(float) * ((size_t)PREP_ROWS * D + PREP_ROWS);
   const int bn = pl.geom == 1 ? GeomB::BN : GeomA::BN, bnp = pl.geom == 1 ? GeomB::BNP : GeomA::BNP;
   {
