@@ -95,6 +95,7 @@ tc_prepare_kernel(const T* __restrict__ feat, int64_t stride_b, int64_t stride_n
   __syncthreads();
 
   const int kcs = KC >> 3, nkb = KP / KC, rgs = tile_rows >> 3, kc_all = KP >> 3;
+  const int PA = k_prefix(D);
   const int total = PREP_ROWS * kc_all;
   for (int ci = threadIdx.x; ci < total; ci += 256) {
     const int r = ci & 7;
@@ -126,17 +127,17 @@ tc_prepare_kernel(const T* __restrict__ feat, int64_t stride_b, int64_t stride_n
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       const int c = c0 + e;
+      // columns: [hi (D) | e_hi e_lo | 0.. -> PA | second (D) | third (D) | 0..];  A = [hi | hi | lo], B = [hi | lo | hi]
       float v = 0.f;
-      if (c < 3 * D) {
-        const int seg = c / D;
-        const float x = src[c - seg * D] * kScale;
+      const int seg = c < D ? 0 : (c >= PA && c < PA + D) ? 1 : (c >= PA + D && c < PA + 2 * D) ? 2 : -1;
+      if (seg >= 0) {
+        const float x = src[seg == 0 ? c : c - PA - (seg - 1) * D] * kScale;
         const float hi = __half2float(__float2half_rn(x));
-        // A = [hi | hi | lo], B = [hi | lo | hi]
         const bool want_lo = IS_KEY ? (seg == 1) : (seg == 2);
         v = want_lo ? (x - hi) : hi;
-      } else if (c == 3 * D) {
+      } else if (c == D) {
         v = extra_hi;
-      } else if (c == 3 * D + 1) {
+      } else if (c == D + 1) {
         v = extra_lo;
       }
       out[e] = __float2half_rn(v);
@@ -201,7 +202,7 @@ __global__ void __launch_bounds__(PREP_THREADS)
 tc_prepare_rows_kernel(const T* __restrict__ feat, int64_t stride_b, int64_t stride_n, float* __restrict__ hat,
                        float* __restrict__ sq, __half* __restrict__ op, int G, int rows, int KC, int tiles,
                        int tile_rows, int tile_keys, int write_hat) {
-  constexpr int KP = (3 * D + 2 + 15) / 16 * 16;
+  constexpr int KP = k_padded(D), PA = k_prefix(D);
   const long long p = blockIdx.y;
   const int g = (int)(p % G);
   const long long b = p / G;
@@ -252,16 +253,17 @@ tc_prepare_rows_kernel(const T* __restrict__ feat, int64_t stride_b, int64_t str
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       const int c = kcI * 8 + e;                  // compile-time after unrolling
+      // columns: [hi (D) | e_hi e_lo | 0.. -> PA | second (D) | third (D) | 0..];  A = [hi | hi | lo], B = [hi | lo | hi]
       float val = 0.f;
-      if (c < 3 * D) {
-        const int seg = c / D;
-        const float x = v[c - seg * D] * kScale;
+      const int seg = c < D ? 0 : (c >= PA && c < PA + D) ? 1 : (c >= PA + D && c < PA + 2 * D) ? 2 : -1;
+      if (seg >= 0) {
+        const float x = v[seg == 0 ? c : c - PA - (seg - 1) * D] * kScale;
         const float hi = __half2float(__float2half_rn(x));
-        const bool want_lo = IS_KEY ? (seg == 1) : (seg == 2);   // A = [hi | hi | lo], B = [hi | lo | hi]
+        const bool want_lo = IS_KEY ? (seg == 1) : (seg == 2);
         val = want_lo ? (x - hi) : hi;
-      } else if (c == 3 * D) {
+      } else if (c == D) {
         val = extra_hi;
-      } else if (c == 3 * D + 1) {
+      } else if (c == D + 1) {
         val = extra_lo;
       }
       out[e] = __float2half_rn(val);
@@ -274,6 +276,67 @@ tc_prepare_rows_kernel(const T* __restrict__ feat, int64_t stride_b, int64_t str
 // ------------------------------------------------------------------------------------
 // sorted candidate list (registers)
 // ------------------------------------------------------------------------------------
+// ------------------------------------------------------------------------------------
+// exact re-rank of rows whose approximate order is ambiguous (a few per thousand)
+// ------------------------------------------------------------------------------------
+// One warp per listed row; lane c (and c + 32) owns candidate c of the row's <= TL candidates: exact fp32
+// distance with the arithmetic of knn_exact.cu, rank by counting over (distance, id), dilated pick.  The
+// row goes on to the brute-force fix-up when a key outside the candidate list could still belong to the
+// k*d nearest.  List entry: [row, np, approx bound of the keys outside, ids[TL], approx values[TL]].
+__global__ void __launch_bounds__(256)
+knn_rerank_kernel(const int* __restrict__ rr_count, const int* __restrict__ rr_list, int rr_cap, int TL,
+                  const float* __restrict__ xhat, const float* __restrict__ xsq, const float* __restrict__ yhat,
+                  const float* __restrict__ ysq, const float* __restrict__ relpos, int32_t* __restrict__ idx_out,
+                  int* fix_count, int* fix_rows, unsigned int* stats, int N, int M, int D, int k, int dilation,
+                  float delta) {
+  const int lane = threadIdx.x & 31;
+  const int total = min(*rr_count, rr_cap);
+  const int kd = k * dilation;
+  const int stride = 2 * TL + 3;
+  for (int e = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); e < total; e += gridDim.x * (blockDim.x >> 5)) {
+    const int* ent = rr_list + (size_t)e * stride;
+    const int row = ent[0], np = ent[1];
+    const float a_last = __int_as_float(ent[2]);
+    const int p = row / N, n = row - p * N;
+    const float* xr = xhat + (size_t)row * D;
+    const float xs = xsq[row];
+    const float* relrow = relpos ? relpos + (size_t)n * M : nullptr;
+    float ev[2];
+    int id[2];
+    float maxerr = 0.f;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int c = lane + 32 * h;
+      ev[h] = INFINITY;
+      id[h] = 0x7fffffff;
+      if (c < np) {
+        id[h] = ent[3 + c];
+        ev[h] = exact_dist(xr, yhat + ((size_t)p * M + id[h]) * D, D, xs, ysq[(size_t)p * M + id[h]], relrow, id[h]);
+        maxerr = fmaxf(maxerr, fabsf((ev[h] - xs) - __int_as_float(ent[3 + TL + c])));
+      }
+    }
+    int rank[2] = {0, 0};
+    for (int j = 0; j < np; ++j) {
+      const float vj = __shfl_sync(0xffffffffu, j < 32 ? ev[0] : ev[1], j & 31);
+      const int ij = __shfl_sync(0xffffffffu, j < 32 ? id[0] : id[1], j & 31);
+#pragma unroll
+      for (int h = 0; h < 2; ++h) rank[h] += (vj < ev[h]) || (vj == ev[h] && ij < id[h]);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) maxerr = fmaxf(maxerr, __shfl_xor_sync(0xffffffffu, maxerr, o));
+    if (lane == 0) atomicMax(stats + 1, __float_as_uint(maxerr));
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      if (lane + 32 * h >= np) continue;
+      if (rank[h] < kd && rank[h] % dilation == 0) idx_out[(size_t)row * k + rank[h] / dilation] = id[h];
+      // the kd-th nearest candidate decides whether a key outside the list could still matter
+      // (every key is in the list when np == M: nothing outside to worry about)
+      if (rank[h] == kd - 1 && np < M && a_last - delta <= (ev[h] - xs) + delta)
+        fix_rows[atomicAdd(fix_count, 1)] = row;
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------
 // exact fix-up for rows whose candidate set could not be certified (rare)
 // ------------------------------------------------------------------------------------
@@ -331,10 +394,19 @@ knn_fixup_kernel(const int* __restrict__ count, const int* __restrict__ rows, co
 }
 
 struct TcWorkspace {
-  __half* a_op; __half* b_op; int* fix_count; int* fix_rows; unsigned int* stats; size_t bytes;
+  __half* a_op; __half* b_op; int* fix_count; int* fix_rows; unsigned int* stats;
+  int* rr_count; int* rr_list; int rr_cap; size_t bytes;
 };
 
-TcWorkspace carve_tc(void* base, const Plan& pl, int P, int N) {
+// rows the re-rank list can hold (ambiguous rows are a few per thousand; beyond the cap they take the
+// brute-force fix-up, which is always correct)
+static int rerank_cap(int P, int N) {
+  const long long rows = (long long)P * N;
+  const long long cap = rows / 4 > 4096 ? rows / 4 : 4096;
+  return (int)(cap < rows ? cap : rows);
+}
+
+TcWorkspace carve_tc(void* base, const Plan& pl, int P, int N, int T) {
   TcWorkspace w;
   size_t off = 0;
   char* b = static_cast<char*>(base);
@@ -343,7 +415,10 @@ TcWorkspace carve_tc(void* base, const Plan& pl, int P, int N) {
   w.b_op = static_cast<__half*>(take(pl.b_op_bytes));
   w.fix_count = static_cast<int*>(take(256));
   w.stats = reinterpret_cast<unsigned int*>(w.fix_count ? w.fix_count + 4 : nullptr);
+  w.rr_count = w.fix_count ? w.fix_count + 8 : nullptr;
   w.fix_rows = static_cast<int*>(take(sizeof(int) * (size_t)P * N));
+  w.rr_cap = rerank_cap(P, N);
+  w.rr_list = static_cast<int*>(take(sizeof(int) * (size_t)w.rr_cap * (2 * (T + 3) + 3)));
   w.bytes = off;
   return w;
 }
@@ -370,7 +445,7 @@ size_t knn_tc_workspace_bytes(int P, int N, int M, int D, int k, int dilation, b
   (void)self_keys;
   Plan pl = make_plan(P, N, M, D, t_bucket(k * dilation + 2));
   if (!pl.ok) return 0;
-  return carve_tc(nullptr, pl, P, N).bytes;
+  return carve_tc(nullptr, pl, P, N, t_bucket(k * dilation + 2)).bytes;
 }
 
 // row-per-thread path: D in {20, 40, 80}, rows 16-byte aligned
@@ -445,7 +520,7 @@ int launch_knn_tc_prepare(const KnnWorkspace& w, void* extra_ws, const void* x, 
   Plan pl = make_plan(P, N, M, D, t_bucket(k * dilation + 2));
   GKG_CHECK_ARG(pl.ok, "knn_tc: no tiling for D=%d", D);
   GKG_CHECK_ARG(P <= 65535, "knn_tc: B*G=%d > 65535", P);
-  TcWorkspace t = carve_tc(extra_ws, pl, P, N);
+  TcWorkspace t = carve_tc(extra_ws, pl, P, N, t_bucket(k * dilation + 2));
   if (dtype == GKG_F32)
     return launch_prepare_typed<float>(w, t, pl, x, x_sb, x_sn, y, y_sb, y_sn, P, G, N, M, D, self_keys, stream);
   return launch_prepare_typed<__nv_bfloat16>(w, t, pl, x, x_sb, x_sn, y, y_sb, y_sn, P, G, N, M, D, self_keys,
@@ -458,7 +533,8 @@ int launch_knn_tc(const KnnWorkspace& w, void* extra_ws, const float* relpos, co
   (void)self_keys;
   Plan pl = make_plan(P, N, M, D, t_bucket(k * dilation + 2));
   GKG_CHECK_ARG(pl.ok, "knn_tc: no tiling for D=%d", D);
-  TcWorkspace t = carve_tc(extra_ws, pl, P, N);
+  const int T = t_bucket(k * dilation + 2);
+  TcWorkspace t = carve_tc(extra_ws, pl, P, N, T);
   cudaError_t e = cudaMemsetAsync(t.fix_count, 0, 256, stream);
   if (e != cudaSuccess) {
     set_error("knn_tc: memset: %s", cudaGetErrorString(e));
@@ -470,19 +546,20 @@ int launch_knn_tc(const KnnWorkspace& w, void* extra_ws, const float* relpos, co
   prm.xhat = w.xhat; prm.xsq = w.xsq; prm.yhat = w.yhat; prm.ysq = w.ysq;
   prm.relpos = relpos; prm.idx_out = idx_out;
   prm.fix_count = t.fix_count; prm.fix_rows = t.fix_rows; prm.stats = t.stats;
+  prm.rr_count = t.rr_count; prm.rr_list = t.rr_list; prm.rr_cap = t.rr_cap;
   prm.dbg_dist = g_dbg_dist;
   prm.trace = g_trace; prm.trace_tiles = g_trace_tiles;
   prm.P = P; prm.N = N; prm.M = M; prm.D = D; prm.k = k; prm.dilation = dilation; prm.kd = k * dilation;
-  prm.H = pl.H; prm.KP = pl.KP; prm.KC = pl.KC; prm.NKB = pl.NKB; prm.NA = pl.NA; prm.NS = pl.NS; prm.QT = pl.QT;
+  prm.KP = pl.KP; prm.PA = pl.PA; prm.KC = pl.KC; prm.NKB = pl.NKB; prm.NKBA = pl.NKBA; prm.NA = pl.NA; prm.NS = pl.NS; prm.QT = pl.QT;
   prm.QI = pl.QI; prm.QTP = pl.QTP; prm.KT = pl.KT;
   prm.a_tile_bytes = pl.a_tile_bytes; prm.b_block_bytes = pl.b_block_bytes;
   prm.force_rerank = g_force_rerank;
+  prm.delta = tc_delta(pl.KP);
   prm.sep_a = sep.a; prm.sep_b = sep.b; prm.grid_w = sep.grid_w > 0 ? sep.grid_w : 1;
   prm.sep_mh = sep.kw > 0 ? M / sep.kw : 1;
   const int bn = pl.geom == 1 ? GeomB::BN : GeomA::BN;
   const int sepw = pl.geom == 1 ? GeomB::SEPW : GeomA::SEPW;
   prm.sep_mhp = sep.kw > 0 ? pl.KT * bn / sep.kw : 1;
-  const int T = prm.kd + 2;
   int bias = relpos != nullptr ? 1 : 0;
   if (bias && sep.a != nullptr && sep.b != nullptr && (sep.kw == 9 || sep.kw == 18 || sep.kw == 36) &&
       sep.grid_w > 0 && N % sep.grid_w == 0 && M % sep.kw == 0 &&
@@ -497,6 +574,13 @@ int launch_knn_tc(const KnnWorkspace& w, void* extra_ws, const float* relpos, co
     default: rc = tc::launch_select<1>(prm, pl, T, stream); break;
   }
   if (rc != GKG_OK) return rc;
+  {
+    const int blocks = (t.rr_cap + 7) / 8 < 148 * 4 ? (t.rr_cap + 7) / 8 : 148 * 4;
+    knn_rerank_kernel<<<blocks, 256, 0, stream>>>(t.rr_count, t.rr_list, t.rr_cap, T + 3, w.xhat, w.xsq, w.yhat, w.ysq,
+                                                  relpos, idx_out, t.fix_count, t.fix_rows, t.stats, N, M, D, k,
+                                                  dilation, prm.delta);
+    GKG_CHECK_LAUNCH("knn_rerank_kernel");
+  }
   const size_t fsmem = sizeof(float) * (size_t)M;
   GKG_CHECK_ARG(fsmem <= 200 * 1024, "knn_tc: M=%d too large for the fix-up kernel", M);
   static size_t fix_configured = 0;

@@ -16,7 +16,11 @@ constexpr float kNegHalfS2 = -0.5f * 256.f * 256.f;   // beta = kNegHalfS2 * rel
 constexpr float kScoreToDist = 1.f / kNegHalfS2;      // dist - |xh|^2 = score * kScoreToDist
 constexpr float kPadKey = -60000.f;  // B extra column of padded keys -> score ~ -1.5e7 (dist ~ +468)
 constexpr float kScoreFloor = -8e6f; // initial threshold: above every padded key, below every real one (dist < 244)
-constexpr float kDelta = 4e-6f;    // bound on |approx - exact| of the fp16x3 GEMM (dist units)
+// Bound on |approx - exact| of the fp16x3 GEMM in distance units: every K=16 accumulation step rounds
+// the fp32 accumulator (|acc| <= 1.5 S^2 -> 3.6e-7 per step), plus the 2^-21 relative split error.
+inline float tc_delta(int KP) { return 3.6e-7f * (float)(KP / 16) + 1.2e-6f; }
+// |single-plane - fp16x3| <= S^2 * 2^-10 * sum|xh_i yh_i| <= 64 (Cauchy-Schwarz, unit rows); + fp32 accumulation
+constexpr float kSweepSlack = 66.f;
 constexpr int MAX_STAGES = 8;
 constexpr size_t kSmemBudget = 227 * 1024;
 
@@ -24,36 +28,40 @@ constexpr size_t kSmemBudget = 227 * 1024;
 // every B block that streams through shared memory feeds RS MMAs, so RS = 2 halves the operand
 // traffic per query and doubles the epilogue warps (latency hiding) at the price of a log per row.
 //   BN   real keys per key tile (multiple of CH)      BNP  UMMA N (BN rounded up to 16; pad rows never read)
-//   NACC accumulator slots per row set                CHK  log-capacity checks per chunk
-template <int RS_, int BN_, int BNP_, int NACC_, int ACC_STRIDE_, int CHK_, int SEPW_>
+//   NACC accumulator slots per row set
+template <int RS_, int BN_, int BNP_, int NACC_, int ACC_STRIDE_, int SEPW_>
 struct Geom {
-  static constexpr int RS = RS_, BN = BN_, BNP = BNP_, NACC = NACC_, ACC_STRIDE = ACC_STRIDE_, CHK = CHK_;
+  static constexpr int RS = RS_, BN = BN_, BNP = BNP_, NACC = NACC_, ACC_STRIDE = ACC_STRIDE_;
   static constexpr int NCH = BN / CH;             // chunks per accumulator
   static constexpr int NEPI = 4 * RS;             // epilogue warps
   static constexpr int NTHREADS = 64 + 32 * NEPI; // warp 0 TMA, warp 1 MMA, then the epilogue warps
   static constexpr int ROWS = BM * RS;
   static constexpr uint32_t LOG_STRIDE = ROWS * 16;   // bytes between consecutive log slots of a row
-  static constexpr int SLACK = 12 / CHK;          // triplets that can be logged between two checks
   static constexpr int SEPW = SEPW_;              // staged floats of the separable bias table B per epilogue warp
   static constexpr size_t kBarBytes = 1024 + (size_t)NEPI * SEPW * 4;
   // kind::f16 instruction descriptor: D=f32 (bit 4), A=B=f16 (0), K-major both, N>>3 at 17, M>>4 at 24.
   static constexpr uint32_t kIdesc = (1u << 4) | ((uint32_t)(BNP >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
   static_assert(BN % CH == 0 && BNP % 16 == 0 && BNP >= BN && RS * NACC * ACC_STRIDE <= 512 && ACC_STRIDE >= BNP, "geometry");
-  // Log capacity per row: T + 1 survivors (one tie) + H slots of headroom + the triplets logged between
-  // two checks.  The compaction that reclaims dead entries runs when a row of the warp exceeds
-  // T + 1 + H entries; more headroom means fewer compactions.  The slots from T + 1 on double as the
-  // (score, id) pair list of the final selection (2 pairs per slot).
-  __host__ __device__ static constexpr int log_cap(int T, int H) {
-    return T + 1 + ((T + 4) / 2 > H + SLACK ? (T + 4) / 2 : H + SLACK);
+  // Triplet log of a row: log_valid(T) entries can be kept (the second sweep logs ~T + 1 on average, see
+  // the kernel); behind them log_slack(T) slots absorb the triplets logged between two capacity checks
+  // (6 per half chunk) and later hold the (score, id) pair list of the final selection (2 pairs per slot).
+  __host__ __device__ static constexpr int log_valid(int T) { return T + 8; }
+  __host__ __device__ static constexpr int log_slack(int T) { return (T + 4) / 2 > 6 ? (T + 4) / 2 : 6; }
+  __host__ __device__ static constexpr size_t cand_bytes(int T) {
+    return (size_t)ROWS * (log_valid(T) + log_slack(T)) * 16;
   }
-  __host__ __device__ static constexpr size_t cand_bytes(int T, int H) { return (size_t)ROWS * log_cap(T, H) * 16; }
 };
-using GeomA = Geom<1, 144, 144, 3, 160, 1, 512>;   // 128 rows / item: any shape
-using GeomB = Geom<2, 72, 80, 3, 80, 2, 384>;     // 256 rows / item: small operands (D <= 80), short lists
+using GeomA = Geom<1, 144, 144, 3, 160, 512>;   // 128 rows / item: any shape
+using GeomB = Geom<2, 72, 80, 3, 80, 384>;      // 256 rows / item: small operands (D <= 80), short lists
+
+// K layout of the operands (see tc_prepare_*): [x_hi (D) | e_hi e_lo | 0.. -> PA | second (D) | third (D) | 0.. -> KP]
+// so that the first PA columns alone give the single-plane product S^2 (x_hi.y_hi - |yh|^2/2) of sweep A.
+__host__ __device__ constexpr int k_prefix(int D) { return (D + 2 + 15) / 16 * 16; }
+__host__ __device__ constexpr int k_padded(int D) { return k_prefix(D) + (2 * D + 15) / 16 * 16; }
 
 struct Plan {
   int geom;                        // 0 = GeomA, 1 = GeomB
-  int KP, KC, NKB, NA, NS, QT, QI, QTP, KT, H;
+  int KP, PA, KC, NKB, NKBA, NA, NS, QT, QI, QTP, KT;
   uint32_t a_tile_bytes, b_block_bytes;
   size_t smem_bytes;
   size_t a_op_bytes, b_op_bytes;   // per launch operand buffers
@@ -68,65 +76,57 @@ struct Plan {
 template <class G>
 inline Plan make_plan_g(int P, int N, int M, int D, int T, bool strict) {
   Plan pl{};
-  pl.KP = (3 * D + 2 + 15) / 16 * 16;
+  pl.KP = k_padded(D);
+  pl.PA = k_prefix(D);
   pl.QT = (N + BM - 1) / BM;
   pl.QI = (pl.QT + G::RS - 1) / G::RS;
   pl.QTP = pl.QI * G::RS;
   pl.KT = (M + G::BN - 1) / G::BN;
   pl.a_tile_bytes = (uint32_t)BM * pl.KP * 2;
   pl.ok = false;
-  size_t cand = 0;
-  static const int kHeadroom[] = {24, 12, 9, 6, 2};
+  const size_t cand = G::cand_bytes(T);
   if (pl.KP <= 256) {
-    // preference order: a well fed pipeline first (A double-buffered, >= 3 B stages), then log headroom
+    // preference order: a well fed pipeline first (>= 3 B stages of a decent size), A double-buffered if it fits
     for (int pass = 0; pass < (strict ? 1 : 2) && !pl.ok; ++pass) {
-      for (int hi = 0; hi < 5 && !pl.ok; ++hi) {
-        const int H = kHeadroom[hi];
-        if (strict && H < 9) break;
-        cand = G::cand_bytes(T, H);
-        for (int na = 2; na >= 1 && !pl.ok; --na) {
-          const size_t fixed = cand + G::kBarBytes + (size_t)na * G::RS * pl.a_tile_bytes;
-          if (fixed >= kSmemBudget) continue;
-          const size_t room = kSmemBudget - fixed;
-          for (int kc = pl.KP; kc >= 16; kc -= 16) {
-            if (pl.KP % kc) continue;
-            const size_t blk = (size_t)G::BNP * kc * 2;
-            int ns = (int)(room / blk);
-            if (ns > MAX_STAGES) ns = MAX_STAGES;
-            const int want = (na == 1) ? 2 : 3;
-            const bool good = ns >= 3 && (size_t)ns * blk >= 40 * 1024;
-            const bool usable = ns >= want || (ns >= 2 && kc == 16);
-            if (pass == 0 ? good : usable) {
-              pl.NA = na; pl.KC = kc; pl.NKB = pl.KP / kc; pl.NS = ns; pl.H = H;
-              pl.b_block_bytes = (uint32_t)blk;
-              pl.ok = true;
-              break;
-            }
+      for (int na = 2; na >= 1 && !pl.ok; --na) {
+        const size_t fixed = cand + G::kBarBytes + (size_t)na * G::RS * pl.a_tile_bytes;
+        if (fixed >= kSmemBudget) continue;
+        const size_t room = kSmemBudget - fixed;
+        for (int kc = pl.KP; kc >= 16; kc -= 16) {
+          if (pl.KP % kc) continue;
+          const size_t blk = (size_t)G::BNP * kc * 2;
+          int ns = (int)(room / blk);
+          if (ns > MAX_STAGES) ns = MAX_STAGES;
+          const int want = (na == 1) ? 2 : 3;
+          const bool good = ns >= 3 && (size_t)ns * blk >= 40 * 1024;
+          const bool usable = ns >= want || (ns >= 2 && kc == 16);
+          if (pass == 0 ? good : usable) {
+            pl.NA = na; pl.KC = kc; pl.NS = ns;
+            pl.b_block_bytes = (uint32_t)blk;
+            pl.ok = true;
+            break;
           }
         }
       }
     }
   }
-  if (!pl.ok && !strict) {
-    for (int hi = 0; hi < 5 && !pl.ok; ++hi) {
-      const int H = kHeadroom[hi];
-      cand = G::cand_bytes(T, H);
-      if (cand + G::kBarBytes >= kSmemBudget) continue;
-      const size_t room = kSmemBudget - cand - G::kBarBytes;
-      for (int kc = 64; kc >= 16 && !pl.ok; kc -= 16) {
-        if (pl.KP % kc) continue;
-        const size_t blk = (size_t)(G::ROWS + G::BNP) * kc * 2;
-        int ns = (int)(room / blk);
-        if (ns > MAX_STAGES) ns = MAX_STAGES;
-        if (ns >= 4 || (ns >= 2 && kc == 16)) {
-          pl.NA = 0; pl.KC = kc; pl.NKB = pl.KP / kc; pl.NS = ns; pl.H = H;
-          pl.b_block_bytes = (uint32_t)((size_t)G::BNP * kc * 2);
-          pl.ok = true;
-        }
+  if (!pl.ok && !strict && cand + G::kBarBytes < kSmemBudget) {
+    const size_t room = kSmemBudget - cand - G::kBarBytes;
+    for (int kc = 64; kc >= 16 && !pl.ok; kc -= 16) {
+      if (pl.KP % kc) continue;
+      const size_t blk = (size_t)(G::ROWS + G::BNP) * kc * 2;
+      int ns = (int)(room / blk);
+      if (ns > MAX_STAGES) ns = MAX_STAGES;
+      if (ns >= 4 || (ns >= 2 && kc == 16)) {
+        pl.NA = 0; pl.KC = kc; pl.NS = ns;
+        pl.b_block_bytes = (uint32_t)((size_t)G::BNP * kc * 2);
+        pl.ok = true;
       }
     }
   }
   if (!pl.ok) return pl;
+  pl.NKB = pl.KP / pl.KC;
+  pl.NKBA = (pl.PA + pl.KC - 1) / pl.KC;
   const size_t stage = pl.b_block_bytes + (pl.NA == 0 ? (size_t)G::ROWS * pl.KC * 2 : 0);
   pl.smem_bytes = cand + G::kBarBytes + (size_t)pl.NA * G::RS * pl.a_tile_bytes + (size_t)pl.NS * stage;
   pl.a_op_bytes = (size_t)P * pl.QTP * pl.a_tile_bytes;
@@ -274,11 +274,16 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo,
 // Everything is ranked in the SCALED SCORE domain  s = acc + beta,  acc = S^2 (xh.yh - |yh|^2/2)
 // straight out of TMEM and beta = -(S^2/2) * relative_pos, so that
 //     dist - |xh|^2 = s * (-2 / S^2)          (both factors are powers of two: exact)
-// and "nearest" == "largest score".  Keys are examined three at a time: a TRIPLET is logged
-// (its three scores + the id of its first key, one 16-byte shared-memory store) when its largest
-// score beats the running threshold tau = T-th largest triplet maximum seen so far.  Because
-// the T largest triplet maxima are T distinct keys, tau never exceeds the T-th largest score,
-// so every key that can still be among the T best lives in a logged triplet.
+// and "nearest" == "largest score".  The keys of an item are swept TWICE:
+//   sweep A  (tensor cores: the first PA operand columns only = single-plane fp16 product, 3/8 of the
+//            MMA work at D = 40) keeps, per row, the TA = T - 1 largest maxima of 18-key groups in a
+//            sorted register list (branch-free insertion).  They are TA distinct keys, so the TA-th
+//            largest score of the row is >= tauA - kSweepSlack, where kSweepSlack bounds the
+//            difference between the single-plane and the fp16x3 product;
+//   sweep B  (all KP columns = fp16x3 product) logs every TRIPLET of keys (three scores + the id of
+//            the first, one predicated 16-byte shared-memory store) whose maximum beats that fixed
+//            threshold: ~T + 1 triplets per row, no list maintenance, no log compaction.
+// The final selection then works on the logged triplets only.
 __device__ __forceinline__ float fmax3(float a, float b, float c) { return fmaxf(fmaxf(a, b), c); }  // FMNMX3
 
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, float a, float b, float c, float d) {
@@ -316,62 +321,7 @@ struct TopList {
 
 // Per-row triplet log in shared memory: entry e of the row handled by thread t lives at
 // log_base(t) + e * LOG_STRIDE (16 bytes per thread, consecutive lanes adjacent -> conflict-free
-// 128-bit accesses).  [0, ns) survivors of the last compaction, [ns, cnt) entries logged since.
-//
-// Fold the new entries into the threshold list, then keep only the entries whose triplet can still
-// hold one of the T best keys.  New entries are "raw" (scores without the B term of their key group);
-// the first pass adds it back in place, so that survivors never pay for the lookup again.  Loop trip
-// counts are warp-uniform; bodies are predicated; entries are fetched four at a time so that the
-// shared-memory latency is paid once per batch.  (Reads may run up to 3 slots past a row's last
-// entry: still inside this CTA's shared memory, values unused.)
-template <uint32_t LOG_STRIDE, int T, int BIAS>
-__device__ __forceinline__ void compact_log(TopList<T>& top, float& tau, int& cnt, int& ns, bool& overflow,
-                                            uint32_t log_base, const float* brow) {
-  const int mx_new = __reduce_max_sync(0xffffffffu, cnt - ns);
-  for (int i0 = 0; i0 < mx_new; i0 += 4) {
-    float4 c[4];
-    float x[4];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) c[u] = ld_shared_v4(log_base + (uint32_t)(ns + i0 + u) * LOG_STRIDE);
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const bool valid = ns + i0 + u < cnt;
-      if (BIAS > 1) {
-        const float bg = brow[valid ? (__float_as_uint(c[u].w) >> 16) : 0u];   // .w = key id | key group << 16
-        c[u].x += bg; c[u].y += bg; c[u].z += bg;
-        if (valid) st_shared_v4(log_base + (uint32_t)(ns + i0 + u) * LOG_STRIDE, c[u].x, c[u].y, c[u].z, c[u].w);
-      }
-      x[u] = valid ? fmax3(c[u].x, c[u].y, c[u].z) : kScoreFloor;
-    }
-#pragma unroll
-    for (int u = 0; u < 4; ++u) top.insert(x[u]);
-  }
-  tau = top.v[T - 1];
-  const int mx_all = __reduce_max_sync(0xffffffffu, cnt);
-  int nw = 0;
-  for (int e0 = 0; e0 < mx_all; e0 += 4) {
-    float4 c[4];
-    bool keep[4];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) c[u] = ld_shared_v4(log_base + (uint32_t)(e0 + u) * LOG_STRIDE);
-#pragma unroll
-    for (int u = 0; u < 4; ++u) keep[u] = (e0 + u < cnt) && fmax3(c[u].x, c[u].y, c[u].z) >= tau;
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      if (keep[u]) {
-        st_shared_v4(log_base + (uint32_t)nw * LOG_STRIDE, c[u].x, c[u].y, c[u].z, c[u].w);
-        ++nw;
-      }
-    }
-  }
-  if (nw > T + 1) {   // a pile of exact ties at the threshold: certify by fix-up
-    nw = T + 1;
-    overflow = true;
-  }
-  ns = nw;
-  cnt = nw;
-}
-
+// 128-bit accesses).
 // One chunk of a query row in flight: CH accumulator columns and the bias terms that go with them.
 template <bool DENSE, int NG>
 struct Chunk {
@@ -390,13 +340,15 @@ struct TcParams {
   int grid_w, sep_mh, sep_mhp;
   int32_t* idx_out;
   int* fix_count; int* fix_rows; unsigned int* stats;   // stats: [0] ambiguous rows, [1] max err bits
+  int* rr_count; int* rr_list; int rr_cap;              // rows whose candidates go to the exact re-rank kernel
   float* dbg_dist;
   long long* trace;                // debug: clock64 stamps of CTA 0, 8 slots per key tile (see tools/knn_trace.py)
   int trace_tiles;
   int P, N, M, D, k, dilation, kd;
-  int KP, KC, NKB, NA, NS, QT, QI, QTP, KT, H;
+  int KP, PA, KC, NKB, NKBA, NA, NS, QT, QI, QTP, KT;
   uint32_t a_tile_bytes, b_block_bytes;
   int force_rerank;
+  float delta;                     // bound on |approx - exact| of the fp16x3 GEMM (dist units), see tc_delta()
 };
 
 __device__ __forceinline__ float exact_dist(const float* __restrict__ xr, const float* __restrict__ yr, int D,
@@ -417,12 +369,15 @@ __global__ void __launch_bounds__(G::NTHREADS, 1) knn_tc_kernel(const TcParams p
   constexpr bool HAS_REL = BIAS != 0;
   constexpr bool DENSE = BIAS == 1;
   constexpr int KW = BIAS > 1 ? BIAS : CH;      // columns that share one B term (whole chunk if none)
+  constexpr int TA = T - 1;                     // sweep-A list: TA >= k*d + 1 distinct keys
   constexpr int TL = T + 3;                     // (score, id) pairs sorted at the end of a row
+  constexpr int LC = G::log_valid(T);           // log entries a row may keep
   constexpr int NCH = G::NCH;                   // chunks per accumulator
   constexpr int NG = CH / KW;                   // key groups per chunk
   constexpr int RS = G::RS, NACC = G::NACC;
   constexpr uint32_t LOG_STRIDE = G::LOG_STRIDE;
-  static_assert(TL <= 2 * (G::log_cap(T, 2) - T - 1), "pair list must fit its slots");
+  static_assert(TL <= 2 * G::log_slack(T), "pair list must fit the slack slots");
+  static_assert(KW == 9 || KW == 18 || KW == 36, "bias period");
   extern __shared__ __align__(1024) uint8_t smem[];
   // carve-up: [A tiles x NA x RS][ring x NS: B block (+ A slices when streaming)][triplet log][barriers + tmem ptr][staged B rows]
   const uint32_t a_blk_bytes = (uint32_t)(BM * prm.KC * 2);                    // one K slice of one A tile
@@ -430,7 +385,7 @@ __global__ void __launch_bounds__(G::NTHREADS, 1) knn_tc_kernel(const TcParams p
   uint8_t* sA = smem;
   uint8_t* sB = sA + (size_t)prm.NA * RS * prm.a_tile_bytes;
   uint8_t* cand = sB + (size_t)prm.NS * stage_bytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(cand + G::cand_bytes(T, prm.H));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(cand + G::cand_bytes(T));
   uint64_t* a_full = bars;                    // [2 * RS]
   uint64_t* a_empty = a_full + 4;             // [2 * RS]
   uint64_t* b_full = a_empty + 4;             // [MAX_STAGES]
@@ -465,7 +420,8 @@ __global__ void __launch_bounds__(G::NTHREADS, 1) knn_tc_kernel(const TcParams p
   if (warp == 0) {
     // ================================ TMA producer ===================================
     // The whole warp walks the loops (converged control flow); one elected lane issues the copies.
-    int ab = 0, aph = 0, bs = 0, bph = 0, tseq = 0;
+    // Per item: sweep A streams the first NKBA K blocks of every key tile, sweep B all NKB of them.
+    int ab = 0, aph = 0, bs = 0, bph = 0;
     for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
       const int p = item / prm.QI, qi = item - p * prm.QI;
       const uint8_t* asrc = reinterpret_cast<const uint8_t*>(prm.a_op) +
@@ -486,28 +442,28 @@ __global__ void __launch_bounds__(G::NTHREADS, 1) knn_tc_kernel(const TcParams p
       }
       const uint8_t* bsrc = reinterpret_cast<const uint8_t*>(prm.b_op) +
                             (size_t)p * prm.KT * prm.NKB * prm.b_block_bytes;
-      for (int kt = 0; kt < prm.KT; ++kt) {
-        for (int kb = 0; kb < prm.NKB; ++kb) {
-          mbar_wait<true>(smem_u32(b_empty + bs), bph ^ 1);
-          if (elect_one()) {
-            mbar_expect_tx(smem_u32(b_full + bs), stage_bytes);
-            uint8_t* dst = sB + (size_t)bs * stage_bytes;
-            tma_bulk_g2s(smem_u32(dst), bsrc + (size_t)(kt * prm.NKB + kb) * prm.b_block_bytes, prm.b_block_bytes,
-                         smem_u32(b_full + bs));
-            if (prm.NA == 0) {
+      for (int sweep = 0; sweep < 2; ++sweep) {
+        const int nkb = sweep == 0 ? prm.NKBA : prm.NKB;
+        for (int kt = 0; kt < prm.KT; ++kt) {
+          for (int kb = 0; kb < nkb; ++kb) {
+            mbar_wait<true>(smem_u32(b_empty + bs), bph ^ 1);
+            if (elect_one()) {
+              mbar_expect_tx(smem_u32(b_full + bs), stage_bytes);
+              uint8_t* dst = sB + (size_t)bs * stage_bytes;
+              tma_bulk_g2s(smem_u32(dst), bsrc + (size_t)(kt * prm.NKB + kb) * prm.b_block_bytes, prm.b_block_bytes,
+                           smem_u32(b_full + bs));
+              if (prm.NA == 0) {
 #pragma unroll
-              for (int r = 0; r < RS; ++r)
-                tma_bulk_g2s(smem_u32(dst + prm.b_block_bytes + r * a_blk_bytes),
-                             asrc + (size_t)r * prm.a_tile_bytes + (size_t)kb * a_blk_bytes, a_blk_bytes,
-                             smem_u32(b_full + bs));
+                for (int r = 0; r < RS; ++r)
+                  tma_bulk_g2s(smem_u32(dst + prm.b_block_bytes + r * a_blk_bytes),
+                               asrc + (size_t)r * prm.a_tile_bytes + (size_t)kb * a_blk_bytes, a_blk_bytes,
+                               smem_u32(b_full + bs));
+              }
             }
+            __syncwarp();
+            if (++bs == prm.NS) { bs = 0; bph ^= 1; }
           }
-          __syncwarp();
-          if (++bs == prm.NS) { bs = 0; bph ^= 1; }
         }
-        if (prm.trace != nullptr && blockIdx.x == 0 && lane == 0 && tseq < prm.trace_tiles)
-          prm.trace[tseq * 8 + 6] = clock64();
-        ++tseq;
       }
     }
   } else if (warp == 1) {
@@ -519,7 +475,6 @@ __global__ void __launch_bounds__(G::NTHREADS, 1) knn_tc_kernel(const TcParams p
     // descriptor halves: hi = SBO | version, lo = start address | LBO (both in 16-byte units)
     const uint32_t desc_hi = ((uint32_t)(prm.KC >> 3) * 128u >> 4) | (1u << 14);
     const uint32_t lbo_field = (128u >> 4) << 16;
-    const int ksteps = prm.KC >> 4;
     for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
       uint32_t a_base[RS];
 #pragma unroll
@@ -532,46 +487,53 @@ __global__ void __launch_bounds__(G::NTHREADS, 1) knn_tc_kernel(const TcParams p
         }
         tc_fence_after();
       }
-      for (int kt = 0; kt < prm.KT; ++kt) {
-        if (tr && tseq < prm.trace_tiles) prm.trace[tseq * 8 + 0] = clock64();
+      for (int sweep = 0; sweep < 2; ++sweep) {
+        const int nkb = sweep == 0 ? prm.NKBA : prm.NKB;
+        const int kcols = sweep == 0 ? prm.PA : prm.KP;     // operand columns this sweep multiplies
+        for (int kt = 0; kt < prm.KT; ++kt) {
+          if (tr && tseq < prm.trace_tiles) prm.trace[tseq * 8 + 0] = clock64();
 #pragma unroll
-        for (int r = 0; r < RS; ++r) mbar_wait<true>(smem_u32(t_empty + r * NACC + tb), tph ^ 1);
-        tc_fence_after();
-        if (tr && tseq < prm.trace_tiles) prm.trace[tseq * 8 + 1] = clock64();
-        long long bwait = 0;
-        for (int kb = 0; kb < prm.NKB; ++kb) {
-          const long long tw0 = tr ? clock64() : 0;
-          mbar_wait<true>(smem_u32(b_full + bs), bph);
+          for (int r = 0; r < RS; ++r) mbar_wait<true>(smem_u32(t_empty + r * NACC + tb), tph ^ 1);
           tc_fence_after();
-          if (tr) bwait += clock64() - tw0;
-          const uint32_t b_addr = smem_u32(sB + (size_t)bs * stage_bytes);
-          if (elect_one()) {
-            const uint32_t b_lo = ((b_addr & 0x3FFFFu) >> 4) | lbo_field;
+          if (tr && tseq < prm.trace_tiles) prm.trace[tseq * 8 + 1] = clock64();
+          long long bwait = 0, tissue = 0;
+          for (int kb = 0; kb < nkb; ++kb) {
+            const long long tw0 = tr ? clock64() : 0;
+            mbar_wait<true>(smem_u32(b_full + bs), bph);
+            tc_fence_after();
+            if (tr) bwait += clock64() - tw0;
+            const uint32_t b_addr = smem_u32(sB + (size_t)bs * stage_bytes);
+            const int ksteps = min(prm.KC, kcols - kb * prm.KC) >> 4;
+            const long long ti0 = tr ? clock64() : 0;
+            if (elect_one()) {
+              const uint32_t b_lo = ((b_addr & 0x3FFFFu) >> 4) | lbo_field;
 #pragma unroll
-            for (int r = 0; r < RS; ++r) {
-              const uint32_t d_tmem = tmem_base + (uint32_t)((r * NACC + tb) * G::ACC_STRIDE);
-              const uint32_t a_addr = prm.NA > 0 ? a_base[r] + (uint32_t)kb * a_blk_bytes
-                                                 : b_addr + prm.b_block_bytes + r * a_blk_bytes;
-              const uint32_t a_lo = ((a_addr & 0x3FFFFu) >> 4) | lbo_field;
+              for (int r = 0; r < RS; ++r) {
+                const uint32_t d_tmem = tmem_base + (uint32_t)((r * NACC + tb) * G::ACC_STRIDE);
+                const uint32_t a_addr = prm.NA > 0 ? a_base[r] + (uint32_t)kb * a_blk_bytes
+                                                   : b_addr + prm.b_block_bytes + r * a_blk_bytes;
+                const uint32_t a_lo = ((a_addr & 0x3FFFFu) >> 4) | lbo_field;
 #pragma unroll 4
-              for (int ks = 0; ks < ksteps; ++ks) {   // one K=16 step = two core matrices = 256 bytes = 16 units
-                const uint64_t ad = ((uint64_t)desc_hi << 32) | (a_lo + (uint32_t)ks * 16u);
-                const uint64_t bd = ((uint64_t)desc_hi << 32) | (b_lo + (uint32_t)ks * 16u);
-                umma_f16(d_tmem, ad, bd, G::kIdesc, (kb | ks) != 0 ? 1u : 0u);
+                for (int ks = 0; ks < ksteps; ++ks) {   // one K=16 step = two core matrices = 256 bytes = 16 units
+                  const uint64_t ad = ((uint64_t)desc_hi << 32) | (a_lo + (uint32_t)ks * 16u);
+                  const uint64_t bd = ((uint64_t)desc_hi << 32) | (b_lo + (uint32_t)ks * 16u);
+                  umma_f16(d_tmem, ad, bd, G::kIdesc, (kb | ks) != 0 ? 1u : 0u);
+                }
+              }
+              umma_commit(smem_u32(b_empty + bs));       // frees the stage when the MMAs retire
+              if (kb == nkb - 1) {
+#pragma unroll
+                for (int r = 0; r < RS; ++r) umma_commit(smem_u32(t_full + r * NACC + tb));   // accumulators ready
               }
             }
-            umma_commit(smem_u32(b_empty + bs));       // frees the stage when the MMAs retire
-            if (kb == prm.NKB - 1) {
-#pragma unroll
-              for (int r = 0; r < RS; ++r) umma_commit(smem_u32(t_full + r * NACC + tb));   // accumulators ready
-            }
+            __syncwarp();
+            if (tr) tissue += clock64() - ti0;
+            if (++bs == prm.NS) { bs = 0; bph ^= 1; }
           }
-          __syncwarp();
-          if (++bs == prm.NS) { bs = 0; bph ^= 1; }
+          if (tr && tseq < prm.trace_tiles) { prm.trace[tseq * 8 + 2] = clock64(); prm.trace[tseq * 8 + 7] = bwait; prm.trace[tseq * 8 + 6] = tissue; }
+          ++tseq;
+          if (++tb == NACC) { tb = 0; tph ^= 1; }
         }
-        if (tr && tseq < prm.trace_tiles) { prm.trace[tseq * 8 + 2] = clock64(); prm.trace[tseq * 8 + 7] = bwait; }
-        ++tseq;
-        if (++tb == NACC) { tb = 0; tph ^= 1; }
       }
       if (prm.NA > 0) {
         if (elect_one()) {
@@ -589,26 +551,20 @@ __global__ void __launch_bounds__(G::NTHREADS, 1) knn_tc_kernel(const TcParams p
     const int q = warp & 3;                      // TMEM lane quarter this warp may read
     const int row_t = q * 32 + lane;
     const uint32_t log_base = smem_u32(cand) + (uint32_t)(rset * BM + row_t) * 16;
-    const int log_full = T + 1 + prm.H;           // compaction trigger (entries)
-    const uint32_t pair_base = log_base + (uint32_t)(T + 1) * LOG_STRIDE;   // (score, id) pairs of the final selection: 2 per slot
+    const uint32_t log_end = log_base + (uint32_t)LC * LOG_STRIDE;          // first slack slot
+    const uint32_t pair_base = log_end;          // (score, id) pairs of the final selection: 2 per slack slot
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(rset * NACC * G::ACC_STRIDE);
     uint64_t* my_full = t_full + rset * NACC;
     uint64_t* my_empty = t_empty + rset * NACC;
     const bool tracer = prm.trace != nullptr && blockIdx.x == 0 && threadIdx.x == 64;
     int ltb = 0, ltph = 0, rtb = 0;              // accumulator ring: load side (slot, phase), release side
     int lseq = 0, rseq = 0;                      // running tile numbers for the debug trace
-    TopList<T> top;
     for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
       const int p = item / prm.QI, qi = item - p * prm.QI;
       const int n = (qi * RS + rset) * BM + row_t;
       const bool row_ok = n < prm.N;
       const int n_c = row_ok ? n : prm.N - 1;
       const float* relrow = HAS_REL ? prm.relpos + (size_t)n_c * prm.M : nullptr;
-      top.init();
-      float tau = kScoreFloor;                     // T-th largest triplet maximum so far
-      int cnt = 0;                                 // entries in this row's log
-      int ns = 0;                                  // survivors at the front of the log
-      bool overflow = false;
 
       // ---- separable bias: A row -> registers, B rows of this warp's 32 rows -> shared memory
       float areg[BIAS > 1 ? KW : 1];
@@ -632,8 +588,8 @@ __global__ void __launch_bounds__(G::NTHREADS, 1) knn_tc_kernel(const TcParams p
         brow = mine + (n_c / prm.grid_w - h0) * prm.sep_mhp;
       }
 
-      // ---- sweep over the keys: chunks of CH accumulator columns, software pipelined (the TMEM
-      // load and the bias terms of chunk i+1 are in flight while chunk i is ranked)
+      // ---- chunk pipeline: CH accumulator columns at a time, software pipelined (the TMEM load and
+      // the bias terms of chunk i+1 are in flight while chunk i is ranked); shared by both sweeps
       const int total_chunks = prm.KT * NCH;
       auto issue = [&](int ci, Chunk<DENSE, NG>& ch) {
         const int kt = ci / NCH, c = ci - kt * NCH;
@@ -680,53 +636,14 @@ __global__ void __launch_bounds__(G::NTHREADS, 1) knn_tc_kernel(const TcParams p
           if (++rtb == NACC) rtb = 0;
         }
       };
-      auto process = [&](int ci, Chunk<DENSE, NG>& ch) {
-        const int kt = ci / NCH;
-        const int m0 = kt * G::BN + (ci - kt * NCH) * CH;
-        // id word of a logged triplet: first key id | key group index << 16 (group = slot in brow)
-        const int idw = m0 | (BIAS > 1 ? (m0 / KW) << 16 : 0);
-        if (prm.dbg_dist != nullptr && row_ok) {
-#pragma unroll
-          for (int j = 0; j < CH; ++j) {
-            if (m0 + j < prm.M) {
-              float s = __uint_as_float(ch.r[j]);
-              if (DENSE) s = fmaf(ch.bias[DENSE ? j : 0], kNegHalfS2, s);
-              if (BIAS > 1) s += areg[BIAS > 1 ? j % KW : 0] + ch.bg[j / KW];
-              prm.dbg_dist[((size_t)p * prm.N + n) * prm.M + m0 + j] = s * kScoreToDist;
-            }
-          }
-        }
-#pragma unroll
-        for (int g = 0; g < NG; ++g) {
-          // per key group: fold the B term into the threshold (added back when the log is compacted)
-          const float thr = tau - ch.bg[g];
-#pragma unroll
-          for (int t = 0; t < KW / 3; ++t) {
-            const int j = g * KW + 3 * t;
-            float s0 = __uint_as_float(ch.r[j]), s1 = __uint_as_float(ch.r[j + 1]), s2 = __uint_as_float(ch.r[j + 2]);
-            if (DENSE) {
-              s0 = fmaf(ch.bias[DENSE ? j : 0], kNegHalfS2, s0);
-              s1 = fmaf(ch.bias[DENSE ? j + 1 : 0], kNegHalfS2, s1);
-              s2 = fmaf(ch.bias[DENSE ? j + 2 : 0], kNegHalfS2, s2);
-            } else if (BIAS > 1) {
-              s0 += areg[BIAS > 1 ? 3 * t : 0];
-              s1 += areg[BIAS > 1 ? 3 * t + 1 : 0];
-              s2 += areg[BIAS > 1 ? 3 * t + 2 : 0];
-            }
-            if (fmax3(s0, s1, s2) > thr) {
-              st_shared_v4(log_base + (uint32_t)cnt * LOG_STRIDE, s0, s1, s2,
-                           __int_as_float(idw + (j | (BIAS > 1 ? g << 16 : 0))));
-              ++cnt;
-            }
-            // the log must always have room for the SLACK triplets up to the next check
-            if ((j / 3 + 1) % G::SLACK == 0) {
-              if (__any_sync(0xffffffffu, cnt > log_full))
-                compact_log<LOG_STRIDE, T, BIAS>(top, tau, cnt, ns, overflow, log_base, brow);
-            }
-          }
-        }
+      // score of column j of a chunk WITHOUT the B term of its key group (added per group)
+      auto raw = [&](const Chunk<DENSE, NG>& ch, int j) {
+        float v = __uint_as_float(ch.r[j]);
+        if (DENSE) v = fmaf(ch.bias[DENSE ? j : 0], kNegHalfS2, v);
+        else if (BIAS > 1) v += areg[BIAS > 1 ? j % KW : 0];
+        return v;
       };
-      {
+      auto sweep = [&](auto&& process) {
         Chunk<DENSE, NG> c0, c1;
         issue(0, c0);
 #pragma unroll 1
@@ -740,37 +657,131 @@ __global__ void __launch_bounds__(G::NTHREADS, 1) knn_tc_kernel(const TcParams p
             process(ci + 1, c1);
           }
         }
+      };
+
+      // ---- sweep A: TA largest 18-key group maxima (single-plane scores) ------------------------
+      float thr_base;
+      {
+        TopList<TA> la;
+        la.init();
+        sweep([&](int ci, Chunk<DENSE, NG>& ch) {
+          (void)ci;
+          float tm[CH / 3];
+#pragma unroll
+          for (int t = 0; t < CH / 3; ++t) tm[t] = fmax3(raw(ch, 3 * t), raw(ch, 3 * t + 1), raw(ch, 3 * t + 2));
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            float gm;
+            if (KW >= 18) {
+              gm = fmaxf(fmax3(tm[6 * h], tm[6 * h + 1], tm[6 * h + 2]), fmax3(tm[6 * h + 3], tm[6 * h + 4], tm[6 * h + 5])) +
+                   ch.bg[(18 * h) / KW];
+            } else {
+              gm = fmaxf(fmax3(tm[6 * h], tm[6 * h + 1], tm[6 * h + 2]) + ch.bg[(2 * h) % NG],
+                         fmax3(tm[6 * h + 3], tm[6 * h + 4], tm[6 * h + 5]) + ch.bg[(2 * h + 1) % NG]);
+            }
+            la.insert(gm);
+          }
+        });
+        // fewer than TA real groups (tiny M): the floor stays -> everything is logged -> fix-up
+        thr_base = la.v[TA - 1] - kSweepSlack;
       }
-      compact_log<LOG_STRIDE, T, BIAS>(top, tau, cnt, ns, overflow, log_base, brow);
+
+      // ---- sweep B: log the triplets that beat the threshold (fp16x3 scores) --------------------
+      uint32_t lp = log_base;                      // next free log slot of this row
+      uint32_t lp_max = log_base;
+      sweep([&](int ci, Chunk<DENSE, NG>& ch) {
+        const int kt = ci / NCH;
+        const int m0 = kt * G::BN + (ci - kt * NCH) * CH;
+        // id word of a logged triplet: first key id | key group index << 16 (group = slot in brow)
+        const int idw = m0 | (BIAS > 1 ? (m0 / KW) << 16 : 0);
+        if (prm.dbg_dist != nullptr && row_ok) {
+#pragma unroll
+          for (int j = 0; j < CH; ++j)
+            if (m0 + j < prm.M)
+              prm.dbg_dist[((size_t)p * prm.N + n) * prm.M + m0 + j] = (raw(ch, j) + ch.bg[j / KW]) * kScoreToDist;
+        }
+        // half a chunk (6 triplets) at a time: all scores, maxima and hit predicates first, then the
+        // predicated stores -- the triplets are independent, which hides the FMNMX3 -> FSETP -> STS latency
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          float s[6][3];
+          int idv[6];
+#pragma unroll
+          for (int u = 0; u < 6; ++u) {
+            const int j = 3 * (6 * h + u);
+#pragma unroll
+            for (int i = 0; i < 3; ++i) s[u][i] = raw(ch, j + i);
+            idv[u] = idw + (j | (BIAS > 1 ? (j / KW) << 16 : 0));
+          }
+          // all six (s0, s1, s2, id) quads exist before the first store: the compiler may not recycle one
+          // quad of registers for every triplet (which serialises the chain through WAR hazards)
+          asm volatile("" : "+f"(s[0][0]), "+f"(s[0][1]), "+f"(s[0][2]), "+f"(s[1][0]), "+f"(s[1][1]), "+f"(s[1][2]),
+                            "+f"(s[2][0]), "+f"(s[2][1]), "+f"(s[2][2]), "+f"(s[3][0]), "+f"(s[3][1]), "+f"(s[3][2]),
+                            "+f"(s[4][0]), "+f"(s[4][1]), "+f"(s[4][2]), "+f"(s[5][0]), "+f"(s[5][1]), "+f"(s[5][2]),
+                            "+r"(idv[0]), "+r"(idv[1]), "+r"(idv[2]), "+r"(idv[3]), "+r"(idv[4]), "+r"(idv[5]));
+          bool hit[6];
+#pragma unroll
+          for (int u = 0; u < 6; ++u)   // the B term of the key group is folded into the threshold
+            hit[u] = fmax3(s[u][0], s[u][1], s[u][2]) > thr_base - ch.bg[(3 * (6 * h + u)) / KW];
+#pragma unroll
+          for (int u = 0; u < 6; ++u) {
+            if (hit[u]) {
+              st_shared_v4(lp, s[u][0], s[u][1], s[u][2], __int_as_float(idv[u]));
+              lp += LOG_STRIDE;
+            }
+          }
+          lp_max = max(lp_max, lp);                // the slack slots hold the 6 triplets of a half chunk
+          lp = min(lp, log_end);
+        }
+      });
+      const bool overflow = lp_max > log_end;        // more candidates than the log keeps: certify by fix-up
+      const int cnt = (int)((lp - log_base) / LOG_STRIDE);
 
       // ---------------- finalise the row -------------------------------------------
-      // tau is the T-th largest TRIPLET maximum; neighbouring keys are often similar, so the surviving
-      // triplets can hold far more than T keys above it.  Tighten to the T-th largest KEY: the list
-      // already holds the triplet maxima, add the other two keys of every survivor.
-      const int mx_ns = __reduce_max_sync(0xffffffffu, ns);
-      for (int e = 0; e < mx_ns; ++e) {
+      // Add the B terms back (in place) and find the T-th largest KEY among the logged triplets.
+      TopList<T> top;
+      top.init();
+      const int mx_cnt = __reduce_max_sync(0xffffffffu, cnt);
+      for (int e0 = 0; e0 < mx_cnt; e0 += 2) {
+        float4 c[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) c[u] = ld_shared_v4(log_base + (uint32_t)(e0 + u) * LOG_STRIDE);
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const bool valid = e0 + u < cnt;
+          if (BIAS > 1) {
+            const float bg = brow[valid ? (__float_as_uint(c[u].w) >> 16) : 0u];
+            c[u].x += bg; c[u].y += bg; c[u].z += bg;
+            if (valid) st_shared_v4(log_base + (uint32_t)(e0 + u) * LOG_STRIDE, c[u].x, c[u].y, c[u].z, c[u].w);
+          }
+          top.insert(valid ? fmax3(c[u].x, c[u].y, c[u].z) : kScoreFloor);
+        }
+      }
+      // neighbouring keys are often similar: the other two keys of a triplet may rank as well
+      for (int e = 0; e < mx_cnt; ++e) {
         float x1 = kScoreFloor, x2 = kScoreFloor;
-        if (e < ns) {
+        if (e < cnt) {
           const float4 c = ld_shared_v4(log_base + (uint32_t)e * LOG_STRIDE);
           const float mx = fmax3(c.x, c.y, c.z);
           const bool is0 = c.x == mx, is1 = !is0 && c.y == mx;      // the one copy of the maximum already listed
           x1 = is0 ? c.y : c.x;
           x2 = (is0 || is1) ? c.z : c.y;
         }
-        if (__any_sync(0xffffffffu, fmaxf(x1, x2) > tau)) {
+        if (__any_sync(0xffffffffu, fmaxf(x1, x2) > top.v[T - 1])) {
           top.insert(x1);
           top.insert(x2);
         }
       }
-      tau = top.v[T - 1];                          // T-th largest key score (approximate)
-      // keys of the surviving triplets that reach the threshold -> (score, id) pair list
+      // T-th largest logged key; keys that were never logged are all <= thr_base
+      const float tau = fmaxf(top.v[T - 1], thr_base);
+      // keys of the logged triplets that reach the threshold -> (score, id) pair list
       int np = 0;
       {
-        for (int e = 0; e < mx_ns; ++e) {
-          if (e < ns) {
+        for (int e = 0; e < mx_cnt; ++e) {
+          if (e < cnt) {
             const float4 c = ld_shared_v4(log_base + (uint32_t)e * LOG_STRIDE);
             const int id = (int)(__float_as_uint(c.w) & 0xffffu);
-            const float sc[3] = {c.x, c.y, c.z};       // B term already added by compact_log
+            const float sc[3] = {c.x, c.y, c.z};
 #pragma unroll
             for (int i = 0; i < 3; ++i) {
               if (sc[i] >= tau && id + i < prm.M) {
@@ -782,7 +793,7 @@ __global__ void __launch_bounds__(G::NTHREADS, 1) knn_tc_kernel(const TcParams p
           }
         }
       }
-      if (np > TL) overflow = true;
+      bool unsure_set = overflow || np > TL;
       // pairs -> registers as (dist - |xh|^2, id), sorted ascending by (value, id)
       float cv[TL];
       int cid[TL];
@@ -793,14 +804,14 @@ __global__ void __launch_bounds__(G::NTHREADS, 1) knn_tc_kernel(const TcParams p
         cv[s] = have ? c.x * kScoreToDist : INFINITY;
         cid[s] = have ? __float_as_int(c.y) : 0x7fffffff;
       }
-      // odd-even transposition sort; the first (approximate) pass ignores ids: equal values are a
-      // zero gap, which sends the row through the exact re-rank below, sorted with ids as tie-break
-      auto sort_pairs = [&](bool by_id) {
+      // odd-even transposition sort by approximate value; equal values are a zero gap, which sends the
+      // row to the exact re-rank (sorted there with ids as tie-break)
+      {
 #pragma unroll
         for (int pass = 0; pass < TL; ++pass) {
 #pragma unroll
           for (int s = pass & 1; s + 1 < TL; s += 2) {
-            const bool sw = (cv[s + 1] < cv[s]) || (by_id && cv[s + 1] == cv[s] && cid[s + 1] < cid[s]);
+            const bool sw = cv[s + 1] < cv[s];
             const float tv = sw ? cv[s] : cv[s + 1];
             const int ti = sw ? cid[s] : cid[s + 1];
             cv[s] = sw ? cv[s + 1] : cv[s];
@@ -809,45 +820,29 @@ __global__ void __launch_bounds__(G::NTHREADS, 1) knn_tc_kernel(const TcParams p
             cid[s + 1] = ti;
           }
         }
-      };
-      sort_pairs(false);
+      }
 
       const int kd = prm.kd;
-      bool amb = prm.force_rerank != 0 || overflow;
+      bool amb = prm.force_rerank > 0 || unsure_set;   // (< 0: debug counters only)
 #pragma unroll
       for (int s = 0; s + 1 < TL; ++s)
-        if (s < kd && (cv[s + 1] - cv[s]) < 2.f * kDelta) amb = true;
+        if (s < kd && (cv[s + 1] - cv[s]) < 2.f * prm.delta) amb = true;
       if (row_ok && amb) {
-        // exact fp32 re-rank of the candidates (identical arithmetic to knn_exact.cu)
-        const float* xr = prm.xhat + ((size_t)p * prm.N + n) * prm.D;
-        const float xs = prm.xsq[(size_t)p * prm.N + n];
-        const float* yb = prm.yhat + (size_t)p * prm.M * prm.D;
-        const float* ysb = prm.ysq + (size_t)p * prm.M;
-        const float a_last = tau * kScoreToDist;   // every key outside the pair list has approx >= a_last
-        float maxerr = 0.f;
-#pragma unroll
-        for (int s = 0; s < TL; ++s) {
-          const int m = cid[s];
-          if (m < prm.M) {
-            const float e = exact_dist(xr, yb + (size_t)m * prm.D, prm.D, xs, ysb[m], relrow, m);
-            maxerr = fmaxf(maxerr, fabsf((e - xs) - cv[s]));
-            cv[s] = e;
-          } else {
-            cv[s] = INFINITY;
-          }
-        }
-        sort_pairs(true);
+        // The approximate order of this row is not certified (a gap below 2 delta, or the candidate set is in
+        // doubt).  Hand it over: the candidate ids go to knn_rerank_kernel (exact fp32 distances of the <= TL
+        // candidates, a warp per row) and rows without a trustworthy candidate set to the brute-force fix-up.
+        // Doing either here would stall the whole item behind one thread's chain of dependent global loads.
         atomicAdd(prm.stats + 0, 1u);
-        atomicMax(prm.stats + 1, __float_as_uint(maxerr));
-        float e_kd = -INFINITY;               // sorted ascending: kd-th value == max of the first kd
+        int slot = unsure_set ? prm.rr_cap : atomicAdd(prm.rr_count, 1);
+        if (slot < prm.rr_cap) {
+          int* dst = prm.rr_list + (size_t)slot * (2 * TL + 3);
+          dst[0] = p * prm.N + n;
+          dst[1] = np;
+          dst[2] = __float_as_int(tau * kScoreToDist);   // every key outside the pair list has approx dist >= this
 #pragma unroll
-        for (int s = 0; s < TL; ++s)
-          if (s < kd) e_kd = fmaxf(e_kd, cv[s]);
-        // every key is in the pair list when np == M: nothing outside to worry about
-        const bool unsure = overflow || (np < prm.M && a_last - kDelta <= (e_kd - xs) + kDelta);
-        if (unsure) {
-          const int slot = atomicAdd(prm.fix_count, 1);
-          prm.fix_rows[slot] = p * prm.N + n;
+          for (int s = 0; s < TL; ++s) { dst[3 + s] = cid[s]; dst[3 + TL + s] = __float_as_int(cv[s]); }
+        } else {
+          prm.fix_rows[atomicAdd(prm.fix_count, 1)] = p * prm.N + n;
         }
       }
       // stage the ids in this thread's pair slots so that the dilated pick is a shared-memory

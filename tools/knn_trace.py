@@ -29,7 +29,7 @@ t = buf.view(tiles, 8).cpu()
 t0 = int(t[0, 0])
 rows = (t - t0).tolist()
 for i, r in enumerate(rows):
-    r[7] = int(t[i, 7])
+    r[7] = int(t[i, 7]); r[6] = int(t[i, 6])
 os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
 json.dump(rows, open(os.path.join(ROOT, "gpurun_out", "knn_trace.json"), "w"))
 import statistics as st
@@ -43,6 +43,6 @@ for kt in range(KT):
     sel = [i for i in range(tiles) if i % KT == kt and i >= KT]
     print(kt, "epi wait", int(st.mean(epi_wait[i] for i in sel)), "tile time", int(st.mean(rows[i][5] - rows[i - 1][5] for i in sel)),
           "full->epi lag", int(st.mean(rows[i][4] - rows[i][2] for i in sel)), "mma wait", int(st.mean(mma_wait[i] for i in sel)),
-          "mma work", int(st.mean(mma_work[i] for i in sel)), "of which b_full wait", int(st.mean(rows[i][7] for i in sel)), "release->mma lag", int(st.mean(rows[i][1] - rows[i - 3][5] for i in sel)))
+          "mma work", int(st.mean(mma_work[i] for i in sel)), "of which b_full wait", int(st.mean(rows[i][7] for i in sel)), "issue", int(st.mean(rows[i][6] for i in sel)), "release->mma lag", int(st.mean(rows[i][1] - rows[i - 3][5] for i in sel)))
 for r in rows[2 * KT:4 * KT]:
     print(r)
