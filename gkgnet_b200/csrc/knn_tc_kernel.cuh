@@ -34,7 +34,7 @@ struct Geom {
   static constexpr int RS = RS_, BN = BN_, BNP = BNP_, NACC = NACC_, ACC_STRIDE = ACC_STRIDE_;
   static constexpr int NCH = BN / CH;             // chunks per accumulator
   static constexpr int NEPI = 4 * RS;             // epilogue warps
-  static constexpr int NTHREADS = 64 + 32 * NEPI; // warp 0 TMA, warp 1 MMA, then the epilogue warps
+  static constexpr int NTHREADS = 32 * (1 + RS + NEPI); // warp 0 TMA, warps 1..RS MMA (one per row set), then the epilogue warps
   static constexpr int ROWS = BM * RS;
   static constexpr uint32_t LOG_STRIDE = ROWS * 16;   // bytes between consecutive log slots of a row
   static constexpr int SEPW = SEPW_;              // staged floats of the separable bias table B per epilogue warp
@@ -400,7 +400,7 @@ __global__ void __launch_bounds__(G::NTHREADS, 1) knn_tc_kernel(const TcParams p
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < 4; ++i) { mbar_init(smem_u32(a_full + i), 1); mbar_init(smem_u32(a_empty + i), 1); }
-    for (int i = 0; i < MAX_STAGES; ++i) { mbar_init(smem_u32(b_full + i), 1); mbar_init(smem_u32(b_empty + i), 1); }
+    for (int i = 0; i < MAX_STAGES; ++i) { mbar_init(smem_u32(b_full + i), 1); mbar_init(smem_u32(b_empty + i), RS); }
     for (int i = 0; i < 8; ++i) { mbar_init(smem_u32(t_full + i), 1); mbar_init(smem_u32(t_empty + i), 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -466,25 +466,22 @@ __global__ void __launch_bounds__(G::NTHREADS, 1) knn_tc_kernel(const TcParams p
         }
       }
     }
-  } else if (warp == 1) {
-    // ================================ MMA issuer =====================================
+  } else if (warp <= RS) {
+    // ================================ MMA issuers ====================================
+    // One warp per row set (two independent issue streams hide each other's barrier latencies).
     // Converged warp, one elected lane issues tcgen05.mma / tcgen05.commit (the commits must come from
     // the thread that issued the MMAs they track; elect.sync picks the same lane every time).
+    const int r = warp - 1;                      // row set of this issuer
     int ab = 0, aph = 0, bs = 0, bph = 0, tb = 0, tph = 0, tseq = 0;
-    const bool tr = prm.trace != nullptr && blockIdx.x == 0 && lane == 0;
+    const bool tr = prm.trace != nullptr && blockIdx.x == 0 && lane == 0 && r == 0;
     // descriptor halves: hi = SBO | version, lo = start address | LBO (both in 16-byte units)
     const uint32_t desc_hi = ((uint32_t)(prm.KC >> 3) * 128u >> 4) | (1u << 14);
     const uint32_t lbo_field = (128u >> 4) << 16;
     for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
-      uint32_t a_base[RS];
-#pragma unroll
-      for (int r = 0; r < RS; ++r) a_base[r] = 0;
+      uint32_t a_base = 0;
       if (prm.NA > 0) {
-#pragma unroll
-        for (int r = 0; r < RS; ++r) {
-          mbar_wait<true>(smem_u32(a_full + ab * RS + r), aph);
-          a_base[r] = smem_u32(sA + (size_t)(ab * RS + r) * prm.a_tile_bytes);
-        }
+        mbar_wait<true>(smem_u32(a_full + ab * RS + r), aph);
+        a_base = smem_u32(sA + (size_t)(ab * RS + r) * prm.a_tile_bytes);
         tc_fence_after();
       }
       for (int sweep = 0; sweep < 2; ++sweep) {
@@ -492,11 +489,11 @@ __global__ void __launch_bounds__(G::NTHREADS, 1) knn_tc_kernel(const TcParams p
         const int kcols = sweep == 0 ? prm.PA : prm.KP;     // operand columns this sweep multiplies
         for (int kt = 0; kt < prm.KT; ++kt) {
           if (tr && tseq < prm.trace_tiles) prm.trace[tseq * 8 + 0] = clock64();
-#pragma unroll
-          for (int r = 0; r < RS; ++r) mbar_wait<true>(smem_u32(t_empty + r * NACC + tb), tph ^ 1);
+          mbar_wait<true>(smem_u32(t_empty + r * NACC + tb), tph ^ 1);
           tc_fence_after();
           if (tr && tseq < prm.trace_tiles) prm.trace[tseq * 8 + 1] = clock64();
           long long bwait = 0, tissue = 0;
+          const uint32_t d_tmem = tmem_base + (uint32_t)((r * NACC + tb) * G::ACC_STRIDE);
           for (int kb = 0; kb < nkb; ++kb) {
             const long long tw0 = tr ? clock64() : 0;
             mbar_wait<true>(smem_u32(b_full + bs), bph);
@@ -507,24 +504,17 @@ __global__ void __launch_bounds__(G::NTHREADS, 1) knn_tc_kernel(const TcParams p
             const long long ti0 = tr ? clock64() : 0;
             if (elect_one()) {
               const uint32_t b_lo = ((b_addr & 0x3FFFFu) >> 4) | lbo_field;
-#pragma unroll
-              for (int r = 0; r < RS; ++r) {
-                const uint32_t d_tmem = tmem_base + (uint32_t)((r * NACC + tb) * G::ACC_STRIDE);
-                const uint32_t a_addr = prm.NA > 0 ? a_base[r] + (uint32_t)kb * a_blk_bytes
-                                                   : b_addr + prm.b_block_bytes + r * a_blk_bytes;
-                const uint32_t a_lo = ((a_addr & 0x3FFFFu) >> 4) | lbo_field;
+              const uint32_t a_addr = prm.NA > 0 ? a_base + (uint32_t)kb * a_blk_bytes
+                                                 : b_addr + prm.b_block_bytes + r * a_blk_bytes;
+              const uint32_t a_lo = ((a_addr & 0x3FFFFu) >> 4) | lbo_field;
 #pragma unroll 4
-                for (int ks = 0; ks < ksteps; ++ks) {   // one K=16 step = two core matrices = 256 bytes = 16 units
-                  const uint64_t ad = ((uint64_t)desc_hi << 32) | (a_lo + (uint32_t)ks * 16u);
-                  const uint64_t bd = ((uint64_t)desc_hi << 32) | (b_lo + (uint32_t)ks * 16u);
-                  umma_f16(d_tmem, ad, bd, G::kIdesc, (kb | ks) != 0 ? 1u : 0u);
-                }
+              for (int ks = 0; ks < ksteps; ++ks) {   // one K=16 step = two core matrices = 256 bytes = 16 units
+                const uint64_t ad = ((uint64_t)desc_hi << 32) | (a_lo + (uint32_t)ks * 16u);
+                const uint64_t bd = ((uint64_t)desc_hi << 32) | (b_lo + (uint32_t)ks * 16u);
+                umma_f16(d_tmem, ad, bd, G::kIdesc, (kb | ks) != 0 ? 1u : 0u);
               }
-              umma_commit(smem_u32(b_empty + bs));       // frees the stage when the MMAs retire
-              if (kb == nkb - 1) {
-#pragma unroll
-                for (int r = 0; r < RS; ++r) umma_commit(smem_u32(t_full + r * NACC + tb));   // accumulators ready
-              }
+              umma_commit(smem_u32(b_empty + bs));       // this row set is done with the stage when its MMAs retire
+              if (kb == nkb - 1) umma_commit(smem_u32(t_full + r * NACC + tb));   // accumulator ready
             }
             __syncwarp();
             if (tr) tissue += clock64() - ti0;
@@ -536,17 +526,14 @@ __global__ void __launch_bounds__(G::NTHREADS, 1) knn_tc_kernel(const TcParams p
         }
       }
       if (prm.NA > 0) {
-        if (elect_one()) {
-#pragma unroll
-          for (int r = 0; r < RS; ++r) umma_commit(smem_u32(a_empty + ab * RS + r));   // A tiles may be overwritten
-        }
+        if (elect_one()) umma_commit(smem_u32(a_empty + ab * RS + r));   // the A tile may be overwritten
         __syncwarp();
         if (++ab == prm.NA) { ab = 0; aph ^= 1; }
       }
     }
   } else {
     // ================================ epilogue / selection ===========================
-    const int ew = warp - 2;                     // epilogue warp index
+    const int ew = warp - 1 - RS;                // epilogue warp index
     const int rset = ew >> 2;                    // row set this warp works on
     const int q = warp & 3;                      // TMEM lane quarter this warp may read
     const int row_t = q * 32 + lane;
@@ -556,7 +543,7 @@ __global__ void __launch_bounds__(G::NTHREADS, 1) knn_tc_kernel(const TcParams p
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(rset * NACC * G::ACC_STRIDE);
     uint64_t* my_full = t_full + rset * NACC;
     uint64_t* my_empty = t_empty + rset * NACC;
-    const bool tracer = prm.trace != nullptr && blockIdx.x == 0 && threadIdx.x == 64;
+    const bool tracer = prm.trace != nullptr && blockIdx.x == 0 && threadIdx.x == 32 * (1 + RS);
     int ltb = 0, ltph = 0, rtb = 0;              // accumulator ring: load side (slot, phase), release side
     int lseq = 0, rseq = 0;                      // running tile numbers for the debug trace
     for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
@@ -650,11 +637,11 @@ __global__ void __launch_bounds__(G::NTHREADS, 1) knn_tc_kernel(const TcParams p
         for (int ci = 0; ci < total_chunks; ci += 2) {
           complete(ci, c0);
           if (ci + 1 < total_chunks) issue(ci + 1, c1);
-          process(ci, c0);
+          if (prm.force_rerank != -2) process(ci, c0);
           if (ci + 1 < total_chunks) {
             complete(ci + 1, c1);
             if (ci + 2 < total_chunks) issue(ci + 2, c0);
-            process(ci + 1, c1);
+            if (prm.force_rerank != -2) process(ci + 1, c1);
           }
         }
       };

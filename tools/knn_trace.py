@@ -22,6 +22,9 @@ tiles = 36 * KT
 buf = torch.zeros(tiles * 8, dtype=torch.int64, device="cuda")
 lib.gkg_debug_knn_tc_trace.argtypes = [ctypes.c_void_p, ctypes.c_int]
 lib.gkg_debug_knn_tc_trace(buf.data_ptr(), tiles)
+if os.environ.get("GKG_SKIP_PROCESS"):
+    lib.gkg_debug_knn_tc.argtypes = [ctypes.c_int, ctypes.c_void_p]
+    lib.gkg_debug_knn_tc(-2, None)
 ops.knn_graph(x, y, rel, groups=2, k=9, dilation=1, algo=_lib.KNN_TCGEN05, separable=sep)
 torch.cuda.synchronize()
 lib.gkg_debug_knn_tc_trace(None, 0)
