@@ -277,6 +277,79 @@ tc_prepare_rows_kernel(const T* __restrict__ feat, int64_t stride_b, int64_t str
 // sorted candidate list (registers)
 // ------------------------------------------------------------------------------------
 // ------------------------------------------------------------------------------------
+// final selection: candidates of a row -> sorted neighbour ids (one thread per row)
+// ------------------------------------------------------------------------------------
+// knn_tc_kernel leaves, per row, the keys whose fp16x3 score reaches the row's threshold (>= k*d + 1 of
+// them, ~T on average; every key that is not listed scores <= the threshold).  Here: the L = T + 3 best by
+// branch-free sorted insertion, the gap test that certifies the approximate order (gaps >= 2 delta), the
+// dilated pick.  Rows that fail the test go to knn_rerank_kernel, rows without a trustworthy candidate set
+// to the brute-force fix-up.  Layout of `cand`: [item][slot][row of the item] so that loads coalesce.
+template <int L>
+__global__ void __launch_bounds__(256)
+knn_finalize_kernel(const float2* __restrict__ cand, const int* __restrict__ cand_count,
+                    const float* __restrict__ cand_thr, int cand_slots, int rows_per_item, int row_sets, int QI,
+                    int32_t* __restrict__ idx_out, int* rr_count, int* rr_list, int rr_cap, int* fix_count,
+                    int* fix_rows, unsigned int* stats, long long total_rows, int N, int M, int k, int dilation,
+                    float delta, int force_rerank) {
+  const long long gr = (long long)blockIdx.x * blockDim.x + threadIdx.x;     // item * rows_per_item + row
+  if (gr >= total_rows) return;
+  const int item = (int)(gr / rows_per_item), r = (int)(gr - (long long)item * rows_per_item);
+  const int p = item / QI, qi = item - p * QI;
+  const int n = (qi * row_sets + r / BM) * BM + (r % BM);
+  if (n >= N) return;
+  const int row = p * N + n;
+  const int np = cand_count[gr];
+  if (np < 0 || (np < k * dilation + 1 && np < M)) {   // no trustworthy candidate set
+    if (force_rerank != 0) atomicAdd(stats + 0, 1u);
+    fix_rows[atomicAdd(fix_count, 1)] = row;
+    return;
+  }
+  float v[L];
+  int id[L];
+#pragma unroll
+  for (int j = 0; j < L; ++j) { v[j] = -INFINITY; id[j] = 0x7fffffff; }
+  float rej = cand_thr[gr];                     // best approximate score among the keys that are not in the list
+  const float2* src = cand + (size_t)item * cand_slots * rows_per_item + r;
+  for (int s = 0; s < np; ++s) {
+    const float2 c = src[(size_t)s * rows_per_item];
+    const float x = c.x;
+    const int xid = __float_as_int(c.y);
+    rej = fmaxf(rej, fminf(x, v[L - 1]));       // what drops off the end (or fails to enter)
+#pragma unroll
+    for (int j = L - 1; j >= 1; --j) {
+      const bool up = x > v[j - 1];             // the slot above moves down
+      const bool in = x > v[j];
+      id[j] = up ? id[j - 1] : (in ? xid : id[j]);
+      v[j] = up ? v[j - 1] : (in ? x : v[j]);
+    }
+    if (x > v[0]) { v[0] = x; id[0] = xid; }
+  }
+  const int kd = k * dilation;
+  bool amb = force_rerank > 0;
+#pragma unroll
+  for (int j = 0; j + 1 < L; ++j)
+    if (j < kd && (v[j] - v[j + 1]) * (-kScoreToDist) < 2.f * delta) amb = true;
+  if (amb) {
+    atomicAdd(stats + 0, 1u);
+    const int slot = atomicAdd(rr_count, 1);
+    if (slot < rr_cap) {
+      int* dst = rr_list + (size_t)slot * (2 * L + 3);
+      dst[0] = row;
+      dst[1] = np < L ? np : L;
+      dst[2] = __float_as_int(rej * kScoreToDist);   // every key outside the list has approx dist >= this
+#pragma unroll
+      for (int j = 0; j < L; ++j) { dst[3 + j] = id[j]; dst[3 + L + j] = __float_as_int(v[j] * kScoreToDist); }
+    } else {
+      fix_rows[atomicAdd(fix_count, 1)] = row;
+    }
+  }
+  int32_t* out = idx_out + (size_t)row * k;
+#pragma unroll
+  for (int j = 0; j < L; ++j)
+    if (j < kd && j % dilation == 0) out[j / dilation] = id[j];
+}
+
+// ------------------------------------------------------------------------------------
 // exact re-rank of rows whose approximate order is ambiguous (a few per thousand)
 // ------------------------------------------------------------------------------------
 // One warp per listed row; lane c (and c + 32) owns candidate c of the row's <= TL candidates: exact fp32
@@ -395,7 +468,8 @@ knn_fixup_kernel(const int* __restrict__ count, const int* __restrict__ rows, co
 
 struct TcWorkspace {
   __half* a_op; __half* b_op; int* fix_count; int* fix_rows; unsigned int* stats;
-  int* rr_count; int* rr_list; int rr_cap; size_t bytes;
+  int* rr_count; int* rr_list; int rr_cap;
+  float2* cand; int* cand_count; float* cand_thr; int cand_slots; size_t bytes;
 };
 
 // rows the re-rank list can hold (ambiguous rows are a few per thousand; beyond the cap they take the
@@ -419,6 +493,14 @@ TcWorkspace carve_tc(void* base, const Plan& pl, int P, int N, int T) {
   w.fix_rows = static_cast<int*>(take(sizeof(int) * (size_t)P * N));
   w.rr_cap = rerank_cap(P, N);
   w.rr_list = static_cast<int*>(take(sizeof(int) * (size_t)w.rr_cap * (2 * (T + 3) + 3)));
+  {   // candidate hand-over of the select kernel: per item (pl.QI items of rows_per_item rows per problem)
+    const int rows_per_item = (pl.geom == 1 ? GeomB::ROWS : GeomA::ROWS);
+    const size_t item_rows = (size_t)P * pl.QI * rows_per_item;
+    w.cand_slots = T + 9;
+    w.cand = static_cast<float2*>(take(sizeof(float2) * item_rows * w.cand_slots));
+    w.cand_count = static_cast<int*>(take(sizeof(int) * item_rows));
+    w.cand_thr = static_cast<float*>(take(sizeof(float) * item_rows));
+  }
   w.bytes = off;
   return w;
 }
@@ -547,6 +629,7 @@ int launch_knn_tc(const KnnWorkspace& w, void* extra_ws, const float* relpos, co
   prm.relpos = relpos; prm.idx_out = idx_out;
   prm.fix_count = t.fix_count; prm.fix_rows = t.fix_rows; prm.stats = t.stats;
   prm.rr_count = t.rr_count; prm.rr_list = t.rr_list; prm.rr_cap = t.rr_cap;
+  prm.cand = t.cand; prm.cand_count = t.cand_count; prm.cand_thr = t.cand_thr; prm.cand_slots = t.cand_slots;
   prm.dbg_dist = g_dbg_dist;
   prm.trace = g_trace; prm.trace_tiles = g_trace_tiles;
   prm.P = P; prm.N = N; prm.M = M; prm.D = D; prm.k = k; prm.dilation = dilation; prm.kd = k * dilation;
@@ -574,6 +657,19 @@ int launch_knn_tc(const KnnWorkspace& w, void* extra_ws, const float* relpos, co
     default: rc = tc::launch_select<1>(prm, pl, T, stream); break;
   }
   if (rc != GKG_OK) return rc;
+  {
+    const int rows_per_item = (pl.geom == 1 ? GeomB::ROWS : GeomA::ROWS);
+    const int row_sets = rows_per_item / BM;
+    const long long total_rows = (long long)P * pl.QI * rows_per_item;
+    const unsigned blocks = (unsigned)((total_rows + 255) / 256);
+#define GKG_FINALIZE(LL)                                                                                          \
+    knn_finalize_kernel<LL><<<blocks, 256, 0, stream>>>(t.cand, t.cand_count, t.cand_thr, t.cand_slots, rows_per_item, \
+        row_sets, pl.QI, idx_out, t.rr_count, t.rr_list, t.rr_cap, t.fix_count, t.fix_rows, t.stats, total_rows, N, M,  \
+        k, dilation, prm.delta, g_force_rerank)
+    if (T == 11) GKG_FINALIZE(14); else if (T == 20) GKG_FINALIZE(23); else if (T == 29) GKG_FINALIZE(32); else GKG_FINALIZE(41);
+#undef GKG_FINALIZE
+    GKG_CHECK_LAUNCH("knn_finalize_kernel");
+  }
   {
     const int blocks = (t.rr_cap + 7) / 8 < 148 * 4 ? (t.rr_cap + 7) / 8 : 148 * 4;
     knn_rerank_kernel<<<blocks, 256, 0, stream>>>(t.rr_count, t.rr_list, t.rr_cap, T + 3, w.xhat, w.xsq, w.yhat, w.ysq,

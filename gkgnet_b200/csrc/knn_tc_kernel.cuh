@@ -44,9 +44,9 @@ struct Geom {
   static_assert(BN % CH == 0 && BNP % 16 == 0 && BNP >= BN && RS * NACC * ACC_STRIDE <= 512 && ACC_STRIDE >= BNP, "geometry");
   // Triplet log of a row: log_valid(T) entries can be kept (the second sweep logs ~T + 1 on average, see
   // the kernel); behind them log_slack(T) slots absorb the triplets logged between two capacity checks
-  // (6 per half chunk) and later hold the (score, id) pair list of the final selection (2 pairs per slot).
+  // (6 per half chunk).
   __host__ __device__ static constexpr int log_valid(int T) { return T + 8; }
-  __host__ __device__ static constexpr int log_slack(int T) { return (T + 4) / 2 > 6 ? (T + 4) / 2 : 6; }
+  __host__ __device__ static constexpr int log_slack(int T) { return 6; }
   __host__ __device__ static constexpr size_t cand_bytes(int T) {
     return (size_t)ROWS * (log_valid(T) + log_slack(T)) * 16;
   }
@@ -341,6 +341,7 @@ struct TcParams {
   int32_t* idx_out;
   int* fix_count; int* fix_rows; unsigned int* stats;   // stats: [0] ambiguous rows, [1] max err bits
   int* rr_count; int* rr_list; int rr_cap;              // rows whose candidates go to the exact re-rank kernel
+  float2* cand; int* cand_count; float* cand_thr; int cand_slots;   // per item: [slot][row] (score, id), [row] count / threshold
   float* dbg_dist;
   long long* trace;                // debug: clock64 stamps of CTA 0, 8 slots per key tile (see tools/knn_trace.py)
   int trace_tiles;
@@ -370,13 +371,11 @@ __global__ void __launch_bounds__(G::NTHREADS, 1) knn_tc_kernel(const TcParams p
   constexpr bool DENSE = BIAS == 1;
   constexpr int KW = BIAS > 1 ? BIAS : CH;      // columns that share one B term (whole chunk if none)
   constexpr int TA = T - 1;                     // sweep-A list: TA >= k*d + 1 distinct keys
-  constexpr int TL = T + 3;                     // (score, id) pairs sorted at the end of a row
   constexpr int LC = G::log_valid(T);           // log entries a row may keep
   constexpr int NCH = G::NCH;                   // chunks per accumulator
   constexpr int NG = CH / KW;                   // key groups per chunk
   constexpr int RS = G::RS, NACC = G::NACC;
   constexpr uint32_t LOG_STRIDE = G::LOG_STRIDE;
-  static_assert(TL <= 2 * G::log_slack(T), "pair list must fit the slack slots");
   static_assert(KW == 9 || KW == 18 || KW == 36, "bias period");
   extern __shared__ __align__(1024) uint8_t smem[];
   // carve-up: [A tiles x NA x RS][ring x NS: B block (+ A slices when streaming)][triplet log][barriers + tmem ptr][staged B rows]
@@ -539,7 +538,6 @@ __global__ void __launch_bounds__(G::NTHREADS, 1) knn_tc_kernel(const TcParams p
     const int row_t = q * 32 + lane;
     const uint32_t log_base = smem_u32(cand) + (uint32_t)(rset * BM + row_t) * 16;
     const uint32_t log_end = log_base + (uint32_t)LC * LOG_STRIDE;          // first slack slot
-    const uint32_t pair_base = log_end;          // (score, id) pairs of the final selection: 2 per slack slot
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(rset * NACC * G::ACC_STRIDE);
     uint64_t* my_full = t_full + rset * NACC;
     uint64_t* my_empty = t_empty + rset * NACC;
@@ -724,46 +722,52 @@ __global__ void __launch_bounds__(G::NTHREADS, 1) knn_tc_kernel(const TcParams p
       const bool overflow = lp_max > log_end;        // more candidates than the log keeps: certify by fix-up
       const int cnt = (int)((lp - log_base) / LOG_STRIDE);
 
-      // ---------------- finalise the row -------------------------------------------
-      // Add the B terms back (in place) and find the T-th largest KEY among the logged triplets.
-      TopList<T> top;
-      top.init();
-      const int mx_cnt = __reduce_max_sync(0xffffffffu, cnt);
-      for (int e0 = 0; e0 < mx_cnt; e0 += 2) {
-        float4 c[2];
-#pragma unroll
-        for (int u = 0; u < 2; ++u) c[u] = ld_shared_v4(log_base + (uint32_t)(e0 + u) * LOG_STRIDE);
-#pragma unroll
-        for (int u = 0; u < 2; ++u) {
-          const bool valid = e0 + u < cnt;
-          if (BIAS > 1) {
-            const float bg = brow[valid ? (__float_as_uint(c[u].w) >> 16) : 0u];
-            c[u].x += bg; c[u].y += bg; c[u].z += bg;
-            if (valid) st_shared_v4(log_base + (uint32_t)(e0 + u) * LOG_STRIDE, c[u].x, c[u].y, c[u].z, c[u].w);
-          }
-          top.insert(valid ? fmax3(c[u].x, c[u].y, c[u].z) : kScoreFloor);
-        }
-      }
-      // neighbouring keys are often similar: the other two keys of a triplet may rank as well
-      for (int e = 0; e < mx_cnt; ++e) {
-        float x1 = kScoreFloor, x2 = kScoreFloor;
-        if (e < cnt) {
-          const float4 c = ld_shared_v4(log_base + (uint32_t)e * LOG_STRIDE);
-          const float mx = fmax3(c.x, c.y, c.z);
-          const bool is0 = c.x == mx, is1 = !is0 && c.y == mx;      // the one copy of the maximum already listed
-          x1 = is0 ? c.y : c.x;
-          x2 = (is0 || is1) ? c.z : c.y;
-        }
-        if (__any_sync(0xffffffffu, fmaxf(x1, x2) > top.v[T - 1])) {
-          top.insert(x1);
-          top.insert(x2);
-        }
-      }
-      // T-th largest logged key; keys that were never logged are all <= thr_base
-      const float tau = fmaxf(top.v[T - 1], thr_base);
-      // keys of the logged triplets that reach the threshold -> (score, id) pair list
-      int np = 0;
+      // ---------------- hand the candidates over -----------------------------------
+      // The keys of the logged triplets that reach the threshold (B terms added back) go to global
+      // memory, slot-major per item so that a warp writes 256 contiguous bytes; knn_finalize_kernel
+      // (one thread per row, full occupancy) sorts them, checks the gaps and writes the neighbour ids.
+      // Keeping that work here would hold the accumulators -- and the tensor pipe -- for ~15 % of an item.
       {
+        const size_t rbase = (size_t)item * G::ROWS + (size_t)(rset * BM + row_t);
+        float2* cdst = prm.cand + (size_t)item * prm.cand_slots * G::ROWS + (size_t)(rset * BM + row_t);
+        const int mx_cnt = __reduce_max_sync(0xffffffffu, cnt);
+        // T-th largest KEY among the logged triplets (neighbouring keys are often similar: several keys of one
+        // triplet may rank); first the triplet maxima, with the B term added back in place ...
+        TopList<T> top;
+        top.init();
+        for (int e0 = 0; e0 < mx_cnt; e0 += 2) {
+          float4 c[2];
+#pragma unroll
+          for (int u = 0; u < 2; ++u) c[u] = ld_shared_v4(log_base + (uint32_t)(e0 + u) * LOG_STRIDE);
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            const bool valid = e0 + u < cnt;
+            if (BIAS > 1) {
+              const float bg = brow[valid ? (__float_as_uint(c[u].w) >> 16) : 0u];
+              c[u].x += bg; c[u].y += bg; c[u].z += bg;
+              if (valid) st_shared_v4(log_base + (uint32_t)(e0 + u) * LOG_STRIDE, c[u].x, c[u].y, c[u].z, c[u].w);
+            }
+            top.insert(valid ? fmax3(c[u].x, c[u].y, c[u].z) : kScoreFloor);
+          }
+        }
+        // ... then the other two keys of a triplet, when they can matter for some row of the warp
+        for (int e = 0; e < mx_cnt; ++e) {
+          float x1 = kScoreFloor, x2 = kScoreFloor;
+          if (e < cnt) {
+            const float4 c = ld_shared_v4(log_base + (uint32_t)e * LOG_STRIDE);
+            const float mx = fmax3(c.x, c.y, c.z);
+            const bool is0 = c.x == mx, is1 = !is0 && c.y == mx;      // the one copy of the maximum already listed
+            x1 = is0 ? c.y : c.x;
+            x2 = (is0 || is1) ? c.z : c.y;
+          }
+          if (__any_sync(0xffffffffu, fmaxf(x1, x2) > top.v[T - 1])) {
+            top.insert(x1);
+            top.insert(x2);
+          }
+        }
+        // keys that were never logged are all <= thr_base
+        const float tau = fmaxf(top.v[T - 1], thr_base);
+        int np = 0;
         for (int e = 0; e < mx_cnt; ++e) {
           if (e < cnt) {
             const float4 c = ld_shared_v4(log_base + (uint32_t)e * LOG_STRIDE);
@@ -772,78 +776,16 @@ __global__ void __launch_bounds__(G::NTHREADS, 1) knn_tc_kernel(const TcParams p
 #pragma unroll
             for (int i = 0; i < 3; ++i) {
               if (sc[i] >= tau && id + i < prm.M) {
-                if (np < TL) st_shared_v2(pair_base + (uint32_t)(np >> 1) * LOG_STRIDE + (np & 1) * 8, sc[i],
-                                          __int_as_float(id + i));
+                if (np < prm.cand_slots) cdst[(size_t)np * G::ROWS] = make_float2(sc[i], __int_as_float(id + i));
                 ++np;
               }
             }
           }
         }
-      }
-      bool unsure_set = overflow || np > TL;
-      // pairs -> registers as (dist - |xh|^2, id), sorted ascending by (value, id)
-      float cv[TL];
-      int cid[TL];
-#pragma unroll
-      for (int s = 0; s < TL; ++s) {
-        const float2 c = ld_shared_v2(pair_base + (uint32_t)(s >> 1) * LOG_STRIDE + (s & 1) * 8);
-        const bool have = s < np;
-        cv[s] = have ? c.x * kScoreToDist : INFINITY;
-        cid[s] = have ? __float_as_int(c.y) : 0x7fffffff;
-      }
-      // odd-even transposition sort by approximate value; equal values are a zero gap, which sends the
-      // row to the exact re-rank (sorted there with ids as tie-break)
-      {
-#pragma unroll
-        for (int pass = 0; pass < TL; ++pass) {
-#pragma unroll
-          for (int s = pass & 1; s + 1 < TL; s += 2) {
-            const bool sw = cv[s + 1] < cv[s];
-            const float tv = sw ? cv[s] : cv[s + 1];
-            const int ti = sw ? cid[s] : cid[s + 1];
-            cv[s] = sw ? cv[s + 1] : cv[s];
-            cid[s] = sw ? cid[s + 1] : cid[s];
-            cv[s + 1] = tv;
-            cid[s + 1] = ti;
-          }
-        }
-      }
-
-      const int kd = prm.kd;
-      bool amb = prm.force_rerank > 0 || unsure_set;   // (< 0: debug counters only)
-#pragma unroll
-      for (int s = 0; s + 1 < TL; ++s)
-        if (s < kd && (cv[s + 1] - cv[s]) < 2.f * prm.delta) amb = true;
-      if (row_ok && amb) {
-        // The approximate order of this row is not certified (a gap below 2 delta, or the candidate set is in
-        // doubt).  Hand it over: the candidate ids go to knn_rerank_kernel (exact fp32 distances of the <= TL
-        // candidates, a warp per row) and rows without a trustworthy candidate set to the brute-force fix-up.
-        // Doing either here would stall the whole item behind one thread's chain of dependent global loads.
-        atomicAdd(prm.stats + 0, 1u);
-        int slot = unsure_set ? prm.rr_cap : atomicAdd(prm.rr_count, 1);
-        if (slot < prm.rr_cap) {
-          int* dst = prm.rr_list + (size_t)slot * (2 * TL + 3);
-          dst[0] = p * prm.N + n;
-          dst[1] = np;
-          dst[2] = __float_as_int(tau * kScoreToDist);   // every key outside the pair list has approx dist >= this
-#pragma unroll
-          for (int s = 0; s < TL; ++s) { dst[3 + s] = cid[s]; dst[3 + TL + s] = __float_as_int(cv[s]); }
-        } else {
-          prm.fix_rows[atomicAdd(prm.fix_count, 1)] = p * prm.N + n;
-        }
-      }
-      // stage the ids in this thread's pair slots so that the dilated pick is a shared-memory
-      // index, not a dynamic register index
-      __syncwarp();
-#pragma unroll
-      for (int s = 0; s < TL; ++s)
-        st_shared_v2(pair_base + (uint32_t)(s >> 1) * LOG_STRIDE + (s & 1) * 8, 0.f, __int_as_float(cid[s]));
-      if (row_ok) {
-        int32_t* out = prm.idx_out + ((size_t)p * prm.N + n) * prm.k;
-        for (int j = 0; j < prm.k; ++j) {
-          const int s = j * prm.dilation;
-          out[j] = __float_as_int(ld_shared_v2(pair_base + (uint32_t)(s >> 1) * LOG_STRIDE + (s & 1) * 8).y);
-        }
+        thr_base = tau;                            // every key that is not handed over scores <= tau
+        // count < 0: the candidate set is not trustworthy (log or slot overflow) -> brute-force fix-up
+        prm.cand_count[rbase] = (overflow || np > prm.cand_slots) ? -1 : np;
+        prm.cand_thr[rbase] = thr_base;
       }
     }
   }
