@@ -323,24 +323,47 @@ def run_ours(args):
     value = world * B / (ms_per_step * 1e-3)
 
     # ---- e2e: host buffers -> device -> hot path -> host, every step ------------------
+    # Every step copies its inputs from pinned host memory and its result back; the three legs run on
+    # three streams over two sets of device buffers, so step i+1's upload and step i-1's download overlap
+    # step i's kernels (all of it inside the timed region).
     xp, yp = xh.pin_memory(), yh.pin_memory()
     out_host = torch.empty(hp.out.shape, dtype=hp.out.dtype).pin_memory()
-    e2e_steps = max(3, min(args.steps, 10))
+    e2e_steps = max(4, min(args.steps, 10))
+    hps = [hp, HotPath(torch.empty_like(x), torch.empty_like(y), rel, algo, dense_bias=args.dense_bias)]
+    s_in, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+    s_cmp = hp.stream
+    hps[1].stream = s_cmp
+    ev_in = [torch.cuda.Event() for _ in range(2)]
+    ev_cmp = [torch.cuda.Event() for _ in range(2)]
+    ev_out = [torch.cuda.Event() for _ in range(2)]
 
-    def e2e_step():
-        hp.x.copy_(xp, non_blocking=True)
-        hp.y.copy_(yp, non_blocking=True)
-        hp.step()
-        out_host.copy_(hp.out, non_blocking=True)
+    def e2e_loop(n):
+        for i in range(n):
+            h, j = hps[i % 2], i % 2
+            with torch.cuda.stream(s_in):
+                s_in.wait_event(ev_cmp[j])            # the kernels that last read these input buffers
+                h.x.copy_(xp, non_blocking=True)
+                h.y.copy_(yp, non_blocking=True)
+                ev_in[j].record(s_in)
+            s_cmp.wait_event(ev_in[j])
+            s_cmp.wait_event(ev_out[j])               # the download that last read this output buffer
+            h.step()
+            ev_cmp[j].record(s_cmp)
+            with torch.cuda.stream(s_out):
+                s_out.wait_event(ev_cmp[j])
+                out_host.copy_(h.out, non_blocking=True)
+                ev_out[j].record(s_out)
 
-    for _ in range(2):
-        e2e_step()
+    e2e_loop(2)
+    torch.cuda.synchronize()
     barrier(world)
     s2, t2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    s2.record(hp.stream)
-    for _ in range(e2e_steps):
-        e2e_step()
-    t2.record(hp.stream)
+    s2.record(s_in)
+    e2e_loop(e2e_steps)
+    s_out.wait_stream(s_cmp)
+    s_out.wait_stream(s_in)
+    t2.record(s_out)
+    torch.cuda.synchronize()
     barrier(world)
     e2e_ms = max_over_ranks(s2.elapsed_time(t2) / e2e_steps, world, dev)
     h2d = xp.numel() * xp.element_size() + yp.numel() * yp.element_size()
@@ -365,7 +388,8 @@ def run_ours(args):
             traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
         except Exception:
             traffic = None
-    roofline = {"kernel": "gkg_knn_select (distance + fused top-k)", "bound": "tensor", "achieved": tf,
+    roofline = {"kernel": "gkg_knn_select (tcgen05 distance + fused top-k kernel, finalize, re-rank and fix-up "
+                          "kernels; the first is ~90 % of the time)", "bound": "tensor", "achieved": tf,
                 "peak": peak_tf, "unit": "TFLOP/s", "frac": tf / peak_tf, "traffic": traffic,
                 "peak_source": f"{peak_src} bf16_tflops_sustained (kernel timed inside the step)",
                 "algorithmic_flop": flop_knn, "ms": knn_ms}
