@@ -29,7 +29,7 @@ extern "C" const char* gkg_last_error(void) { return g_err; }
 extern "C" uint64_t gkg_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 static int resolve_algo(int algo, int N, int M, int D, int k, int dilation) {
-  if (algo == GKG_KNN_AUTO) return knn_tc_supported(N, M, D, k, dilation) ? GKG_KNN_TCGEN05 : GKG_KNN_EXACT_FP32;
+  if (algo == GKG_KNN_AUTO) return knn_tc_preferred(N, M, D, k, dilation) ? GKG_KNN_TCGEN05 : GKG_KNN_EXACT_FP32;
   return algo;
 }
 

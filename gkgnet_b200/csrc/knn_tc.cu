@@ -496,7 +496,7 @@ TcWorkspace carve_tc(void* base, const Plan& pl, int P, int N, int T) {
   {   // candidate hand-over of the select kernel: per item (pl.QI items of rows_per_item rows per problem)
     const int rows_per_item = (pl.geom == 1 ? GeomB::ROWS : GeomA::ROWS);
     const size_t item_rows = (size_t)P * pl.QI * rows_per_item;
-    w.cand_slots = T + 9;
+    w.cand_slots = T + (T / 2 + 1 > 9 ? T / 2 + 1 : 9);
     w.cand = static_cast<float2*>(take(sizeof(float2) * item_rows * w.cand_slots));
     w.cand_count = static_cast<int*>(take(sizeof(int) * item_rows));
     w.cand_thr = static_cast<float*>(take(sizeof(float) * item_rows));
@@ -521,6 +521,12 @@ bool knn_tc_supported(int N, int M, int D, int k, int dilation) {
   if (N < 1 || M < 1 || M > 65000) return false;   // key ids travel in 16 bits of a log entry
   Plan pl = make_plan(1, N, M, D, t_bucket(kd + 2));
   return pl.ok;
+}
+
+// AUTO picks the tensor-core path only when the threshold sweep has enough key groups to work with
+// (tiny key sets would send every row to the brute-force fix-up: correct, but the exact kernel is faster).
+bool knn_tc_preferred(int N, int M, int D, int k, int dilation) {
+  return knn_tc_supported(N, M, D, k, dilation) && M / 3 >= 2 * t_bucket(k * dilation + 2);
 }
 
 size_t knn_tc_workspace_bytes(int P, int N, int M, int D, int k, int dilation, bool self_keys) {
@@ -638,6 +644,7 @@ int launch_knn_tc(const KnnWorkspace& w, void* extra_ws, const float* relpos, co
   prm.a_tile_bytes = pl.a_tile_bytes; prm.b_block_bytes = pl.b_block_bytes;
   prm.force_rerank = g_force_rerank;
   prm.delta = tc_delta(pl.KP);
+  const int ga = (M / 18 >= 4 * (T - 1)) ? 18 : (M / 6 >= 4 * (T - 1)) ? 6 : 3;
   prm.sep_a = sep.a; prm.sep_b = sep.b; prm.grid_w = sep.grid_w > 0 ? sep.grid_w : 1;
   prm.sep_mh = sep.kw > 0 ? M / sep.kw : 1;
   const int bn = pl.geom == 1 ? GeomB::BN : GeomA::BN;
@@ -650,11 +657,11 @@ int launch_knn_tc(const KnnWorkspace& w, void* extra_ws, const float* relpos, co
     bias = sep.kw;
   int rc;
   switch (bias) {
-    case 0: rc = tc::launch_select<0>(prm, pl, T, stream); break;
-    case 9: rc = tc::launch_select<9>(prm, pl, T, stream); break;
-    case 18: rc = tc::launch_select<18>(prm, pl, T, stream); break;
-    case 36: rc = tc::launch_select<36>(prm, pl, T, stream); break;
-    default: rc = tc::launch_select<1>(prm, pl, T, stream); break;
+    case 0: rc = tc::launch_select<0>(prm, pl, T, ga, stream); break;
+    case 9: rc = tc::launch_select<9>(prm, pl, T, ga, stream); break;
+    case 18: rc = tc::launch_select<18>(prm, pl, T, ga, stream); break;
+    case 36: rc = tc::launch_select<36>(prm, pl, T, ga, stream); break;
+    default: rc = tc::launch_select<1>(prm, pl, T, ga, stream); break;
   }
   if (rc != GKG_OK) return rc;
   {

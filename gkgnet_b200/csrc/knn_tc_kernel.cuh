@@ -45,7 +45,7 @@ struct Geom {
   // Triplet log of a row: log_valid(T) entries can be kept (the second sweep logs ~T + 1 on average, see
   // the kernel); behind them log_slack(T) slots absorb the triplets logged between two capacity checks
   // (6 per half chunk).
-  __host__ __device__ static constexpr int log_valid(int T) { return T + 8; }
+  __host__ __device__ static constexpr int log_valid(int T) { return T + (T / 2 > 8 ? T / 2 : 8); }
   __host__ __device__ static constexpr int log_slack(int T) { return 6; }
   __host__ __device__ static constexpr size_t cand_bytes(int T) {
     return (size_t)ROWS * (log_valid(T) + log_slack(T)) * 16;
@@ -322,6 +322,76 @@ struct TopList {
 // Per-row triplet log in shared memory: entry e of the row handled by thread t lives at
 // log_base(t) + e * LOG_STRIDE (16 bytes per thread, consecutive lanes adjacent -> conflict-free
 // 128-bit accesses).
+// T-th largest KEY score among the `cnt` log entries of this thread's row (kScoreFloor when the row has logged
+// fewer than T keys); end of the item only: it converts the log to true scores on the way.  Triplet maxima first; the other two keys of a triplet are inserted only when
+// they can matter for some row of the warp (neighbouring keys are often similar).  Warp-uniform trip counts.
+template <uint32_t LOG_STRIDE, int T, int BIAS>
+__device__ __forceinline__ float log_tth_key(uint32_t log_base, int cnt, int mx_cnt, const float* brow) {
+  TopList<T> top;
+  top.init();
+  // first pass: the B term of the key group is added back IN PLACE (from here on the log holds true scores)
+  for (int e0 = 0; e0 < mx_cnt; e0 += 2) {
+    float4 c[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) c[u] = ld_shared_v4(log_base + (uint32_t)(e0 + u) * LOG_STRIDE);
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const bool valid = e0 + u < cnt;
+      if (BIAS > 1) {
+        const float bg = brow[valid ? (__float_as_uint(c[u].w) >> 16) : 0u];
+        c[u].x += bg; c[u].y += bg; c[u].z += bg;
+        if (valid) st_shared_v4(log_base + (uint32_t)(e0 + u) * LOG_STRIDE, c[u].x, c[u].y, c[u].z, c[u].w);
+      }
+      top.insert(valid ? fmax3(c[u].x, c[u].y, c[u].z) : kScoreFloor);
+    }
+  }
+  for (int e = 0; e < mx_cnt; ++e) {
+    float x1 = kScoreFloor, x2 = kScoreFloor;
+    if (e < cnt) {
+      const float4 c = ld_shared_v4(log_base + (uint32_t)e * LOG_STRIDE);
+      const float mx = fmax3(c.x, c.y, c.z);
+      const bool is0 = c.x == mx, is1 = !is0 && c.y == mx;      // the one copy of the maximum already listed
+      x1 = is0 ? c.y : c.x;
+      x2 = (is0 || is1) ? c.z : c.y;
+    }
+    if (__any_sync(0xffffffffu, fmaxf(x1, x2) > top.v[T - 1])) {
+      top.insert(x1);
+      top.insert(x2);
+    }
+  }
+  return top.v[T - 1];
+}
+
+// Rare path of sweep B: a row is past its LC valid log entries because its sweep-A threshold was loose.
+// Raise the threshold to the T-th largest TRIPLET maximum logged so far (T distinct keys reach it; a key
+// that ties with it must stay a candidate: a hair of slack) and drop the entries below, which leaves at
+// most T (+ ties) of them.  Small on purpose: it is inlined at every capacity check of the chunk loop.
+template <uint32_t LOG_STRIDE, int T, int BIAS>
+__device__ __forceinline__ void log_compact(uint32_t log_base, uint32_t& lp, float& thr_base, const float* brow) {
+  const int cnt_now = (int)((lp - log_base) / LOG_STRIDE);
+  const int mx_now = __reduce_max_sync(0xffffffffu, cnt_now);
+  TopList<T> top;
+  top.init();
+#pragma unroll 1
+  for (int e = 0; e < mx_now; ++e) {
+    const float4 c = ld_shared_v4(log_base + (uint32_t)e * LOG_STRIDE);
+    const float bg = BIAS > 1 ? brow[e < cnt_now ? (__float_as_uint(c.w) >> 16) : 0u] : 0.f;
+    top.insert(e < cnt_now ? fmax3(c.x, c.y, c.z) + bg : kScoreFloor);
+  }
+  thr_base = fmaxf(thr_base, top.v[T - 1] - 1.f);
+  uint32_t wp = log_base;
+#pragma unroll 1
+  for (int e = 0; e < mx_now; ++e) {
+    const float4 c = ld_shared_v4(log_base + (uint32_t)e * LOG_STRIDE);
+    const float bg = BIAS > 1 ? brow[e < cnt_now ? (__float_as_uint(c.w) >> 16) : 0u] : 0.f;
+    if (e < cnt_now && fmax3(c.x, c.y, c.z) + bg > thr_base) {
+      st_shared_v4(wp, c.x, c.y, c.z, c.w);
+      wp += LOG_STRIDE;
+    }
+  }
+  lp = wp;
+}
+
 // One chunk of a query row in flight: CH accumulator columns and the bias terms that go with them.
 template <bool DENSE, int NG>
 struct Chunk {
@@ -365,7 +435,7 @@ __device__ __forceinline__ float exact_dist(const float* __restrict__ xr, const 
 // bias  relpos[n, m] = A[n % grid_w][m % KW] + B[n / grid_w][m / KW]  with the A row in registers
 // and the needed B rows staged in shared memory (the analytic table of the reference has this
 // form: pos_embed.py + the flattened bicubic resize, see gkgnet_b200/pos_embed.py).
-template <class G, int T, int BIAS>
+template <class G, int T, int BIAS, int GA>
 __global__ void __launch_bounds__(G::NTHREADS, 1) knn_tc_kernel(const TcParams prm) {
   constexpr bool HAS_REL = BIAS != 0;
   constexpr bool DENSE = BIAS == 1;
@@ -651,20 +721,32 @@ __global__ void __launch_bounds__(G::NTHREADS, 1) knn_tc_kernel(const TcParams p
         la.init();
         sweep([&](int ci, Chunk<DENSE, NG>& ch) {
           (void)ci;
-          float tm[CH / 3];
+          float tm[CH / 3];              // triplet maxima, without the B term of the key group
 #pragma unroll
           for (int t = 0; t < CH / 3; ++t) tm[t] = fmax3(raw(ch, 3 * t), raw(ch, 3 * t + 1), raw(ch, 3 * t + 2));
+          // group size of the list: 18 keys when the row has plenty of groups for its TA entries, finer when
+          // the list is long relative to the keys (the excess of keys above the TA-th group maximum grows
+          // like TA / (2 * groups)); GA is picked by the host
+          if (GA == 18) {
 #pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            float gm;
-            if (KW >= 18) {
-              gm = fmaxf(fmax3(tm[6 * h], tm[6 * h + 1], tm[6 * h + 2]), fmax3(tm[6 * h + 3], tm[6 * h + 4], tm[6 * h + 5])) +
-                   ch.bg[(18 * h) / KW];
-            } else {
-              gm = fmaxf(fmax3(tm[6 * h], tm[6 * h + 1], tm[6 * h + 2]) + ch.bg[(2 * h) % NG],
-                         fmax3(tm[6 * h + 3], tm[6 * h + 4], tm[6 * h + 5]) + ch.bg[(2 * h + 1) % NG]);
+            for (int h = 0; h < 2; ++h) {
+              float gm;
+              if (KW >= 18) {
+                gm = fmaxf(fmax3(tm[6 * h], tm[6 * h + 1], tm[6 * h + 2]), fmax3(tm[6 * h + 3], tm[6 * h + 4], tm[6 * h + 5])) +
+                     ch.bg[(18 * h) / KW];
+              } else {
+                gm = fmaxf(fmax3(tm[6 * h], tm[6 * h + 1], tm[6 * h + 2]) + ch.bg[(2 * h) % NG],
+                           fmax3(tm[6 * h + 3], tm[6 * h + 4], tm[6 * h + 5]) + ch.bg[(2 * h + 1) % NG]);
+              }
+              la.insert(gm);
             }
-            la.insert(gm);
+          } else if (GA == 6) {
+#pragma unroll
+            for (int u = 0; u < CH / 6; ++u)
+              la.insert(fmaxf(tm[2 * u] + ch.bg[(6 * u) / KW], tm[2 * u + 1] + ch.bg[(6 * u + 3) / KW]));
+          } else {
+#pragma unroll
+            for (int t = 0; t < CH / 3; ++t) la.insert(tm[t] + ch.bg[(3 * t) / KW]);
           }
         });
         // fewer than TA real groups (tiny M): the floor stays -> everything is logged -> fix-up
@@ -673,7 +755,7 @@ __global__ void __launch_bounds__(G::NTHREADS, 1) knn_tc_kernel(const TcParams p
 
       // ---- sweep B: log the triplets that beat the threshold (fp16x3 scores) --------------------
       uint32_t lp = log_base;                      // next free log slot of this row
-      uint32_t lp_max = log_base;
+      bool overflow = false;
       sweep([&](int ci, Chunk<DENSE, NG>& ch) {
         const int kt = ci / NCH;
         const int m0 = kt * G::BN + (ci - kt * NCH) * CH;
@@ -685,8 +767,7 @@ __global__ void __launch_bounds__(G::NTHREADS, 1) knn_tc_kernel(const TcParams p
             if (m0 + j < prm.M)
               prm.dbg_dist[((size_t)p * prm.N + n) * prm.M + m0 + j] = (raw(ch, j) + ch.bg[j / KW]) * kScoreToDist;
         }
-        // half a chunk (6 triplets) at a time: all scores, maxima and hit predicates first, then the
-        // predicated stores -- the triplets are independent, which hides the FMNMX3 -> FSETP -> STS latency
+        // half a chunk (6 triplets) between two capacity checks
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
           float s[6][3];
@@ -698,32 +779,30 @@ __global__ void __launch_bounds__(G::NTHREADS, 1) knn_tc_kernel(const TcParams p
             for (int i = 0; i < 3; ++i) s[u][i] = raw(ch, j + i);
             idv[u] = idw + (j | (BIAS > 1 ? (j / KW) << 16 : 0));
           }
-          // all six (s0, s1, s2, id) quads exist before the first store: the compiler may not recycle one
-          // quad of registers for every triplet (which serialises the chain through WAR hazards)
-          asm volatile("" : "+f"(s[0][0]), "+f"(s[0][1]), "+f"(s[0][2]), "+f"(s[1][0]), "+f"(s[1][1]), "+f"(s[1][2]),
-                            "+f"(s[2][0]), "+f"(s[2][1]), "+f"(s[2][2]), "+f"(s[3][0]), "+f"(s[3][1]), "+f"(s[3][2]),
-                            "+f"(s[4][0]), "+f"(s[4][1]), "+f"(s[4][2]), "+f"(s[5][0]), "+f"(s[5][1]), "+f"(s[5][2]),
-                            "+r"(idv[0]), "+r"(idv[1]), "+r"(idv[2]), "+r"(idv[3]), "+r"(idv[4]), "+r"(idv[5]));
           bool hit[6];
 #pragma unroll
           for (int u = 0; u < 6; ++u)   // the B term of the key group is folded into the threshold
             hit[u] = fmax3(s[u][0], s[u][1], s[u][2]) > thr_base - ch.bg[(3 * (6 * h + u)) / KW];
 #pragma unroll
           for (int u = 0; u < 6; ++u) {
-            if (hit[u]) {
+            if (hit[u]) {                            // logged without the B term (looked up again from the id word)
               st_shared_v4(lp, s[u][0], s[u][1], s[u][2], __int_as_float(idv[u]));
               lp += LOG_STRIDE;
             }
           }
-          lp_max = max(lp_max, lp);                // the slack slots hold the 6 triplets of a half chunk
-          lp = min(lp, log_end);
+          // The slack slots took the <= 6 triplets of this half chunk.  A row past its LC valid entries had a
+          // loose sweep-A threshold (smooth features: its nearest keys share a few 18-key groups): raise the
+          // threshold to the T-th largest key logged so far and drop what falls below.  Rare on random data.
+          if (__any_sync(0xffffffffu, lp > log_end)) {
+            log_compact<LOG_STRIDE, T, BIAS>(log_base, lp, thr_base, brow);
+            if (lp > log_end) { overflow = true; lp = log_end; }   // a pile of ties: certify by fix-up
+          }
         }
       });
-      const bool overflow = lp_max > log_end;        // more candidates than the log keeps: certify by fix-up
       const int cnt = (int)((lp - log_base) / LOG_STRIDE);
 
       // ---------------- hand the candidates over -----------------------------------
-      // The keys of the logged triplets that reach the threshold (B terms added back) go to global
+      // The keys of the logged triplets that reach the threshold go to global
       // memory, slot-major per item so that a warp writes 256 contiguous bytes; knn_finalize_kernel
       // (one thread per row, full occupancy) sorts them, checks the gaps and writes the neighbour ids.
       // Keeping that work here would hold the accumulators -- and the tensor pipe -- for ~15 % of an item.
@@ -731,42 +810,8 @@ __global__ void __launch_bounds__(G::NTHREADS, 1) knn_tc_kernel(const TcParams p
         const size_t rbase = (size_t)item * G::ROWS + (size_t)(rset * BM + row_t);
         float2* cdst = prm.cand + (size_t)item * prm.cand_slots * G::ROWS + (size_t)(rset * BM + row_t);
         const int mx_cnt = __reduce_max_sync(0xffffffffu, cnt);
-        // T-th largest KEY among the logged triplets (neighbouring keys are often similar: several keys of one
-        // triplet may rank); first the triplet maxima, with the B term added back in place ...
-        TopList<T> top;
-        top.init();
-        for (int e0 = 0; e0 < mx_cnt; e0 += 2) {
-          float4 c[2];
-#pragma unroll
-          for (int u = 0; u < 2; ++u) c[u] = ld_shared_v4(log_base + (uint32_t)(e0 + u) * LOG_STRIDE);
-#pragma unroll
-          for (int u = 0; u < 2; ++u) {
-            const bool valid = e0 + u < cnt;
-            if (BIAS > 1) {
-              const float bg = brow[valid ? (__float_as_uint(c[u].w) >> 16) : 0u];
-              c[u].x += bg; c[u].y += bg; c[u].z += bg;
-              if (valid) st_shared_v4(log_base + (uint32_t)(e0 + u) * LOG_STRIDE, c[u].x, c[u].y, c[u].z, c[u].w);
-            }
-            top.insert(valid ? fmax3(c[u].x, c[u].y, c[u].z) : kScoreFloor);
-          }
-        }
-        // ... then the other two keys of a triplet, when they can matter for some row of the warp
-        for (int e = 0; e < mx_cnt; ++e) {
-          float x1 = kScoreFloor, x2 = kScoreFloor;
-          if (e < cnt) {
-            const float4 c = ld_shared_v4(log_base + (uint32_t)e * LOG_STRIDE);
-            const float mx = fmax3(c.x, c.y, c.z);
-            const bool is0 = c.x == mx, is1 = !is0 && c.y == mx;      // the one copy of the maximum already listed
-            x1 = is0 ? c.y : c.x;
-            x2 = (is0 || is1) ? c.z : c.y;
-          }
-          if (__any_sync(0xffffffffu, fmaxf(x1, x2) > top.v[T - 1])) {
-            top.insert(x1);
-            top.insert(x2);
-          }
-        }
-        // keys that were never logged are all <= thr_base
-        const float tau = fmaxf(top.v[T - 1], thr_base);
+        // T-th largest KEY among the logged triplets; keys that were never logged are all <= thr_base
+        const float tau = fmaxf(log_tth_key<LOG_STRIDE, T, BIAS>(log_base, cnt, mx_cnt, brow), thr_base);
         int np = 0;
         for (int e = 0; e < mx_cnt; ++e) {
           if (e < cnt) {
@@ -799,7 +844,7 @@ __global__ void __launch_bounds__(G::NTHREADS, 1) knn_tc_kernel(const TcParams p
 
 // launcher for one bias mode; instantiated in knn_tc_inst.cu
 template <int BIAS>
-int launch_select(const TcParams& prm, const Plan& pl, int T, cudaStream_t stream);
+int launch_select(const TcParams& prm, const Plan& pl, int T, int ga, cudaStream_t stream);
 
 }  // namespace tc
 }  // namespace gkg
