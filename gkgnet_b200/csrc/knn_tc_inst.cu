@@ -6,7 +6,7 @@ namespace tc {
 
 template <class G, int T, int BIAS, int GA>
 static int launch_select_tb(const TcParams& prm, const Plan& pl, cudaStream_t stream) {
-  auto kern = knn_tc_kernel<G, T, BIAS, GA>;
+  auto kern = (prm.dbg_dist != nullptr || prm.trace != nullptr) ? knn_tc_kernel<G, T, BIAS, GA, true> : knn_tc_kernel<G, T, BIAS, GA, false>;
   size_t smem = pl.smem_bytes < 120 * 1024 ? 120 * 1024 : pl.smem_bytes;   // 512 TMEM columns: 1 CTA / SM
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) {

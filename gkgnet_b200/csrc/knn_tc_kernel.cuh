@@ -435,7 +435,9 @@ __device__ __forceinline__ float exact_dist(const float* __restrict__ xr, const 
 // bias  relpos[n, m] = A[n % grid_w][m % KW] + B[n / grid_w][m / KW]  with the A row in registers
 // and the needed B rows staged in shared memory (the analytic table of the reference has this
 // form: pos_embed.py + the flattened bicubic resize, see gkgnet_b200/pos_embed.py).
-template <class G, int T, int BIAS, int GA>
+// DBG: the instantiation that can dump the raw distance matrix (tests); kept out of the production kernel,
+// where the dump code alone was a third of the sweep-B loop body (instruction cache).
+template <class G, int T, int BIAS, int GA, bool DBG>
 __global__ void __launch_bounds__(G::NTHREADS, 1) knn_tc_kernel(const TcParams prm) {
   constexpr bool HAS_REL = BIAS != 0;
   constexpr bool DENSE = BIAS == 1;
@@ -542,7 +544,7 @@ __global__ void __launch_bounds__(G::NTHREADS, 1) knn_tc_kernel(const TcParams p
     // the thread that issued the MMAs they track; elect.sync picks the same lane every time).
     const int r = warp - 1;                      // row set of this issuer
     int ab = 0, aph = 0, bs = 0, bph = 0, tb = 0, tph = 0, tseq = 0;
-    const bool tr = prm.trace != nullptr && blockIdx.x == 0 && lane == 0 && r == 0;
+    const bool tr = DBG && prm.trace != nullptr && blockIdx.x == 0 && lane == 0 && r == 0;
     // descriptor halves: hi = SBO | version, lo = start address | LBO (both in 16-byte units)
     const uint32_t desc_hi = ((uint32_t)(prm.KC >> 3) * 128u >> 4) | (1u << 14);
     const uint32_t lbo_field = (128u >> 4) << 16;
@@ -611,7 +613,7 @@ __global__ void __launch_bounds__(G::NTHREADS, 1) knn_tc_kernel(const TcParams p
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(rset * NACC * G::ACC_STRIDE);
     uint64_t* my_full = t_full + rset * NACC;
     uint64_t* my_empty = t_empty + rset * NACC;
-    const bool tracer = prm.trace != nullptr && blockIdx.x == 0 && threadIdx.x == 32 * (1 + RS);
+    const bool tracer = DBG && prm.trace != nullptr && blockIdx.x == 0 && threadIdx.x == 32 * (1 + RS);
     int ltb = 0, ltph = 0, rtb = 0;              // accumulator ring: load side (slot, phase), release side
     int lseq = 0, rseq = 0;                      // running tile numbers for the debug trace
     for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
@@ -761,7 +763,7 @@ __global__ void __launch_bounds__(G::NTHREADS, 1) knn_tc_kernel(const TcParams p
         const int m0 = kt * G::BN + (ci - kt * NCH) * CH;
         // id word of a logged triplet: first key id | key group index << 16 (group = slot in brow)
         const int idw = m0 | (BIAS > 1 ? (m0 / KW) << 16 : 0);
-        if (prm.dbg_dist != nullptr && row_ok) {
+        if (DBG && prm.dbg_dist != nullptr && row_ok) {
 #pragma unroll
           for (int j = 0; j < CH; ++j)
             if (m0 + j < prm.M)

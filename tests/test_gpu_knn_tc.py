@@ -173,3 +173,33 @@ def test_tc_similar_neighbouring_keys_stay_on_fast_path(N, M, D, bias):
     dist = O.knn_distance_matrix(_ref_layout(x, G), _ref_layout(y, G), rel)
     rep = O.check_knn_against_distances(idx.cpu(), dist, 9, 1, 1e-6)
     assert rep["rows_bad"] == 0, rep
+
+
+def test_tc_smooth_key_field_compacts_instead_of_fixup():
+    """Real feature maps are spatially smooth: the nearest keys of a query sit next to each other, i.e.
+    in one or two 18-key groups of the threshold sweep, whose threshold is then far too loose.  The
+    logging sweep must tighten it by compacting the row's log (regression: 20 % of the stage-1 rows of
+    GKGNet-576 went to the brute-force fix-up kernel) and still return the exact neighbours."""
+    from gkgnet_b200 import _lib, ops
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(9)
+    B, G, D, side = 1, 2, 40, 36
+    C, M, N = G * D, side * side, 1024
+    # low-pass random field over the 36 x 36 key grid: neighbouring keys are nearly parallel
+    f = torch.randn(B, C, side, side, generator=g)
+    for _ in range(6):
+        f = torch.nn.functional.avg_pool2d(torch.nn.functional.pad(f, (1, 1, 1, 1), mode="replicate"), 3, 1)
+    y = f.permute(0, 2, 3, 1).reshape(B, M, C).contiguous()
+    pick = torch.randint(0, M, (N,), generator=g)
+    x = (y[:, pick] + 0.05 * y.std() * torch.randn(B, N, C, generator=g)).contiguous()
+    _debug(lib, -1, None)
+    try:
+        idx = ops.knn_graph(x.cuda(), y.cuda(), None, groups=G, k=9, dilation=1, algo=_lib.KNN_TCGEN05)
+        torch.cuda.synchronize()
+        st = _stats(lib)
+    finally:
+        _debug(lib, 0, None)
+    assert st["fixups"] <= 0.01 * B * G * N, st
+    dist = O.knn_distance_matrix(_ref_layout(x, G), _ref_layout(y, G), None)
+    rep = O.check_knn_against_distances(idx.cpu(), dist, 9, 1, 1e-6)
+    assert rep["rows_bad"] == 0, rep
