@@ -185,3 +185,46 @@ def mr_aggregate(x, idx, y=None, *, groups=1):
     if idx.shape[0] != B * groups or idx.shape[1] != N:
         raise ValueError(f"idx shape {tuple(idx.shape)} does not match B*G={B * groups}, N={N}")
     return _MRAggregate.apply(x, y, idx, groups)
+
+
+# ----------------------------------------------------------------------------------------
+# grouped 1x1 FC (+ folded norm + activation) on the tensor cores, inference form
+# ----------------------------------------------------------------------------------------
+_ACT = {None: 0, "none": 0, "relu": 1, "gelu": 2}
+
+
+def grouped_fc_supported(c2: int) -> bool:
+    return bool(_lib.load().gkg_grouped_fc_supported(int(c2)))
+
+
+def grouped_fc_weights(weight):
+    """Conv2d(2C, 2C, 1, groups=4) weight ``(2C, 2C/4, 1, 1)`` -> bf16 tensor-core operand order
+    ``[4][NP/8][KP/8][8][8]`` (K-major 8x8 core matrices, NP = KP = ceil16(2C/4), zero padded)."""
+    c2, cg = weight.shape[0], weight.shape[1]
+    if c2 != 4 * cg:
+        raise ValueError(f"expected a groups=4 1x1 conv weight, got {tuple(weight.shape)}")
+    kp = (cg + 15) // 16 * 16
+    w = weight.reshape(4, cg, cg).to(torch.bfloat16)                   # [q][n (out)][k (in)]
+    wp = torch.zeros((4, kp, kp), dtype=torch.bfloat16, device=weight.device)
+    wp[:, :cg, :cg] = w
+    return wp.view(4, kp // 8, 8, kp // 8, 8).permute(0, 1, 3, 2, 4).contiguous()
+
+
+def grouped_fc(x, w_op, scale, shift, act="gelu"):
+    """``act(scale * conv1x1_groups4(x) + shift)`` on token-major bf16 ``x (..., 2C)``: the eval-mode
+    ``BasicConv([2C, 2C])`` of the reference (torch_nn.py:57-81) in one pass.  ``w_op`` from
+    :func:`grouped_fc_weights`; ``scale`` / ``shift`` fp32 ``(2C,)`` with the conv bias and the batch-norm
+    statistics folded in."""
+    _require_cuda(x, w_op, scale, shift)
+    if x.dtype != torch.bfloat16:
+        raise TypeError("grouped_fc runs on bf16 activations")
+    if act not in _ACT:
+        raise NotImplementedError(f"activation [{act}] is not fused")
+    c2 = x.shape[-1]
+    x = x.contiguous()
+    out = torch.empty_like(x)
+    rows = x.numel() // c2
+    rc = _lib.load().gkg_grouped_fc_fwd(x.data_ptr(), w_op.data_ptr(), scale.data_ptr(), shift.data_ptr(),
+                                        out.data_ptr(), rows, c2, _ACT[act], _stream(x))
+    _lib.check(rc, "gkg_grouped_fc_fwd")
+    return out

@@ -49,7 +49,49 @@ class MRConv2d(nn.Module):
         where (H, W) = hw or (N, 1)."""
         agg = ops.mr_aggregate(xt, nn_idx, yt, groups=groups)          # (B, N, 2C) interleaved
         H, W = hw if hw is not None else (xt.shape[1], 1)
+        fused = self._fused_fc(agg)
+        if fused is not None:
+            return tokens_to_nchw(fused, H, W)
         return self.nn(tokens_to_nchw(agg, H, W))
+
+    def _fused_fc(self, agg):
+        """Eval-mode ``self.nn`` (grouped 1x1 conv -> batch norm -> activation, torch_nn.py:57-81) as ONE
+        tensor-core kernel with the norm folded into a per-channel affine map; None when the stack or the
+        call does not qualify (training, gradients, fp32 activations, widths beyond the kernel)."""
+        if self.training or torch.is_grad_enabled() or agg.dtype != torch.bfloat16 or not agg.is_cuda:
+            return None
+        mods = list(self.nn)
+        if not mods or not isinstance(mods[0], nn.Conv2d) or mods[0].groups != 4 or mods[0].kernel_size != (1, 1):
+            return None
+        conv, rest = mods[0], mods[1:]
+        bn = rest.pop(0) if rest and isinstance(rest[0], (nn.BatchNorm2d, nn.SyncBatchNorm)) else None
+        act = None
+        if rest and isinstance(rest[0], nn.GELU) and getattr(rest[0], "approximate", "none") == "none":
+            act, rest = "gelu", rest[1:]
+        elif rest and isinstance(rest[0], nn.ReLU):
+            act, rest = "relu", rest[1:]
+        if rest or conv.in_channels != conv.out_channels or conv.in_channels != agg.shape[-1]:
+            return None
+        if bn is not None and (bn.running_mean is None or not bn.track_running_stats):
+            return None
+        if not ops.grouped_fc_supported(conv.out_channels):
+            return None
+        tensors = [conv.weight, conv.bias] + ([bn.weight, bn.bias, bn.running_mean, bn.running_var] if bn is not None else [])
+        key = tuple((t.data_ptr(), t._version) for t in tensors if t is not None)
+        cache = getattr(self, "_fc_cache", None)
+        if cache is None or cache[0] != key:
+            with torch.no_grad():
+                c2 = conv.out_channels
+                scale = torch.ones(c2, device=agg.device)
+                shift = torch.zeros(c2, device=agg.device) if conv.bias is None else conv.bias.detach().float().clone()
+                if bn is not None:
+                    g = bn.weight.detach().float() if bn.weight is not None else torch.ones_like(scale)
+                    b = bn.bias.detach().float() if bn.bias is not None else torch.zeros_like(scale)
+                    scale = g / torch.sqrt(bn.running_var.float() + bn.eps)
+                    shift = (shift - bn.running_mean.float()) * scale + b
+                cache = (key, ops.grouped_fc_weights(conv.weight.detach()), scale.contiguous(), shift.contiguous())
+            self._fc_cache = cache
+        return ops.grouped_fc(agg, cache[1], cache[2], cache[3], act)
 
     def forward(self, x, edge_index, y=None):
         P, D, N, _ = x.shape

@@ -1,0 +1,83 @@
+"""GPU: the tcgen05 grouped 1x1 FC (+ folded BN + GELU) against the PyTorch ops of the reference's
+BasicConv (torch_nn.py:57-81) on the same inputs.  bf16 tolerance 2e-2 (north-star)."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _reference(x, conv, bn, act):
+    """fp32 reference of Conv2d(groups=4) -> BatchNorm2d(eval) -> act on token-major x (R, 2C)."""
+    y = torch.nn.functional.conv2d(x.float().t().reshape(1, -1, x.shape[0], 1), conv.weight.float(), conv.bias.float(),
+                                   groups=4)
+    y = torch.nn.functional.batch_norm(y, bn.running_mean, bn.running_var, bn.weight, bn.bias, False, 0.0, bn.eps)
+    if act == "gelu":
+        y = torch.nn.functional.gelu(y)
+    elif act == "relu":
+        y = torch.relu(y)
+    return y.reshape(-1, x.shape[0]).t()
+
+
+@pytest.mark.parametrize("C2,rows,act", [(160, 1000, "gelu"), (160, 128 * 37, "gelu"), (320, 777, "gelu"),
+                                         (64, 300, "relu"), (160, 5, None)])
+def test_grouped_fc_matches_conv_bn_act(C2, rows, act):
+    from gkgnet_b200 import ops
+    torch.manual_seed(C2 + rows)
+    conv = torch.nn.Conv2d(C2, C2, 1, groups=4).cuda()
+    bn = torch.nn.BatchNorm2d(C2).cuda().eval()
+    with torch.no_grad():
+        bn.running_mean.normal_(0, 0.5)
+        bn.running_var.uniform_(0.5, 2.0)
+        bn.weight.uniform_(0.5, 1.5)
+        bn.bias.normal_(0, 0.3)
+        conv.bias.normal_(0, 0.3)
+    x = torch.randn(rows, C2, device="cuda").to(torch.bfloat16)
+    assert ops.grouped_fc_supported(C2)
+    scale = (bn.weight / torch.sqrt(bn.running_var + bn.eps)).float()
+    shift = ((conv.bias - bn.running_mean) * scale + bn.bias).float()
+    w_op = ops.grouped_fc_weights(conv.weight.detach())
+    got = ops.grouped_fc(x, w_op, scale.detach(), shift.detach(), act)
+    # same bf16-rounded weights as the kernel sees
+    conv_r = torch.nn.Conv2d(C2, C2, 1, groups=4).cuda()
+    with torch.no_grad():
+        conv_r.weight.copy_(conv.weight.to(torch.bfloat16).float())
+        conv_r.bias.copy_(conv.bias)
+    want = _reference(x, conv_r, bn, act)
+    err = (got.float() - want).abs().max().item()
+    assert err < 2e-2 * max(1.0, want.abs().max().item()), err
+
+
+def test_grouped_fc_unsupported_width():
+    from gkgnet_b200 import ops
+    assert not ops.grouped_fc_supported(800)       # CG = 200: four accumulators exceed the tensor memory
+    assert not ops.grouped_fc_supported(100)
+
+
+def test_mrconv_eval_uses_fused_fc_and_matches_unfused():
+    """MRConv2d in eval mode under bf16 autocast takes the fused tensor-core FC; it must agree with the
+    unfused conv -> BN -> GELU stack of the same module (which the reference runs)."""
+    import gkgnet_b200 as G
+    from gkgnet_b200 import ops
+    torch.manual_seed(3)
+    G.set_norm_type("BN")
+    B, C, H, W, groups, k = 2, 80, 24, 24, 2, 9
+    m = G.vertex.MRConv2d(C, 2 * C, "gelu", "batch", True).cuda().eval()
+    with torch.no_grad():
+        m.nn[1].running_mean.normal_(0, 0.3)
+        m.nn[1].running_var.uniform_(0.5, 2.0)
+        m.nn[0].bias.normal_(0, 0.2)
+    xt = torch.randn(B, H * W, C, device="cuda").to(torch.bfloat16)
+    idx = ops.knn_graph(xt, None, None, groups=groups, k=k, dilation=1)
+    calls = []
+    orig = ops.grouped_fc
+    ops.grouped_fc = lambda *a, **kw: (calls.append(1), orig(*a, **kw))[1]
+    try:
+        with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+            fused = m.forward_tokens(xt, idx, None, groups=groups, hw=(H, W))
+            agg = ops.mr_aggregate(xt, idx, None, groups=groups)
+            plain = m.nn(G.vertex.tokens_to_nchw(agg, H, W))
+    finally:
+        ops.grouped_fc = orig
+    assert calls, "the fused FC was not used"
+    err = (fused.float() - plain.float()).abs().max().item()
+    assert err < 2e-2 * max(1.0, plain.float().abs().max().item()), err
