@@ -228,3 +228,45 @@ def grouped_fc(x, w_op, scale, shift, act="gelu"):
                                         out.data_ptr(), rows, c2, _ACT[act], _stream(x))
     _lib.check(rc, "gkg_grouped_fc_fwd")
     return out
+
+
+class _GroupedFC(torch.autograd.Function):
+    """Training form of the grouped 1x1 FC: ``x (.., 2C) bf16 -> conv1x1_groups4(x) + bias`` (pre-norm).
+    Forward and the data gradient (the same product with the transposed weights) run on the tcgen05
+    kernel; the weight gradient is a (CG x CG) reduction over all rows per group, left to a library
+    batched GEMM."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        c2 = x.shape[-1]
+        ones = torch.ones(c2, device=x.device, dtype=torch.float32)
+        shift = bias.detach().float() if bias is not None else torch.zeros(c2, device=x.device)
+        out = grouped_fc(x, grouped_fc_weights(weight.detach()), ones, shift.contiguous(), None)
+        ctx.save_for_backward(x, weight)
+        ctx.has_bias = bias is not None
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        x, weight = ctx.saved_tensors
+        c2 = x.shape[-1]
+        cg = c2 // 4
+        go = grad_out.contiguous()
+        gx = gw = gb = None
+        if ctx.needs_input_grad[0]:
+            wt = weight.detach().reshape(4, cg, cg).transpose(1, 2).reshape(c2, cg, 1, 1)   # per-group transpose
+            zeros = torch.zeros(c2, device=x.device, dtype=torch.float32)
+            gx = grouped_fc(go.to(torch.bfloat16), grouped_fc_weights(wt), torch.ones_like(zeros), zeros, None)
+        if ctx.needs_input_grad[1]:
+            g3 = go.reshape(-1, 4, cg).transpose(0, 1)                                      # (4, R, CG_out)
+            x3 = x.reshape(-1, 4, cg).transpose(0, 1)                                       # (4, R, CG_in)
+            gw = torch.bmm(g3.transpose(1, 2), x3).float().reshape(c2, cg, 1, 1).to(weight.dtype)
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            gb = go.reshape(-1, c2).float().sum(0)
+        return gx, gw, gb
+
+
+def grouped_fc_train(x, weight, bias):
+    """Differentiable ``conv1x1_groups4(x) + bias`` on token-major bf16 ``x (..., 2C)`` (pre-norm output)."""
+    _require_cuda(x, weight)
+    return _GroupedFC.apply(x, weight, bias)

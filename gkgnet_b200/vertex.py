@@ -52,6 +52,15 @@ class MRConv2d(nn.Module):
         fused = self._fused_fc(agg)
         if fused is not None:
             return tokens_to_nchw(fused, H, W)
+        conv = self.nn[0] if len(self.nn) else None
+        if (torch.is_grad_enabled() and agg.dtype == torch.bfloat16 and isinstance(conv, nn.Conv2d) and conv.groups == 4
+                and conv.kernel_size == (1, 1) and conv.in_channels == conv.out_channels == agg.shape[-1]
+                and ops.grouped_fc_supported(conv.out_channels)):
+            # training: the FC and its data gradient on the tensor-core kernel, norm / act stay modules
+            h = tokens_to_nchw(ops.grouped_fc_train(agg, conv.weight, conv.bias), H, W)
+            for mod in list(self.nn)[1:]:
+                h = mod(h)
+            return h
         return self.nn(tokens_to_nchw(agg, H, W))
 
     def _fused_fc(self, agg):

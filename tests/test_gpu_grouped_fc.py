@@ -81,3 +81,23 @@ def test_mrconv_eval_uses_fused_fc_and_matches_unfused():
     assert calls, "the fused FC was not used"
     err = (fused.float() - plain.float()).abs().max().item()
     assert err < 2e-2 * max(1.0, plain.float().abs().max().item()), err
+
+
+def test_grouped_fc_train_gradients_match_conv():
+    """Training form: output and the three gradients against Conv2d(groups=4) under bf16 autocast."""
+    from gkgnet_b200 import ops
+    torch.manual_seed(5)
+    C2, R = 160, 3000
+    conv = torch.nn.Conv2d(C2, C2, 1, groups=4).cuda()
+    x = torch.randn(R, C2, device="cuda").to(torch.bfloat16).requires_grad_(True)
+    g = torch.randn(R, C2, device="cuda").to(torch.bfloat16)
+    out = ops.grouped_fc_train(x, conv.weight, conv.bias)
+    out.backward(g)
+    gx, gw, gb = x.grad.clone(), conv.weight.grad.clone(), conv.bias.grad.clone()
+    x.grad = None; conv.weight.grad = None; conv.bias.grad = None
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        ref = conv(x.t().reshape(1, C2, R, 1)).reshape(C2, R).t()
+    ref.backward(g)
+    def close(a, b, tol=2e-2):
+        return (a.float() - b.float()).abs().max().item() <= tol * max(1.0, b.float().abs().max().item())
+    assert close(out, ref) and close(gx, x.grad) and close(gw, conv.weight.grad, 3e-2) and close(gb, conv.bias.grad, 3e-2)
