@@ -322,6 +322,26 @@ def run_ours(args):
     ms_per_step = max_over_ranks(total_ms / args.steps, world, dev)
     value = world * B / (ms_per_step * 1e-3)
 
+    # ---- the grouped 1x1 FC that follows the aggregate, timed beside the step: the
+    # step itself keeps the definition of BASELINE configs[1] (kNN + aggregate fwd + bwd)
+    fc_ms = None
+    if dtype == torch.bfloat16:
+        from gkgnet_b200 import ops
+        c2 = 2 * hp.C
+        if ops.grouped_fc_supported(c2):
+            gfc = torch.Generator(device="cpu").manual_seed(1)
+            w_op = ops.grouped_fc_weights((torch.randn(c2, c2 // 4, 1, 1, generator=gfc) * (2.0 / (c2 // 4)) ** 0.5).to(dev))
+            sh = torch.zeros(c2, device=dev)
+            for _ in range(3):
+                ops.grouped_fc(hp.out, w_op, sh, "gelu")
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(hp.stream)
+            for _ in range(reps):
+                ops.grouped_fc(hp.out, w_op, sh, "gelu")
+            e1.record(hp.stream)
+            torch.cuda.synchronize()
+            fc_ms = e0.elapsed_time(e1) / reps
+
     # ---- e2e: host buffers -> device -> hot path -> host, every step ------------------
     # Every step copies its inputs from pinned host memory and its result back; the three legs run on
     # three streams over two sets of device buffers, so step i+1's upload and step i-1's download overlap
@@ -402,6 +422,12 @@ def run_ours(args):
         "roofline_agg_bwd": {"bound": "hbm", "achieved": bwd_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                              "frac": bwd_gbs / peaks["hbm_gbs"], "algorithmic_bytes": bytes_bwd},
     }
+    if fc_ms is not None:
+        bytes_fc = 2 * es * B * 2 * C * N
+        extra["phase_ms"]["fc_fwd (outside the step)"] = fc_ms
+        extra["roofline_fc_fwd"] = {"bound": "hbm", "achieved": bytes_fc / (fc_ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"],
+                                    "unit": "GB/s", "frac": bytes_fc / (fc_ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                                    "algorithmic_bytes": bytes_fc}
     cpu_val, cpu_s = time_cpu_reference(args.cpu_images, 2) if world == 1 and not args.no_cpu else (None, None)
     line = {
         "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,

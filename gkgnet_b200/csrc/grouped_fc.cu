@@ -4,15 +4,15 @@
 // Reference: MRConv2d.nn = BasicConv([2C, 2C]) = Conv2d(2C, 2C, 1, groups=4, bias) -> norm -> act
 // (torch_nn.py:57-81, used at torch_vertex.py:45,61).  In eval mode the batch norm is an affine map per
 // output channel, so the whole stack is
-//     out[r, o] = act( scale[o] * sum_i W[o, i] * in[r, q*CG + i] + shift[o] ),   q = o / CG, CG = 2C / 4
-// with scale = gamma / sqrt(var + eps) and shift = (bias - mean) * scale + beta folded by the caller.
+//     out[r, o] = act( sum_i (scale[o] * W[o, i]) * in[r, q*CG + i] + shift[o] ),   q = o / CG, CG = 2C / 4
+// with scale = gamma / sqrt(var + eps) folded into the weights and shift = (bias - mean) * scale + beta by the caller.
 // One pass over the (rows, 2C) activation instead of the three of conv / norm / act.
 //
 // Kernel: a CTA owns tiles of 128 rows.  All threads copy the tile into shared memory in the UMMA K-major
 // core-matrix order (8 rows x 16 bytes contiguous; one A sub-tile of KP = ceil16(CG) columns per conv
 // group, zero padded), one thread issues tcgen05.mma kind::f16 (bf16 operands, fp32 accumulate; M = 128,
 // N = NP = ceil16(CG), K = 16 per instruction) for the four groups into 4 * NP TMEM columns, the warps read
-// their accumulator rows back with tcgen05.ld (thread == row), apply scale / shift / activation and store
+// their accumulator rows back with tcgen05.ld (thread == row, one conv group per warp), apply scale / shift / activation and store
 // bf16.  The weights sit in shared memory for the CTA's lifetime in the same core-matrix order (built by
 // the caller, see gkgnet_b200/ops.py:grouped_fc_weights).  Memory bound: 2 * rows * 2C * 2 bytes.
 #include "common.cuh"
@@ -21,7 +21,7 @@ namespace gkg {
 namespace fc {
 
 constexpr int BM = 128;
-constexpr int THREADS = 256;
+constexpr int THREADS = 512;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
@@ -51,9 +51,24 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-__device__ __forceinline__ float activate(float v, int act) {
-  if (act == 1) return fmaxf(v, 0.f);
-  if (act == 2) return 0.5f * v * (1.f + erff(v * 0.70710678118654752f));    // nn.GELU() (erf form)
+// erf by Abramowitz & Stegun 7.1.26 (|error| <= 1.5e-7, far below bf16 resolution): one reciprocal, one
+// exponential and a degree-5 polynomial instead of libdevice's erff (half the instructions of an epilogue
+// that evaluates 2C of them per row)
+__device__ __forceinline__ float fast_erf(float x) {
+  const float ax = fabsf(x);
+  float t;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, ax, 1.f)));
+  float p = fmaf(1.061405429f, t, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  const float e = 1.f - p * t * __expf(-ax * ax);
+  return copysignf(e, x);
+}
+template <int ACT>
+__device__ __forceinline__ float activate(float v) {
+  if (ACT == 1) return fmaxf(v, 0.f);
+  if (ACT == 2) return 0.5f * v * (1.f + fast_erf(v * 0.70710678118654752f));    // nn.GELU() (erf form)
   return v;
 }
 
@@ -61,21 +76,22 @@ struct Params {
   const __nv_bfloat16* in;       // (rows, C2) contiguous
   __nv_bfloat16* out;            // (rows, C2) contiguous
   const __nv_bfloat16* w_op;     // 4 groups x [NP/8][KP/8][8][8] core matrices (K-major)
-  const float* scale;            // (C2)
-  const float* shift;            // (C2)
+  const float* shift;            // (C2); the per-channel scale is folded into w_op by the caller
   long long rows;
   int C2, CG, KP, NP, act;
 };
 
+// CGT: channels per conv group at compile time (the two wide layers), 0 = run-time value
+template <int CGT, int ACT>
 __global__ void __launch_bounds__(THREADS, 2) grouped_fc_kernel(const Params prm) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  const int KP = prm.KP, NP = prm.NP, CG = prm.CG, C2 = prm.C2;
+  const int CG = CGT > 0 ? CGT : prm.CG;
+  const int KP = (CG + 15) / 16 * 16, NP = KP, C2 = 4 * CG;
   const uint32_t a_group_bytes = (uint32_t)BM * KP * 2;
   const uint32_t b_group_bytes = (uint32_t)NP * KP * 2;
   uint8_t* sA = smem;                                   // 4 x [BM/8][KP/8][8][8]
   uint8_t* sB = sA + 4 * a_group_bytes;                 // 4 x [NP/8][KP/8][8][8]
-  float* s_scale = reinterpret_cast<float*>(sB + 4 * b_group_bytes);
-  float* s_shift = s_scale + C2;
+  float* s_shift = reinterpret_cast<float*>(sB + 4 * b_group_bytes);   // (the scale is folded into the weights)
   uint64_t* bar = reinterpret_cast<uint64_t*>(s_shift + C2);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -84,7 +100,7 @@ __global__ void __launch_bounds__(THREADS, 2) grouped_fc_kernel(const Params prm
   // ---- one-time setup: weights, affine vectors, barrier, TMEM
   for (uint32_t i = threadIdx.x; i < 4 * b_group_bytes / 16; i += THREADS)
     reinterpret_cast<uint4*>(sB)[i] = __ldg(reinterpret_cast<const uint4*>(prm.w_op) + i);
-  for (int i = threadIdx.x; i < C2; i += THREADS) { s_scale[i] = prm.scale[i]; s_shift[i] = prm.shift[i]; }
+  for (int i = threadIdx.x; i < C2; i += THREADS) s_shift[i] = prm.shift[i];
   // zero the K padding of the A sub-tiles once (columns CG..KP never change)
   for (uint32_t i = threadIdx.x; i < 4 * a_group_bytes / 16; i += THREADS)
     reinterpret_cast<uint4*>(sA)[i] = make_uint4(0, 0, 0, 0);
@@ -140,25 +156,33 @@ __global__ void __launch_bounds__(THREADS, 2) grouped_fc_kernel(const Params prm
     mbar_wait(smem_u32(bar), phase);
     phase ^= 1;
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    // ---- epilogue: warp w reads TMEM lanes 32*(w%4).., conv groups {2*(w/4), 2*(w/4)+1}
+    // ---- epilogue: warp w reads TMEM lanes 32*(w%4).., conv group w/4
     {
       const int row = (warp & 3) * 32 + lane;
       const bool row_ok = r0 + row < prm.rows;
       __nv_bfloat16* orow = prm.out + (r0 + row) * C2;
-      for (int q = (warp >> 2) * 2; q < (warp >> 2) * 2 + 2; ++q) {
+      {
+        const int q = warp >> 2;
         for (int c0 = 0; c0 < CG; c0 += 16) {             // CG is a multiple of 8: the last piece may be half valid
           uint32_t acc[16];
           tmem_ld16(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(q * NP + c0), acc);
-          __align__(16) __nv_bfloat16 o[16];
+          __align__(16) __nv_bfloat162 o[8];
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const int c = q * CG + c0 + j;
-            const float v = c0 + j < CG ? fmaf(__uint_as_float(acc[j]), s_scale[c], s_shift[c]) : 0.f;
-            o[j] = __float2bfloat16_rn(activate(v, prm.act));
+          for (int j4 = 0; j4 < 16; j4 += 4) {             // CG is a multiple of 8: groups of 4 never straddle the end
+            float v[4] = {0.f, 0.f, 0.f, 0.f};
+            if (c0 + j4 < CG) {
+              const float4 sh = *reinterpret_cast<const float4*>(s_shift + q * CG + c0 + j4);
+              v[0] = activate<ACT>(__uint_as_float(acc[j4]) + sh.x);
+              v[1] = activate<ACT>(__uint_as_float(acc[j4 + 1]) + sh.y);
+              v[2] = activate<ACT>(__uint_as_float(acc[j4 + 2]) + sh.z);
+              v[3] = activate<ACT>(__uint_as_float(acc[j4 + 3]) + sh.w);
+            }
+            o[j4 >> 1] = __floats2bfloat162_rn(v[0], v[1]);
+            o[(j4 >> 1) + 1] = __floats2bfloat162_rn(v[2], v[3]);
           }
           if (row_ok) {
             *reinterpret_cast<uint4*>(orow + q * CG + c0) = *reinterpret_cast<const uint4*>(o);
-            if (c0 + 8 < CG) *reinterpret_cast<uint4*>(orow + q * CG + c0 + 8) = *reinterpret_cast<const uint4*>(o + 8);
+            if (c0 + 8 < CG) *reinterpret_cast<uint4*>(orow + q * CG + c0 + 8) = *reinterpret_cast<const uint4*>(o + 4);
           }
         }
       }
@@ -182,27 +206,30 @@ extern "C" int gkg_grouped_fc_supported(int C2) {
   return 4 * NP <= 512 ? 1 : 0;                         // the four accumulators must fit the TMEM columns
 }
 
-extern "C" int gkg_grouped_fc_fwd(const void* in, const void* w_op, const float* scale, const float* shift,
-                                  void* out, long long rows, int C2, int act, gkg_stream_t stream_) {
+extern "C" int gkg_grouped_fc_fwd(const void* in, const void* w_op, const float* shift, void* out, long long rows,
+                                  int C2, int act, gkg_stream_t stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   GKG_CHECK_ARG(rows >= 0 && gkg_grouped_fc_supported(C2), "grouped_fc_fwd: unsupported shape rows=%lld 2C=%d", rows, C2);
   GKG_CHECK_ARG(act >= 0 && act <= 2, "grouped_fc_fwd: bad activation %d", act);
   if (rows == 0) return GKG_OK;
-  GKG_CHECK_ARG(in && w_op && scale && shift && out, "grouped_fc_fwd: null pointer");
+  GKG_CHECK_ARG(in && w_op && shift && out, "grouped_fc_fwd: null pointer");
   GKG_CHECK_ARG(((uintptr_t)in % 16) == 0 && ((uintptr_t)out % 16) == 0 && ((uintptr_t)w_op % 16) == 0,
                 "grouped_fc_fwd: pointers must be 16-byte aligned");
   fc::Params prm{};
   prm.in = static_cast<const __nv_bfloat16*>(in);
   prm.out = static_cast<__nv_bfloat16*>(out);
   prm.w_op = static_cast<const __nv_bfloat16*>(w_op);
-  prm.scale = scale; prm.shift = shift; prm.rows = rows;
+  prm.shift = shift; prm.rows = rows;
   prm.C2 = C2; prm.CG = C2 / 4; prm.KP = (prm.CG + 15) / 16 * 16; prm.NP = prm.KP; prm.act = act;
-  const size_t smem = 4 * (size_t)fc::BM * prm.KP * 2 + 4 * (size_t)prm.NP * prm.KP * 2 + 2 * (size_t)C2 * 4 + 64;
-  static size_t configured = 0;
-  if (smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(fc::grouped_fc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  const size_t smem = 4 * (size_t)fc::BM * prm.KP * 2 + 4 * (size_t)prm.NP * prm.KP * 2 + (size_t)C2 * 4 + 64;
+  void (*kern)(const fc::Params) = nullptr;
+#define GKG_FC_PICK(AA)                                                                                        \
+  kern = prm.CG == 40 ? fc::grouped_fc_kernel<40, AA> : prm.CG == 80 ? fc::grouped_fc_kernel<80, AA> : fc::grouped_fc_kernel<0, AA>
+  if (act == 0) { GKG_FC_PICK(0); } else if (act == 1) { GKG_FC_PICK(1); } else { GKG_FC_PICK(2); }
+#undef GKG_FC_PICK
+  {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { set_error("grouped_fc_fwd: smem attribute %zu: %s", smem, cudaGetErrorString(e)); return GKG_ECUDA; }
-    configured = smem;
   }
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
@@ -210,7 +237,7 @@ extern "C" int gkg_grouped_fc_fwd(const void* in, const void* w_op, const float*
   const long long tiles = (rows + fc::BM - 1) / fc::BM;
   const int ctas_per_sm = (4 * prm.NP <= 256 && smem <= 110 * 1024) ? 2 : 1;
   const int grid = (int)(tiles < (long long)sms * ctas_per_sm ? tiles : (long long)sms * ctas_per_sm);
-  fc::grouped_fc_kernel<<<grid, fc::THREADS, smem, stream>>>(prm);
+  kern<<<grid, fc::THREADS, smem, stream>>>(prm);
   GKG_CHECK_LAUNCH("grouped_fc_kernel");
   return GKG_OK;
 }

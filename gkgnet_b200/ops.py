@@ -197,25 +197,29 @@ def grouped_fc_supported(c2: int) -> bool:
     return bool(_lib.load().gkg_grouped_fc_supported(int(c2)))
 
 
-def grouped_fc_weights(weight):
+def grouped_fc_weights(weight, scale=None):
     """Conv2d(2C, 2C, 1, groups=4) weight ``(2C, 2C/4, 1, 1)`` -> bf16 tensor-core operand order
-    ``[4][NP/8][KP/8][8][8]`` (K-major 8x8 core matrices, NP = KP = ceil16(2C/4), zero padded)."""
+    ``[4][NP/8][KP/8][8][8]`` (K-major 8x8 core matrices, NP = KP = ceil16(2C/4), zero padded).
+    ``scale`` (2C,), e.g. the folded batch-norm gain, multiplies the output channels in fp32 first."""
     c2, cg = weight.shape[0], weight.shape[1]
     if c2 != 4 * cg:
         raise ValueError(f"expected a groups=4 1x1 conv weight, got {tuple(weight.shape)}")
     kp = (cg + 15) // 16 * 16
-    w = weight.reshape(4, cg, cg).to(torch.bfloat16)                   # [q][n (out)][k (in)]
+    w = weight.reshape(c2, cg).float()
+    if scale is not None:
+        w = w * scale.reshape(c2, 1).float()
+    w = w.reshape(4, cg, cg).to(torch.bfloat16)                        # [q][n (out)][k (in)]
     wp = torch.zeros((4, kp, kp), dtype=torch.bfloat16, device=weight.device)
     wp[:, :cg, :cg] = w
     return wp.view(4, kp // 8, 8, kp // 8, 8).permute(0, 1, 3, 2, 4).contiguous()
 
 
-def grouped_fc(x, w_op, scale, shift, act="gelu"):
-    """``act(scale * conv1x1_groups4(x) + shift)`` on token-major bf16 ``x (..., 2C)``: the eval-mode
+def grouped_fc(x, w_op, shift, act="gelu"):
+    """``act(conv1x1_groups4(x; scale * W) + shift)`` on token-major bf16 ``x (..., 2C)``: the eval-mode
     ``BasicConv([2C, 2C])`` of the reference (torch_nn.py:57-81) in one pass.  ``w_op`` from
-    :func:`grouped_fc_weights`; ``scale`` / ``shift`` fp32 ``(2C,)`` with the conv bias and the batch-norm
-    statistics folded in."""
-    _require_cuda(x, w_op, scale, shift)
+    :func:`grouped_fc_weights` (batch-norm gain folded in); ``shift`` fp32 ``(2C,)`` carries the conv
+    bias and the rest of the norm."""
+    _require_cuda(x, w_op, shift)
     if x.dtype != torch.bfloat16:
         raise TypeError("grouped_fc runs on bf16 activations")
     if act not in _ACT:
@@ -224,8 +228,8 @@ def grouped_fc(x, w_op, scale, shift, act="gelu"):
     x = x.contiguous()
     out = torch.empty_like(x)
     rows = x.numel() // c2
-    rc = _lib.load().gkg_grouped_fc_fwd(x.data_ptr(), w_op.data_ptr(), scale.data_ptr(), shift.data_ptr(),
-                                        out.data_ptr(), rows, c2, _ACT[act], _stream(x))
+    rc = _lib.load().gkg_grouped_fc_fwd(x.data_ptr(), w_op.data_ptr(), shift.data_ptr(), out.data_ptr(), rows, c2,
+                                        _ACT[act], _stream(x))
     _lib.check(rc, "gkg_grouped_fc_fwd")
     return out
 
@@ -239,9 +243,8 @@ class _GroupedFC(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, weight, bias):
         c2 = x.shape[-1]
-        ones = torch.ones(c2, device=x.device, dtype=torch.float32)
         shift = bias.detach().float() if bias is not None else torch.zeros(c2, device=x.device)
-        out = grouped_fc(x, grouped_fc_weights(weight.detach()), ones, shift.contiguous(), None)
+        out = grouped_fc(x, grouped_fc_weights(weight.detach()), shift.contiguous(), None)
         ctx.save_for_backward(x, weight)
         ctx.has_bias = bias is not None
         return out
@@ -256,7 +259,7 @@ class _GroupedFC(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             wt = weight.detach().reshape(4, cg, cg).transpose(1, 2).reshape(c2, cg, 1, 1)   # per-group transpose
             zeros = torch.zeros(c2, device=x.device, dtype=torch.float32)
-            gx = grouped_fc(go.to(torch.bfloat16), grouped_fc_weights(wt), torch.ones_like(zeros), zeros, None)
+            gx = grouped_fc(go.to(torch.bfloat16), grouped_fc_weights(wt), zeros, None)
         if ctx.needs_input_grad[1]:
             g3 = go.reshape(-1, 4, cg).transpose(0, 1)                                      # (4, R, CG_out)
             x3 = x.reshape(-1, 4, cg).transpose(0, 1)                                       # (4, R, CG_in)

@@ -98,9 +98,9 @@ class MRConv2d(nn.Module):
                     b = bn.bias.detach().float() if bn.bias is not None else torch.zeros_like(scale)
                     scale = g / torch.sqrt(bn.running_var.float() + bn.eps)
                     shift = (shift - bn.running_mean.float()) * scale + b
-                cache = (key, ops.grouped_fc_weights(conv.weight.detach()), scale.contiguous(), shift.contiguous())
+                cache = (key, ops.grouped_fc_weights(conv.weight.detach(), scale), shift.contiguous())
             self._fc_cache = cache
-        return ops.grouped_fc(agg, cache[1], cache[2], cache[3], act)
+        return ops.grouped_fc(agg, cache[1], cache[2], act)
 
     def forward(self, x, edge_index, y=None):
         P, D, N, _ = x.shape

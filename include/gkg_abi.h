@@ -135,18 +135,19 @@ int gkg_mr_aggregate_bwd(const void* grad_out, const int32_t* idx, const uint8_t
  * Grouped 1x1 FC of the max-relative convolution with norm and activation folded in (inference form).
  * Replaces MRConv2d.nn = BasicConv([2C, 2C]) = Conv2d(2C, 2C, 1, groups=4, bias) -> norm -> act
  * (torch_nn.py:57-81; torch_vertex.py:45,61) in eval mode, where the batch norm is an affine map:
- *     out[r, o] = act(scale[o] * sum_i W[o, i] * in[r, (o / CG) * CG + i] + shift[o]),   CG = C2 / 4
+ *     out[r, o] = act(sum_i (scale[o] * W[o, i]) * in[r, (o / CG) * CG + i] + shift[o]),   CG = C2 / 4
+ * with scale[o] = gamma / sqrt(running_var + eps) (1 when there is no norm).
  *   in, out   bf16 (rows, C2) contiguous (token-major: rows = B * N, C2 = 2C interleaved channels)
- *   w_op      bf16 weights in tensor-core operand order: 4 groups x [NP/8][KP/8][8][8] with
- *             element [q][n/8][k/8][n%8][k%8] = W[q*CG + n][k] (zero for n, k >= CG), NP = KP = ceil16(CG)
- *   scale     fp32 (C2): gamma / sqrt(running_var + eps)      (1 when there is no norm)
+ *   w_op      bf16 SCALED weights in tensor-core operand order: 4 groups x [NP/8][KP/8][8][8] with
+ *             element [q][n/8][k/8][n%8][k%8] = scale[q*CG + n] * W[q*CG + n][k] (zero for n, k >= CG),
+ *             NP = KP = ceil16(CG)
  *   shift     fp32 (C2): (conv_bias - running_mean) * scale + beta
  *   act       0 none, 1 relu, 2 gelu (erf form, nn.GELU())
  * gkg_grouped_fc_supported(C2) != 0 when the four accumulators fit the tensor memory (CG <= 128).
  */
 int gkg_grouped_fc_supported(int C2);
-int gkg_grouped_fc_fwd(const void* in, const void* w_op, const float* scale, const float* shift,
-                       void* out, long long rows, int C2, int act, gkg_stream_t stream);
+int gkg_grouped_fc_fwd(const void* in, const void* w_op, const float* shift, void* out, long long rows,
+                       int C2, int act, gkg_stream_t stream);
 
 /* Number of kernels this library has launched since load (for bench accounting). */
 uint64_t gkg_launch_count(void);
