@@ -42,11 +42,15 @@ namespace {
 // so that a warp writes 4 contiguous 128-byte core matrices.
 constexpr int PREP_ROWS = 32;
 
-template <typename T, bool IS_KEY>
+// DT: group width at compile time (the wide stages: 200, 320 -- every index split below becomes a constant
+// division), 0 = run-time value.
+template <typename T, bool IS_KEY, int DT>
 __global__ void __launch_bounds__(256)
 tc_prepare_kernel(const T* __restrict__ feat, int64_t stride_b, int64_t stride_n, float* __restrict__ hat,
-                  float* __restrict__ sq, __half* __restrict__ op, int G, int rows, int D, int KP, int KC,
+                  float* __restrict__ sq, __half* __restrict__ op, int G, int rows, int D_rt, int KP_rt, int KC,
                   int tiles, int tile_rows, int tile_keys, int write_hat) {
+  const int D = DT > 0 ? DT : D_rt;
+  const int KP = DT > 0 ? k_padded(DT > 0 ? DT : 1) : KP_rt;
   extern __shared__ float prep_s[];              // [PREP_ROWS][D] normalised rows + [PREP_ROWS] norms
   float* xs = prep_s;
   float* sqs = prep_s + PREP_ROWS * D;
@@ -587,16 +591,17 @@ static int launch_prepare_typed(const KnnWorkspace& w, const TcWorkspace& t, con
   const int bn = pl.geom == 1 ? GeomB::BN : GeomA::BN, bnp = pl.geom == 1 ? GeomB::BNP : GeomA::BNP;
   {
     dim3 grid((pl.QTP * BM + PREP_ROWS - 1) / PREP_ROWS, P);
-    tc_prepare_kernel<T, false><<<grid, 256, smem, stream>>>(static_cast<const T*>(x), x_sb, x_sn, w.xhat, w.xsq,
-                                                            t.a_op, G, N, D, pl.KP, pl.KC, pl.QTP, BM, BM, 1);
+    auto kq = D == 200 ? tc_prepare_kernel<T, false, 200> : D == 320 ? tc_prepare_kernel<T, false, 320> : tc_prepare_kernel<T, false, 0>;
+    kq<<<grid, 256, smem, stream>>>(static_cast<const T*>(x), x_sb, x_sn, w.xhat, w.xsq, t.a_op, G, N, D, pl.KP, pl.KC,
+                                    pl.QTP, BM, BM, 1);
     GKG_CHECK_LAUNCH("tc_prepare_kernel<query>");
   }
   {
     dim3 grid((pl.KT * bnp + PREP_ROWS - 1) / PREP_ROWS, P);
     const T* src = static_cast<const T*>(self_keys ? x : y);
-    tc_prepare_kernel<T, true><<<grid, 256, smem, stream>>>(src, self_keys ? x_sb : y_sb, self_keys ? x_sn : y_sn,
-                                                           w.yhat, w.ysq, t.b_op, G, M, D, pl.KP, pl.KC, pl.KT,
-                                                           bnp, bn, self_keys ? 0 : 1);
+    auto kk = D == 200 ? tc_prepare_kernel<T, true, 200> : D == 320 ? tc_prepare_kernel<T, true, 320> : tc_prepare_kernel<T, true, 0>;
+    kk<<<grid, 256, smem, stream>>>(src, self_keys ? x_sb : y_sb, self_keys ? x_sn : y_sn, w.yhat, w.ysq, t.b_op, G, M, D,
+                                    pl.KP, pl.KC, pl.KT, bnp, bn, self_keys ? 0 : 1);
     GKG_CHECK_LAUNCH("tc_prepare_kernel<key>");
   }
   return GKG_OK;

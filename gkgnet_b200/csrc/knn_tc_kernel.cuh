@@ -425,7 +425,17 @@ struct TcParams {
 __device__ __forceinline__ float exact_dist(const float* __restrict__ xr, const float* __restrict__ yr, int D,
                                             float xs, float ys, const float* relrow, int m) {
   float acc = 0.f;
-  for (int d = 0; d < D; ++d) acc = fmaf(xr[d], yr[d], acc);
+  if ((D & 3) == 0) {      // same fma chain, 128-bit loads (rows start on 16-byte boundaries when D % 4 == 0)
+    const float4* x4 = reinterpret_cast<const float4*>(xr);
+    const float4* y4 = reinterpret_cast<const float4*>(yr);
+#pragma unroll 4
+    for (int d = 0; d < (D >> 2); ++d) {
+      const float4 a = __ldg(x4 + d), b = __ldg(y4 + d);
+      acc = fmaf(a.x, b.x, acc); acc = fmaf(a.y, b.y, acc); acc = fmaf(a.z, b.z, acc); acc = fmaf(a.w, b.w, acc);
+    }
+  } else {
+    for (int d = 0; d < D; ++d) acc = fmaf(xr[d], yr[d], acc);
+  }
   float v = (xs + (-2.f * acc)) + ys;
   if (relrow != nullptr) v += relrow[m];
   return v;
