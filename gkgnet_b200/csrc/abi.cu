@@ -48,7 +48,7 @@ static int check_knn_common(int B, int G, int N, int M, int D, int k, int dilati
                             int& algo, void* workspace, size_t workspace_bytes) {
   GKG_CHECK_ARG(B >= 0 && G > 0 && N >= 0 && D > 0 && k > 0 && dilation > 0,
                 "knn_graph: bad shape B=%d G=%d N=%d D=%d k=%d dilation=%d", B, G, N, D, k, dilation);
-  GKG_CHECK_ARG(D <= 320, "knn_graph: D=%d > 320 channels per group is not supported", D);
+  GKG_CHECK_ARG(D <= 640, "knn_graph: D=%d > 640 channels per group is not supported", D);
   if ((long long)B * N == 0) return GKG_OK;
   // torch.topk raises when k*dilation exceeds the row length (reference: size < 192 fails)
   GKG_CHECK_ARG(k * dilation <= M, "knn_graph: k*dilation=%d exceeds the %d keys", k * dilation, M);

@@ -2,16 +2,17 @@
 // shared memory.  Implements, in the reference's association order,
 //   dist = (|xh|^2 + (-2 * xh.yh)) + |yh|^2  [+ relative_pos]     torch_edge.py:48-51,102-103
 //   topk(-dist, k*d) sorted ascending, keep ranks 0, d, 2d, ...   torch_edge.py:104,148
-// This is the always-available path (any D <= 320, any k*d <= 64) and the exactness
+// This is the always-available path (any D <= 640, any k*d <= 64) and the exactness
 // yard-stick for the tcgen05 kernel; it never materialises the N x M matrix either.
 #include "common.cuh"
 
 namespace gkg {
 
-constexpr int kExactRows = 128;   // query rows per CTA (one per thread)
+constexpr int kExactRowsWide = 128;   // query rows per CTA (one per thread); 32 for D > 320 (shared memory)
 constexpr int kExactKeys = 32;    // keys per shared-memory tile
 constexpr int kExactMaxKD = 64;   // max k*dilation
 
+template <int kExactRows>
 __global__ void __launch_bounds__(kExactRows)
 knn_exact_kernel(const float* __restrict__ xhat, const float* __restrict__ xsq,
                  const float* __restrict__ yhat, const float* __restrict__ ysq,
@@ -119,22 +120,20 @@ int launch_knn_exact(const KnnWorkspace& w, const float* relpos, int32_t* idx_ou
                 kExactMaxKD);
   GKG_CHECK_ARG(P <= 65535, "knn_exact: B*G=%d > 65535", P);
   const int D4 = (D + 3) / 4;
-  const size_t smem = sizeof(float4) * ((size_t)D4 * kExactRows + (size_t)kExactKeys * D4) +
+  const int rows_per_cta = D <= 320 ? kExactRowsWide : 32;
+  const size_t smem = sizeof(float4) * ((size_t)D4 * rows_per_cta + (size_t)kExactKeys * D4) +
                       sizeof(float) * kExactKeys;
   GKG_CHECK_ARG(smem <= 227 * 1024, "knn_exact: D=%d needs %zu B of shared memory", D, smem);
-  static size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(knn_exact_kernel,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  auto kern = D <= 320 ? knn_exact_kernel<kExactRowsWide> : knn_exact_kernel<32>;
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) {
       set_error("knn_exact: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
       return GKG_ECUDA;
     }
-    configured = smem;
   }
-  dim3 grid((N + kExactRows - 1) / kExactRows, P);
-  knn_exact_kernel<<<grid, kExactRows, smem, stream>>>(w.xhat, w.xsq, w.yhat, w.ysq, relpos,
-                                                       idx_out, N, M, D, k, dilation);
+  dim3 grid((N + rows_per_cta - 1) / rows_per_cta, P);
+  kern<<<grid, rows_per_cta, smem, stream>>>(w.xhat, w.xsq, w.yhat, w.ysq, relpos, idx_out, N, M, D, k, dilation);
   GKG_CHECK_LAUNCH("knn_exact");
   return GKG_OK;
 }

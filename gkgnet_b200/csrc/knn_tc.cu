@@ -591,6 +591,10 @@ static int launch_prepare_typed(const KnnWorkspace& w, const TcWorkspace& t, con
   const int bn = pl.geom == 1 ? GeomB::BN : GeomA::BN, bnp = pl.geom == 1 ? GeomB::BNP : GeomA::BNP;
   {
     dim3 grid((pl.QTP * BM + PREP_ROWS - 1) / PREP_ROWS, P);
+    if (smem > 48 * 1024) {   // wide groups (D > 380): opt in to the larger dynamic shared memory
+      cudaFuncSetAttribute(tc_prepare_kernel<T, false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      cudaFuncSetAttribute(tc_prepare_kernel<T, true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    }
     auto kq = D == 200 ? tc_prepare_kernel<T, false, 200> : D == 320 ? tc_prepare_kernel<T, false, 320> : tc_prepare_kernel<T, false, 0>;
     kq<<<grid, 256, smem, stream>>>(static_cast<const T*>(x), x_sb, x_sn, w.xhat, w.xsq, t.a_op, G, N, D, pl.KP, pl.KC,
                                     pl.QTP, BM, BM, 1);

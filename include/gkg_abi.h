@@ -72,6 +72,7 @@ size_t gkg_knn_workspace_bytes(int B, int G, int N, int M, int D, int k, int dil
  *   y        keys, (B, M, G*D) via strides, or NULL -> keys are the queries (M == N)
  *   relpos   fp32 (N, M) row-major bias shared by all problems, or NULL
  *   idx_out  int32 (B*G, N, k): neighbour ids (edge_index[0]; edge_index[1][p,n,:] == n)
+ *   limits   D <= 640 channels per group, k*dilation <= 36 (tensor-core path) / 64 (exact path)
  *
  * Ties: the smaller key id wins (torch.topk leaves tie order unspecified).
  *

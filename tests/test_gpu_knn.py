@@ -95,6 +95,8 @@ def test_knn_xy_random(algo, B, G, N, M, D, k, d, bias):
     (2, 2, 324, 320, 9, 3),     # stage 4
     (1, 2, 1296, 200, 9, 3),    # stage 3, k*d = 27
     (2, 2, 100, 80, 9, 2),
+    (1, 1, 324, 640, 9, 3),     # stage 4 with num_group = 1 (BASELINE configs[4] sweep)
+    (1, 1, 784, 400, 9, 2),     # stage 3 at 448 px with num_group = 1
 ])
 def test_knn_self_random(algo, B, G, N, D, k, d):
     rep = _run_case(B, G, N, None, D, k, d, True, _algo(algo), self_keys=True)
