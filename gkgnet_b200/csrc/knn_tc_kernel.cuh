@@ -763,6 +763,8 @@ __global__ void __launch_bounds__(G::NTHREADS, 1) knn_tc_kernel(const TcParams p
         });
         // fewer than TA real groups (tiny M): the floor stays -> everything is logged -> fix-up
         thr_base = la.v[TA - 1] - kSweepSlack;
+        // rows past N are all-zero operand rows: every key ties, and logging them would flood the log
+        if (!row_ok) thr_base = INFINITY;
       }
 
       // ---- sweep B: log the triplets that beat the threshold (fp16x3 scores) --------------------

@@ -11,14 +11,20 @@ from gkgnet_b200 import _lib, ops
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 32
 lib = _lib.load()
-x, y, rel = bench.make_inputs(B, "cpu", torch.bfloat16, 0)
-x, y, rel = x.cuda(), y.cuda(), rel.cuda()
-sep = ops.fit_separable_bias(rel)
+if os.environ.get("GKG_LABEL"):          # label-head shape: 80 queries against all stage-1 patches, no bias
+    torch.manual_seed(0)
+    x = torch.randn(B, 80, 80).to(torch.bfloat16).cuda()
+    y = torch.randn(B, 20736, 80).to(torch.bfloat16).cuda()
+    rel, sep = None, None
+else:
+    x, y, rel = bench.make_inputs(B, "cpu", torch.bfloat16, 0)
+    x, y, rel = x.cuda(), y.cuda(), rel.cuda()
+    sep = ops.fit_separable_bias(rel)
 for _ in range(2):
     ops.knn_graph(x, y, rel, groups=2, k=9, dilation=1, algo=_lib.KNN_TCGEN05, separable=sep)
 torch.cuda.synchronize()
 KT = int(sys.argv[2]) if len(sys.argv) > 2 else 18
-tiles = 36 * KT
+tiles = (1 if os.environ.get('GKG_LABEL') else 36) * KT
 buf = torch.zeros(tiles * 8, dtype=torch.int64, device="cuda")
 lib.gkg_debug_knn_tc_trace.argtypes = [ctypes.c_void_p, ctypes.c_int]
 lib.gkg_debug_knn_tc_trace(buf.data_ptr(), tiles)
@@ -47,5 +53,5 @@ for kt in range(KT):
     print(kt, "epi wait", int(st.mean(epi_wait[i] for i in sel)), "tile time", int(st.mean(rows[i][5] - rows[i - 1][5] for i in sel)),
           "full->epi lag", int(st.mean(rows[i][4] - rows[i][2] for i in sel)), "mma wait", int(st.mean(mma_wait[i] for i in sel)),
           "mma work", int(st.mean(mma_work[i] for i in sel)), "of which b_full wait", int(st.mean(rows[i][7] for i in sel)), "issue", int(st.mean(rows[i][6] for i in sel)), "release->mma lag", int(st.mean(rows[i][1] - rows[i - 3][5] for i in sel)))
-for r in rows[2 * KT:4 * KT]:
+for r in rows[2 * KT:4 * KT][:8]:
     print(r)
