@@ -128,23 +128,42 @@ tc_prepare_kernel(const T* __restrict__ feat, int64_t stride_b, int64_t stride_n
     }
     __align__(16) __half out[8];
     const int c0 = kcI * 8;
-#pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      const int c = c0 + e;
-      // columns: [hi (D) | e_hi e_lo | 0.. -> PA | second (D) | third (D) | 0..];  A = [hi | hi | lo], B = [hi | lo | hi]
-      float v = 0.f;
-      const int seg = c < D ? 0 : (c >= PA && c < PA + D) ? 1 : (c >= PA + D && c < PA + 2 * D) ? 2 : -1;
+    // columns: [hi (D) | e_hi e_lo | 0.. -> PA | second (D) | third (D) | 0..];  A = [hi | hi | lo], B = [hi | lo | hi]
+    if ((D & 7) == 0) {
+      // 8-column pieces never straddle a segment: one decision per piece, no per-element compares
+      const int seg = c0 < D ? 0 : (c0 >= PA && c0 < PA + D) ? 1 : (c0 >= PA + D && c0 < PA + 2 * D) ? 2 : -1;
       if (seg >= 0) {
-        const float x = src[seg == 0 ? c : c - PA - (seg - 1) * D] * kScale;
-        const float hi = __half2float(__float2half_rn(x));
+        const float* s8 = src + (seg == 0 ? c0 : c0 - PA - (seg - 1) * D);
         const bool want_lo = IS_KEY ? (seg == 1) : (seg == 2);
-        v = want_lo ? (x - hi) : hi;
-      } else if (c == D) {
-        v = extra_hi;
-      } else if (c == D + 1) {
-        v = extra_lo;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const float x = s8[e] * kScale;
+          const __half h = __float2half_rn(x);
+          out[e] = want_lo ? __float2half_rn(x - __half2float(h)) : h;
+        }
+      } else {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) out[e] = __float2half_rn(0.f);
+        if (c0 == D) { out[0] = __float2half_rn(extra_hi); out[1] = __float2half_rn(extra_lo); }
       }
-      out[e] = __float2half_rn(v);
+    } else {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const int c = c0 + e;
+        float v = 0.f;
+        const int seg = c < D ? 0 : (c >= PA && c < PA + D) ? 1 : (c >= PA + D && c < PA + 2 * D) ? 2 : -1;
+        if (seg >= 0) {
+          const float x = src[seg == 0 ? c : c - PA - (seg - 1) * D] * kScale;
+          const float hi = __half2float(__float2half_rn(x));
+          const bool want_lo = IS_KEY ? (seg == 1) : (seg == 2);
+          v = want_lo ? (x - hi) : hi;
+        } else if (c == D) {
+          v = extra_hi;
+        } else if (c == D + 1) {
+          v = extra_lo;
+        }
+        out[e] = __float2half_rn(v);
+      }
     }
     const long long chunk = ((((p * tiles + tile) * nkb + kb) * rgs + rg) * (long long)kcs + kc) * 8 + r;
     *reinterpret_cast<uint4*>(op + chunk * 8) = *reinterpret_cast<const uint4*>(out);
@@ -653,7 +672,7 @@ int launch_knn_tc(const KnnWorkspace& w, void* extra_ws, const float* relpos, co
   prm.a_tile_bytes = pl.a_tile_bytes; prm.b_block_bytes = pl.b_block_bytes;
   prm.force_rerank = g_force_rerank;
   prm.delta = tc_delta(pl.KP);
-  const int ga = (M / 18 >= 4 * (T - 1)) ? 18 : (M / 6 >= 4 * (T - 1)) ? 6 : 3;
+  const int ga = (M / 18 >= 3 * (T - 1)) ? 18 : (M / 6 >= 3 * (T - 1)) ? 6 : 3;
   prm.sep_a = sep.a; prm.sep_b = sep.b; prm.grid_w = sep.grid_w > 0 ? sep.grid_w : 1;
   prm.sep_mh = sep.kw > 0 ? M / sep.kw : 1;
   const int bn = pl.geom == 1 ? GeomB::BN : GeomA::BN;
