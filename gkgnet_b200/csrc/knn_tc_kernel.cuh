@@ -824,24 +824,35 @@ __global__ void __launch_bounds__(G::NTHREADS, 1) knn_tc_kernel(const TcParams p
         const size_t rbase = (size_t)item * G::ROWS + (size_t)(rset * BM + row_t);
         float2* cdst = prm.cand + (size_t)item * prm.cand_slots * G::ROWS + (size_t)(rset * BM + row_t);
         const int mx_cnt = __reduce_max_sync(0xffffffffu, cnt);
-        // T-th largest KEY among the logged triplets; keys that were never logged are all <= thr_base
-        const float tau = fmaxf(log_tth_key<LOG_STRIDE, T, BIAS>(log_base, cnt, mx_cnt, brow), thr_base);
-        int np = 0;
-        for (int e = 0; e < mx_cnt; ++e) {
-          if (e < cnt) {
-            const float4 c = ld_shared_v4(log_base + (uint32_t)e * LOG_STRIDE);
-            const int id = (int)(__float_as_uint(c.w) & 0xffffu);
-            const float sc[3] = {c.x, c.y, c.z};
+        // keys of the logged triplets that reach `tau` -> candidate slots; ADD_BG: the log still holds raw scores
+        auto dump = [&](float tau, bool add_bg) {
+          int np = 0;
+          for (int e = 0; e < mx_cnt; ++e) {
+            if (e < cnt) {
+              const float4 c = ld_shared_v4(log_base + (uint32_t)e * LOG_STRIDE);
+              const int id = (int)(__float_as_uint(c.w) & 0xffffu);
+              const float bg = (BIAS > 1 && add_bg) ? brow[__float_as_uint(c.w) >> 16] : 0.f;
+              const float sc[3] = {c.x + bg, c.y + bg, c.z + bg};
 #pragma unroll
-            for (int i = 0; i < 3; ++i) {
-              if (sc[i] >= tau && id + i < prm.M) {
-                if (np < prm.cand_slots) cdst[(size_t)np * G::ROWS] = make_float2(sc[i], __int_as_float(id + i));
-                ++np;
+              for (int i = 0; i < 3; ++i) {
+                if (sc[i] >= tau && id + i < prm.M) {
+                  if (np < prm.cand_slots) cdst[(size_t)np * G::ROWS] = make_float2(sc[i], __int_as_float(id + i));
+                  ++np;
+                }
               }
             }
           }
+          return np;
+        };
+        // Usually every key above the sweep threshold fits the candidate slots (~T + 1 keys on random
+        // features).  Only when some row of the warp has more -- neighbouring keys are often similar -- is the
+        // threshold tightened to the T-th largest KEY of the log (which also converts the log to true scores).
+        int np = dump(thr_base, true);
+        if (__any_sync(0xffffffffu, np > prm.cand_slots)) {
+          thr_base = fmaxf(log_tth_key<LOG_STRIDE, T, BIAS>(log_base, cnt, mx_cnt, brow), thr_base);
+          np = dump(thr_base, false);
         }
-        thr_base = tau;                            // every key that is not handed over scores <= tau
+        // every key that is not handed over scores <= thr_base
         // count < 0: the candidate set is not trustworthy (log or slot overflow) -> brute-force fix-up
         prm.cand_count[rbase] = (overflow || np > prm.cand_slots) ? -1 : np;
         prm.cand_thr[rbase] = thr_base;
