@@ -12,7 +12,7 @@ from __future__ import annotations
 import torch
 from torch import nn
 
-from .layers import DropPath, act_layer, build_norm_layer, norm_cfg
+from .layers import DropPath, FoldedSequential, act_layer, build_norm_layer, norm_cfg
 from .registry import BACKBONES, register_into_mmcls
 from .vertex import Grapher, GrapherLabel
 
@@ -29,9 +29,9 @@ class FFN(nn.Module):
         super().__init__()
         out_features = out_features or in_features
         hidden_features = hidden_features or in_features
-        self.fc1 = nn.Sequential(*_conv_bn(in_features, hidden_features))
+        self.fc1 = FoldedSequential(*_conv_bn(in_features, hidden_features))
         self.act = act_layer(act)
-        self.fc2 = nn.Sequential(*_conv_bn(hidden_features, out_features))
+        self.fc2 = FoldedSequential(*_conv_bn(hidden_features, out_features))
         self.drop_path = DropPath(drop_path) if drop_path > 0.0 else nn.Identity()
 
     def forward(self, x):
@@ -43,7 +43,7 @@ class Stem(nn.Module):
 
     def __init__(self, img_size=224, in_dim=3, out_dim=768, act="relu"):
         super().__init__()
-        self.convs = nn.Sequential(
+        self.convs = FoldedSequential(
             *_conv_bn(in_dim, out_dim // 2, 3, 2, 1), act_layer(act),
             *_conv_bn(out_dim // 2, out_dim, 3, 2, 1), act_layer(act),
             *_conv_bn(out_dim, out_dim, 3, 1, 1))
@@ -57,7 +57,7 @@ class Downsample(nn.Module):
 
     def __init__(self, in_dim=3, out_dim=768):
         super().__init__()
-        self.conv = nn.Sequential(*_conv_bn(in_dim, out_dim, 3, 2, 1))
+        self.conv = FoldedSequential(*_conv_bn(in_dim, out_dim, 3, 2, 1))
 
     def forward(self, x):
         return self.conv(x)

@@ -57,6 +57,46 @@ def norm_layer(norm, nc):
     raise NotImplementedError("normalization layer [%s] is not found" % norm)
 
 
+class FoldedSequential(nn.Sequential):
+    """``nn.Sequential`` (same sub-module names, hence the same state-dict keys as the reference's conv -> norm
+    stacks: torch_vertex.py:290-306, gkgnet.py:52-65,82-95,108-112) that, in eval mode without autograd, folds
+    every ``Conv2d -> BatchNorm`` pair into one convolution:  w' = w * g / sqrt(var + eps),
+    b' = (b - mean) * g / sqrt(var + eps) + beta.  Training and gradient passes run the modules as written."""
+
+    def forward(self, x):
+        if self.training or torch.is_grad_enabled():
+            return super().forward(x)
+        mods = list(self)
+        i = 0
+        while i < len(mods):
+            m = mods[i]
+            nxt = mods[i + 1] if i + 1 < len(mods) else None
+            if (isinstance(m, nn.Conv2d) and isinstance(nxt, (nn.BatchNorm2d, nn.SyncBatchNorm))
+                    and nxt.track_running_stats and nxt.running_mean is not None and not nxt.training):
+                w, b = self._folded(i, m, nxt, x.dtype if not torch.is_autocast_enabled() else torch.get_autocast_dtype("cuda"))
+                x = torch.nn.functional.conv2d(x.to(w.dtype), w, b, m.stride, m.padding, m.dilation, m.groups)
+                i += 2
+            else:
+                x = m(x)
+                i += 1
+        return x
+
+    def _folded(self, i, conv, bn, dtype):
+        tensors = [conv.weight, conv.bias, bn.weight, bn.bias, bn.running_mean, bn.running_var]
+        key = (dtype,) + tuple((t.data_ptr(), t._version) for t in tensors if t is not None)
+        cache = self.__dict__.setdefault("_fold_cache", {})
+        hit = cache.get(i)
+        if hit is None or hit[0] != key:
+            with torch.no_grad():
+                scale = (bn.weight.float() if bn.weight is not None else 1.0) / torch.sqrt(bn.running_var.float() + bn.eps)
+                w = (conv.weight.float() * scale.view(-1, 1, 1, 1)).to(dtype)
+                b0 = conv.bias.float() if conv.bias is not None else torch.zeros_like(bn.running_mean, dtype=torch.float32)
+                b = (b0 - bn.running_mean.float()) * scale + (bn.bias.float() if bn.bias is not None else 0.0)
+                hit = (key, w.contiguous(), b.to(dtype).contiguous())
+            cache[i] = hit
+        return hit[1], hit[2]
+
+
 class BasicConv(nn.Sequential):
     """Stack of grouped(4) 1x1 convs, each followed by norm / act / dropout
     (torch_nn.py:57-81).  Sub-module order -- and therefore the state-dict keys

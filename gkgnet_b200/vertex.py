@@ -15,7 +15,7 @@ from torch import nn
 
 from . import ops
 from .graph import DenseDilatedKnnGraph, edge_index_from_neighbors
-from .layers import BasicConv, DropPath, act_layer, build_norm_layer, norm_cfg
+from .layers import BasicConv, DropPath, FoldedSequential, act_layer, build_norm_layer, norm_cfg
 from .pos_embed import relative_pos_table
 
 
@@ -223,8 +223,8 @@ class DyGraphLabel(DyGraphLabelMultiGroup):
 
 
 def _conv_bn(cin, cout):
-    return nn.Sequential(nn.Conv2d(cin, cout, 1, stride=1, padding=0),
-                         build_norm_layer(norm_cfg, cout, postfix=1)[1])
+    return FoldedSequential(nn.Conv2d(cin, cout, 1, stride=1, padding=0),
+                            build_norm_layer(norm_cfg, cout, postfix=1)[1])
 
 
 class Grapher(nn.Module):

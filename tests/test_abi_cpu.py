@@ -83,3 +83,27 @@ def test_grapher_dilation_schedule_and_registry():
     ref = O.head_losses(head.state_dict(), lab, gap, tgt)
     for k in ("bce_loss", "asy_loss"):
         assert torch.allclose(got[k], ref[k], atol=1e-5, rtol=1e-5)
+
+
+def test_folded_sequential_matches_plain_modules_in_eval():
+    """Eval-mode Conv2d -> BatchNorm folding (layers.FoldedSequential) is the same function as running the two
+    modules, keeps the reference's state-dict keys and stays out of the way in training / under autograd."""
+    from torch import nn
+    from gkgnet_b200.layers import FoldedSequential
+    torch.manual_seed(0)
+    seq = FoldedSequential(nn.Conv2d(6, 10, 3, stride=2, padding=1), nn.BatchNorm2d(10), nn.GELU(),
+                           nn.Conv2d(10, 4, 1), nn.BatchNorm2d(4))
+    with torch.no_grad():
+        for m in seq:
+            if isinstance(m, nn.BatchNorm2d):
+                m.running_mean.normal_(0, 0.5); m.running_var.uniform_(0.5, 2.0)
+                m.weight.uniform_(0.5, 1.5); m.bias.normal_(0, 0.3)
+    assert list(seq.state_dict().keys())[:2] == ["0.weight", "0.bias"]
+    x = torch.randn(2, 6, 9, 9)
+    seq.eval()
+    with torch.no_grad():
+        folded = seq(x)
+    plain = nn.Sequential.forward(seq, x)           # grad enabled -> the modules as written
+    assert torch.allclose(folded, plain, atol=1e-5, rtol=1e-5)
+    seq.train()
+    assert seq(x).requires_grad
