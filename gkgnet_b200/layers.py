@@ -74,7 +74,13 @@ class FoldedSequential(nn.Sequential):
             if (isinstance(m, nn.Conv2d) and isinstance(nxt, (nn.BatchNorm2d, nn.SyncBatchNorm))
                     and nxt.track_running_stats and nxt.running_mean is not None and not nxt.training):
                 w, b = self._folded(i, m, nxt, x.dtype if not torch.is_autocast_enabled() else torch.get_autocast_dtype("cuda"))
-                x = torch.nn.functional.conv2d(x.to(w.dtype), w, b, m.stride, m.padding, m.dilation, m.groups)
+                x = x.to(w.dtype)
+                if (m.kernel_size == (1, 1) and m.stride == (1, 1) and m.padding == (0, 0) and m.groups == 1
+                        and x.is_contiguous(memory_format=torch.channels_last)):
+                    # token-major 1x1 conv == one GEMM with the bias in its epilogue (conv2d adds it in a second pass)
+                    x = torch.nn.functional.linear(x.permute(0, 2, 3, 1), w.view(w.shape[0], -1), b).permute(0, 3, 1, 2)
+                else:
+                    x = torch.nn.functional.conv2d(x, w, b, m.stride, m.padding, m.dilation, m.groups)
                 i += 2
             else:
                 x = m(x)
