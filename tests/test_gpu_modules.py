@@ -131,3 +131,25 @@ def test_gkgnet_576_bf16_smoke():
     assert torch.isfinite(loss)
     missing = [n for n, p in net.named_parameters() if p.requires_grad and p.grad is None]
     assert not missing, missing[:5]
+
+
+@pytest.mark.parametrize("name", ["grapher_r2"])   # (the r = 1 fixture has 8-dim groups: bf16 ties flip too many neighbours)
+def test_grapher_eval_bf16_fast_paths_agree_with_module_stack(name):
+    """Inference fast paths (Conv -> BN folding, 1x1 convs as GEMMs, tcgen05 grouped FC with folded norm +
+    GELU) under no_grad + bf16 autocast against the same module run as written (autograd on) and against the
+    reference's fp32 output.  bf16 bar: 2e-2 of the output scale; near-tied neighbours may flip when the
+    kNN inputs differ in the last bf16 bit, so a small fraction of positions is allowed to differ more."""
+    import gkgnet_b200 as G
+    g = load_golden(name)
+    m = G.Grapher(16, g["k"], g["dilation"], "mr", "gelu", "batch", True, False, 0.2, g["r"], 64, 0.0, True, True, 2)
+    m.load_state_dict(g["sd"], strict=True)
+    m = m.cuda().eval()
+    x = g["x"].cuda().contiguous(memory_format=torch.channels_last)
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        with torch.no_grad():
+            fast = m(x).float()
+        plain = m(x).float().detach()
+    scale = g["out"].abs().max().item()
+    for want in (plain.cpu(), g["out"]):
+        bad = ((fast.cpu() - want).abs() > 2e-2 * scale).float().mean().item()
+        assert bad < 0.02, bad
