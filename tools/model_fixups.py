@@ -1,6 +1,7 @@
 #!/usr/bin/env python
 """Debug: per-kNN-call counters of the tcgen05 path inside a whole GKGNet-576 forward (rows sent to the
-brute-force fix-up / exact re-rank), to check that every layer shape stays on the fast path."""
+brute-force fix-up / exact re-rank), to check that every layer shape stays on the fast path, and the number of
+rows whose neighbour ids differ from the CUDA-core exact fp32 kernel on the same (real-model) features."""
 import ctypes, os, struct, sys
 import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -24,9 +25,12 @@ def wrapped(x, y=None, relative_pos=None, **kw):
     M = N if y is None else y.shape[1]
     g = kw.get("groups", 1)
     rows = Bx * g * N
+    kw2 = dict(kw); kw2.pop("separable", None); kw2["algo"] = _lib.KNN_EXACT_FP32
+    ref = orig(x, y, relative_pos, **kw2)                      # CUDA-core exact kernel on the same features
+    differ = int((idx != ref).any(-1).sum())
     print(f"N={N:6d} M={M:6d} D={C // g:4d} k={kw.get('k')} d={kw.get('dilation')} bias={relative_pos is not None} "
           f"rows={rows:8d} fixups={arr[0]:7d} ({100.0 * arr[0] / rows:6.3f}%) reranked={arr[1]:7d} "
-          f"max_err={struct.unpack('f', struct.pack('I', arr[2]))[0]:.2e}", flush=True)
+          f"max_err={struct.unpack('f', struct.pack('I', arr[2]))[0]:.2e} rows_differ_from_exact_kernel={differ}", flush=True)
     return idx
 
 ops.knn_graph = wrapped
