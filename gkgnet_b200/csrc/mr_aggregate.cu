@@ -13,6 +13,7 @@
 // x reads, idx reads, out writes are coalesced and every neighbour row is fetched with
 // 128-bit loads (served from L2: the key set of one image is <= a few hundred KB).
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace gkg {
 
@@ -301,6 +302,157 @@ mr_aggregate_fwd_bf16_smem_kernel(const __nv_bfloat16* __restrict__ x, int64_t x
   }
 }
 
+// ---- bf16 fast path, warp-autonomous form --------------------------------------------------------
+// Same idea (keys of one image slice resident in shared memory), without the CTA-wide idx tiles and
+// their two barriers per tile: a warp owns NPW = 32 / CPN consecutive nodes per pass (CPN = 16-byte
+// chunks per node slice), the SUB lanes that share a neighbour list (same node, same channel group)
+// load it with coalesced LDG.32 one pass ahead and hand the ids round with SHFL, the running maximum
+// and its arg-max are kept packed (HMNMX2 / HSET2 mask / LOP3), the 32 output bytes of a lane leave
+// in one 256-bit store.  With CS = 80 at stage 1 a CTA covers whole x / out rows (dense 128-byte
+// lines: the 40-channel slices of the kernel above touched twice the lines per request), one
+// 1024-thread CTA per SM, the only barriers are at image boundaries.
+constexpr size_t kAggWarpSmemMax = 226 * 1024;
+
+__device__ __forceinline__ uint32_t bf2_gt_mask(uint32_t a, uint32_t b) {
+  return __hgt2_mask(*reinterpret_cast<__nv_bfloat162*>(&a), *reinterpret_cast<__nv_bfloat162*>(&b));
+}
+
+template <int K, int CPN, int SUB, bool ARG>
+__global__ void __launch_bounds__(1024, 1)
+mr_aggregate_fwd_bf16_warp_kernel(const __nv_bfloat16* __restrict__ x, int64_t x_sb, int64_t x_sn,
+                                  const __nv_bfloat16* __restrict__ y, int64_t y_sb, int64_t y_sn,
+                                  const int32_t* __restrict__ idx, __nv_bfloat16* __restrict__ out,
+                                  uint8_t* __restrict__ argmax, int B, int G, int N, int M, int D, int wide_store) {
+  constexpr int CS = CPN * 8;                                   // channels per slice
+  constexpr int NPW = 32 / CPN;                                 // nodes per warp pass
+  constexpr int NR = (K + SUB - 1) / SUB;                       // idx registers per lane
+  constexpr uint32_t row_bytes = CS * 2;
+  extern __shared__ __align__(16) uint8_t agg_smem[];          // [M][CS] bf16 keys
+  const int C = G * D, NSL = C / CS;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  // lanes past NPW * CPN shadow the last working lane (same addresses: no extra sectors, no divergence)
+  const bool lane_on = lane < NPW * CPN;
+  const int eff = lane_on ? lane : NPW * CPN - 1;
+  const int q = eff / CPN, ch = eff - q * CPN;
+  const int slice = blockIdx.x % NSL;
+  const int range = blockIdx.x / NSL, nranges = gridDim.x / NSL;
+  if (range >= nranges) return;
+  const int c0 = slice * CS, cc = c0 + ch * 8;
+  const int g = cc / D;                                         // channel group of this lane's chunk
+  const int s = ch % SUB, sub_base = eff - s;                   // lanes [sub_base, sub_base + SUB) share a list
+  const long long R = (long long)B * N;
+  const long long per = (R + nranges - 1) / nranges;
+  long long r = (long long)range * per;
+  const long long r_end = r + per < R ? r + per : R;
+  const uint32_t keys_s = (uint32_t)__cvta_generic_to_shared(agg_smem);
+  const uint32_t my_s = keys_s + ch * 16;
+  while (r < r_end) {
+    const long long b = r / N;
+    const int n_lo = (int)(r - b * N);
+    const int n_hi = (int)((long long)n_lo + (r_end - r) < (long long)N ? n_lo + (r_end - r) : N);
+    __syncthreads();                                            // gathers of the previous image are done
+    {
+      const __nv_bfloat16* src = y + b * y_sb + c0;
+      const int pieces = M * CPN;
+      for (int p = threadIdx.x; p < pieces; p += blockDim.x) {
+        const int m = p / CPN, pc = p - m * CPN;
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(keys_s + (uint32_t)p * 16),
+                     "l"(src + (long long)m * y_sn + pc * 8) : "memory");
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+    const int32_t* ib = idx + ((b * G + g) * N) * (long long)K + s;
+    const __nv_bfloat16* xb = x + b * x_sb + cc;
+    const int npass = (n_hi - n_lo + NPW - 1) / NPW;
+    auto load_idx = [&](int node, int (&ir)[NR]) {
+#pragma unroll
+      for (int i = 0; i < NR; ++i)
+        ir[i] = (node < n_hi && i * SUB + s < K) ? __ldg(ib + (long long)node * K + i * SUB) : 0;
+    };
+    auto load_x = [&](int node) {
+      return node < n_hi ? *reinterpret_cast<const uint4*>(xb + (long long)node * x_sn) : make_uint4(0, 0, 0, 0);
+    };
+    int pass = warp;
+    int ir[NR];
+    uint4 xv;
+    load_idx(n_lo + pass * NPW + q, ir);
+    xv = load_x(n_lo + pass * NPW + q);
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();                                            // keys have landed
+    for (; pass < npass; pass += nwarps) {
+      const int node = n_lo + pass * NPW + q;
+      int irn[NR];
+      load_idx(node + nwarps * NPW, irn);
+      const uint4 xn = load_x(node + nwarps * NPW);
+      uint32_t b0, b1, b2, b3, a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+#pragma unroll
+      for (int j = 0; j < K; ++j) {
+        const uint32_t m = (uint32_t)__shfl_sync(0xffffffffu, ir[j / SUB], sub_base + (j % SUB));
+        uint32_t v0, v1, v2, v3;
+        asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                     : "=r"(v0), "=r"(v1), "=r"(v2), "=r"(v3) : "r"(my_s + m * row_bytes));
+        if (j == 0) {
+          b0 = v0; b1 = v1; b2 = v2; b3 = v3;
+        } else {
+          if (ARG) {                                            // strictly greater: the smallest j wins ties
+            const uint32_t jj = (uint32_t)j * 0x00010001u;
+            uint32_t t;
+            t = bf2_gt_mask(v0, b0); a0 = (a0 & ~t) | (jj & t);
+            t = bf2_gt_mask(v1, b1); a1 = (a1 & ~t) | (jj & t);
+            t = bf2_gt_mask(v2, b2); a2 = (a2 & ~t) | (jj & t);
+            t = bf2_gt_mask(v3, b3); a3 = (a3 & ~t) | (jj & t);
+          }
+          b0 = bf2_max(b0, v0); b1 = bf2_max(b1, v1); b2 = bf2_max(b2, v2); b3 = bf2_max(b3, v3);
+        }
+      }
+      if (lane_on && node < n_hi) {
+        uint4 o0, o1;
+        bf2_emit(xv.x, b0, o0.x, o0.y); bf2_emit(xv.y, b1, o0.z, o0.w);
+        bf2_emit(xv.z, b2, o1.x, o1.y); bf2_emit(xv.w, b3, o1.z, o1.w);
+        const long long bn = b * N + node;
+        __nv_bfloat16* op = out + (bn * C + cc) * 2;
+        if (wide_store) {
+          asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(op), "r"(o0.x), "r"(o0.y),
+                       "r"(o0.z), "r"(o0.w), "r"(o1.x), "r"(o1.y), "r"(o1.z), "r"(o1.w) : "memory");
+        } else {
+          reinterpret_cast<uint4*>(op)[0] = o0;
+          reinterpret_cast<uint4*>(op)[1] = o1;
+        }
+        if (ARG) {
+          uint2 a;
+          a.x = __byte_perm(a0, a1, 0x6420);
+          a.y = __byte_perm(a2, a3, 0x6420);
+          *reinterpret_cast<uint2*>(argmax + bn * C + cc) = a;
+        }
+      }
+      xv = xn;
+#pragma unroll
+      for (int i = 0; i < NR; ++i) ir[i] = irn[i];
+    }
+    r += n_hi - n_lo;
+  }
+}
+
+// Slice geometry of the warp-autonomous kernel: CS in {80, 40} channels, a slice either holds whole
+// channel groups or lies inside one, neighbour lists shared by SUB in {5, 10} lanes.
+struct AggWarpPlan { int cpn, sub, ctas_per_sm, threads; size_t smem; };
+static bool agg_warp_plan(int N, int M, int D, int C, AggWarpPlan* p) {
+  if (N < 1024 || N < M) return false;               // label heads: few queries, nothing to amortise
+  for (int cs = 80; cs >= 40; cs -= 40) {
+    if (C % cs) continue;
+    int sub;
+    if (D % cs == 0) sub = cs / 8; else if (cs % D == 0 && D % 8 == 0) sub = D / 8; else continue;
+    if (sub != 5 && sub != 10) continue;
+    const size_t smem = (size_t)M * cs * 2;
+    if (smem > kAggWarpSmemMax) continue;
+    p->cpn = cs / 8; p->sub = sub; p->smem = smem;
+    p->ctas_per_sm = smem <= 110 * 1024 ? 2 : 1;
+    p->threads = p->ctas_per_sm == 2 ? 512 : 1024;
+    return true;
+  }
+  return false;
+}
+
 // Channel-slice width for the shared-memory path: the widest multiple of 8 that divides D (a slice
 // stays inside one channel group) whose keys fit; 0 = use the L2 gather kernel.
 static int agg_smem_slice(int N, int M, int D) {
@@ -365,7 +517,39 @@ extern "C" int gkg_mr_aggregate_fwd(const void* x, int64_t x_sb, int64_t x_sn, c
     if (vec == 4) LAUNCH(float, 4); else if (vec == 2) LAUNCH(float, 2); else LAUNCH(float, 1);
   } else if (vec == 8 && (k == 9 || k == 18)) {
     const int cs = agg_smem_slice(N, M, D);
-    if (cs > 0) {
+    AggWarpPlan wp;
+    static const bool old_path = getenv("GKG_AGG_OLD") != nullptr;   // A/B switch for measurements
+    if (!old_path && agg_warp_plan(N, M, D, C, &wp)) {
+      int dev = 0, sms = 148;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+      const int nsl = C / (wp.cpn * 8), npw = 32 / wp.cpn;
+      int nranges = wp.ctas_per_sm * sms / nsl;
+      if (nranges < 1) nranges = 1;
+      const long long passes = ((long long)B * N + npw - 1) / npw;
+      if (nranges > passes) nranges = (int)passes;
+      const int wgrid = nranges * nsl;
+      const int wide = ((uintptr_t)out % 32) == 0;
+#define LAUNCH_W(KK, CP, SB, AA)                                                                    \
+  do {                                                                                               \
+    auto kern = mr_aggregate_fwd_bf16_warp_kernel<KK, CP, SB, AA>;                                   \
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kAggWarpSmemMax); \
+    if (e != cudaSuccess) { set_error("mr_aggregate_fwd: smem attribute: %s", cudaGetErrorString(e)); return GKG_ECUDA; } \
+    kern<<<wgrid, wp.threads, wp.smem, stream>>>(static_cast<const __nv_bfloat16*>(x), x_sb, x_sn,   \
+        static_cast<const __nv_bfloat16*>(y), y_sb, y_sn, idx, static_cast<__nv_bfloat16*>(out), argmax, \
+        B, G, N, M, D, wide);                                                                        \
+  } while (0)
+#define LAUNCH_WK(KK, AA)                                                       \
+  do {                                                                           \
+    if (wp.cpn == 10 && wp.sub == 5) LAUNCH_W(KK, 10, 5, AA);                    \
+    else if (wp.cpn == 10) LAUNCH_W(KK, 10, 10, AA);                             \
+    else LAUNCH_W(KK, 5, 5, AA);                                                 \
+  } while (0)
+      if (k == 9) { if (argmax) LAUNCH_WK(9, true); else LAUNCH_WK(9, false); }
+      else { if (argmax) LAUNCH_WK(18, true); else LAUNCH_WK(18, false); }
+#undef LAUNCH_WK
+#undef LAUNCH_W
+    } else if (cs > 0) {
       const int nsl = C / cs, npp = kAggSmemThreads / (cs / 8);
       const size_t smem = (size_t)M * cs * 2 + 2 * (size_t)npp * k * 4;
       int dev = 0, sms = 148;
