@@ -342,6 +342,25 @@ def run_ours(args):
             torch.cuda.synchronize()
             fc_ms = e0.elapsed_time(e1) / reps
 
+    # ---- the aggregate in its inference form (no arg-max plane written), timed beside the step: exactly the
+    # traffic of SURVEY 8(d)'s BYTES_agg; inside the step the kernel also writes the uint8 arg-max (B*C*N bytes)
+    agg_inf_ms = None
+    if True:
+        s_ = hp.stream.cuda_stream
+        def agg_inf():
+            _lib.check(hp.lib.gkg_mr_aggregate_fwd(x.data_ptr(), x.stride(0), x.stride(1), y.data_ptr(), y.stride(0),
+                                                   y.stride(1), hp.idx.data_ptr(), hp.out.data_ptr(), None, hp.B, hp.G,
+                                                   hp.N, hp.M, hp.D, hp.k, hp.dt, s_), "agg_fwd")
+        for _ in range(3):
+            agg_inf()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(hp.stream)
+        for _ in range(reps):
+            agg_inf()
+        e1.record(hp.stream)
+        torch.cuda.synchronize()
+        agg_inf_ms = e0.elapsed_time(e1) / reps
+
     # ---- e2e: host buffers -> device -> hot path -> host, every step ------------------
     # Every step copies its inputs from pinned host memory and its result back; the three legs run on
     # three streams over two sets of device buffers, so step i+1's upload and step i-1's download overlap
@@ -422,6 +441,16 @@ def run_ours(args):
         "roofline_agg_bwd": {"bound": "hbm", "achieved": bwd_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                              "frac": bwd_gbs / peaks["hbm_gbs"], "algorithmic_bytes": bytes_bwd},
     }
+    extra["roofline_agg_fwd"]["note"] = ("training form: the launch also writes the uint8 arg-max plane (B*C*N bytes) the "
+                                         "backward reads; SURVEY 8(d)'s BYTES_agg does not count it")
+    extra["roofline_agg_fwd"]["achieved_with_argmax"] = (bytes_agg + B * C * N) / (phases[2] * 1e-3) / 1e9
+    extra["roofline_agg_fwd"]["frac_with_argmax"] = extra["roofline_agg_fwd"]["achieved_with_argmax"] / peaks["hbm_gbs"]
+    if agg_inf_ms is not None:
+        extra["phase_ms"]["agg_fwd inference form (outside the step)"] = agg_inf_ms
+        extra["roofline_agg_fwd_infer"] = {"bound": "hbm", "achieved": bytes_agg / (agg_inf_ms * 1e-3) / 1e9,
+                                           "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                                           "frac": bytes_agg / (agg_inf_ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                                           "algorithmic_bytes": bytes_agg}
     if fc_ms is not None:
         bytes_fc = 2 * es * B * 2 * C * N
         extra["phase_ms"]["fc_fwd (outside the step)"] = fc_ms

@@ -306,12 +306,24 @@ mr_aggregate_fwd_bf16_smem_kernel(const __nv_bfloat16* __restrict__ x, int64_t x
 // Same idea (keys of one image slice resident in shared memory), without the CTA-wide idx tiles and
 // their two barriers per tile: a warp owns NPW = 32 / CPN consecutive nodes per pass (CPN = 16-byte
 // chunks per node slice), the SUB lanes that share a neighbour list (same node, same channel group)
-// load it with coalesced LDG.32 one pass ahead and hand the ids round with SHFL, the running maximum
-// and its arg-max are kept packed (HMNMX2 / HSET2 mask / LOP3), the 32 output bytes of a lane leave
-// in one 256-bit store.  With CS = 80 at stage 1 a CTA covers whole x / out rows (dense 128-byte
-// lines: the 40-channel slices of the kernel above touched twice the lines per request), one
-// 1024-thread CTA per SM, the only barriers are at image boundaries.
+// load it with coalesced LDG.32 one pass ahead (two ids packed per register) and hand the ids round
+// with SHFL, the running maximum and its arg-max are kept packed (HMNMX2 / HSET2 mask / LOP3), the
+// 32 output bytes of a lane leave in one 256-bit store.  With CS = 80 at stage 1 a CTA covers whole
+// x / out rows (dense 128-byte lines: the 40-channel slices of the kernel above touched twice the
+// lines per request), one 1024-thread CTA per SM, the only barriers are at image boundaries.
+//
+// Bank conflicts: a 128-bit LDS is served a quarter warp (8 lanes, 128 bytes) at a time.  With
+// 160-byte key rows the 8 lanes straddle two random rows and collide 7 times out of 8.  For CS = 80
+// the rows are therefore split: chunks 0-7 live in a main array of pitch 128 bytes (chunk c always
+// in 16-byte bank group c), chunks 8-9 in an aux array of pitch 32 bytes.  Lanes 8i..8i+7 take
+// chunks 0-7 of node i (always conflict free, whatever the rows), lanes 24+2i, 25+2i its chunks 8-9
+// (three random pairs over four positions: 1.7 wavefronts on average): 4.7 wavefronts per gather
+// instruction instead of 7.4, same shared-memory footprint.
 constexpr size_t kAggWarpSmemMax = 226 * 1024;
+#ifndef GKG_AGG_PF
+#define GKG_AGG_PF 4
+#endif
+constexpr int kAggPrefetchPasses = GKG_AGG_PF;                  // L2 prefetch distance, in passes of the warp
 
 __device__ __forceinline__ uint32_t bf2_gt_mask(uint32_t a, uint32_t b) {
   return __hgt2_mask(*reinterpret_cast<__nv_bfloat162*>(&a), *reinterpret_cast<__nv_bfloat162*>(&b));
@@ -325,27 +337,39 @@ mr_aggregate_fwd_bf16_warp_kernel(const __nv_bfloat16* __restrict__ x, int64_t x
                                   uint8_t* __restrict__ argmax, int B, int G, int N, int M, int D, int wide_store) {
   constexpr int CS = CPN * 8;                                   // channels per slice
   constexpr int NPW = 32 / CPN;                                 // nodes per warp pass
-  constexpr int NR = (K + SUB - 1) / SUB;                       // idx registers per lane
-  constexpr uint32_t row_bytes = CS * 2;
-  extern __shared__ __align__(16) uint8_t agg_smem[];          // [M][CS] bf16 keys
+  constexpr int H = (K + 1) / 2;                                // id pairs (j, j + H) per list
+  constexpr int NR = (H + SUB - 1) / SUB;                       // pair registers per lane
+  constexpr bool SPLIT = CPN == 10;                             // main (8 chunks) + aux (2 chunks) key arrays
+  extern __shared__ __align__(16) uint8_t agg_smem[];
   const int C = G * D, NSL = C / CS;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   // lanes past NPW * CPN shadow the last working lane (same addresses: no extra sectors, no divergence)
   const bool lane_on = lane < NPW * CPN;
   const int eff = lane_on ? lane : NPW * CPN - 1;
-  const int q = eff / CPN, ch = eff - q * CPN;
+  int q, ch;                                                    // node within the pass, chunk within the slice
+  if (SPLIT) {
+    if (eff < 24) { q = eff >> 3; ch = eff & 7; } else { q = (eff - 24) >> 1; ch = 8 + ((eff - 24) & 1); }
+  } else {
+    q = eff / CPN; ch = eff - q * CPN;
+  }
   const int slice = blockIdx.x % NSL;
   const int range = blockIdx.x / NSL, nranges = gridDim.x / NSL;
   if (range >= nranges) return;
   const int c0 = slice * CS, cc = c0 + ch * 8;
   const int g = cc / D;                                         // channel group of this lane's chunk
-  const int s = ch % SUB, sub_base = eff - s;                   // lanes [sub_base, sub_base + SUB) share a list
+  const int s = ch % SUB, sub0 = ch - s;                        // chunks [sub0, sub0 + SUB) share a neighbour list
+  auto src_lane = [&](int u) {                                  // lane that owns chunk sub0 + u of my node
+    const int ci = sub0 + u;
+    return SPLIT ? (ci < 8 ? 8 * q + ci : 16 + 2 * q + ci) : q * CPN + ci;
+  };
   const long long R = (long long)B * N;
   const long long per = (R + nranges - 1) / nranges;
   long long r = (long long)range * per;
   const long long r_end = r + per < R ? r + per : R;
   const uint32_t keys_s = (uint32_t)__cvta_generic_to_shared(agg_smem);
-  const uint32_t my_s = keys_s + ch * 16;
+  const uint32_t aux_s = keys_s + (uint32_t)M * 128;
+  const uint32_t pitch = SPLIT ? (ch < 8 ? 128u : 32u) : (uint32_t)CS * 2;
+  const uint32_t my_s = SPLIT ? (ch < 8 ? keys_s + ch * 16 : aux_s + (ch - 8) * 16) : keys_s + ch * 16;
   while (r < r_end) {
     const long long b = r / N;
     const int n_lo = (int)(r - b * N);
@@ -356,45 +380,66 @@ mr_aggregate_fwd_bf16_warp_kernel(const __nv_bfloat16* __restrict__ x, int64_t x
       const int pieces = M * CPN;
       for (int p = threadIdx.x; p < pieces; p += blockDim.x) {
         const int m = p / CPN, pc = p - m * CPN;
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(keys_s + (uint32_t)p * 16),
-                     "l"(src + (long long)m * y_sn + pc * 8) : "memory");
+        const uint32_t dst = SPLIT ? (pc < 8 ? keys_s + (uint32_t)m * 128 + pc * 16 : aux_s + (uint32_t)m * 32 + (pc - 8) * 16)
+                                   : keys_s + (uint32_t)p * 16;
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src + (long long)m * y_sn + pc * 8)
+                     : "memory");
       }
       asm volatile("cp.async.commit_group;" ::: "memory");
     }
     const int32_t* ib = idx + ((b * G + g) * N) * (long long)K + s;
     const __nv_bfloat16* xb = x + b * x_sb + cc;
     const int npass = (n_hi - n_lo + NPW - 1) / NPW;
-    auto load_idx = [&](int node, int (&ir)[NR]) {
+    // ids of pair t = s + i * SUB: t (later the low half) and t + H (high half); packed only when the
+    // registers rotate, so that nothing waits on these loads inside the pass that issues them
+    auto load_idx = [&](int node, uint32_t (&lo)[NR], uint32_t (&hi)[NR]) {
 #pragma unroll
-      for (int i = 0; i < NR; ++i)
-        ir[i] = (node < n_hi && i * SUB + s < K) ? __ldg(ib + (long long)node * K + i * SUB) : 0;
+      for (int i = 0; i < NR; ++i) {
+        const int t = i * SUB + s;
+        const int32_t* ip = ib + (long long)node * K + i * SUB;
+        lo[i] = (node < n_hi && t < H) ? (uint32_t)__ldg(ip) : 0u;
+        hi[i] = (node < n_hi && t < H && t + H < K) ? (uint32_t)__ldg(ip + H) : 0u;
+      }
     };
     auto load_x = [&](int node) {
       return node < n_hi ? *reinterpret_cast<const uint4*>(xb + (long long)node * x_sn) : make_uint4(0, 0, 0, 0);
     };
+    auto prefetch_l2 = [&](int node) {                           // DRAM -> L2 a few passes ahead (no registers held)
+      if (node < n_hi) {
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(xb + (long long)node * x_sn));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(ib + (long long)node * K));
+      }
+    };
     int pass = warp;
-    int ir[NR];
+    uint32_t ir[NR], irn[NR], irh[NR];
     uint4 xv;
-    load_idx(n_lo + pass * NPW + q, ir);
+    load_idx(n_lo + pass * NPW + q, irn, irh);
     xv = load_x(n_lo + pass * NPW + q);
+#pragma unroll
+    for (int d = 1; d < kAggPrefetchPasses; ++d) prefetch_l2(n_lo + (pass + d * nwarps) * NPW + q);
+#pragma unroll
+    for (int i = 0; i < NR; ++i) ir[i] = irn[i] | (irh[i] << 16);
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();                                            // keys have landed
     for (; pass < npass; pass += nwarps) {
       const int node = n_lo + pass * NPW + q;
-      int irn[NR];
-      load_idx(node + nwarps * NPW, irn);
+      load_idx(node + nwarps * NPW, irn, irh);
       const uint4 xn = load_x(node + nwarps * NPW);
+      prefetch_l2(node + kAggPrefetchPasses * nwarps * NPW);
+      uint32_t pv[H];
+#pragma unroll
+      for (int t = 0; t < H; ++t) pv[t] = __shfl_sync(0xffffffffu, ir[t / SUB], src_lane(t % SUB));
       uint32_t b0, b1, b2, b3, a0 = 0, a1 = 0, a2 = 0, a3 = 0;
 #pragma unroll
-      for (int j = 0; j < K; ++j) {
-        const uint32_t m = (uint32_t)__shfl_sync(0xffffffffu, ir[j / SUB], sub_base + (j % SUB));
+      for (int j = 0; j < K; ++j) {                              // in list order: the smallest j wins ties
+        const uint32_t m = j < H ? (pv[j] & 0xffffu) : (pv[j - H] >> 16);
         uint32_t v0, v1, v2, v3;
         asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
-                     : "=r"(v0), "=r"(v1), "=r"(v2), "=r"(v3) : "r"(my_s + m * row_bytes));
+                     : "=r"(v0), "=r"(v1), "=r"(v2), "=r"(v3) : "r"(my_s + m * pitch));
         if (j == 0) {
           b0 = v0; b1 = v1; b2 = v2; b3 = v3;
         } else {
-          if (ARG) {                                            // strictly greater: the smallest j wins ties
+          if (ARG) {
             const uint32_t jj = (uint32_t)j * 0x00010001u;
             uint32_t t;
             t = bf2_gt_mask(v0, b0); a0 = (a0 & ~t) | (jj & t);
@@ -427,7 +472,7 @@ mr_aggregate_fwd_bf16_warp_kernel(const __nv_bfloat16* __restrict__ x, int64_t x
       }
       xv = xn;
 #pragma unroll
-      for (int i = 0; i < NR; ++i) ir[i] = irn[i];
+      for (int i = 0; i < NR; ++i) ir[i] = irn[i] | (irh[i] << 16);
     }
     r += n_hi - n_lo;
   }
@@ -437,7 +482,7 @@ mr_aggregate_fwd_bf16_warp_kernel(const __nv_bfloat16* __restrict__ x, int64_t x
 // channel groups or lies inside one, neighbour lists shared by SUB in {5, 10} lanes.
 struct AggWarpPlan { int cpn, sub, ctas_per_sm, threads; size_t smem; };
 static bool agg_warp_plan(int N, int M, int D, int C, AggWarpPlan* p) {
-  if (N < 1024 || N < M) return false;               // label heads: few queries, nothing to amortise
+  if (N < 1024 || N < M || M > 65535) return false;  // label heads: few queries, nothing to amortise; ids travel as 16 bits
   for (int cs = 80; cs >= 40; cs -= 40) {
     if (C % cs) continue;
     int sub;
