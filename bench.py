@@ -361,6 +361,23 @@ def run_ours(args):
         torch.cuda.synchronize()
         agg_inf_ms = e0.elapsed_time(e1) / reps
 
+    # ---- the key pooling in front of the kNN (y = avg_pool2d(x, r, r)), timed beside the step
+    pool_ms = None
+    if True:
+        from gkgnet_b200 import ops
+        side = int(round(hp.N ** 0.5))
+        rr = WORKLOAD.get("r", 4)
+        with torch.no_grad():
+            for _ in range(3):
+                ops.pool_keys(x, side, side, rr)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(hp.stream)
+            for _ in range(reps):
+                ops.pool_keys(x, side, side, rr)
+            e1.record(hp.stream)
+            torch.cuda.synchronize()
+        pool_ms = e0.elapsed_time(e1) / reps
+
     # ---- e2e: host buffers -> device -> hot path -> host, every step ------------------
     # Every step copies its inputs from pinned host memory and its result back; the three legs run on
     # three streams over two sets of device buffers, so step i+1's upload and step i-1's download overlap
@@ -451,6 +468,12 @@ def run_ours(args):
                                            "peak": peaks["hbm_gbs"], "unit": "GB/s",
                                            "frac": bytes_agg / (agg_inf_ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
                                            "algorithmic_bytes": bytes_agg}
+    if pool_ms is not None:
+        bytes_pool = es * B * C * N + es * B * C * M
+        extra["phase_ms"]["pool_keys (outside the step)"] = pool_ms
+        extra["roofline_pool_keys"] = {"bound": "hbm", "achieved": bytes_pool / (pool_ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"],
+                                       "unit": "GB/s", "frac": bytes_pool / (pool_ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                                       "algorithmic_bytes": bytes_pool}
     if fc_ms is not None:
         bytes_fc = 2 * es * B * 2 * C * N
         extra["phase_ms"]["fc_fwd (outside the step)"] = fc_ms

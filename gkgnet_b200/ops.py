@@ -188,6 +188,46 @@ def mr_aggregate(x, idx, y=None, *, groups=1):
 
 
 # ----------------------------------------------------------------------------------------
+# key pooling (avg_pool2d(x, r, r) on the token-major layout)
+# ----------------------------------------------------------------------------------------
+class _PoolKeys(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, H, W, r):
+        lib = _lib.load()
+        x = _token_major(x)
+        B, N, C = x.shape
+        y = torch.empty((B, (H // r) * (W // r), C), dtype=x.dtype, device=x.device)
+        rc = lib.gkg_pool_keys_fwd(x.data_ptr(), x.stride(0), x.stride(1), y.data_ptr(), B, H, W, C, r,
+                                   _DT[x.dtype], _stream(x))
+        _lib.check(rc, "gkg_pool_keys_fwd")
+        ctx.meta = (B, H, W, C, r, x.dtype)
+        return y
+
+    @staticmethod
+    def backward(ctx, grad_y):
+        B, H, W, C, r, dtype = ctx.meta
+        lib = _lib.load()
+        grad_y = grad_y.to(dtype).contiguous()
+        gx = torch.empty((B, H * W, C), dtype=dtype, device=grad_y.device)
+        rc = lib.gkg_pool_keys_bwd(grad_y.data_ptr(), gx.data_ptr(), B, H, W, C, r, _DT[dtype], _stream(grad_y))
+        _lib.check(rc, "gkg_pool_keys_bwd")
+        return gx, None, None, None
+
+
+def pool_keys(x, H, W, r):
+    """Keys of the dynamic graph convolution: ``avg_pool2d(x, r, r)`` (torch_vertex.py:194-196) on a
+    token-major ``x (B, H*W, C)``; returns ``(B, (H//r)*(W//r), C)``.  Differentiable w.r.t. x."""
+    _require_cuda(x)
+    if x.dtype not in _DT:
+        raise TypeError(f"unsupported dtype {x.dtype}")
+    if x.shape[1] != H * W:
+        raise ValueError(f"x has {x.shape[1]} nodes, expected H*W = {H * W}")
+    if H // r < 1 or W // r < 1:
+        raise ValueError(f"pooling window {r} larger than the {H}x{W} map")
+    return _PoolKeys.apply(x, int(H), int(W), int(r))
+
+
+# ----------------------------------------------------------------------------------------
 # grouped 1x1 FC (+ folded norm + activation) on the tensor cores, inference form
 # ----------------------------------------------------------------------------------------
 _ACT = {None: 0, "none": 0, "relu": 1, "gelu": 2}

@@ -163,7 +163,7 @@ class DyGraphConv2dMultiGroup(_DynamicGraphBase):
         xt = nchw_to_tokens(x)
         yt = None
         if self.r > 1:
-            yt = nchw_to_tokens(F.avg_pool2d(x, self.r, self.r))
+            yt = ops.pool_keys(xt, H, W, self.r)      # avg_pool2d(x, r, r), token-major
         nn_idx = self.dilated_knn_graph.neighbors(xt, yt, relative_pos, groups=self.num_head,
                                                   separable=separable)
         out = self.gconv.forward_tokens(xt, nn_idx, yt, groups=self.num_head, hw=(H, W))

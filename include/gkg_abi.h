@@ -150,6 +150,21 @@ int gkg_grouped_fc_supported(int C2);
 int gkg_grouped_fc_fwd(const void* in, const void* w_op, const float* shift, void* out, long long rows,
                        int C2, int act, gkg_stream_t stream);
 
+/*
+ * Key pooling of the dynamic graph convolution.  Replaces `y = F.avg_pool2d(x, r, r)` of
+ * DyGraphConv2dMultiGroup.forward / DyGraphConv2d.forward (torch_vertex.py:194-196, :221-223) on the
+ * token-major layout: window r x r, stride r, no padding, floor mode (rows / columns past
+ * floor(H/r)*r are dropped), fp32 accumulation in row-major window order, one division by r*r.
+ *   x        (B, H*W, C) via strides, dtype
+ *   y        (B, (H/r)*(W/r), C) contiguous, dtype
+ * Backward (what autograd derives for avg_pool2d): grad_x[b, ih, iw, c] = grad_y[b, ih/r, iw/r, c] / r^2,
+ * zero in the dropped rows / columns.  grad_y and grad_x are contiguous, dtype.
+ */
+int gkg_pool_keys_fwd(const void* x, int64_t x_stride_b, int64_t x_stride_n, void* y,
+                      int B, int H, int W, int C, int r, int dtype, gkg_stream_t stream);
+int gkg_pool_keys_bwd(const void* grad_y, void* grad_x,
+                      int B, int H, int W, int C, int r, int dtype, gkg_stream_t stream);
+
 /* Number of kernels this library has launched since load (for bench accounting). */
 uint64_t gkg_launch_count(void);
 

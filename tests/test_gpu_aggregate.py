@@ -97,6 +97,58 @@ def test_aggregate_backward(dtype, tol, self_keys):
         assert (yc.grad.float().cpu() - yo.grad).abs().max() <= tol * scale * (8 if dtype == torch.bfloat16 else 1)
 
 
+@pytest.mark.parametrize("quantised", [False, True])
+@pytest.mark.parametrize("B,G,N,M,D,k,self_keys", [
+    (2, 2, 1100, 300, 40, 9, False),     # warp-autonomous kernel: 80-channel slices holding both groups
+    (2, 2, 1100, 300, 40, 18, False),    # k = 18: two id pairs per lane
+    (1, 2, 1200, 300, 80, 9, False),     # 80-channel slices, one group per slice
+    (1, 2, 1296, 1296, 200, 9, True),    # stage-3 geometry: 40-channel slices, self keys
+    (3, 2, 1100, 300, 16, 9, False),     # CTA-tiled shared-memory kernel
+])
+def test_aggregate_backward_large(B, G, N, M, D, k, self_keys, quantised):
+    """Backward through the bf16 shared-memory forward kernels (N >= 1024): the arg-max plane they write
+    routes grad_y.  With features quantised to steps of 1/4 most maxima are tied: the smallest list
+    position must win, like torch.max on the CPU (first maximal value)."""
+    from gkgnet_b200 import ops
+    g = torch.Generator().manual_seed(5)
+    C = G * D
+    dtype, tol = torch.bfloat16, 2e-2
+    q = (lambda t: (t * 4).round() / 4) if quantised else (lambda t: t)
+    x = q(torch.randn(B, N, C, generator=g)).to(dtype)
+    y = None if self_keys else q(torch.randn(B, M, C, generator=g)).to(dtype)
+    idx = torch.randint(0, N if self_keys else M, (B * G, N, k), generator=g, dtype=torch.int32)
+    w = torch.randn(B, N, 2 * C, generator=g).to(dtype)
+
+    xc = x.cuda().requires_grad_(True)
+    yc = None if y is None else y.cuda().requires_grad_(True)
+    out = ops.mr_aggregate(xc, idx.cuda(), yc, groups=G)
+    out.backward(w.cuda())
+
+    xo = x.float().requires_grad_(True)
+    yo = None if y is None else y.float().requires_grad_(True)
+    oo = _oracle_agg(xo, idx, yo, G)
+    assert torch.equal(out.detach().cpu(), oo.detach().to(dtype))
+    (oo * w.float()).sum().backward()
+    scale = max(1.0, float(xo.grad.abs().max()))
+    assert (xc.grad.float().cpu() - xo.grad).abs().max() <= tol * scale * 8
+    if not self_keys:
+        scale = max(1.0, float(yo.grad.abs().max()))
+        assert (yc.grad.float().cpu() - yo.grad).abs().max() <= tol * scale * 8
+
+
+def test_aggregate_many_keys_fall_back():
+    """More than 65535 keys: ids no longer fit the 16-bit hand-over of the warp-autonomous kernel."""
+    from gkgnet_b200 import ops
+    g = torch.Generator().manual_seed(6)
+    B, G, N, D, k = 1, 2, 70000, 40, 9
+    C = G * D
+    x = torch.randn(B, N, C, generator=g).bfloat16()
+    idx = torch.randint(0, N, (B * G, N, k), generator=g, dtype=torch.int32)
+    idx[:, :, 0] = N - 1 - torch.arange(N, dtype=torch.int32)        # ids above 65535 in use
+    out = ops.mr_aggregate(x.cuda(), idx.cuda(), None, groups=G)
+    assert torch.equal(out.cpu(), _oracle_agg(x.float(), idx, None, G).bfloat16())
+
+
 def test_golden_mrconv_module():
     """Reference-layout MRConv2d.forward(x, edge_index, y) with the reference's weights."""
     import gkgnet_b200 as G
