@@ -113,10 +113,11 @@ class FoldedSequential(nn.Sequential):
         return hit[1], hit[2]
 
 
-class BasicConv(nn.Sequential):
+class BasicConv(FoldedSequential):
     """Stack of grouped(4) 1x1 convs, each followed by norm / act / dropout
     (torch_nn.py:57-81).  Sub-module order -- and therefore the state-dict keys
-    ``0.weight, 0.bias, 1.<bn>`` -- matches the reference."""
+    ``0.weight, 0.bias, 1.<bn>`` -- matches the reference.  Widths the tensor-core grouped FC does not take
+    (stages 3-4) run here; in eval mode the batch norm is folded into the grouped convolution."""
 
     def __init__(self, channels, act="relu", norm=None, bias=True, drop=0.0):
         mods = []
