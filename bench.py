@@ -223,7 +223,20 @@ def cpu_reference_step(x, y, rel, grad_out):
     return out
 
 
+def use_all_host_threads():
+    """The CPU arm uses every host core this process may run on.  torchrun exports OMP_NUM_THREADS=1 when it
+    starts more than one rank, which would silently make the reference single-threaded."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    if torch.get_num_threads() != n:
+        torch.set_num_threads(n)
+    return torch.get_num_threads()
+
+
 def time_cpu_reference(n_img, reps, seed=0):
+    use_all_host_threads()
     x, y, rel = make_inputs(n_img, "cpu", torch.float32, seed)
     grad_out = torch.randn(n_img, 2 * WORKLOAD["C"], x.shape[1], 1)
     cpu_reference_step(x[:1], y[:1], rel, grad_out[:1])     # warm-up (thread pool, allocator)
@@ -240,6 +253,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    use_all_host_threads()
     n_img = args.ref_images
     x, y, rel = make_inputs(n_img, "cpu", torch.float32, 0)
     grad_out = torch.randn(n_img, 2 * WORKLOAD["C"], x.shape[1], 1)
