@@ -322,7 +322,7 @@ knn_finalize_kernel(const float2* __restrict__ cand, const int* __restrict__ can
   if (n >= N) return;
   const int row = p * N + n;
   const int np = cand_count[gr];
-  if (np < 0 || (np < k * dilation + 1 && np < M)) {   // no trustworthy candidate set
+  if (force_rerank == 3 || np < 0 || (np < k * dilation + 1 && np < M)) {   // no trustworthy candidate set (3: test hook)
     if (force_rerank != 0) atomicAdd(stats + 0, 1u);
     fix_rows[atomicAdd(fix_count, 1)] = row;
     return;
@@ -436,54 +436,116 @@ knn_rerank_kernel(const int* __restrict__ rr_count, const int* __restrict__ rr_l
 // ------------------------------------------------------------------------------------
 // exact fix-up for rows whose candidate set could not be certified (rare)
 // ------------------------------------------------------------------------------------
+// Per listed row, one CTA: exact distances to all M keys, then the k*d nearest by (distance, id).  Selection:
+// a 1024-bin histogram over [min, max] (the bin index is monotone in the distance) locates the bin that holds
+// the k*d-th nearest; the keys up to that bin -- a superset of the answer, every other key is strictly farther --
+// are compacted and ranked by counting among themselves.  A handful of barriers per row instead of two per
+// selected neighbour; when all distances fall into one bin the counting runs over all M keys (still exact).
+constexpr int kFixBins = 1024;
+constexpr int kFixCand = 2048;                 // candidate slots (keys up to the selected bin)
 __global__ void __launch_bounds__(256)
 knn_fixup_kernel(const int* __restrict__ count, const int* __restrict__ rows, const float* __restrict__ xhat,
                  const float* __restrict__ xsq, const float* __restrict__ yhat, const float* __restrict__ ysq,
                  const float* __restrict__ relpos, int32_t* __restrict__ idx_out, int N, int M, int D, int k,
                  int dilation) {
-  extern __shared__ float dist_s[];            // [M]
-  __shared__ float red_v[8];
-  __shared__ int red_i[8];
-  __shared__ float sel_v;
-  __shared__ int sel_i;
+  extern __shared__ float dist_s[];            // [M] distances, [cap] candidate distances, [cap] candidate ids
+  const int cap = M < kFixCand ? M : kFixCand;
+  float* cand_v = dist_s + M;
+  int* cand_i = reinterpret_cast<int*>(dist_s + M + cap);
+  __shared__ int hist[kFixBins];
+  __shared__ float red_lo[8], red_hi[8];
+  __shared__ int bin_sel, ncand, nsel_s;
   const int total = *count;
   const int kd = k * dilation;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (int item = blockIdx.x; item < total; item += gridDim.x) {
     const int id = rows[item];
     const int p = id / N, n = id - p * N;
     const float* xr = xhat + (size_t)id * D;
     const float xs = xsq[id];
     const float* relrow = relpos ? relpos + (size_t)n * M : nullptr;
-    for (int m = threadIdx.x; m < M; m += blockDim.x)
-      dist_s[m] = exact_dist(xr, yhat + ((size_t)p * M + m) * D, D, xs, ysq[(size_t)p * M + m], relrow, m);
+    float lo = INFINITY, hi = -INFINITY;
+    for (int m = threadIdx.x; m < M; m += blockDim.x) {
+      const float v = exact_dist(xr, yhat + ((size_t)p * M + m) * D, D, xs, ysq[(size_t)p * M + m], relrow, m);
+      dist_s[m] = v;
+      lo = fminf(lo, v);
+      hi = fmaxf(hi, v);
+    }
+    for (int q = threadIdx.x; q < kFixBins; q += blockDim.x) hist[q] = 0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+      hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+    }
+    if (lane == 0) { red_lo[warp] = lo; red_hi[warp] = hi; }
+    if (threadIdx.x == 0) ncand = 0;
     __syncthreads();
-    float last_v = -INFINITY;
-    int last_i = -1;
-    for (int r = 0; r < kd; ++r) {
-      float bv = INFINITY;
-      int bi = 0x7fffffff;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) { lo = fminf(lo, red_lo[w]); hi = fmaxf(hi, red_hi[w]); }
+    const float scale = hi > lo ? (float)kFixBins / (hi - lo) : 0.f;
+    auto bin_of = [&](float v) {
+      const int q = (int)((v - lo) * scale);
+      return q < 0 ? 0 : (q < kFixBins ? q : kFixBins - 1);
+    };
+    for (int m = threadIdx.x; m < M; m += blockDim.x) atomicAdd(&hist[bin_of(dist_s[m])], 1);
+    __syncthreads();
+    if (warp == 0) {                           // first bin whose prefix count reaches k*d
+      constexpr int PER = kFixBins / 32;
+      int part = 0;
+      for (int q = 0; q < PER; ++q) part += hist[lane * PER + q];
+      int incl = part;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+      }
+      const unsigned reach = __ballot_sync(0xffffffffu, incl >= kd);
+      const int first = reach ? __ffs(reach) - 1 : 31;
+      if (lane == first) {
+        int run = incl - part, q = 0;
+        for (; q < PER - 1; ++q) {
+          run += hist[lane * PER + q];
+          if (run >= kd) break;
+        }
+        bin_sel = reach ? lane * PER + q : kFixBins - 1;
+        nsel_s = reach ? run : M;               // keys up to and including that bin
+      }
+    }
+    __syncthreads();
+    const int nsel = nsel_s;
+    const int bsel = bin_sel;
+    if (nsel <= cap) {
       for (int m = threadIdx.x; m < M; m += blockDim.x) {
         const float v = dist_s[m];
-        const bool after = (v > last_v) || (v == last_v && m > last_i);
-        if (after && (v < bv || (v == bv && m < bi))) { bv = v; bi = m; }
-      }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
-        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-        if (ov < bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
-      }
-      if ((threadIdx.x & 31) == 0) { red_v[threadIdx.x >> 5] = bv; red_i[threadIdx.x >> 5] = bi; }
-      __syncthreads();
-      if (threadIdx.x == 0) {
-        for (int w = 1; w < 8; ++w)
-          if (red_v[w] < bv || (red_v[w] == bv && red_i[w] < bi)) { bv = red_v[w]; bi = red_i[w]; }
-        sel_v = bv; sel_i = bi;
-        if (r % dilation == 0) idx_out[(size_t)id * k + r / dilation] = bi;
+        if (bin_of(v) <= bsel) {
+          const int pos = atomicAdd(&ncand, 1);
+          cand_v[pos] = v;
+          cand_i[pos] = m;
+        }
       }
       __syncthreads();
-      last_v = sel_v;
-      last_i = sel_i;
+      const int nc = ncand;
+      for (int c = threadIdx.x; c < nc; c += blockDim.x) {
+        const float v = cand_v[c];
+        const int m = cand_i[c];
+        int rank = 0;
+        for (int j = 0; j < nc; ++j) {
+          const float u = cand_v[j];
+          rank += (u < v) || (u == v && cand_i[j] < m);
+        }
+        if (rank < kd && rank % dilation == 0) idx_out[(size_t)id * k + rank / dilation] = m;
+      }
+    } else {                                   // (nearly) all distances in one bin: count over every key
+      for (int m = threadIdx.x; m < M; m += blockDim.x) {
+        const float v = dist_s[m];
+        if (bin_of(v) > bsel) continue;
+        int rank = 0;
+        for (int j = 0; j < M && rank < kd; ++j) {
+          const float u = dist_s[j];
+          rank += (u < v) || (u == v && j < m);
+        }
+        if (rank < kd && rank % dilation == 0) idx_out[(size_t)id * k + rank / dilation] = m;
+      }
     }
     __syncthreads();
   }
@@ -712,7 +774,7 @@ int launch_knn_tc(const KnnWorkspace& w, void* extra_ws, const float* relpos, co
                                                   dilation, prm.delta);
     GKG_CHECK_LAUNCH("knn_rerank_kernel");
   }
-  const size_t fsmem = sizeof(float) * (size_t)M;
+  const size_t fsmem = sizeof(float) * ((size_t)M + 2 * (size_t)(M < kFixCand ? M : kFixCand));
   GKG_CHECK_ARG(fsmem <= 200 * 1024, "knn_tc: M=%d too large for the fix-up kernel", M);
   static size_t fix_configured = 0;
   if (fsmem > 48 * 1024 && fsmem > fix_configured) {

@@ -203,3 +203,39 @@ def test_tc_smooth_key_field_compacts_instead_of_fixup():
     dist = O.knn_distance_matrix(_ref_layout(x, G), _ref_layout(y, G), None)
     rep = O.check_knn_against_distances(idx.cpu(), dist, 9, 1, 1e-6)
     assert rep["rows_bad"] == 0, rep
+
+
+@pytest.mark.parametrize("B,G,N,M,D,k,d,keys", [
+    (1, 2, 200, 300, 40, 9, 1, "random"),
+    (1, 2, 150, 270, 200, 9, 3, "random"),      # k*d = 27
+    (1, 1, 64, 2500, 40, 9, 2, "random"),       # more keys than candidate slots: the selected bin keeps few of them
+    (1, 2, 96, 128, 8, 9, 2, "grid"),           # coarse grid: piles of exactly equal distances
+    (1, 1, 48, 300, 16, 9, 2, "constant"),      # every distance ties: one bin, all keys are candidates
+    (1, 1, 32, 2500, 16, 9, 1, "constant"),     # ... and more of them than candidate slots: count over all keys
+])
+def test_tc_fixup_kernel_matches_exact_kernel(B, G, N, M, D, k, d, keys):
+    """Debug hook 3 routes every row to the brute-force fix-up kernel (histogram select + rank by counting):
+    its ids must equal the CUDA-core exact kernel's bit for bit, ties included (smaller key id first)."""
+    from gkgnet_b200 import _lib, ops
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(13)
+    C = G * D
+    x = torch.randn(B, N, C, generator=g)
+    y = torch.randn(B, M, C, generator=g)
+    if keys == "grid":
+        x, y = (x * 2).round() / 2, (y * 2).round() / 2
+    elif keys == "constant":
+        y = y[:, :1].expand(B, M, C).contiguous()
+    x, y = x.cuda(), y.cuda()
+    _debug(lib, 3, None)
+    try:
+        got = ops.knn_graph(x, y, None, groups=G, k=k, dilation=d, algo=_lib.KNN_TCGEN05)
+        torch.cuda.synchronize()
+        st = _stats(lib)
+    finally:
+        _debug(lib, 0, None)
+    assert st["fixups"] == B * G * N, st
+    want = ops.knn_graph(x, y, None, groups=G, k=k, dilation=d, algo=_lib.KNN_EXACT_FP32)
+    assert torch.equal(got, want)
+    if keys == "constant":
+        assert torch.equal(got[0, 0].cpu(), torch.arange(0, k * d, d, dtype=torch.int32))
