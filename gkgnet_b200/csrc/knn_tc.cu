@@ -41,6 +41,10 @@ namespace {
 //   [tile][k-block][row group (tile_rows/8)][k chunk (KC/8)][row (8)][elem (8)]
 // so that a warp writes 4 contiguous 128-byte core matrices.
 constexpr int PREP_ROWS = 32;
+// Row stride of the staged rows in shared memory: == 1 (mod 8) floats.  Phase 2 reads, per warp, element e of
+// 8 rows x 4 consecutive 8-column pieces; with a stride of D floats (D = 200: 8 mod 32) those 32 addresses fall
+// into 4 banks (8-way conflict), with a stride == 1, 9, 17 or 25 (mod 32) into 32 different ones.
+__host__ __device__ constexpr int prep_stride(int D) { return D + ((1 - D % 8) + 8) % 8; }
 
 // DT: group width at compile time (the wide stages: 200, 320 -- every index split below becomes a constant
 // division), 0 = run-time value.
@@ -52,8 +56,9 @@ tc_prepare_kernel(const T* __restrict__ feat, int64_t stride_b, int64_t stride_n
   const int D = DT > 0 ? DT : D_rt;
   const int KP = DT > 0 ? k_padded(DT > 0 ? DT : 1) : KP_rt;
   extern __shared__ float prep_s[];              // [PREP_ROWS][D] normalised rows + [PREP_ROWS] norms
+  const int DS = prep_stride(D);
   float* xs = prep_s;
-  float* sqs = prep_s + PREP_ROWS * D;
+  float* sqs = prep_s + PREP_ROWS * DS;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const long long p = blockIdx.y;
   const int g = (int)(p % G);
@@ -66,7 +71,7 @@ tc_prepare_kernel(const T* __restrict__ feat, int64_t stride_b, int64_t stride_n
 
   for (int rl = warp; rl < PREP_ROWS; rl += 8) {
     const int row = key_of(r0 + rl);
-    float* dst = xs + rl * D;
+    float* dst = xs + rl * DS;
     if (row < rows) {
       const T* src = feat + b * stride_b + (long long)row * stride_n + (long long)g * D;
       float ss = 0.f;
@@ -112,7 +117,7 @@ tc_prepare_kernel(const T* __restrict__ feat, int64_t stride_b, int64_t stride_n
     const int rg = (prow - tile * tile_rows) >> 3;
     const int kb = kcI / kcs, kc = kcI - kb * kcs;
     const bool valid = key_of(prow) < rows;
-    const float* src = xs + rl * D;
+    const float* src = xs + rl * DS;
     float extra_hi = 0.f, extra_lo = 0.f;
     if (IS_KEY) {
       if (valid) {
@@ -668,7 +673,7 @@ static int launch_prepare_typed(const KnnWorkspace& w, const TcWorkspace& t, con
       default: break;
     }
   }
-  const size_t smem = sizeof(float) * ((size_t)PREP_ROWS * D + PREP_ROWS);
+  const size_t smem = sizeof(float) * ((size_t)PREP_ROWS * prep_stride(D) + PREP_ROWS);
   const int bn = pl.geom == 1 ? GeomB::BN : GeomA::BN, bnp = pl.geom == 1 ? GeomB::BNP : GeomA::BNP;
   {
     dim3 grid((pl.QTP * BM + PREP_ROWS - 1) / PREP_ROWS, P);
