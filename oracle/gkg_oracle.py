@@ -75,7 +75,7 @@ def dense_dilated_knn_graph(x, y=None, k=9, dilation=1, relative_pos=None):
         P, N, _ = dist.shape
         kd = k * dilation
         nn_idx = torch.topk(-dist, k=kd).indices
-        center = torch.arange(N).view(1, N, 1).expand(P, N, kd)
+        center = torch.arange(N, device=dist.device).view(1, N, 1).expand(P, N, kd)
         edge_index = torch.stack((nn_idx, center), dim=0)
         return edge_index[:, :, :, ::dilation]
 
@@ -90,7 +90,7 @@ def gather_neighbors(x, idx):
     P, C, M = x.shape[:3]
     _, N, K = idx.shape
     flat = x.squeeze(-1).transpose(1, 2).reshape(P * M, C)
-    rows = (idx + torch.arange(P).view(P, 1, 1) * M).reshape(-1)
+    rows = (idx + torch.arange(P, device=idx.device).view(P, 1, 1) * M).reshape(-1)
     return flat[rows].view(P, N, K, C).permute(0, 3, 1, 2)
 
 
