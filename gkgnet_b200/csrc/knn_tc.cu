@@ -338,6 +338,47 @@ knn_finalize_kernel(const float2* __restrict__ cand, const int* __restrict__ can
   for (int j = 0; j < L; ++j) { v[j] = -INFINITY; id[j] = 0x7fffffff; }
   float rej = cand_thr[gr];                     // best approximate score among the keys that are not in the list
   const float2* src = cand + (size_t)item * cand_slots * rows_per_item + r;
+  // Short lists (k*d <= 18): all NS candidate slots are loaded at once (independent loads; slots past np read as
+  // -inf) and sorted by Batcher's merge-exchange network -- 103 compare-exchanges for 20 slots, 186 for 31, five ALU
+  // operations each -- instead of np insertions into a sorted list of L (6 operations per list slot and candidate:
+  // the kernel was bound by the ALU pipe).  Equal scores may come out in either order: their gap is below 2*delta,
+  // so the row is re-ranked exactly anyway.
+  constexpr int NS = L == 14 ? 20 : (L == 23 ? 31 : 0);
+  if (NS > 0 && cand_slots == NS) {
+    constexpr int NSA = NS > 0 ? NS : 1;
+    float sv[NSA];
+    int sid[NSA];
+#pragma unroll
+    for (int s = 0; s < NSA; ++s) {
+      float2 c = make_float2(-INFINITY, __int_as_float(0x7fffffff));
+      if (s < np) c = src[(size_t)s * rows_per_item];
+      sv[s] = c.x;
+      sid[s] = __float_as_int(c.y);
+    }
+#pragma unroll
+    for (int p2 = 1; p2 < NSA; p2 <<= 1) {
+#pragma unroll
+      for (int kk = p2; kk >= 1; kk >>= 1) {
+#pragma unroll
+        for (int j = kk % p2; j <= NSA - 1 - kk; j += 2 * kk) {
+#pragma unroll
+          for (int i = 0; i <= (kk - 1 < NSA - j - kk - 1 ? kk - 1 : NSA - j - kk - 1); ++i) {
+            if ((i + j) / (2 * p2) == (i + j + kk) / (2 * p2)) {
+              const int a = i + j, b = i + j + kk;
+              const bool sw = sv[b] > sv[a];
+              const float fa = sv[a], fb = sv[b];
+              const int ia = sid[a], ib = sid[b];
+              sv[a] = sw ? fb : fa; sv[b] = sw ? fa : fb;
+              sid[a] = sw ? ib : ia; sid[b] = sw ? ia : ib;
+            }
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < L; ++j) { v[j] = sv[j < NSA ? j : 0]; id[j] = sid[j < NSA ? j : 0]; }
+    if (L < NSA) rej = fmaxf(rej, sv[L < NSA ? L : 0]);   // the best of what did not make the list
+  } else
   for (int s = 0; s < np; ++s) {
     const float2 c = src[(size_t)s * rows_per_item];
     const float x = c.x;
