@@ -41,10 +41,13 @@ namespace {
 //   [tile][k-block][row group (tile_rows/8)][k chunk (KC/8)][row (8)][elem (8)]
 // so that a warp writes 4 contiguous 128-byte core matrices.
 constexpr int PREP_ROWS = 32;
-// Row stride of the staged rows in shared memory: == 1 (mod 8) floats.  Phase 2 reads, per warp, element e of
-// 8 rows x 4 consecutive 8-column pieces; with a stride of D floats (D = 200: 8 mod 32) those 32 addresses fall
-// into 4 banks (8-way conflict), with a stride == 1, 9, 17 or 25 (mod 32) into 32 different ones.
-__host__ __device__ constexpr int prep_stride(int D) { return D + ((1 - D % 8) + 8) % 8; }
+// Row stride of the staged rows in shared memory (floats).  D % 8 == 0: phase 2 reads 8-column pieces with two
+// LDS.128; the 8 lanes of a quarter warp read the same piece of 8 consecutive rows, so the stride in 16-byte units
+// must be odd (D = 200: 50 -> 51).  Otherwise (scalar reads): stride == 1 (mod 8) floats spreads the 8 rows x 4
+// pieces of a warp over all 32 banks.
+__host__ __device__ constexpr int prep_stride(int D) {
+  return D % 8 == 0 ? ((D / 4) % 2 == 0 ? D + 4 : D) : D + ((1 - D % 8) + 8) % 8;
+}
 
 // DT: group width at compile time (the wide stages: 200, 320 -- every index split below becomes a constant
 // division), 0 = run-time value.
@@ -55,7 +58,7 @@ tc_prepare_kernel(const T* __restrict__ feat, int64_t stride_b, int64_t stride_n
                   int tiles, int tile_rows, int tile_keys, int write_hat) {
   const int D = DT > 0 ? DT : D_rt;
   const int KP = DT > 0 ? k_padded(DT > 0 ? DT : 1) : KP_rt;
-  extern __shared__ float prep_s[];              // [PREP_ROWS][D] normalised rows + [PREP_ROWS] norms
+  extern __shared__ __align__(16) float prep_s[];   // [PREP_ROWS][DS] normalised rows + [PREP_ROWS] norms
   const int DS = prep_stride(D);
   float* xs = prep_s;
   float* sqs = prep_s + PREP_ROWS * DS;
@@ -105,6 +108,74 @@ tc_prepare_kernel(const T* __restrict__ feat, int64_t stride_b, int64_t stride_n
 
   const int kcs = KC >> 3, nkb = KP / KC, rgs = tile_rows >> 3, kc_all = KP >> 3;
   const int PA = k_prefix(D);
+  if ((D & 7) == 0) {
+    // One thread per (row, 8-column piece of the normalised row): two LDS.128, hi / lo split once, then the three
+    // 16-byte core-matrix rows that piece feeds (A = [hi | hi | lo], B = [hi | lo | hi]); the remaining chunks of a row
+    // (the extra column pair behind the first segment, zero padding) are a few more items.  Same arithmetic, hence the
+    // same operand bits, as the per-chunk loop below -- at a third of its instructions.
+    const int npiece = D >> 3;
+    const int nmid = (PA - D) >> 3;                                 // chunks between the first segment and PA
+    const int nother = nmid + ((KP - PA - 2 * D) >> 3);
+    const int per_row = npiece + nother;
+    const int items = PREP_ROWS * per_row;
+    for (int ci = threadIdx.x; ci < items; ci += 256) {
+      const int r = ci & 7;
+      const int it = (ci >> 3) % per_row;
+      const int rl = ((ci >> 3) / per_row) * 8 + r;
+      const int prow = r0 + rl;
+      const int tile = prow / tile_rows;
+      if (tile >= tiles) continue;
+      const int rg = (prow - tile * tile_rows) >> 3;
+      const long long tbase = (p * tiles + tile) * (long long)nkb;
+      auto store = [&](int kcI, const uint4& val) {
+        const int kb = kcI / kcs, kc = kcI - kb * kcs;
+        const long long chunk = (((tbase + kb) * rgs + rg) * (long long)kcs + kc) * 8 + r;
+        *reinterpret_cast<uint4*>(op + chunk * 8) = val;
+      };
+      if (it < npiece) {
+        const float4 f0 = *reinterpret_cast<const float4*>(xs + rl * DS + it * 8);
+        const float4 f1 = *reinterpret_cast<const float4*>(xs + rl * DS + it * 8 + 4);
+        const float f[8] = {f0.x, f0.y, f0.z, f0.w, f1.x, f1.y, f1.z, f1.w};
+        __align__(16) __half hi[8], lo[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const float x = f[e] * kScale;
+          hi[e] = __float2half_rn(x);
+          lo[e] = __float2half_rn(x - __half2float(hi[e]));
+        }
+        const uint4 H = *reinterpret_cast<const uint4*>(hi), Lo = *reinterpret_cast<const uint4*>(lo);
+        store(it, H);
+        store((PA >> 3) + it, IS_KEY ? Lo : H);
+        store(((PA + D) >> 3) + it, IS_KEY ? H : Lo);
+      } else {
+        const int o = it - npiece;
+        const int kcI = o < nmid ? npiece + o : ((PA + 2 * D) >> 3) + (o - nmid);
+        __align__(16) __half z[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) z[e] = __float2half_rn(0.f);
+        if (kcI == npiece) {                                          // columns D, D + 1: the extra pair
+          const bool valid = key_of(prow) < rows;
+          float extra_hi, extra_lo;
+          if (IS_KEY) {
+            if (valid) {
+              const float c = -0.5f * sqs[rl] * kScale;
+              extra_hi = __half2float(__float2half_rn(c));
+              extra_lo = c - extra_hi;
+            } else {
+              extra_hi = kPadKey; extra_lo = 0.f;
+            }
+          } else {
+            extra_hi = valid ? kScale : 0.f;
+            extra_lo = extra_hi;
+          }
+          z[0] = __float2half_rn(extra_hi);
+          z[1] = __float2half_rn(extra_lo);
+        }
+        store(kcI, *reinterpret_cast<const uint4*>(z));
+      }
+    }
+    return;
+  }
   const int total = PREP_ROWS * kc_all;
   for (int ci = threadIdx.x; ci < total; ci += 256) {
     const int r = ci & 7;
