@@ -78,15 +78,40 @@ tc_prepare_kernel(const T* __restrict__ feat, int64_t stride_b, int64_t stride_n
     if (row < rows) {
       const T* src = feat + b * stride_b + (long long)row * stride_n + (long long)g * D;
       float ss = 0.f;
-      for (int d = lane; d < D; d += 32) {
-        const float v = to_f32<T>(src[d]);
-        ss = fmaf(v, v, ss);
+      constexpr int NV = DT > 0 ? (DT + 31) / 32 : 1;     // compile-time width: the lane's elements stay in registers
+      float xv[NV];
+      if (DT > 0) {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+          const int d = lane + 32 * i;
+          xv[i] = d < D ? to_f32<T>(src[d]) : 0.f;
+        }
+#pragma unroll
+        for (int i = 0; i < NV; ++i)
+          if (lane + 32 * i < D) ss = fmaf(xv[i], xv[i], ss);
+      } else {
+        for (int d = lane; d < D; d += 32) {
+          const float v = to_f32<T>(src[d]);
+          ss = fmaf(v, v, ss);
+        }
       }
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
       const float denom = fmaxf(sqrtf(ss), 1e-12f);
       float s2 = 0.f;
       float* gh = hat + (p * rows + row) * (long long)D;
+      if (DT > 0) {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+          const int d = lane + 32 * i;
+          if (d < D) {
+            const float v = xv[i] / denom;
+            dst[d] = v;
+            if (write_hat) gh[d] = v;
+            s2 = fmaf(v, v, s2);
+          }
+        }
+      } else
       for (int d = lane; d < D; d += 32) {
         const float v = to_f32<T>(src[d]) / denom;
         dst[d] = v;
