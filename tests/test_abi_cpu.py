@@ -46,6 +46,10 @@ def test_kernels_refuse_cpu_tensors():
         ops.knn_graph(x, None, None, groups=1, k=2)
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         ops.mr_aggregate(x, torch.zeros(1, 8, 2, dtype=torch.int32), None, groups=1)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        ops.pool_keys(x, 4, 2, 2)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        ops.grouped_fc(x.bfloat16(), x.bfloat16(), x[0, 0], "gelu")
 
 
 def test_state_dict_layout_matches_reference():
@@ -83,6 +87,27 @@ def test_grapher_dilation_schedule_and_registry():
     ref = O.head_losses(head.state_dict(), lab, gap, tgt)
     for k in ("bce_loss", "asy_loss"):
         assert torch.allclose(got[k], ref[k], atol=1e-5, rtol=1e-5)
+
+
+def test_basic_conv_folds_its_norm_in_eval():
+    """BasicConv (torch_nn.py:57-81) on the library path: the eval-mode fold of the grouped conv + batch norm equals
+    the modules as written, and the state-dict keys stay the reference's."""
+    from gkgnet_b200.layers import BasicConv
+    torch.manual_seed(0)
+    m = BasicConv([32, 32], "gelu", "batch", True)
+    assert list(m.state_dict().keys())[:3] == ["0.weight", "0.bias", "1.weight"]
+    m[1].running_mean.normal_()
+    m[1].running_var.uniform_(0.5, 2.0)
+    m[1].weight.data.normal_()
+    m[1].bias.data.normal_()
+    m.eval()
+    x = torch.randn(2, 32, 5, 3)
+    with torch.no_grad():
+        got = m(x)
+        want = x
+        for mod in m:
+            want = mod(want)
+    assert torch.allclose(got, want, atol=1e-5, rtol=1e-5)
 
 
 def test_folded_sequential_matches_plain_modules_in_eval():
