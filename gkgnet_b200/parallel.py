@@ -21,6 +21,8 @@ def init_distributed(backend: str | None = None) -> tuple[int, int, int]:
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1 and os.environ.get("GKG_PIN_CORES", "0") == "1":
+        pin_host_cores(local, int(os.environ.get("LOCAL_WORLD_SIZE", world)))
     if world > 1 and not dist.is_initialized():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         if backend is None:
@@ -31,6 +33,21 @@ def init_distributed(backend: str | None = None) -> tuple[int, int, int]:
         else:
             dist.init_process_group(backend)
     return world, rank, local
+
+
+def pin_host_cores(local: int, local_world: int) -> list[int]:
+    """Give every rank of the box its own contiguous slice of the host cores this process may use (the launch
+    threads of the ranks otherwise migrate over each other).  Opt-in: GKG_PIN_CORES=1."""
+    try:
+        cores = sorted(os.sched_getaffinity(0))
+    except AttributeError:
+        return []
+    per = len(cores) // max(local_world, 1)
+    if per < 1:
+        return cores
+    mine = cores[local * per:(local + 1) * per]
+    os.sched_setaffinity(0, mine)
+    return mine
 
 
 def shard_range(total: int, rank: int, world: int) -> tuple[int, int]:
@@ -75,6 +92,7 @@ def data_parallel(module: torch.nn.Module, device: torch.device | None = None, *
         return module
     from torch.nn.parallel import DistributedDataParallel as DDP
     kw.setdefault("broadcast_buffers", False)
+    kw.setdefault("gradient_as_bucket_view", True)      # gradients live in the all-reduce buckets: no copy per step
     if device is not None and device.type == "cuda":
         return DDP(module, device_ids=[device.index], output_device=device.index, **kw)
     return DDP(module, **kw)
