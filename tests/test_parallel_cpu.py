@@ -91,3 +91,29 @@ def test_world2_gloo_gradient_allreduce(tmp_path):
     total.backward()
     for k, p in head.named_parameters():
         assert torch.allclose(p.grad, r0["grads"][k], atol=1e-6, rtol=1e-5), k
+
+
+def test_pin_host_cores_partitions_the_affinity_mask():
+    """Opt-in per-rank core pinning (GKG_PIN_CORES=1): disjoint contiguous slices that cover floor(n / world) cores each;
+    checked in a child process so that the test runner's own affinity stays untouched."""
+    import subprocess
+    import sys
+    code = (
+        "import os, json, sys; sys.path.insert(0, %r)\n"
+        "from gkgnet_b200 import parallel as P\n"
+        "before = sorted(os.sched_getaffinity(0))\n"
+        "mine = P.pin_host_cores(int(sys.argv[1]), int(sys.argv[2]))\n"
+        "print(json.dumps([before, mine, sorted(os.sched_getaffinity(0))]))\n"
+    ) % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    import json
+    world = 2
+    seen = []
+    for local in range(world):
+        out = subprocess.run([sys.executable, "-c", code, str(local), str(world)], capture_output=True, text=True, check=True)
+        before, mine, after = json.loads(out.stdout.strip().splitlines()[-1])
+        if len(before) < world:
+            assert mine == before
+            return
+        assert mine == after and len(mine) == len(before) // world
+        assert set(mine) <= set(before) and not (set(mine) & set(seen))
+        seen += mine
