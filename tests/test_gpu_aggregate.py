@@ -35,6 +35,8 @@ def _oracle_agg(x, idx, y, G):
     (3, 2, 1100, 300, 16, 9),    # bf16: keys staged in shared memory, CTA ranges crossing images
     (2, 2, 1500, 400, 40, 18),   # bf16: shared-memory path, k = 18
     (1, 2, 1296, 1296, 200, 9),  # stage-3 geometry: 10 channel slices of 40
+    (1, 2, 1030, 520, 200, 9),   # 40-channel slices, six nodes per warp pass, ragged last pass (1030 % 6 = 4)
+    (2, 2, 1027, 300, 80, 18),   # 80-channel slices of one group, k = 18, ragged last pass, ranges crossing images
 ])
 def test_aggregate_forward(dtype, B, G, N, M, D, k):
     from gkgnet_b200 import ops
