@@ -119,7 +119,7 @@ class HotPath:
         dev = x.device
         self.dt = _lib.GKG_BF16 if x.dtype == torch.bfloat16 else _lib.GKG_F32
         self.ws_bytes = self.lib.gkg_knn_workspace_bytes(self.B, self.G, self.N, self.M, self.D, self.k,
-                                                         self.d, 0, algo)
+                                                         self.d, 0, self.dt, algo)
         self.ws = torch.empty(self.ws_bytes, dtype=torch.uint8, device=dev)
         self.idx = torch.empty(self.B * self.G, self.N, self.k, dtype=torch.int32, device=dev)
         self.out = torch.empty(self.B, self.N, 2 * self.C, dtype=x.dtype, device=dev)
@@ -146,8 +146,9 @@ class HotPath:
         if record:
             self.ev[1].record(self.stream)
         sa, sb, sw, skw = self.sep
-        self._lib.check(lib.gkg_knn_select(self.rel.data_ptr(), sa, sb, sw, skw, self.idx.data_ptr(), *a, 0, self.algo,
-                                           self.ws.data_ptr(), self.ws_bytes, s), "knn_select")
+        self._lib.check(lib.gkg_knn_select(x.data_ptr(), x.stride(0), x.stride(1), self.rel.data_ptr(), sa, sb, sw, skw,
+                                           self.idx.data_ptr(), *a, 0, self.dt, self.algo, self.ws.data_ptr(),
+                                           self.ws_bytes, s), "knn_select")
         if record:
             self.ev[2].record(self.stream)
         self._lib.check(lib.gkg_mr_aggregate_fwd(x.data_ptr(), x.stride(0), x.stride(1), y.data_ptr(),

@@ -12,7 +12,7 @@ import subprocess
 import threading
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libgkg_b200.so")
+LIB_PATH = os.environ.get("GKG_LIB", os.path.join(HERE, "libgkg_b200.so"))   # override: A/B timing of two builds
 CSRC = os.path.join(HERE, "csrc")
 
 GKG_F32, GKG_BF16 = 0, 1
@@ -26,11 +26,13 @@ SIGNATURES = {
     "gkg_abi_version": (_i32, []),
     "gkg_last_error": (_c.c_char_p, []),
     "gkg_launch_count": (_c.c_uint64, []),
-    "gkg_knn_workspace_bytes": (_sz, [_i32] * 9),
+    "gkg_knn_workspace_bytes": (_sz, [_i32] * 10),
     "gkg_knn_graph": (_i32, [_vp, _i64, _i64, _vp, _i64, _i64, _vp, _vp, _vp, _i32, _i32, _vp]
                       + [_i32] * 9 + [_vp, _sz, _vp]),
     "gkg_knn_prepare": (_i32, [_vp, _i64, _i64, _vp, _i64, _i64] + [_i32] * 9 + [_vp, _sz, _vp]),
-    "gkg_knn_select": (_i32, [_vp, _vp, _vp, _i32, _i32, _vp] + [_i32] * 9 + [_vp, _sz, _vp]),
+    "gkg_knn_select": (_i32, [_vp, _i64, _i64, _vp, _vp, _vp, _i32, _i32, _vp] + [_i32] * 10 + [_vp, _sz, _vp]),
+    "gkg_knn_graph_debug": (_i32, [_vp, _i64, _i64, _vp, _i64, _i64, _vp, _vp, _vp, _i32, _i32, _vp]
+                            + [_i32] * 9 + [_vp, _sz, _vp] + [_i32, _vp, _vp, _i32, _i32]),
     "gkg_mr_aggregate_fwd": (_i32, [_vp, _i64, _i64, _vp, _i64, _i64, _vp, _vp, _vp] + [_i32] * 7 + [_vp]),
     "gkg_mr_aggregate_bwd": (_i32, [_vp, _vp, _vp, _vp, _vp] + [_i32] * 7 + [_vp]),
     "gkg_pool_keys_fwd": (_i32, [_vp, _i64, _i64, _vp] + [_i32] * 6 + [_vp]),
@@ -73,7 +75,7 @@ def load():
             fn = getattr(lib, name)
             fn.restype = res
             fn.argtypes = args
-        if lib.gkg_abi_version() != 1:
+        if lib.gkg_abi_version() != 2:
             raise RuntimeError("libgkg_b200.so ABI version mismatch")
         _lib = lib
     return _lib

@@ -47,18 +47,26 @@ template <> __device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(flo
 
 // ---- kNN workspace carve-up (shared by host wrappers) -------------------------------
 struct KnnWorkspace {
-  float* xhat;   // (P, N, D) normalised queries, fp32
+  float* xhat;   // (P, N, D) normalised queries, fp32 (exact path only: the tensor-core path rebuilds the few rows it needs)
   float* xsq;    // (P, N)    |xhat|^2
-  float* yhat;   // (P, M, D) normalised keys (== xhat when self)
+  float* yhat;   // (P, M, D) normalised keys (== xhat when self on the exact path)
   float* ysq;    // (P, M)
   size_t bytes;
 };
 
-inline KnnWorkspace carve_knn_workspace(void* base, int P, int N, int M, int D, bool self_keys) {
+inline KnnWorkspace carve_knn_workspace(void* base, int P, int N, int M, int D, bool self_keys, bool tc) {
   KnnWorkspace w;
   size_t off = 0;
   char* b = static_cast<char*>(base);
   auto take = [&](size_t n) { void* p = b ? b + off : nullptr; off += align_up(n, 256); return p; };
+  if (tc) {
+    w.xhat = nullptr;
+    w.xsq = nullptr;
+    w.yhat = static_cast<float*>(take(sizeof(float) * (size_t)P * M * D));
+    w.ysq = static_cast<float*>(take(sizeof(float) * (size_t)P * M));
+    w.bytes = off;
+    return w;
+  }
   w.xhat = static_cast<float*>(take(sizeof(float) * (size_t)P * N * D));
   w.xsq = static_cast<float*>(take(sizeof(float) * (size_t)P * N));
   if (self_keys) {

@@ -5,22 +5,21 @@
 //     dist[n, m] = (|xh_n|^2 - 2 xh_n . yh_m) + |yh_m|^2 + relative_pos[n, m]
 // in ascending order, every `dilation`-th kept.  The N x M matrix never leaves the SM:
 //
-//   * operands: gkg_knn_prepare splits the normalised fp32 rows into fp16 hi/lo parts
-//     (scaled by 256 so the lo part stays normal) and writes them K-concatenated,
-//         A = [x_hi | x_hi | x_lo | S  S ],   B = [y_hi | y_lo | y_hi | c_hi c_lo]
-//     with c = -0.5*|yh|^2*S, so ONE fp16 GEMM with fp32 accumulation yields
-//     S^2 (xh.yh - |yh|^2/2) to ~2^-21 relative -- the "fp16x3" split.  Rows are stored
-//     in the UMMA no-swizzle K-major core-matrix order, tile by tile, so a whole operand
-//     tile is one contiguous TMA bulk copy (cp.async.bulk, mbarrier complete_tx);
-//   * warp 0 streams tiles (A: one 128-row query tile, all K; B: 128-key blocks through a
-//     ring), warp 1 issues tcgen05.mma (M=128, N=128, K=16 per instruction) into one of
-//     four 128-column TMEM accumulators, warps 2-5 drain accumulators with tcgen05.ld
-//     (thread == query row), add the bias and keep a per-row candidate list;
-//   * selection: threshold filter into a per-thread shared-memory buffer (branch-free),
-//     batched insertion into a sorted register list of T = k*d + 2 entries;
-//   * exactness: rows whose approximate gaps are below 2*delta are re-ranked with the
-//     exact fp32 formula (same arithmetic as knn_exact.cu); rows whose candidate set
-//     itself is in doubt go to a tiny exact fix-up kernel.
+//   * operands: gkg_knn_prepare normalises the rows, splits them into fp16 hi/lo parts (scaled by 256 so the lo
+//     part stays normal) and writes them K-concatenated,
+//         A = [x_hi | S  S | 0.. | x_hi | x_lo],   B = [y_hi | c_hi c_lo | 0.. | y_lo | y_hi],   c = -0.5*|yh|^2*S,
+//     so ONE fp16 GEMM with fp32 accumulation yields S^2 (xh.yh - |yh|^2/2) to ~2^-21 relative (the "fp16x3" split),
+//     and its first PA columns alone the single-plane product the threshold sweep uses.  Rows are stored in the UMMA
+//     no-swizzle K-major core-matrix order, tile by tile, so an operand block is one contiguous TMA bulk copy;
+//   * knn_tc_kernel (persistent, warp specialised, see knn_tc_kernel.cuh): warp 0 streams operand blocks, one warp per
+//     row set issues tcgen05.mma into TMEM accumulators, the epilogue warps drain them with tcgen05.ld (thread ==
+//     query row), add the position bias and select in two sweeps over the keys of an item: a threshold sweep (sorted
+//     register list of group maxima) and a logging sweep (predicated 16-byte shared-memory stores of the key triplets
+//     that beat the threshold); the logged keys that reach the threshold go to global memory;
+//   * knn_finalize_kernel sorts the handful of candidates per row, certifies the approximate order by its gaps
+//     (>= 2 delta) and writes the dilated pick; rows that fail are re-ranked with the exact fp32 formula
+//     (knn_rerank_kernel: same arithmetic as knn_exact.cu, the normalised query row rebuilt from the raw features),
+//     rows whose candidate set itself is in doubt go to an exact brute-force kernel (knn_fixup_kernel).
 #include "knn_tc_kernel.cuh"
 
 namespace gkg {
@@ -28,6 +27,8 @@ namespace gkg {
 using namespace tc;
 
 namespace {
+
+constexpr float kEps = 1e-12f;     // F.normalize eps
 
 // ------------------------------------------------------------------------------------
 // operand preparation (phase "prepare"): normalise + split + lay out, one pass over the features
@@ -515,7 +516,41 @@ knn_finalize_kernel(const float2* __restrict__ cand, const int* __restrict__ can
 }
 
 // ------------------------------------------------------------------------------------
-// exact re-rank of rows whose approximate order is ambiguous (a few per thousand)
+// exact arithmetic of the slow paths: the normalised query row rebuilt from the raw features
+// ------------------------------------------------------------------------------------
+struct RawFeat {
+  const void* x; int64_t sb, sn; int dtype; int G;
+};
+// A warp normalises group row (p, n) into dst[0..D) with the arithmetic of knn_prepare.cu (lane-strided sums,
+// xor-shuffle tree, true division); returns |xh|^2.
+__device__ __forceinline__ float normalise_row_warp(const RawFeat& f, int p, int n, int D, float* dst, int lane) {
+  const int g = p % f.G;
+  const long long b = p / f.G;
+  const long long off = b * f.sb + (long long)n * f.sn + (long long)g * D;
+  float ss = 0.f;
+  for (int d = lane; d < D; d += 32) {
+    const float v = f.dtype == GKG_F32 ? static_cast<const float*>(f.x)[off + d]
+                                       : __bfloat162float(static_cast<const __nv_bfloat16*>(f.x)[off + d]);
+    dst[d] = v;
+    ss = fmaf(v, v, ss);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  const float denom = fmaxf(sqrtf(ss), kEps);
+  float s2 = 0.f;
+  for (int d = lane; d < D; d += 32) {
+    const float v = dst[d] / denom;
+    dst[d] = v;
+    s2 = fmaf(v, v, s2);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+  __syncwarp();
+  return s2;
+}
+
+// ------------------------------------------------------------------------------------
+// exact re-rank of rows whose approximate order is ambiguous
 // ------------------------------------------------------------------------------------
 // One warp per listed row; lane c (and c + 32) owns candidate c of the row's <= TL candidates: exact fp32
 // distance with the arithmetic of knn_exact.cu, rank by counting over (distance, id), dilated pick.  The
@@ -523,21 +558,23 @@ knn_finalize_kernel(const float2* __restrict__ cand, const int* __restrict__ can
 // k*d nearest.  List entry: [row, np, approx bound of the keys outside, ids[TL], approx values[TL]].
 __global__ void __launch_bounds__(256)
 knn_rerank_kernel(const int* __restrict__ rr_count, const int* __restrict__ rr_list, int rr_cap, int TL,
-                  const float* __restrict__ xhat, const float* __restrict__ xsq, const float* __restrict__ yhat,
-                  const float* __restrict__ ysq, const float* __restrict__ relpos, int32_t* __restrict__ idx_out,
+                  RawFeat xf, const float* __restrict__ yhat, const float* __restrict__ ysq,
+                  const float* __restrict__ relpos, int32_t* __restrict__ idx_out,
                   int* fix_count, int* fix_rows, unsigned int* stats, int N, int M, int D, int k, int dilation,
                   float delta) {
-  const int lane = threadIdx.x & 31;
+  extern __shared__ __align__(16) float xrow_s[];      // [8 warps][D4 * 4]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float* xr = xrow_s + warp * ((D + 3) / 4 * 4);
   const int total = min(*rr_count, rr_cap);
   const int kd = k * dilation;
   const int stride = 2 * TL + 3;
-  for (int e = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); e < total; e += gridDim.x * (blockDim.x >> 5)) {
+  for (int e = blockIdx.x * (blockDim.x >> 5) + warp; e < total; e += gridDim.x * (blockDim.x >> 5)) {
     const int* ent = rr_list + (size_t)e * stride;
     const int row = ent[0], np = ent[1];
     const float a_last = __int_as_float(ent[2]);
     const int p = row / N, n = row - p * N;
-    const float* xr = xhat + (size_t)row * D;
-    const float xs = xsq[row];
+    __syncwarp();
+    const float xs = normalise_row_warp(xf, p, n, D, xr, lane);
     const float* relrow = relpos ? relpos + (size_t)n * M : nullptr;
     float ev[2];
     int id[2];
@@ -581,46 +618,56 @@ knn_rerank_kernel(const int* __restrict__ rr_count, const int* __restrict__ rr_l
 // Per listed row, one CTA: exact distances to all M keys, then the k*d nearest by (distance, id).  Selection:
 // a 1024-bin histogram over [min, max] (the bin index is monotone in the distance) locates the bin that holds
 // the k*d-th nearest; the keys up to that bin -- a superset of the answer, every other key is strictly farther --
-// are compacted and ranked by counting among themselves.  A handful of barriers per row instead of two per
-// selected neighbour; when all distances fall into one bin the counting runs over all M keys (still exact).
+// are compacted and ranked by counting among themselves.  When they exceed the candidate slots (a pile of tied
+// distances) the counting runs over all M keys (still exact).
 constexpr int kFixBins = 1024;
 constexpr int kFixCand = 2048;                 // candidate slots (keys up to the selected bin)
+constexpr int kFixTile = 8192;                 // keys whose distances live in shared memory at a time
 __global__ void __launch_bounds__(256)
-knn_fixup_kernel(const int* __restrict__ count, const int* __restrict__ rows, const float* __restrict__ xhat,
-                 const float* __restrict__ xsq, const float* __restrict__ yhat, const float* __restrict__ ysq,
-                 const float* __restrict__ relpos, int32_t* __restrict__ idx_out, int N, int M, int D, int k,
-                 int dilation) {
-  extern __shared__ float dist_s[];            // [M] distances, [cap] candidate distances, [cap] candidate ids
+knn_fixup_kernel(const int* __restrict__ count, const int* __restrict__ rows, RawFeat xf,
+                 const float* __restrict__ yhat, const float* __restrict__ ysq,
+                 const float* __restrict__ relpos, int32_t* __restrict__ idx_out, float* __restrict__ dist_g,
+                 int N, int M, int D, int k, int dilation) {
+  extern __shared__ __align__(16) float fix_s[];   // [D4*4] query row, [Ms] distances, [cap] candidate distances, [cap] candidate ids
+  const int Ms = M <= kFixTile ? M : 0;            // more keys than that: the distances go to a global scratch row
   const int cap = M < kFixCand ? M : kFixCand;
-  float* cand_v = dist_s + M;
-  int* cand_i = reinterpret_cast<int*>(dist_s + M + cap);
+  float* xr = fix_s;
+  float* dist_s = fix_s + (D + 3) / 4 * 4;
+  float* cand_v = dist_s + Ms;
+  int* cand_i = reinterpret_cast<int*>(cand_v + cap);
   __shared__ int hist[kFixBins];
   __shared__ float red_lo[8], red_hi[8];
+  __shared__ float xs_s;
   __shared__ int bin_sel, ncand, nsel_s;
   const int total = *count;
   const int kd = k * dilation;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float* dist = Ms > 0 ? dist_s : dist_g + (size_t)blockIdx.x * M;
   for (int item = blockIdx.x; item < total; item += gridDim.x) {
     const int id = rows[item];
     const int p = id / N, n = id - p * N;
-    const float* xr = xhat + (size_t)id * D;
-    const float xs = xsq[id];
+    if (warp == 0) {
+      const float s = normalise_row_warp(xf, p, n, D, xr, lane);
+      if (lane == 0) xs_s = s;
+    }
+    for (int q = threadIdx.x; q < kFixBins; q += blockDim.x) hist[q] = 0;
+    if (threadIdx.x == 0) ncand = 0;
+    __syncthreads();
+    const float xs = xs_s;
     const float* relrow = relpos ? relpos + (size_t)n * M : nullptr;
     float lo = INFINITY, hi = -INFINITY;
     for (int m = threadIdx.x; m < M; m += blockDim.x) {
       const float v = exact_dist(xr, yhat + ((size_t)p * M + m) * D, D, xs, ysq[(size_t)p * M + m], relrow, m);
-      dist_s[m] = v;
+      dist[m] = v;
       lo = fminf(lo, v);
       hi = fmaxf(hi, v);
     }
-    for (int q = threadIdx.x; q < kFixBins; q += blockDim.x) hist[q] = 0;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
       lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o));
       hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o));
     }
     if (lane == 0) { red_lo[warp] = lo; red_hi[warp] = hi; }
-    if (threadIdx.x == 0) ncand = 0;
     __syncthreads();
 #pragma unroll
     for (int w = 0; w < 8; ++w) { lo = fminf(lo, red_lo[w]); hi = fmaxf(hi, red_hi[w]); }
@@ -629,7 +676,7 @@ knn_fixup_kernel(const int* __restrict__ count, const int* __restrict__ rows, co
       const int q = (int)((v - lo) * scale);
       return q < 0 ? 0 : (q < kFixBins ? q : kFixBins - 1);
     };
-    for (int m = threadIdx.x; m < M; m += blockDim.x) atomicAdd(&hist[bin_of(dist_s[m])], 1);
+    for (int m = threadIdx.x; m < M; m += blockDim.x) atomicAdd(&hist[bin_of(dist[m])], 1);
     __syncthreads();
     if (warp == 0) {                           // first bin whose prefix count reaches k*d
       constexpr int PER = kFixBins / 32;
@@ -645,12 +692,13 @@ knn_fixup_kernel(const int* __restrict__ count, const int* __restrict__ rows, co
       const int first = reach ? __ffs(reach) - 1 : 31;
       if (lane == first) {
         int run = incl - part, q = 0;
-        for (; q < PER - 1; ++q) {
+        for (; q < PER; ++q) {                  // keys up to and including bin q of this lane
           run += hist[lane * PER + q];
           if (run >= kd) break;
         }
+        if (q == PER) q = PER - 1;
         bin_sel = reach ? lane * PER + q : kFixBins - 1;
-        nsel_s = reach ? run : M;               // keys up to and including that bin
+        nsel_s = reach ? run : M;
       }
     }
     __syncthreads();
@@ -658,15 +706,14 @@ knn_fixup_kernel(const int* __restrict__ count, const int* __restrict__ rows, co
     const int bsel = bin_sel;
     if (nsel <= cap) {
       for (int m = threadIdx.x; m < M; m += blockDim.x) {
-        const float v = dist_s[m];
+        const float v = dist[m];
         if (bin_of(v) <= bsel) {
           const int pos = atomicAdd(&ncand, 1);
-          cand_v[pos] = v;
-          cand_i[pos] = m;
+          if (pos < cap) { cand_v[pos] = v; cand_i[pos] = m; }
         }
       }
       __syncthreads();
-      const int nc = ncand;
+      const int nc = ncand < cap ? ncand : cap;
       for (int c = threadIdx.x; c < nc; c += blockDim.x) {
         const float v = cand_v[c];
         const int m = cand_i[c];
@@ -679,11 +726,11 @@ knn_fixup_kernel(const int* __restrict__ count, const int* __restrict__ rows, co
       }
     } else {                                   // (nearly) all distances in one bin: count over every key
       for (int m = threadIdx.x; m < M; m += blockDim.x) {
-        const float v = dist_s[m];
+        const float v = dist[m];
         if (bin_of(v) > bsel) continue;
         int rank = 0;
         for (int j = 0; j < M && rank < kd; ++j) {
-          const float u = dist_s[j];
+          const float u = dist[j];
           rank += (u < v) || (u == v && j < m);
         }
         if (rank < kd && rank % dilation == 0) idx_out[(size_t)id * k + rank / dilation] = m;
@@ -692,10 +739,11 @@ knn_fixup_kernel(const int* __restrict__ count, const int* __restrict__ rows, co
     __syncthreads();
   }
 }
+constexpr int kFixBlocks = 148;
 
 struct TcWorkspace {
   __half* a_op; __half* b_op; int* fix_count; int* fix_rows; unsigned int* stats;
-  int* rr_count; int* rr_list; int rr_cap;
+  int* rr_count; int* rr_list; int rr_cap; float* fix_dist;
   float2* cand; int* cand_count; float* cand_thr; int cand_slots; size_t bytes;
 };
 
@@ -707,7 +755,7 @@ static int rerank_cap(int P, int N) {
   return (int)(cap < rows ? cap : rows);
 }
 
-TcWorkspace carve_tc(void* base, const Plan& pl, int P, int N, int T) {
+TcWorkspace carve_tc(void* base, const Plan& pl, int P, int N, int M, int T) {
   TcWorkspace w;
   size_t off = 0;
   char* b = static_cast<char*>(base);
@@ -720,6 +768,7 @@ TcWorkspace carve_tc(void* base, const Plan& pl, int P, int N, int T) {
   w.fix_rows = static_cast<int*>(take(sizeof(int) * (size_t)P * N));
   w.rr_cap = rerank_cap(P, N);
   w.rr_list = static_cast<int*>(take(sizeof(int) * (size_t)w.rr_cap * (2 * (T + 3) + 3)));
+  w.fix_dist = static_cast<float*>(take(M > kFixTile ? sizeof(float) * (size_t)kFixBlocks * M : 0));
   {   // candidate hand-over of the select kernel: per item (pl.QI items of rows_per_item rows per problem)
     const int rows_per_item = (pl.geom == 1 ? GeomB::ROWS : GeomA::ROWS);
     const size_t item_rows = (size_t)P * pl.QI * rows_per_item;
@@ -732,17 +781,12 @@ TcWorkspace carve_tc(void* base, const Plan& pl, int P, int N, int T) {
   return w;
 }
 
-int g_force_rerank = 0;
-float* g_dbg_dist = nullptr;
-long long* g_trace = nullptr;
-int g_trace_tiles = 0;
-unsigned int g_last_stats[4] = {0, 0, 0, 0};
-
 }  // namespace
 
 static int t_bucket(int T) { return T <= 11 ? 11 : T <= 20 ? 20 : T <= 29 ? 29 : 38; }
 
-bool knn_tc_supported(int N, int M, int D, int k, int dilation) {
+bool knn_tc_supported(int N, int M, int D, int k, int dilation, int dtype) {
+  (void)dtype;
   const int kd = k * dilation;
   if (kd + 2 > MAX_T || kd > M) return false;
   if (N < 1 || M < 1 || M > 65000) return false;   // key ids travel in 16 bits of a log entry
@@ -752,15 +796,15 @@ bool knn_tc_supported(int N, int M, int D, int k, int dilation) {
 
 // AUTO picks the tensor-core path only when the threshold sweep has enough key groups to work with
 // (tiny key sets would send every row to the brute-force fix-up: correct, but the exact kernel is faster).
-bool knn_tc_preferred(int N, int M, int D, int k, int dilation) {
-  return knn_tc_supported(N, M, D, k, dilation) && M / 3 >= 2 * t_bucket(k * dilation + 2);
+bool knn_tc_preferred(int N, int M, int D, int k, int dilation, int dtype) {
+  return knn_tc_supported(N, M, D, k, dilation, dtype) && M / 3 >= 2 * t_bucket(k * dilation + 2);
 }
 
-size_t knn_tc_workspace_bytes(int P, int N, int M, int D, int k, int dilation, bool self_keys) {
-  (void)self_keys;
+size_t knn_tc_workspace_bytes(int P, int N, int M, int D, int k, int dilation, int dtype) {
+  (void)dtype;
   Plan pl = make_plan(P, N, M, D, t_bucket(k * dilation + 2));
   if (!pl.ok) return 0;
-  return carve_tc(nullptr, pl, P, N, t_bucket(k * dilation + 2)).bytes;
+  return carve_tc(nullptr, pl, P, N, M, t_bucket(k * dilation + 2)).bytes;
 }
 
 // row-per-thread path: D in {20, 40, 80}, rows 16-byte aligned
@@ -771,16 +815,15 @@ static int launch_prepare_rows(const KnnWorkspace& w, const TcWorkspace& t, cons
   const int bn = pl.geom == 1 ? GeomB::BN : GeomA::BN, bnp = pl.geom == 1 ? GeomB::BNP : GeomA::BNP;
   {
     dim3 grid((pl.QTP * BM + PREP_THREADS - 1) / PREP_THREADS, P);
-    tc_prepare_rows_kernel<T, D, false><<<grid, PREP_THREADS, 0, stream>>>(x, x_sb, x_sn, w.xhat, w.xsq, t.a_op, G, N,
-                                                                           pl.KC, pl.QTP, BM, BM, 1);
+    tc_prepare_rows_kernel<T, D, false><<<grid, PREP_THREADS, 0, stream>>>(x, x_sb, x_sn, nullptr, nullptr, t.a_op, G, N,
+                                                                           pl.KC, pl.QTP, BM, BM, 0);
     GKG_CHECK_LAUNCH("tc_prepare_rows_kernel<query>");
   }
   {
     dim3 grid((pl.KT * bnp + PREP_THREADS - 1) / PREP_THREADS, P);
     const T* src = self_keys ? x : y;
     tc_prepare_rows_kernel<T, D, true><<<grid, PREP_THREADS, 0, stream>>>(
-        src, self_keys ? x_sb : y_sb, self_keys ? x_sn : y_sn, w.yhat, w.ysq, t.b_op, G, M, pl.KC, pl.KT, bnp, bn,
-        self_keys ? 0 : 1);
+        src, self_keys ? x_sb : y_sb, self_keys ? x_sn : y_sn, w.yhat, w.ysq, t.b_op, G, M, pl.KC, pl.KT, bnp, bn, 1);
     GKG_CHECK_LAUNCH("tc_prepare_rows_kernel<key>");
   }
   return GKG_OK;
@@ -814,13 +857,14 @@ static int launch_prepare_typed(const KnnWorkspace& w, const TcWorkspace& t, con
   const int bn = pl.geom == 1 ? GeomB::BN : GeomA::BN, bnp = pl.geom == 1 ? GeomB::BNP : GeomA::BNP;
   {
     dim3 grid((pl.QTP * BM + PREP_ROWS - 1) / PREP_ROWS, P);
-    if (smem > 48 * 1024) {   // wide groups (D > 380): opt in to the larger dynamic shared memory
-      cudaFuncSetAttribute(tc_prepare_kernel<T, false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      cudaFuncSetAttribute(tc_prepare_kernel<T, true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    }
+    static std::atomic<uint64_t> configured{0};
+    configure_once_per_device(configured, [] {   // wide groups (D > 380) need more than 48 KB of dynamic shared memory
+      cudaFuncSetAttribute(tc_prepare_kernel<T, false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+      cudaFuncSetAttribute(tc_prepare_kernel<T, true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+    });
     auto kq = D == 200 ? tc_prepare_kernel<T, false, 200> : D == 320 ? tc_prepare_kernel<T, false, 320> : tc_prepare_kernel<T, false, 0>;
-    kq<<<grid, 256, smem, stream>>>(static_cast<const T*>(x), x_sb, x_sn, w.xhat, w.xsq, t.a_op, G, N, D, pl.KP, pl.KC,
-                                    pl.QTP, BM, BM, 1);
+    kq<<<grid, 256, smem, stream>>>(static_cast<const T*>(x), x_sb, x_sn, nullptr, nullptr, t.a_op, G, N, D, pl.KP, pl.KC,
+                                    pl.QTP, BM, BM, 0);
     GKG_CHECK_LAUNCH("tc_prepare_kernel<query>");
   }
   {
@@ -828,7 +872,7 @@ static int launch_prepare_typed(const KnnWorkspace& w, const TcWorkspace& t, con
     const T* src = static_cast<const T*>(self_keys ? x : y);
     auto kk = D == 200 ? tc_prepare_kernel<T, true, 200> : D == 320 ? tc_prepare_kernel<T, true, 320> : tc_prepare_kernel<T, true, 0>;
     kk<<<grid, 256, smem, stream>>>(src, self_keys ? x_sb : y_sb, self_keys ? x_sn : y_sn, w.yhat, w.ysq, t.b_op, G, M, D,
-                                    pl.KP, pl.KC, pl.KT, bnp, bn, self_keys ? 0 : 1);
+                                    pl.KP, pl.KC, pl.KT, bnp, bn, 1);
     GKG_CHECK_LAUNCH("tc_prepare_kernel<key>");
   }
   return GKG_OK;
@@ -840,21 +884,21 @@ int launch_knn_tc_prepare(const KnnWorkspace& w, void* extra_ws, const void* x, 
   Plan pl = make_plan(P, N, M, D, t_bucket(k * dilation + 2));
   GKG_CHECK_ARG(pl.ok, "knn_tc: no tiling for D=%d", D);
   GKG_CHECK_ARG(P <= 65535, "knn_tc: B*G=%d > 65535", P);
-  TcWorkspace t = carve_tc(extra_ws, pl, P, N, t_bucket(k * dilation + 2));
+  TcWorkspace t = carve_tc(extra_ws, pl, P, N, M, t_bucket(k * dilation + 2));
   if (dtype == GKG_F32)
     return launch_prepare_typed<float>(w, t, pl, x, x_sb, x_sn, y, y_sb, y_sn, P, G, N, M, D, self_keys, stream);
   return launch_prepare_typed<__nv_bfloat16>(w, t, pl, x, x_sb, x_sn, y, y_sb, y_sn, P, G, N, M, D, self_keys,
                                              stream);
 }
 
-int launch_knn_tc(const KnnWorkspace& w, void* extra_ws, const float* relpos, const SepBias& sep,
-                  int32_t* idx_out, int P, int N, int M, int D, int k, int dilation, bool self_keys,
-                  cudaStream_t stream) {
-  (void)self_keys;
+int launch_knn_tc(const KnnWorkspace& w, void* extra_ws, const void* x, int64_t x_sb, int64_t x_sn, int dtype, int G,
+                  const float* relpos, const SepBias& sep, int32_t* idx_out, int P, int N, int M, int D, int k,
+                  int dilation, const KnnDebug* dbg, cudaStream_t stream) {
+  const int flags = dbg ? dbg->flags : 0;
   Plan pl = make_plan(P, N, M, D, t_bucket(k * dilation + 2));
   GKG_CHECK_ARG(pl.ok, "knn_tc: no tiling for D=%d", D);
   const int T = t_bucket(k * dilation + 2);
-  TcWorkspace t = carve_tc(extra_ws, pl, P, N, T);
+  TcWorkspace t = carve_tc(extra_ws, pl, P, N, M, T);
   cudaError_t e = cudaMemsetAsync(t.fix_count, 0, 256, stream);
   if (e != cudaSuccess) {
     set_error("knn_tc: memset: %s", cudaGetErrorString(e));
@@ -863,20 +907,20 @@ int launch_knn_tc(const KnnWorkspace& w, void* extra_ws, const float* relpos, co
   count_launch();
   TcParams prm{};
   prm.a_op = t.a_op; prm.b_op = t.b_op;
-  prm.xhat = w.xhat; prm.xsq = w.xsq; prm.yhat = w.yhat; prm.ysq = w.ysq;
+  prm.yhat = w.yhat; prm.ysq = w.ysq;
   prm.relpos = relpos; prm.idx_out = idx_out;
   prm.fix_count = t.fix_count; prm.fix_rows = t.fix_rows; prm.stats = t.stats;
   prm.rr_count = t.rr_count; prm.rr_list = t.rr_list; prm.rr_cap = t.rr_cap;
   prm.cand = t.cand; prm.cand_count = t.cand_count; prm.cand_thr = t.cand_thr; prm.cand_slots = t.cand_slots;
-  prm.dbg_dist = g_dbg_dist;
-  prm.trace = g_trace; prm.trace_tiles = g_trace_tiles;
+  prm.dbg_dist = dbg ? dbg->dist : nullptr;
   prm.P = P; prm.N = N; prm.M = M; prm.D = D; prm.k = k; prm.dilation = dilation; prm.kd = k * dilation;
   prm.KP = pl.KP; prm.PA = pl.PA; prm.KC = pl.KC; prm.NKB = pl.NKB; prm.NKBA = pl.NKBA; prm.NA = pl.NA; prm.NS = pl.NS; prm.QT = pl.QT;
   prm.QI = pl.QI; prm.QTP = pl.QTP; prm.KT = pl.KT;
   prm.a_tile_bytes = pl.a_tile_bytes; prm.b_block_bytes = pl.b_block_bytes;
-  prm.force_rerank = g_force_rerank;
+  prm.force_rerank = flags;
   prm.delta = tc_delta(pl.KP);
-  const int ga = (M / 18 >= 3 * (T - 1)) ? 18 : (M / 6 >= 3 * (T - 1)) ? 6 : 3;
+  int ga = (M / 18 >= 3 * (T - 1)) ? 18 : (M / 6 >= 3 * (T - 1)) ? 6 : 3;
+  if (dbg && (dbg->ga == 18 || dbg->ga == 6 || dbg->ga == 3)) ga = dbg->ga;
   prm.sep_a = sep.a; prm.sep_b = sep.b; prm.grid_w = sep.grid_w > 0 ? sep.grid_w : 1;
   prm.sep_mh = sep.kw > 0 ? M / sep.kw : 1;
   const int bn = pl.geom == 1 ? GeomB::BN : GeomA::BN;
@@ -904,53 +948,41 @@ int launch_knn_tc(const KnnWorkspace& w, void* extra_ws, const float* relpos, co
 #define GKG_FINALIZE(LL)                                                                                          \
     knn_finalize_kernel<LL><<<blocks, 256, 0, stream>>>(t.cand, t.cand_count, t.cand_thr, t.cand_slots, rows_per_item, \
         row_sets, pl.QI, idx_out, t.rr_count, t.rr_list, t.rr_cap, t.fix_count, t.fix_rows, t.stats, total_rows, N, M,  \
-        k, dilation, prm.delta, g_force_rerank)
+        k, dilation, prm.delta, flags)
     if (T == 11) GKG_FINALIZE(14); else if (T == 20) GKG_FINALIZE(23); else if (T == 29) GKG_FINALIZE(32); else GKG_FINALIZE(41);
 #undef GKG_FINALIZE
     GKG_CHECK_LAUNCH("knn_finalize_kernel");
   }
+  RawFeat xf{x, x_sb, x_sn, dtype, G};
   {
     const int blocks = (t.rr_cap + 7) / 8 < 148 * 4 ? (t.rr_cap + 7) / 8 : 148 * 4;
-    knn_rerank_kernel<<<blocks, 256, 0, stream>>>(t.rr_count, t.rr_list, t.rr_cap, T + 3, w.xhat, w.xsq, w.yhat, w.ysq,
-                                                  relpos, idx_out, t.fix_count, t.fix_rows, t.stats, N, M, D, k,
-                                                  dilation, prm.delta);
+    const size_t rsmem = sizeof(float) * 8 * (size_t)((D + 3) / 4 * 4);
+    knn_rerank_kernel<<<blocks, 256, rsmem, stream>>>(t.rr_count, t.rr_list, t.rr_cap, T + 3, xf, w.yhat, w.ysq,
+                                                      relpos, idx_out, t.fix_count, t.fix_rows, t.stats, N, M, D, k,
+                                                      dilation, prm.delta);
     GKG_CHECK_LAUNCH("knn_rerank_kernel");
   }
-  const size_t fsmem = sizeof(float) * ((size_t)M + 2 * (size_t)(M < kFixCand ? M : kFixCand));
-  GKG_CHECK_ARG(fsmem <= 200 * 1024, "knn_tc: M=%d too large for the fix-up kernel", M);
-  static size_t fix_configured = 0;
-  if (fsmem > 48 * 1024 && fsmem > fix_configured) {
-    cudaFuncSetAttribute(knn_fixup_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem);
-    fix_configured = fsmem;
+  {
+    const size_t fsmem = sizeof(float) * ((size_t)((D + 3) / 4 * 4) + (M <= kFixTile ? (size_t)M : 0) +
+                                          2 * (size_t)(M < kFixCand ? M : kFixCand));
+    static std::atomic<uint64_t> configured{0};
+    configure_once_per_device(configured, [] {
+      cudaFuncSetAttribute(knn_fixup_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    });
+    knn_fixup_kernel<<<kFixBlocks, 256, fsmem, stream>>>(t.fix_count, t.fix_rows, xf, w.yhat, w.ysq, relpos, idx_out,
+                                                         t.fix_dist, N, M, D, k, dilation);
+    GKG_CHECK_LAUNCH("knn_fixup_kernel");
   }
-  knn_fixup_kernel<<<148, 256, fsmem, stream>>>(t.fix_count, t.fix_rows, w.xhat, w.xsq, w.yhat, w.ysq, relpos,
-                                                idx_out, N, M, D, k, dilation);
-  GKG_CHECK_LAUNCH("knn_fixup_kernel");
-  if (g_dbg_dist != nullptr || g_force_rerank) {   // debug only: expose the counters
+  if (dbg && dbg->stats_out) {   // tests only: expose the counters [fix-up rows, ambiguous rows, max error bits]
     cudaStreamSynchronize(stream);
-    cudaMemcpy(g_last_stats, t.fix_count, sizeof(g_last_stats), cudaMemcpyDeviceToHost);
-    // layout: [0] fix_count, [4..] stats -> copy stats separately
-    unsigned int st[2];
-    cudaMemcpy(st, t.stats, sizeof(st), cudaMemcpyDeviceToHost);
-    g_last_stats[1] = st[0];
-    g_last_stats[2] = st[1];
+    unsigned int h[12];
+    cudaMemcpy(h, t.fix_count, sizeof(h), cudaMemcpyDeviceToHost);
+    dbg->stats_out[0] = h[0];
+    dbg->stats_out[1] = h[4];
+    dbg->stats_out[2] = h[5];
   }
   return GKG_OK;
 }
 
 }  // namespace gkg
 
-// debug hooks (not part of the public header; used by tests through ctypes)
-extern "C" void gkg_debug_knn_tc(int force_rerank, float* dbg_dist) {
-  gkg::g_force_rerank = force_rerank;
-  gkg::g_dbg_dist = dbg_dist;
-}
-extern "C" void gkg_debug_knn_tc_trace(long long* buf, int tiles) {
-  gkg::g_trace = buf;
-  gkg::g_trace_tiles = tiles;
-}
-extern "C" void gkg_debug_knn_tc_stats(unsigned int* out3) {
-  out3[0] = gkg::g_last_stats[0];
-  out3[1] = gkg::g_last_stats[1];
-  out3[2] = gkg::g_last_stats[2];
-}

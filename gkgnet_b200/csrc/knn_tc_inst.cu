@@ -6,11 +6,15 @@ namespace tc {
 
 template <class G, int T, int BIAS, int GA>
 static int launch_select_tb(const TcParams& prm, const Plan& pl, cudaStream_t stream) {
-  auto kern = (prm.dbg_dist != nullptr || prm.trace != nullptr) ? knn_tc_kernel<G, T, BIAS, GA, true> : knn_tc_kernel<G, T, BIAS, GA, false>;
-  size_t smem = pl.smem_bytes < 120 * 1024 ? 120 * 1024 : pl.smem_bytes;   // 512 TMEM columns: 1 CTA / SM
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  auto kern = prm.dbg_dist != nullptr ? knn_tc_kernel<G, T, BIAS, GA, true> : knn_tc_kernel<G, T, BIAS, GA, false>;
+  const size_t smem = pl.smem_bytes < 120 * 1024 ? 120 * 1024 : pl.smem_bytes;   // 512 TMEM columns: 1 CTA / SM
+  static std::atomic<uint64_t> configured[2];
+  cudaError_t e = cudaSuccess;
+  configure_once_per_device(configured[prm.dbg_dist != nullptr ? 1 : 0], [&] {
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget);
+  });
   if (e != cudaSuccess) {
-    set_error("knn_tc: cudaFuncSetAttribute(%zu): %s", smem, cudaGetErrorString(e));
+    set_error("knn_tc: cudaFuncSetAttribute(%zu): %s", kSmemBudget, cudaGetErrorString(e));
     return GKG_ECUDA;
   }
   int dev = 0, sms = 148;

@@ -403,7 +403,7 @@ struct Chunk {
 struct TcParams {
   const __half* a_op;
   const __half* b_op;
-  const float* xhat; const float* xsq; const float* yhat; const float* ysq;
+  const float* yhat; const float* ysq;
   const float* relpos;             // dense (N, M) bias, or null
   const float* sep_a;              // separable bias: A (grid_w, KW), B (N / grid_w, M / KW)
   const float* sep_b;
@@ -413,8 +413,6 @@ struct TcParams {
   int* rr_count; int* rr_list; int rr_cap;              // rows whose candidates go to the exact re-rank kernel
   float2* cand; int* cand_count; float* cand_thr; int cand_slots;   // per item: [slot][row] (score, id), [row] count / threshold
   float* dbg_dist;
-  long long* trace;                // debug: clock64 stamps of CTA 0, 8 slots per key tile (see tools/knn_trace.py)
-  int trace_tiles;
   int P, N, M, D, k, dilation, kd;
   int KP, PA, KC, NKB, NKBA, NA, NS, QT, QI, QTP, KT;
   uint32_t a_tile_bytes, b_block_bytes;
@@ -422,6 +420,7 @@ struct TcParams {
   float delta;                     // bound on |approx - exact| of the fp16x3 GEMM (dist units), see tc_delta()
 };
 
+// exact distance in the reference's association order (knn_exact.cu); xr: the normalised query row (shared memory)
 __device__ __forceinline__ float exact_dist(const float* __restrict__ xr, const float* __restrict__ yr, int D,
                                             float xs, float ys, const float* relrow, int m) {
   float acc = 0.f;
@@ -430,14 +429,14 @@ __device__ __forceinline__ float exact_dist(const float* __restrict__ xr, const 
     const float4* y4 = reinterpret_cast<const float4*>(yr);
 #pragma unroll 4
     for (int d = 0; d < (D >> 2); ++d) {
-      const float4 a = __ldg(x4 + d), b = __ldg(y4 + d);
+      const float4 a = x4[d], b = __ldg(y4 + d);
       acc = fmaf(a.x, b.x, acc); acc = fmaf(a.y, b.y, acc); acc = fmaf(a.z, b.z, acc); acc = fmaf(a.w, b.w, acc);
     }
   } else {
-    for (int d = 0; d < D; ++d) acc = fmaf(xr[d], yr[d], acc);
+    for (int d = 0; d < D; ++d) acc = fmaf(xr[d], __ldg(yr + d), acc);
   }
   float v = (xs + (-2.f * acc)) + ys;
-  if (relrow != nullptr) v += relrow[m];
+  if (relrow != nullptr) v += __ldg(relrow + m);
   return v;
 }
 
@@ -553,8 +552,7 @@ __global__ void __launch_bounds__(G::NTHREADS, 1) knn_tc_kernel(const TcParams p
     // Converged warp, one elected lane issues tcgen05.mma / tcgen05.commit (the commits must come from
     // the thread that issued the MMAs they track; elect.sync picks the same lane every time).
     const int r = warp - 1;                      // row set of this issuer
-    int ab = 0, aph = 0, bs = 0, bph = 0, tb = 0, tph = 0, tseq = 0;
-    const bool tr = DBG && prm.trace != nullptr && blockIdx.x == 0 && lane == 0 && r == 0;
+    int ab = 0, aph = 0, bs = 0, bph = 0, tb = 0, tph = 0;
     // descriptor halves: hi = SBO | version, lo = start address | LBO (both in 16-byte units)
     const uint32_t desc_hi = ((uint32_t)(prm.KC >> 3) * 128u >> 4) | (1u << 14);
     const uint32_t lbo_field = (128u >> 4) << 16;
@@ -569,20 +567,14 @@ __global__ void __launch_bounds__(G::NTHREADS, 1) knn_tc_kernel(const TcParams p
         const int nkb = sweep == 0 ? prm.NKBA : prm.NKB;
         const int kcols = sweep == 0 ? prm.PA : prm.KP;     // operand columns this sweep multiplies
         for (int kt = 0; kt < prm.KT; ++kt) {
-          if (tr && tseq < prm.trace_tiles) prm.trace[tseq * 8 + 0] = clock64();
           mbar_wait<true>(smem_u32(t_empty + r * NACC + tb), tph ^ 1);
           tc_fence_after();
-          if (tr && tseq < prm.trace_tiles) prm.trace[tseq * 8 + 1] = clock64();
-          long long bwait = 0, tissue = 0;
           const uint32_t d_tmem = tmem_base + (uint32_t)((r * NACC + tb) * G::ACC_STRIDE);
           for (int kb = 0; kb < nkb; ++kb) {
-            const long long tw0 = tr ? clock64() : 0;
             mbar_wait<true>(smem_u32(b_full + bs), bph);
             tc_fence_after();
-            if (tr) bwait += clock64() - tw0;
             const uint32_t b_addr = smem_u32(sB + (size_t)bs * stage_bytes);
             const int ksteps = min(prm.KC, kcols - kb * prm.KC) >> 4;
-            const long long ti0 = tr ? clock64() : 0;
             if (elect_one()) {
               const uint32_t b_lo = ((b_addr & 0x3FFFFu) >> 4) | lbo_field;
               const uint32_t a_addr = prm.NA > 0 ? a_base + (uint32_t)kb * a_blk_bytes
@@ -598,11 +590,8 @@ __global__ void __launch_bounds__(G::NTHREADS, 1) knn_tc_kernel(const TcParams p
               if (kb == nkb - 1) umma_commit(smem_u32(t_full + r * NACC + tb));   // accumulator ready
             }
             __syncwarp();
-            if (tr) tissue += clock64() - ti0;
             if (++bs == prm.NS) { bs = 0; bph ^= 1; }
           }
-          if (tr && tseq < prm.trace_tiles) { prm.trace[tseq * 8 + 2] = clock64(); prm.trace[tseq * 8 + 7] = bwait; prm.trace[tseq * 8 + 6] = tissue; }
-          ++tseq;
           if (++tb == NACC) { tb = 0; tph ^= 1; }
         }
       }
@@ -619,13 +608,10 @@ __global__ void __launch_bounds__(G::NTHREADS, 1) knn_tc_kernel(const TcParams p
     const int q = warp & 3;                      // TMEM lane quarter this warp may read
     const int row_t = q * 32 + lane;
     const uint32_t log_base = smem_u32(cand) + (uint32_t)(rset * BM + row_t) * 16;
-    const uint32_t log_end = log_base + (uint32_t)LC * LOG_STRIDE;          // first slack slot
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(rset * NACC * G::ACC_STRIDE);
     uint64_t* my_full = t_full + rset * NACC;
     uint64_t* my_empty = t_empty + rset * NACC;
-    const bool tracer = DBG && prm.trace != nullptr && blockIdx.x == 0 && threadIdx.x == 32 * (1 + RS);
     int ltb = 0, ltph = 0, rtb = 0;              // accumulator ring: load side (slot, phase), release side
-    int lseq = 0, rseq = 0;                      // running tile numbers for the debug trace
     for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
       const int p = item / prm.QI, qi = item - p * prm.QI;
       const int n = (qi * RS + rset) * BM + row_t;
@@ -662,11 +648,8 @@ __global__ void __launch_bounds__(G::NTHREADS, 1) knn_tc_kernel(const TcParams p
         const int kt = ci / NCH, c = ci - kt * NCH;
         const int m0 = kt * G::BN + c * CH;
         if (c == 0) {
-          if (tracer && lseq < prm.trace_tiles) prm.trace[lseq * 8 + 3] = clock64();
           mbar_wait<false>(smem_u32(my_full + ltb), ltph);
           tc_fence_after();
-          if (tracer && lseq < prm.trace_tiles) prm.trace[lseq * 8 + 4] = clock64();
-          ++lseq;
         }
         tmem_ld36(lane_addr + (uint32_t)(ltb * G::ACC_STRIDE + c * CH), ch.r);
         if (DENSE) {
@@ -698,8 +681,6 @@ __global__ void __launch_bounds__(G::NTHREADS, 1) knn_tc_kernel(const TcParams p
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(smem_u32(my_empty + rtb));
-          if (tracer && rseq < prm.trace_tiles) prm.trace[rseq * 8 + 5] = clock64();
-          ++rseq;
           if (++rtb == NACC) rtb = 0;
         }
       };
@@ -768,7 +749,7 @@ __global__ void __launch_bounds__(G::NTHREADS, 1) knn_tc_kernel(const TcParams p
       }
 
       // ---- sweep B: log the triplets that beat the threshold (fp16x3 scores) --------------------
-      uint32_t lp = log_base;                      // next free log slot of this row
+      int cnt = 0;                                 // log entries of this row
       bool overflow = false;
       sweep([&](int ci, Chunk<DENSE, NG>& ch) {
         const int kt = ci / NCH;
@@ -799,21 +780,25 @@ __global__ void __launch_bounds__(G::NTHREADS, 1) knn_tc_kernel(const TcParams p
             hit[u] = fmax3(s[u][0], s[u][1], s[u][2]) > thr_base - ch.bg[(3 * (6 * h + u)) / KW];
 #pragma unroll
           for (int u = 0; u < 6; ++u) {
+            // the address is rebuilt from the counter for every store: a running pointer made each increment wait
+            // for the previous store to read it (scoreboard), one stall per triplet
+            const uint32_t addr = log_base + (uint32_t)cnt * LOG_STRIDE;
             if (hit[u]) {                            // logged without the B term (looked up again from the id word)
-              st_shared_v4(lp, s[u][0], s[u][1], s[u][2], __int_as_float(idv[u]));
-              lp += LOG_STRIDE;
+              st_shared_v4(addr, s[u][0], s[u][1], s[u][2], __int_as_float(idv[u]));
+              ++cnt;
             }
           }
           // The slack slots took the <= 6 triplets of this half chunk.  A row past its LC valid entries had a
           // loose sweep-A threshold (smooth features: its nearest keys share a few 18-key groups): raise the
           // threshold to the T-th largest key logged so far and drop what falls below.  Rare on random data.
-          if (__any_sync(0xffffffffu, lp > log_end)) {
+          if (__any_sync(0xffffffffu, cnt > LC)) {
+            uint32_t lp = log_base + (uint32_t)cnt * LOG_STRIDE;
             log_compact<LOG_STRIDE, T, BIAS>(log_base, lp, thr_base, brow);
-            if (lp > log_end) { overflow = true; lp = log_end; }   // a pile of ties: certify by fix-up
+            cnt = (int)((lp - log_base) / LOG_STRIDE);
+            if (cnt > LC) { overflow = true; cnt = LC; }   // a pile of ties: certify by fix-up
           }
         }
       });
-      const int cnt = (int)((lp - log_base) / LOG_STRIDE);
 
       // ---------------- hand the candidates over -----------------------------------
       // The keys of the logged triplets that reach the threshold go to global

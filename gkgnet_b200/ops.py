@@ -69,12 +69,17 @@ def fit_separable_bias(relative_pos, tol=5e-7):
 
 
 def knn_graph(x, y=None, relative_pos=None, *, groups=1, k=9, dilation=1, algo=_lib.KNN_AUTO,
-              separable=None):
+              separable=None, debug=None):
     """Dilated group-kNN neighbour ids, int32 ``(B*G, N, k)``.
 
     x: (B, N, C) queries; y: (B, M, C) keys or None (self); relative_pos: fp32 (N, M) /
     (1, N, M) bias or None.  Equivalent to ``DenseDilatedKnnGraph(k, dilation)(x, y,
     relative_pos)[0]`` of the reference (torch_edge.py:164-176) on the regrouped tensors.
+
+    debug (tests only): dict with optional keys ``flags`` (1 = exact re-rank of every row, 3 = every
+    row through the brute-force fix-up kernel), ``dist`` (fp32 (B*G, N, M) CUDA tensor receiving the
+    approximate distances), ``skip`` / ``ga`` (threshold-sweep overrides); the counters of the call
+    come back in ``debug["stats"]``.  Routed through ``gkg_knn_graph_debug``.
     """
     _require_cuda(x, y, relative_pos)
     lib = _lib.load()
@@ -90,6 +95,8 @@ def knn_graph(x, y=None, relative_pos=None, *, groups=1, k=9, dilation=1, algo=_
         y = _token_major(y)
         if y.dtype != x.dtype or y.shape[0] != B or y.shape[2] != C:
             raise ValueError("keys must match queries in batch, channels and dtype")
+        if y.device != x.device:
+            raise ValueError("keys and queries must live on the same device")
         M = y.shape[1]
     else:
         M = N
@@ -98,6 +105,8 @@ def knn_graph(x, y=None, relative_pos=None, *, groups=1, k=9, dilation=1, algo=_
         rel = relative_pos.reshape(relative_pos.shape[-2], relative_pos.shape[-1])
         if rel.shape != (N, M):
             raise ValueError(f"relative_pos {tuple(rel.shape)} != ({N}, {M})")
+        if rel.device != x.device:
+            raise ValueError("relative_pos must live on the device of the features")
         rel = rel.to(torch.float32).contiguous()
         rel_ptr = rel.data_ptr()
     sep_a = sep_b = None
@@ -110,17 +119,43 @@ def knn_graph(x, y=None, relative_pos=None, *, groups=1, k=9, dilation=1, algo=_
     idx = torch.empty((B * groups, N, k), dtype=torch.int32, device=x.device)
     if B * N == 0:
         return idx
-    ws_bytes = lib.gkg_knn_workspace_bytes(B, groups, N, M, D, k, dilation, int(y is None), algo)
-    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
-    rc = lib.gkg_knn_graph(
-        x.data_ptr(), x.stride(0), x.stride(1),
-        y.data_ptr() if y is not None else None,
-        y.stride(0) if y is not None else 0, y.stride(1) if y is not None else 0,
-        rel_ptr, sep_a, sep_b, sep_w, sep_kw, idx.data_ptr(), B, groups, N, M, D, k, dilation,
-        _DT[x.dtype], algo,
-        ws.data_ptr(), ws_bytes, _stream(x))
-    _lib.check(rc, "gkg_knn_graph")
+    with torch.cuda.device(x.device):
+        ws_bytes = lib.gkg_knn_workspace_bytes(B, groups, N, M, D, k, dilation, int(y is None), _DT[x.dtype], algo)
+        ws = _workspace(x.device, ws_bytes)
+        args = (x.data_ptr(), x.stride(0), x.stride(1),
+                y.data_ptr() if y is not None else None,
+                y.stride(0) if y is not None else 0, y.stride(1) if y is not None else 0,
+                rel_ptr, sep_a, sep_b, sep_w, sep_kw, idx.data_ptr(), B, groups, N, M, D, k, dilation,
+                _DT[x.dtype], algo, ws.data_ptr(), ws_bytes, _stream(x))
+        if debug is None:
+            _lib.check(lib.gkg_knn_graph(*args), "gkg_knn_graph")
+        else:
+            import ctypes
+            stats = (ctypes.c_uint * 3)()
+            dist = debug.get("dist")
+            rc = lib.gkg_knn_graph_debug(*args, int(debug.get("flags", 0)), None if dist is None else dist.data_ptr(),
+                                         stats, int(debug.get("skip", -1)), int(debug.get("ga", 0)))
+            _lib.check(rc, "gkg_knn_graph_debug")
+            import struct
+            debug["stats"] = {"fixups": stats[0], "ambiguous": stats[1],
+                              "max_err": struct.unpack("f", struct.pack("I", stats[2]))[0]}
     return idx
+
+
+# kNN scratch (hundreds of MB at stage 1) is cached per (device, stream): the calls of one stream are ordered, so
+# consecutive layers can share one buffer instead of going through the allocator every call.
+_WS_CACHE = {}
+
+
+def _workspace(device, nbytes):
+    key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+    buf = _WS_CACHE.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = None
+        _WS_CACHE.pop(key, None)
+        buf = torch.empty(int(nbytes * 1.25) if nbytes > (1 << 20) else nbytes, dtype=torch.uint8, device=device)
+        _WS_CACHE[key] = buf
+    return buf
 
 
 class _MRAggregate(torch.autograd.Function):

@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define GKG_ABI_VERSION 1
+#define GKG_ABI_VERSION 2
 
 /* feature dtypes */
 #define GKG_F32 0
@@ -43,7 +43,7 @@ extern "C" {
 /* kNN algorithms */
 #define GKG_KNN_AUTO 0       /* tcgen05 path when the shape allows it, else exact */
 #define GKG_KNN_EXACT_FP32 1 /* CUDA-core fp32 brute force, reference association order */
-#define GKG_KNN_TCGEN05 2    /* fp16x3 split GEMM on tcgen05/TMEM + fused top-k + exact re-rank */
+#define GKG_KNN_TCGEN05 2    /* fp16 GEMM on tcgen05/TMEM (raw 16-bit rows, or the fp16x3 split of fp32 rows) + fused top-k + exact re-rank */
 
 /* error codes */
 #define GKG_OK 0
@@ -56,10 +56,10 @@ typedef void* gkg_stream_t; /* cudaStream_t */
 int gkg_abi_version(void);
 const char* gkg_last_error(void);
 
-/* Bytes of scratch gkg_knn_graph needs for this shape (normalised operands, norms,
- * candidate lists).  self_keys != 0 when y == NULL (keys are the queries). */
+/* Bytes of scratch gkg_knn_graph needs for this shape, dtype and algorithm (normalised keys, norms,
+ * tensor-core operands, candidate lists).  self_keys != 0 when y == NULL (keys are the queries). */
 size_t gkg_knn_workspace_bytes(int B, int G, int N, int M, int D, int k, int dilation,
-                               int self_keys, int algo);
+                               int self_keys, int dtype, int algo);
 
 /*
  * Dilated (group) kNN graph.  Replaces DenseDilatedKnnGraph.forward
@@ -91,19 +91,38 @@ int gkg_knn_graph(const void* x, int64_t x_stride_b, int64_t x_stride_n,
                   int algo, void* workspace, size_t workspace_bytes, gkg_stream_t stream);
 
 /*
- * The two phases of gkg_knn_graph, exposed separately so a caller can time them or reuse
- * the normalised operands.  gkg_knn_prepare fills the workspace (normalised fp32 rows,
- * squared norms, tensor-core operands); gkg_knn_select ranks and writes idx_out.  Same
- * arguments and workspace as gkg_knn_graph; gkg_knn_graph == prepare followed by select.
+ * The two phases of gkg_knn_graph, exposed separately so a caller can time them.  gkg_knn_prepare fills the
+ * workspace (tensor-core operands, normalised fp32 keys, norms); gkg_knn_select ranks and writes idx_out (it
+ * reads the query features again only for the few rows it re-ranks exactly).  Same arguments and workspace
+ * as gkg_knn_graph; gkg_knn_graph == prepare followed by select.
  */
 int gkg_knn_prepare(const void* x, int64_t x_stride_b, int64_t x_stride_n,
                     const void* y, int64_t y_stride_b, int64_t y_stride_n,
                     int B, int G, int N, int M, int D, int k, int dilation, int dtype,
                     int algo, void* workspace, size_t workspace_bytes, gkg_stream_t stream);
-int gkg_knn_select(const float* relpos, const float* relpos_sep_a, const float* relpos_sep_b,
+int gkg_knn_select(const void* x, int64_t x_stride_b, int64_t x_stride_n,
+                   const float* relpos, const float* relpos_sep_a, const float* relpos_sep_b,
                    int sep_grid_w, int sep_kw, int32_t* idx_out,
-                   int B, int G, int N, int M, int D, int k, int dilation, int self_keys,
+                   int B, int G, int N, int M, int D, int k, int dilation, int self_keys, int dtype,
                    int algo, void* workspace, size_t workspace_bytes, gkg_stream_t stream);
+
+/*
+ * Testing only: gkg_knn_graph with per-call debug options (no process state is involved).
+ *   debug_flags  1 = re-rank every row with the exact formula, 3 = send every row through the brute-force
+ *                fix-up kernel, 0 = as gkg_knn_graph
+ *   dbg_dist     fp32 (B*G, N, M) device buffer receiving the approximate distances (minus |xh|^2) as the
+ *                tensor-core kernel ranks them, or NULL
+ *   stats_out    3 HOST words: rows taken by the fix-up kernel, rows re-ranked exactly, bits of the largest
+ *                |approximate - exact| distance seen by the re-rank; NULL = none (non-NULL synchronises)
+ *   skip, ga     tuning overrides of the threshold sweep (-1 / 0 = automatic)
+ */
+int gkg_knn_graph_debug(const void* x, int64_t x_stride_b, int64_t x_stride_n,
+                        const void* y, int64_t y_stride_b, int64_t y_stride_n,
+                        const float* relpos, const float* relpos_sep_a, const float* relpos_sep_b,
+                        int sep_grid_w, int sep_kw, int32_t* idx_out,
+                        int B, int G, int N, int M, int D, int k, int dilation, int dtype,
+                        int algo, void* workspace, size_t workspace_bytes, gkg_stream_t stream,
+                        int debug_flags, float* dbg_dist, unsigned int* stats_out, int skip, int ga);
 
 /*
  * Max-relative aggregation, forward.  Replaces the gather / subtract / max / interleave

@@ -26,14 +26,14 @@ def test_library_exports_every_declared_symbol():
     for name in names:
         assert hasattr(lib, name), name
     assert set(names) == set(_lib.SIGNATURES), set(names) ^ set(_lib.SIGNATURES)
-    assert _lib.load().gkg_abi_version() == 1
+    assert _lib.load().gkg_abi_version() == 2
 
 
 def test_workspace_query_is_host_only():
     from gkgnet_b200 import _lib
     lib = _lib.load()
-    small = lib.gkg_knn_workspace_bytes(1, 2, 64, 16, 8, 3, 1, 0, _lib.KNN_EXACT_FP32)
-    big = lib.gkg_knn_workspace_bytes(32, 2, 20736, 1296, 40, 9, 1, 0, _lib.KNN_EXACT_FP32)
+    small = lib.gkg_knn_workspace_bytes(1, 2, 64, 16, 8, 3, 1, 0, _lib.GKG_F32, _lib.KNN_EXACT_FP32)
+    big = lib.gkg_knn_workspace_bytes(32, 2, 20736, 1296, 40, 9, 1, 0, _lib.GKG_F32, _lib.KNN_EXACT_FP32)
     assert 0 < small < big
     # normalised operands + norms for queries and keys
     assert big >= 4 * 64 * (20736 + 1296) * 41

@@ -1,7 +1,5 @@
 """GPU: bring-up and accuracy checks specific to the tcgen05 kNN kernel (debug hooks of
 libgkg_b200.so: raw approximate distances out of TMEM, forced exact re-rank statistics)."""
-import ctypes
-
 import pytest
 import torch
 
@@ -9,7 +7,7 @@ from oracle import gkg_oracle as O
 
 pytestmark = pytest.mark.gpu
 
-def tc_delta(D):
+def tc_delta(D, dtype=torch.float32):
     """tc_delta() in csrc/knn_tc_kernel.cuh: certified |approx - exact| of the fp16x3 GEMM, distance units."""
     pa = (D + 2 + 15) // 16 * 16
     kp = pa + (2 * D + 15) // 16 * 16
@@ -22,71 +20,75 @@ def _ref_layout(t, G):
     return t.reshape(B, N, G, D).permute(0, 2, 3, 1).reshape(B * G, D, N, 1)
 
 
-def _debug(lib, force, buf):
-    lib.gkg_debug_knn_tc.argtypes = [ctypes.c_int, ctypes.c_void_p]
-    lib.gkg_debug_knn_tc.restype = None
-    lib.gkg_debug_knn_tc(int(force), None if buf is None else buf.data_ptr())
 
-
-def _stats(lib):
-    arr = (ctypes.c_uint * 3)()
-    lib.gkg_debug_knn_tc_stats.argtypes = [ctypes.c_void_p]
-    lib.gkg_debug_knn_tc_stats(arr)
-    import struct
-    return {"fixups": arr[0], "ambiguous": arr[1], "max_err": struct.unpack("f", struct.pack("I", arr[2]))[0]}
-
-
-@pytest.mark.parametrize("B,G,N,M,D,bias", [
-    (1, 2, 200, 300, 40, True),      # KP=128, one k-block
-    (2, 2, 128, 128, 40, False),     # exact tile multiples
-    (1, 2, 260, 140, 80, True),      # KP=256 -> 4 k-blocks of 64
-    (1, 2, 150, 270, 200, True),     # KP=608 -> 19 k-blocks of 32, single A buffer
-    (1, 8, 100, 90, 10, False),      # KP=32
-    (1, 1, 90, 2000, 40, False),     # label-head like: many key tiles
+@pytest.mark.parametrize("B,G,N,M,D,bias,dtype", [
+    (1, 2, 200, 300, 40, True, torch.float32),      # KP = 128, one k-block
+    (2, 2, 128, 128, 40, False, torch.float32),     # exact tile multiples
+    (1, 2, 260, 140, 80, True, torch.float32),      # KP = 256 -> 4 k-blocks of 64
+    (1, 2, 200, 300, 40, True, torch.bfloat16),     # bf16 features
+    (1, 2, 300, 300, 80, True, torch.bfloat16),     # 256-row items
+    (1, 2, 150, 270, 200, True, torch.float32),     # KP = 608 -> 19 k-blocks of 32, single A buffer
+    (1, 2, 150, 270, 200, True, torch.bfloat16),
+    (1, 2, 130, 330, 320, False, torch.bfloat16),   # stage-4 width, operands streamed
+    (1, 8, 100, 90, 10, False, torch.float32),      # KP = 32
+    (1, 1, 90, 2000, 40, False, torch.bfloat16),    # label-head like: many key tiles
 ])
-def test_tc_raw_distances(B, G, N, M, D, bias):
+def test_tc_raw_distances(B, G, N, M, D, bias, dtype):
     from gkgnet_b200 import _lib, ops
-    lib = _lib.load()
     g = torch.Generator().manual_seed(7)
     C = G * D
-    x = torch.randn(B, N, C, generator=g)
-    y = torch.randn(B, M, C, generator=g)
+    x = torch.randn(B, N, C, generator=g).to(dtype)
+    y = torch.randn(B, M, C, generator=g).to(dtype)
     rel = -(0.5 + 0.5 * torch.rand(1, N, M, generator=g)) if bias else None
     dbg = torch.full((B * G, N, M), float("nan"), device="cuda")
-    _debug(lib, 1, dbg)
-    try:
-        idx = ops.knn_graph(x.cuda(), y.cuda(), None if rel is None else rel.cuda(), groups=G, k=9,
-                            dilation=1, algo=_lib.KNN_TCGEN05)
-        torch.cuda.synchronize()
-        st = _stats(lib)
-    finally:
-        _debug(lib, 0, None)
-    xr, yr = _ref_layout(x, G), _ref_layout(y, G)
+    info = {"flags": 1, "dist": dbg}
+    idx = ops.knn_graph(x.cuda(), y.cuda(), None if rel is None else rel.cuda(), groups=G, k=9,
+                        dilation=1, algo=_lib.KNN_TCGEN05, debug=info)
+    torch.cuda.synchronize()
+    st = info["stats"]
+    xr, yr = _ref_layout(x.float(), G), _ref_layout(y.float(), G)
     dist = O.knn_distance_matrix(xr, yr, rel)
     xn = O.l2_normalize(xr, 1).squeeze(-1)
     xsq = (xn * xn).sum(1)                      # (P, N)
     want = dist - xsq.unsqueeze(-1)             # the kernel ranks without the row constant
     err = (dbg.cpu() - want).abs().max().item()
-    assert err < tc_delta(D) / 1.5, err
-    assert st["max_err"] < tc_delta(D) / 1.5, st
+    assert err < tc_delta(D, dtype) / 1.5, err
+    assert st["max_err"] < tc_delta(D, dtype) / 1.5, st
     assert st["ambiguous"] == B * G * N          # forced re-rank touched every row
     rep = O.check_knn_against_distances(idx.cpu(), dist, 9, 1, 1e-6)
     assert rep["rows_bad"] == 0, rep
 
 
-def test_tc_matches_exact_bitwise_on_random_data():
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_tc_matches_exact_bitwise_on_random_data(dtype):
     """After the exact re-rank of ambiguous rows the tcgen05 path must agree with the
     CUDA-core exact kernel except on true ties (random data: none)."""
     from gkgnet_b200 import _lib, ops
     g = torch.Generator(device="cuda").manual_seed(11)
-    x = torch.randn(4, 2304, 80, device="cuda", generator=g)
-    y = torch.randn(4, 576, 80, device="cuda", generator=g)
+    x = torch.randn(4, 2304, 80, device="cuda", generator=g).to(dtype)
+    y = torch.randn(4, 576, 80, device="cuda", generator=g).to(dtype)
     rel = -(0.5 + 0.5 * torch.rand(2304, 576, device="cuda", generator=g))
     a = ops.knn_graph(x, y, rel, groups=2, k=9, dilation=1, algo=_lib.KNN_TCGEN05)
     b = ops.knn_graph(x, y, rel, groups=2, k=9, dilation=1, algo=_lib.KNN_EXACT_FP32)
     assert torch.equal(a, b)
-    a = ops.knn_graph(x[:, :1296], None, None, groups=2, k=9, dilation=3, algo=_lib.KNN_TCGEN05)
-    b = ops.knn_graph(x[:, :1296], None, None, groups=2, k=9, dilation=3, algo=_lib.KNN_EXACT_FP32)
+    for ga in (18, 6, 3):       # keys per group of the threshold sweep: any choice must give the same neighbours
+        a = ops.knn_graph(x, y, rel, groups=2, k=9, dilation=1, algo=_lib.KNN_TCGEN05, debug={"ga": ga})
+        assert torch.equal(a, b), ga
+    xs = x[:, :1296].contiguous()
+    a = ops.knn_graph(xs, None, None, groups=2, k=9, dilation=3, algo=_lib.KNN_TCGEN05)
+    b = ops.knn_graph(xs, None, None, groups=2, k=9, dilation=3, algo=_lib.KNN_EXACT_FP32)
+    assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("D,kd", [(200, 18), (200, 27), (320, 27), (40, 18), (80, 9)])
+def test_tc_wide_groups_bf16_match_exact(D, kd):
+    """Stage 3 / 4 shapes (self keys, wide groups, long lists) in bf16: ids equal the exact kernel's."""
+    from gkgnet_b200 import _lib, ops
+    g = torch.Generator(device="cuda").manual_seed(17)
+    x = torch.randn(2, 1296, 2 * D, device="cuda", generator=g).to(torch.bfloat16)
+    k, d = 9, kd // 9
+    a = ops.knn_graph(x, None, None, groups=2, k=k, dilation=d, algo=_lib.KNN_TCGEN05)
+    b = ops.knn_graph(x, None, None, groups=2, k=k, dilation=d, algo=_lib.KNN_EXACT_FP32)
     assert torch.equal(a, b)
 
 
@@ -102,7 +104,6 @@ def test_tc_separable_bias(C, n, r, G, k, d):
     give the same raw distances as the dense table and the same neighbours as the oracle."""
     from gkgnet_b200 import _lib, ops
     from gkgnet_b200.pos_embed import relative_pos_table
-    lib = _lib.load()
     rel = relative_pos_table(C, n, r)
     side = int(n ** 0.5)
     g = torch.Generator().manual_seed(5)
@@ -116,14 +117,11 @@ def test_tc_separable_bias(C, n, r, G, k, d):
     sep = ops.fit_separable_bias(rel.cuda())
     assert sep is not None and sep[3] in (9, 18, 36), None if sep is None else sep[2:]
     dbg = torch.full((B * G, n, M), float("nan"), device="cuda")
-    _debug(lib, 1, dbg)
-    try:
-        idx = ops.knn_graph(x.cuda(), None if y is None else y.cuda(), rel.cuda(), groups=G, k=k, dilation=d,
-                            algo=_lib.KNN_TCGEN05, separable=sep)
-        torch.cuda.synchronize()
-        st = _stats(lib)
-    finally:
-        _debug(lib, 0, None)
+    info = {"flags": 1, "dist": dbg}
+    idx = ops.knn_graph(x.cuda(), None if y is None else y.cuda(), rel.cuda(), groups=G, k=k, dilation=d,
+                        algo=_lib.KNN_TCGEN05, separable=sep, debug=info)
+    torch.cuda.synchronize()
+    st = info["stats"]
     xr = _ref_layout(x, G)
     yr = None if y is None else _ref_layout(y, G)
     dist = O.knn_distance_matrix(xr, yr, rel)
@@ -153,7 +151,6 @@ def test_tc_similar_neighbouring_keys_stay_on_fast_path(N, M, D, bias):
     close to the query.  Such rows must be ranked by the kernel itself, not by the exact fix-up
     kernel (regression: the pair list overflowed and every row took the slow path)."""
     from gkgnet_b200 import _lib, ops
-    lib = _lib.load()
     g = torch.Generator().manual_seed(3)
     G, B = 2, 1
     C = G * D
@@ -161,14 +158,11 @@ def test_tc_similar_neighbouring_keys_stay_on_fast_path(N, M, D, bias):
     y = base.repeat_interleave(3, dim=1) + 2e-3 * torch.randn(B, M, C, generator=g)
     x = torch.randn(B, N, C, generator=g)
     rel = -(0.5 + 0.5 * torch.rand(1, N, M, generator=g)) if bias else None
-    _debug(lib, 1, None)
-    try:
-        idx = ops.knn_graph(x.cuda(), y.cuda(), None if rel is None else rel.cuda(), groups=G, k=9,
-                            dilation=1, algo=_lib.KNN_TCGEN05)
-        torch.cuda.synchronize()
-        st = _stats(lib)
-    finally:
-        _debug(lib, 0, None)
+    info = {"flags": 1}
+    idx = ops.knn_graph(x.cuda(), y.cuda(), None if rel is None else rel.cuda(), groups=G, k=9,
+                        dilation=1, algo=_lib.KNN_TCGEN05, debug=info)
+    torch.cuda.synchronize()
+    st = info["stats"]
     assert st["fixups"] <= 0.02 * B * G * N, st
     dist = O.knn_distance_matrix(_ref_layout(x, G), _ref_layout(y, G), rel)
     rep = O.check_knn_against_distances(idx.cpu(), dist, 9, 1, 1e-6)
@@ -181,7 +175,6 @@ def test_tc_smooth_key_field_compacts_instead_of_fixup():
     logging sweep must tighten it by compacting the row's log (regression: 20 % of the stage-1 rows of
     GKGNet-576 went to the brute-force fix-up kernel) and still return the exact neighbours."""
     from gkgnet_b200 import _lib, ops
-    lib = _lib.load()
     g = torch.Generator().manual_seed(9)
     B, G, D, side = 1, 2, 40, 36
     C, M, N = G * D, side * side, 1024
@@ -192,13 +185,10 @@ def test_tc_smooth_key_field_compacts_instead_of_fixup():
     y = f.permute(0, 2, 3, 1).reshape(B, M, C).contiguous()
     pick = torch.randint(0, M, (N,), generator=g)
     x = (y[:, pick] + 0.05 * y.std() * torch.randn(B, N, C, generator=g)).contiguous()
-    _debug(lib, -1, None)
-    try:
-        idx = ops.knn_graph(x.cuda(), y.cuda(), None, groups=G, k=9, dilation=1, algo=_lib.KNN_TCGEN05)
-        torch.cuda.synchronize()
-        st = _stats(lib)
-    finally:
-        _debug(lib, 0, None)
+    info = {"flags": 0}
+    idx = ops.knn_graph(x.cuda(), y.cuda(), None, groups=G, k=9, dilation=1, algo=_lib.KNN_TCGEN05, debug=info)
+    torch.cuda.synchronize()
+    st = info["stats"]
     assert st["fixups"] <= 0.01 * B * G * N, st
     dist = O.knn_distance_matrix(_ref_layout(x, G), _ref_layout(y, G), None)
     rep = O.check_knn_against_distances(idx.cpu(), dist, 9, 1, 1e-6)
@@ -217,7 +207,6 @@ def test_tc_fixup_kernel_matches_exact_kernel(B, G, N, M, D, k, d, keys):
     """Debug hook 3 routes every row to the brute-force fix-up kernel (histogram select + rank by counting):
     its ids must equal the CUDA-core exact kernel's bit for bit, ties included (smaller key id first)."""
     from gkgnet_b200 import _lib, ops
-    lib = _lib.load()
     g = torch.Generator().manual_seed(13)
     C = G * D
     x = torch.randn(B, N, C, generator=g)
@@ -227,13 +216,10 @@ def test_tc_fixup_kernel_matches_exact_kernel(B, G, N, M, D, k, d, keys):
     elif keys == "constant":
         y = y[:, :1].expand(B, M, C).contiguous()
     x, y = x.cuda(), y.cuda()
-    _debug(lib, 3, None)
-    try:
-        got = ops.knn_graph(x, y, None, groups=G, k=k, dilation=d, algo=_lib.KNN_TCGEN05)
-        torch.cuda.synchronize()
-        st = _stats(lib)
-    finally:
-        _debug(lib, 0, None)
+    info = {"flags": 3}
+    got = ops.knn_graph(x, y, None, groups=G, k=k, dilation=d, algo=_lib.KNN_TCGEN05, debug=info)
+    torch.cuda.synchronize()
+    st = info["stats"]
     assert st["fixups"] == B * G * N, st
     want = ops.knn_graph(x, y, None, groups=G, k=k, dilation=d, algo=_lib.KNN_EXACT_FP32)
     assert torch.equal(got, want)
