@@ -1,16 +1,20 @@
 #!/usr/bin/env python
 """Benchmark of the GKGNet graph hot path on B200 (see DESIGN.md section "Measurement").
 
-    python bench.py --gpus N --steps K --warmup W            # our CUDA path
+    python bench.py --gpus N --steps K --warmup W            # our CUDA path (both clauses of the metric, one line)
     python bench.py --impl reference --gpus N --steps K ...  # reference algorithm on host cores
-    python bench.py --workload train|infer ...               # whole GKGNet-576 (BASELINE configs[3] / [2])
+    python bench.py --workload layer|train|infer ...         # one of the parts alone
 
-A "step" is one pass of the hot path over one batch of synthetic input: the stage-1 Grapher
-layer of GKGNet-576 (BASELINE.json configs[1]: B=32 images per GPU, C=80, N=144x144 patches,
-M=1296 pooled keys, G=2 groups, k=9): kNN-graph construction (normalise + distance + top-k),
-max-relative aggregation forward and its backward.  Images are independent, so N GPUs each
-process their own batch (weak scaling, no data-path collective); value = images of all ranks
-/ max-over-ranks device time.
+BASELINE.json's metric has two clauses and the default run measures both, in one JSON line:
+
+  * "GKGNet-576 images/sec (fwd+bwd, 1/2/4/8 B200)" -- the headline `value` / `ms_per_step` / `e2e`: one training
+    step of GKGNet-576 (BASELINE configs[3]: pvig_s backbone + label-query head, random init, bf16 autocast,
+    fwd + loss + bwd + grad clip + AdamW, 16 images per GPU).  N GPUs shard by image (DDP): the only collective is
+    the NCCL gradient all-reduce, inside the timed region; value = images of all ranks / max-over-ranks device time.
+  * "Grapher kNN+agg us/layer, % roofline" -- keys `layer`, `phase_ms`, `roofline*`: the stage-1 Grapher layer hot
+    path (BASELINE configs[1]: B=32 images per GPU, C=80, N=144x144 patches, M=1296 pooled keys, G=2, k=9): kNN-graph
+    construction (normalise + distance + top-k), max-relative aggregation forward and backward through the C ABI,
+    plus `roofline_knn_d200`, the kNN of the stage-3 shape (B=64, N=M=1296, D=200, k*d=18 and 27).
 """
 from __future__ import annotations
 
@@ -169,15 +173,8 @@ class HotPath:
 
 
 def dist_setup(n_gpus):
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if world > 1:
-        import torch.distributed as dist
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        torch.cuda.set_device(local)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    return world, rank, local
+    from gkgnet_b200 import parallel as P
+    return P.init_distributed()
 
 
 def barrier(world):
@@ -250,35 +247,72 @@ def time_cpu_reference(n_img, reps, seed=0):
 
 
 def run_reference(args):
+    """--impl reference: the reference's algorithm (oracle port, PyTorch CPU ops, every host core) for the same
+    workloads: GKGNet-576 training step (headline; --workload layer: the stage-1 layer hot path)."""
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    use_all_host_threads()
+    cores = use_all_host_threads()
     n_img = args.ref_images
     x, y, rel = make_inputs(n_img, "cpu", torch.float32, 0)
     grad_out = torch.randn(n_img, 2 * WORKLOAD["C"], x.shape[1], 1)
-    for _ in range(max(1, min(args.warmup, 2))):
-        cpu_reference_step(x, y, rel, grad_out)
-    steps = max(1, min(args.steps, args.ref_max_steps))
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        cpu_reference_step(x, y, rel, grad_out)
-    dt = (time.perf_counter() - t0) / steps
-    val = n_img / dt
-    cores = torch.get_num_threads()
-    sample = (f"{n_img} images per step (of the 32-image batch), fp32, stage-1 Grapher hot path "
-              f"(kNN graph + MR aggregate fwd+bwd), {steps} timed steps")
+
+    def layer_time(steps, warm):
+        for _ in range(warm):
+            cpu_reference_step(x, y, rel, grad_out)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            cpu_reference_step(x, y, rel, grad_out)
+        return (time.perf_counter() - t0) / steps
+
+    if args.workload == "layer":
+        steps = max(1, min(args.steps, args.ref_max_steps))
+        dt = layer_time(steps, max(1, min(args.warmup, 2)))
+        val = n_img / dt
+        sample = (f"{n_img} images per step (of the 32-image batch), fp32, stage-1 Grapher hot path "
+                  f"(kNN graph + MR aggregate fwd+bwd), {steps} timed steps")
+        cfg = config_dict(args.gpus, "reference algorithm (oracle port, PyTorch CPU ops) on host cores")
+        extra = {}
+    else:
+        steps = max(1, min(args.steps, args.ref_train_steps))
+        sd, params = _oracle_state("cpu")
+        opt = torch.optim.AdamW(params, lr=1e-4, weight_decay=0.05)
+        g = torch.Generator().manual_seed(5)
+        nt = args.ref_train_images
+        img = torch.randn(nt, 3, 576, 576, generator=g)
+        tgt = (torch.rand(nt, 80, generator=g) < 0.04).float()
+        _oracle_train_step(sd, params, img[:1], tgt[:1], opt)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            _oracle_train_step(sd, params, img, tgt, opt)
+        dt = (time.perf_counter() - t0) / steps
+        val = nt / dt
+        sample = (f"{nt} images per step (of the 16-image batch), fp32, GKGNet-576 fwd + head losses + bwd + grad clip + "
+                  f"AdamW through oracle/gkg_oracle.py, {steps} timed steps")
+        cfg = train_config(args.gpus, False)
+        cfg["note"] = "reference algorithm (oracle port, PyTorch CPU ops) on host cores"
+        ldt = layer_time(2, 1)
+        extra = {"layer": {"value": n_img / ldt, "unit": "images/s", "ms_per_step": ldt * 1e3,
+                           "sample": f"{n_img} images per step, stage-1 Grapher hot path (BASELINE configs[1]), 2 timed steps"}}
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": "images/s", "n_gpus": args.gpus,
         "steps": steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": config_dict(args.gpus, "reference algorithm (oracle port, PyTorch CPU ops) on host cores"),
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg,
         "cpu_baseline": {"value": val, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
+    line.update(extra)
     print(json.dumps(line), flush=True)
+
+
+def train_config(world, syncbn, B=16):
+    return {"workload": "BASELINE configs[3]: GKGNet-576 training fwd+bwd+AdamW, bf16 autocast, DDP",
+            "images_per_gpu": B, "global_batch": B * world,
+            "parallelism": f"dp{world} (NCCL gradient all-reduce)",
+            "norm": "SyncBN" if syncbn else "per-GPU BN",
+            "l2": "activations per step exceed the 126 MB L2; no explicit flush"}
 
 
 def config_dict(n_gpus, note):
@@ -294,7 +328,8 @@ def config_dict(n_gpus, note):
     }
 
 
-def run_ours(args):
+def run_layer(args):
+    """BASELINE configs[1]: the stage-1 Grapher layer hot path.  Returns the JSON line (rank 0) or None."""
     world, rank, local = dist_setup(args.gpus)
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
     dev = torch.device("cuda", local)
@@ -440,8 +475,9 @@ def run_ours(args):
     h2d = xp.numel() * xp.element_size() + yp.numel() * yp.element_size()
     d2h = out_host.numel() * out_host.element_size()
 
+    d200 = knn_d200_roofline(dev) if dtype == torch.bfloat16 else None
     if rank != 0:
-        return
+        return None
     peaks, peak_src = load_peaks()
     w = WORKLOAD
     N, M, C, G, k = hp.N, hp.M, hp.C, hp.G, hp.k
@@ -452,16 +488,21 @@ def run_ours(args):
     knn_ms = phases[1]
     tf = flop_knn / (knn_ms * 1e-3) / 1e12
     peak_tf = peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops"))
-    traffic = None
+    # DRAM bytes of the select kernels per launch: from the ncu --set full capture of this shape (profiles/, see the
+    # file for the command); bench.py cannot run under a profiler, so the figure is carried, not measured here
+    traffic, traffic_src = None, None
     tpath = os.path.join(ROOT, "profiles", "knn_select_traffic.json")
     if os.path.isfile(tpath):
         try:
-            traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+            tj = json.load(open(tpath))
+            traffic, traffic_src = tj.get("dram_bytes_per_launch"), tj.get("source")
         except Exception:
             traffic = None
     roofline = {"kernel": "gkg_knn_select (tcgen05 distance + fused top-k kernel, finalize, re-rank and fix-up "
                           "kernels; the first is ~90 % of the time)", "bound": "tensor", "achieved": tf,
-                "peak": peak_tf, "unit": "TFLOP/s", "frac": tf / peak_tf, "traffic": traffic,
+                "peak": peak_tf, "unit": "TFLOP/s", "frac": tf / peak_tf, "traffic": traffic, "traffic_source": traffic_src,
+                "measured_in": "layer microbench (BASELINE configs[1]), CUDA events around gkg_knn_select inside the step",
+                "frac_of_burst_peak": tf / peaks.get("bf16_tflops", peak_tf),
                 "peak_source": f"{peak_src} bf16_tflops_sustained (kernel timed inside the step)",
                 "algorithmic_flop": flop_knn, "ms": knn_ms}
     agg_gbs = bytes_agg / (phases[2] * 1e-3) / 1e9
@@ -512,6 +553,12 @@ def run_ours(args):
                       f"(PyTorch CPU ops), best of 2: {cpu_s:.2f} s"},
     }
     line.update(extra)
+    if d200 is not None:
+        peak_b = peaks.get("bf16_tflops", peak_tf)
+        for e in d200:
+            e.update(peak=peak_b, unit="TFLOP/s", frac=e["achieved"] / peak_b, bound="tensor",
+                     peak_source=f"{peak_src} bf16_tflops (burst: kernel timed alone)")
+        line["roofline_knn_d200"] = d200
     # ---- the same restatement of the reference run with PyTorch's own CUDA kernels on this GPU (fp32 eager, full
     # batch): what the reference's code path costs on a B200 today ("the real bar to beat").  A reported
     # baseline like cpu_baseline -- the checker's code, never the product path.
@@ -535,7 +582,50 @@ def run_ours(args):
                           "ops) on the same B200 with ATen/cuBLAS kernels, device-resident, 3 timed steps"}
         except Exception as e:        # e.g. out of memory next to the bench buffers: the line stands without it
             line["eager_gpu_baseline"] = {"unavailable": f"{type(e).__name__}: {str(e)[:120]}"}
-    print(json.dumps(line), flush=True)
+    return line
+
+
+def knn_d200_roofline(dev):
+    """kNN graph (gkg_knn_select phase) of the stage-3 shape of GKGNet-576 -- B=64 images, N=M=1296 (self keys),
+    G=2 groups of D=200, k=9 with dilation 2 and 3 (k*d = 18, 27), bf16, analytic position bias -- where the
+    distance GEMM has enough K for the tensor cores to matter.  Algorithmic FLOP = 2*B*N*M*C."""
+    from gkgnet_b200 import _lib, ops
+    from gkgnet_b200.pos_embed import relative_pos_table
+    lib = _lib.load()
+    B, C, n, G = 64, 400, 1296, 2
+    g = torch.Generator(device="cpu").manual_seed(3)
+    x = torch.randn(B, n, C, generator=g).to(torch.bfloat16).to(dev)
+    rel = relative_pos_table(C, n, 1)[0].contiguous().to(dev)
+    fit = ops.fit_separable_bias(rel)
+    sep = (None, None, 0, 0) if fit is None else (fit[0].data_ptr(), fit[1].data_ptr(), fit[2], fit[3])
+    out = []
+    stream = torch.cuda.current_stream(dev)
+    for d in (2, 3):
+        a = (B, G, n, n, C // G, 9, d)
+        wsb = lib.gkg_knn_workspace_bytes(*a, 1, _lib.GKG_BF16, _lib.KNN_AUTO)
+        ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+        idx = torch.empty(B * G, n, 9, dtype=torch.int32, device=dev)
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        sel_ms = prep_ms = 0.0
+        reps = 6
+        for it in range(reps + 2):
+            ev[0].record(stream)
+            _lib.check(lib.gkg_knn_prepare(x.data_ptr(), x.stride(0), x.stride(1), None, 0, 0, *a, _lib.GKG_BF16,
+                                           _lib.KNN_AUTO, ws.data_ptr(), wsb, stream.cuda_stream), "knn_prepare")
+            ev[1].record(stream)
+            _lib.check(lib.gkg_knn_select(x.data_ptr(), x.stride(0), x.stride(1), rel.data_ptr(), *sep, idx.data_ptr(),
+                                          *a, 1, _lib.GKG_BF16, _lib.KNN_AUTO, ws.data_ptr(), wsb, stream.cuda_stream),
+                       "knn_select")
+            ev[2].record(stream)
+            torch.cuda.synchronize()
+            if it >= 2:
+                prep_ms += ev[0].elapsed_time(ev[1]) / reps
+                sel_ms += ev[1].elapsed_time(ev[2]) / reps
+        flop = 2.0 * B * n * n * C
+        out.append({"kernel": "gkg_knn_select", "shape": f"B={B} N=M={n} D={C // G} G={G} k=9 dilation={d} (k*d={9 * d}), bf16",
+                    "algorithmic_flop": flop, "ms": sel_ms, "prepare_ms": prep_ms,
+                    "achieved": flop / (sel_ms * 1e-3) / 1e12})
+    return out
 
 
 
@@ -618,26 +708,167 @@ def run_model(args):
     launches = _lib.launch_count() - l0
     clocks = sampler.stop()
     e2e_ms = timed(max(3, min(args.steps, 5)), True)
+    coll = None
+    if train and world > 1:
+        # the one collective of the step, timed alone: an all-reduce of the gradient bytes in DDP-sized buckets (25 MB),
+        # back to back on the NCCL stream -- what the step would pay if none of it overlapped the backward pass
+        import torch.distributed as dist
+        nbytes = sum(p.numel() * 4 for p in params)
+        bucket = torch.zeros(25 * 1024 * 1024 // 4, device=dev)
+        nb = max(1, (nbytes + bucket.numel() * 4 - 1) // (bucket.numel() * 4))
+        for _ in range(2):
+            for _ in range(nb):
+                dist.all_reduce(bucket)
+        torch.cuda.synchronize()
+        a, c = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(3):
+            for _ in range(nb):
+                dist.all_reduce(bucket)
+        c.record()
+        torch.cuda.synchronize()
+        coll_ms = P.max_over_ranks(a.elapsed_time(c) / 3, dev)
+        coll = {"name": "NCCL all_reduce of the fp32 gradients (DDP buckets of 25 MB)", "bytes_per_step": nbytes,
+                "buckets": int(nb), "ms_alone": coll_ms, "share_of_step_if_exposed": coll_ms / ms,
+                "bus_gbs": 2.0 * (world - 1) / world * nbytes / (coll_ms * 1e-3) / 1e9}
+        del bucket
+    eager = None
+    if train and world == 1 and not args.no_cpu:
+        eager = eager_train_baseline(model, img, tgt, dev)
     if rank != 0:
-        return
+        return None
     out_bytes = 4 if train else B * 80 * 4
     line = {
         "metric": METRIC, "value": world * B / (ms * 1e-3), "unit": "images/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": ("BASELINE configs[3]: GKGNet-576 training fwd+bwd+AdamW, bf16 autocast, DDP" if train else
-                                "BASELINE configs[2]: GKGNet-576 inference, bf16 autocast, replicas only"),
-                   "images_per_gpu": B, "global_batch": B * world,
-                   "parallelism": f"dp{world}" + (" (NCCL gradient all-reduce)" if train else " (replicas)"),
-                   "norm": "SyncBN" if args.syncbn else "per-GPU BN",
-                   "l2": "activations per step exceed the 126 MB L2; no explicit flush"},
+        "config": train_config(world, args.syncbn, B) if train else {
+            "workload": "BASELINE configs[2]: GKGNet-576 inference, bf16 autocast, replicas only",
+            "images_per_gpu": B, "global_batch": B * world, "parallelism": f"dp{world} (replicas)",
+            "norm": "SyncBN" if args.syncbn else "per-GPU BN",
+            "l2": "activations per step exceed the 126 MB L2; no explicit flush"},
         "clocks": clocks,
         "e2e": {"value": world * B / (e2e_ms * 1e-3), "unit": "images/s", "ms_per_step": e2e_ms,
                 "h2d_bytes_per_step": img_h.numel() * 4 + tgt_h.numel() * 4, "d2h_bytes_per_step": out_bytes},
         "gpu_launches": int(launches),     # launches of libgkg_b200 kernels only (torch ops not counted)
         "roofline": None, "cpu_baseline": None,
     }
-    print(json.dumps(line), flush=True)
+    if coll is not None:
+        line["collective"] = coll
+    if eager is not None:
+        line["eager_gpu_baseline"] = eager
+    if train and world == 1 and not args.no_cpu:
+        v, cores, sample = time_cpu_train(args.ref_train_images, 1)
+        line["cpu_baseline"] = {"value": v, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample}
+    return line
+
+
+def _oracle_train_step(sd, params, img, tgt, opt):
+    from oracle import gkg_oracle as O
+    labels, gap, _ = O.gkgnet_forward(sd, img, choice="s", training=True)
+    losses = O.head_losses(sd, labels, gap, tgt, prefix="head.")
+    loss = sum(losses.values())
+    loss.backward()
+    torch.nn.utils.clip_grad_norm_(params, 5.0)
+    opt.step()
+    opt.zero_grad(set_to_none=True)
+    return loss
+
+
+def _oracle_state(device, dtype=torch.float32):
+    """Random-init GKGNet-576 + head weights as the flat state dict the oracle's functional model takes."""
+    import gkgnet_b200 as G
+    G.set_norm_type("BN")
+    torch.manual_seed(0)
+    net = G.GKGNet(choice="s", n_classes=80, size=576, drop_path=0.0)
+    head = G.LabelQueryHead(80, 640)
+    sd = {k: v.detach().to(device=device, dtype=dtype if v.is_floating_point() else v.dtype).clone()
+          for k, v in net.state_dict().items()}
+    sd.update({"head." + k: v.detach().to(device=device, dtype=dtype).clone() for k, v in head.state_dict().items()})
+    params = []
+    for k, v in sd.items():
+        if v.is_floating_point() and "relative_pos" not in k and "running_" not in k:
+            v.requires_grad_(True)
+            params.append(v)
+    return sd, params
+
+
+def time_cpu_train(n_img, reps):
+    """The reference's algorithm for the headline workload -- GKGNet-576 training step (fwd + head losses + bwd +
+    grad clip + AdamW, fp32) through oracle/gkg_oracle.py (plain PyTorch CPU ops) on the host cores."""
+    cores = use_all_host_threads()
+    sd, params = _oracle_state("cpu")
+    opt = torch.optim.AdamW(params, lr=1e-4, weight_decay=0.05)
+    g = torch.Generator().manual_seed(5)
+    img = torch.randn(n_img, 3, 576, 576, generator=g)
+    tgt = (torch.rand(n_img, 80, generator=g) < 0.04).float()
+    _oracle_train_step(sd, params, img[:1], tgt[:1], opt)          # warm-up (thread pool, allocator)
+    best = float("inf")
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        _oracle_train_step(sd, params, img, tgt, opt)
+        best = min(best, time.perf_counter() - t0)
+    sample = (f"{n_img} images per step, fp32, GKGNet-576 fwd + losses + bwd + AdamW through oracle/gkg_oracle.py "
+              f"(PyTorch CPU ops), best of {reps}: {best:.2f} s")
+    return n_img / best, cores, sample
+
+
+def eager_train_baseline(model, img, tgt, dev):
+    """The same restatement of the reference (oracle functional model: ATen / cuBLAS / cuDNN kernels, the N x M distance
+    matrices materialised) for one training step on this B200, fp32 and under bf16 autocast: what the reference's code
+    path costs on the device today.  A reported baseline -- the checker's code, never the product path."""
+    out = {}
+    try:
+        sd, params = _oracle_state(dev)
+        opt = torch.optim.AdamW(params, lr=1e-4, weight_decay=0.05)
+        for name, ctx in (("fp32", None), ("bf16_autocast", torch.bfloat16)):
+            def one():
+                if ctx is None:
+                    return _oracle_train_step(sd, params, img, tgt, opt)
+                with torch.autocast("cuda", dtype=ctx):
+                    return _oracle_train_step(sd, params, img, tgt, opt)
+            one()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(2):
+                one()
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / 2
+            out[name] = {"value": img.shape[0] / (ms * 1e-3), "unit": "images/s", "ms_per_step": ms}
+        out["kind"] = "port"
+        out["sample"] = (f"{img.shape[0]} images, GKGNet-576 training step through oracle/gkg_oracle.py on the same B200 "
+                         "(eager PyTorch kernels, device-resident), 2 timed steps each")
+        del sd, params, opt
+        torch.cuda.empty_cache()
+    except Exception as e:
+        out = {"unavailable": f"{type(e).__name__}: {str(e)[:160]}"}
+        torch.cuda.empty_cache()
+    return out
+
+
+def run_full(args):
+    """Default: both clauses of the metric in one line (see the module docstring)."""
+    world, rank, local = dist_setup(args.gpus)
+    targs = argparse.Namespace(**vars(args))
+    targs.workload = "train"
+    tline = run_model(targs)
+    torch.cuda.empty_cache()
+    lline = run_layer(args)
+    if rank != 0:
+        return None
+    line = dict(tline)
+    line["config"] = dict(tline["config"])
+    line["config"]["workload"] = (tline["config"]["workload"] + " [headline value / ms_per_step / e2e]; plus " +
+                                  lline["config"]["workload"] + " [keys layer, phase_ms, roofline*]")
+    line["layer"] = {k: lline[k] for k in ("value", "unit", "ms_per_step", "e2e", "gpu_launches", "clocks",
+                                           "cpu_baseline", "eager_gpu_baseline") if k in lline}
+    line["layer"]["config"] = lline["config"]
+    for k, v in lline.items():
+        if k == "phase_ms" or k.startswith("roofline"):
+            line[k] = v
+    return line
+
 
 
 def main():
@@ -653,17 +884,19 @@ def main():
     ap.add_argument("--dense-bias", action="store_true", help="do not use the separable bias fast path")
     ap.add_argument("--ref-images", type=int, default=4)
     ap.add_argument("--ref-max-steps", type=int, default=20)
-    ap.add_argument("--workload", default="layer", choices=["layer", "train", "infer"],
-                    help="layer = stage-1 Grapher hot path (the headline line); train / infer = whole GKGNet-576")
+    ap.add_argument("--ref-train-images", type=int, default=2)
+    ap.add_argument("--ref-train-steps", type=int, default=6)
+    ap.add_argument("--workload", default="full", choices=["full", "layer", "train", "infer"],
+                    help="full = training step (headline) + stage-1 layer microbench in one line; or one part alone")
     ap.add_argument("--batch", type=int, default=0, help="images per GPU for --workload train / infer")
     ap.add_argument("--syncbn", action="store_true", help="keep the reference's SyncBN (default: per-GPU BN)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
-    elif args.workload != "layer":
-        run_model(args)
     else:
-        run_ours(args)
+        line = {"full": run_full, "layer": run_layer}.get(args.workload, run_model)(args)
+        if line is not None:
+            print(json.dumps(line), flush=True)
     if int(os.environ.get("WORLD_SIZE", "1")) > 1:
         import torch.distributed as dist
         if dist.is_initialized():
