@@ -38,7 +38,10 @@ SIGNATURES = {
     "gkg_pool_keys_fwd": (_i32, [_vp, _i64, _i64, _vp] + [_i32] * 6 + [_vp]),
     "gkg_pool_keys_bwd": (_i32, [_vp, _vp] + [_i32] * 6 + [_vp]),
     "gkg_grouped_fc_supported": (_i32, [_i32]),
+    "gkg_grouped_fc_pass_width": (_i32, [_i32]),
     "gkg_grouped_fc_fwd": (_i32, [_vp, _vp, _vp, _vp, _c.c_longlong, _i32, _i32, _vp]),
+    "gkg_grouped_fc_pack_weights": (_i32, [_vp, _vp, _vp, _i32, _i32, _vp]),
+    "gkg_grouped_fc_wgrad": (_i32, [_vp, _vp, _vp, _c.c_longlong, _i32, _vp]),
 }
 
 _lib = None

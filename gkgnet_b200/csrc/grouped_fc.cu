@@ -15,7 +15,7 @@
 // their accumulator rows back with tcgen05.ld (thread == row, one conv group per warp), apply scale / shift / activation and store
 // bf16.  The weights sit in shared memory for the CTA's lifetime in the same core-matrix order (built by
 // the caller, see gkgnet_b200/ops.py:grouped_fc_weights).  Memory bound: 2 * rows * 2C * 2 bytes.
-#include "common.cuh"
+#include "knn_tc.cuh"
 
 namespace gkg {
 namespace fc {
@@ -195,15 +195,282 @@ __global__ void __launch_bounds__(THREADS, 2) grouped_fc_kernel(const Params prm
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
 }
 
+
+// ------------------------------------------------------------------------------------
+// wide groups (CG > 96: stages 3 - 4 of pvig_s, CG = 200 / 320; arch 't' stage 3, CG = 120)
+// ------------------------------------------------------------------------------------
+// Four accumulators of ceil16(CG) columns no longer fit the tensor memory, nor four weight blocks the shared memory.
+// A work item is (conv group q, column pass, 128-row tile): the A sub-tile of group q (128 x KP) and the weight block
+// of the pass (NT x KP, NT <= 160 output channels) sit in shared memory, one accumulator of NT columns in TMEM.  Items
+// are ordered (q, pass)-major, so a CTA reloads its weight block only when it moves to the next (q, pass): ~8 times per
+// launch.  Same arithmetic and epilogue as the kernel above.
+struct WideParams {
+  const __nv_bfloat16* in;
+  __nv_bfloat16* out;
+  const __nv_bfloat16* w_op;     // [4][passes][NT/8][KP/8][8][8]
+  const float* shift;
+  long long rows;
+  int C2, CG, KP, NT, passes;
+};
+
+template <int ACT>
+__global__ void __launch_bounds__(THREADS, 1) grouped_fc_wide_kernel(const WideParams prm) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int CG = prm.CG, KP = prm.KP, NT = prm.NT, C2 = prm.C2;
+  const uint32_t a_bytes = (uint32_t)BM * KP * 2, b_bytes = (uint32_t)NT * KP * 2;
+  uint8_t* sA = smem;
+  uint8_t* sB = sA + a_bytes;
+  float* s_shift = reinterpret_cast<float*>(sB + b_bytes);          // [NT] of the current (q, pass)
+  uint64_t* bar = reinterpret_cast<uint64_t*>(s_shift + NT);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t tmem_cols = NT <= 128 ? 128u : 256u;
+
+  for (uint32_t i = threadIdx.x; i < a_bytes / 16; i += THREADS) reinterpret_cast<uint4*>(sA)[i] = make_uint4(0, 0, 0, 0);
+  if (threadIdx.x == 0) {
+    mbar_init(smem_u32(bar), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(tmem_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NT >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+  const uint32_t sbo = (uint32_t)(KP >> 3) * 128u;
+  const int cg_chunks = CG >> 3;
+  const long long tiles = (prm.rows + BM - 1) / BM;
+  const long long items = tiles * 4 * prm.passes;
+  uint32_t phase = 0;
+  int cur_qp = -1;
+
+  for (long long item = blockIdx.x; item < items; item += gridDim.x) {
+    const int qp = (int)(item / tiles);
+    const long long tile = item - (long long)qp * tiles;
+    const int q = qp / prm.passes, pass = qp - q * prm.passes;
+    const long long r0 = tile * BM;
+    if (qp != cur_qp) {            // new weight block + shifts (the previous item's MMAs have retired: barrier below)
+      const uint4* wsrc = reinterpret_cast<const uint4*>(prm.w_op) + (size_t)qp * (b_bytes / 16);
+      for (uint32_t i = threadIdx.x; i < b_bytes / 16; i += THREADS) reinterpret_cast<uint4*>(sB)[i] = __ldg(wsrc + i);
+      for (int i = threadIdx.x; i < NT; i += THREADS) {
+        const int o = pass * NT + i;
+        s_shift[i] = o < CG ? prm.shift[q * CG + o] : 0.f;
+      }
+      cur_qp = qp;
+    }
+    for (int i = threadIdx.x; i < BM * cg_chunks; i += THREADS) {
+      const int r = i / cg_chunks, c8 = i - r * cg_chunks;
+      uint4 v = make_uint4(0, 0, 0, 0);
+      if (r0 + r < prm.rows) v = __ldg(reinterpret_cast<const uint4*>(prm.in + (r0 + r) * C2 + q * CG) + c8);
+      *reinterpret_cast<uint4*>(sA + ((uint32_t)((r >> 3) * (KP >> 3) + c8) << 7) + ((r & 7) << 4)) = v;
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t a_addr = smem_u32(sA), b_addr = smem_u32(sB);
+      for (int ks = 0; ks < (KP >> 4); ++ks) {
+        const uint64_t ad = make_desc(a_addr + ks * 256, 128, sbo), bd = make_desc(b_addr + ks * 256, 128, sbo);
+        const uint32_t acc = ks != 0;
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                     "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                     ::"r"(tmem_base), "l"(ad), "l"(bd), "r"(idesc), "r"(acc) : "memory");
+      }
+      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+    }
+    mbar_wait(smem_u32(bar), phase);
+    phase ^= 1;
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    {
+      // warp w reads TMEM lanes 32*(w%4).., columns (w/4) * 16, + 64, ... (four warps per lane quarter)
+      const int row = (warp & 3) * 32 + lane;
+      const bool row_ok = r0 + row < prm.rows;
+      __nv_bfloat16* orow = prm.out + (r0 + row) * C2 + q * CG + pass * NT;
+      const int ncol = min(NT, CG - pass * NT);            // valid output channels of this pass (multiple of 8)
+      for (int c0 = (warp >> 2) * 16; c0 < ncol; c0 += 64) {
+        uint32_t acc[16];
+        tmem_ld16(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)c0, acc);
+        __align__(16) __nv_bfloat162 o[8];
+#pragma unroll
+        for (int j4 = 0; j4 < 16; j4 += 4) {
+          float v[4] = {0.f, 0.f, 0.f, 0.f};
+          if (c0 + j4 < ncol) {
+            const float4 sh = *reinterpret_cast<const float4*>(s_shift + c0 + j4);
+            v[0] = activate<ACT>(__uint_as_float(acc[j4]) + sh.x);
+            v[1] = activate<ACT>(__uint_as_float(acc[j4 + 1]) + sh.y);
+            v[2] = activate<ACT>(__uint_as_float(acc[j4 + 2]) + sh.z);
+            v[3] = activate<ACT>(__uint_as_float(acc[j4 + 3]) + sh.w);
+          }
+          o[j4 >> 1] = __floats2bfloat162_rn(v[0], v[1]);
+          o[(j4 >> 1) + 1] = __floats2bfloat162_rn(v[2], v[3]);
+        }
+        if (row_ok) {
+          *reinterpret_cast<uint4*>(orow + c0) = *reinterpret_cast<const uint4*>(o);
+          if (c0 + 8 < ncol) *reinterpret_cast<uint4*>(orow + c0 + 8) = *reinterpret_cast<const uint4*>(o + 4);
+        }
+      }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+  }
+  if (warp == 0)
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
+}
+
+// ------------------------------------------------------------------------------------
+// weight gradient: gw[q][o][i] = sum_r go[r, q*CG + o] * x[r, q*CG + i]
+// ------------------------------------------------------------------------------------
+// Per conv group a (CG x R) . (R x CG) product with the reduction over ALL rows: both operands are read exactly as
+// they lie in memory -- row r holds the CG channels of a group contiguously, which is the UMMA "MN-major" operand
+// form (channel index fastest, K = row index strided), so no transposition is needed on the way to shared memory.
+// A CTA owns (group q, 128-channel slab of output channels, column pass of <= 256 input channels, row split s): it
+// walks its rows in blocks of 64 (K = 64 per block, 4 MMAs of M = 128, N = NT), accumulates in TMEM and adds its
+// partial (fp32) into gw with atomics at the end (split-R reduction; gw must be zero-filled by the caller).
+constexpr int WG_KB = 64;
+struct WgradParams {
+  const __nv_bfloat16* go;       // (rows, C2)
+  const __nv_bfloat16* x;        // (rows, C2)
+  float* gw;                     // (4, CG, CG) fp32, zero-filled
+  long long rows;
+  int C2, CG, NT, mtiles, passes, splits;
+  long long rows_per_split;      // multiple of WG_KB
+};
+
+__global__ void __launch_bounds__(256, 2) grouped_fc_wgrad_kernel(const WgradParams prm) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int CG = prm.CG, NT = prm.NT, C2 = prm.C2;
+  constexpr uint32_t kSbo = (WG_KB / 8) * 128;                       // bytes between groups of 8 channels
+  const uint32_t a_bytes = 16 * kSbo, b_bytes = (uint32_t)(NT / 8) * kSbo;
+  uint8_t* sA = smem;                                               // 2 x [16 channel groups][8 row groups][8 rows][8 channels]
+  uint8_t* sB = sA + 2 * a_bytes;                                   // 2 x [NT/8 channel groups][...]
+  uint64_t* bar = reinterpret_cast<uint64_t*>(sB + 2 * b_bytes);    // [2]: MMAs of a buffer retired
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 2);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  int it = blockIdx.x;
+  const int s = it % prm.splits; it /= prm.splits;
+  const int pass = it % prm.passes; it /= prm.passes;
+  const int mt = it % prm.mtiles;
+  const int q = it / prm.mtiles;
+  const int o0 = mt * 128, i0 = pass * NT;                          // first output / input channel of this CTA (in the group)
+  const long long rbeg = (long long)s * prm.rows_per_split;
+  const long long rend = min(prm.rows, rbeg + prm.rows_per_split);
+
+  if (threadIdx.x == 0) {
+    mbar_init(smem_u32(bar), 1); mbar_init(smem_u32(bar + 1), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(256) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+  // D = f32, A = B = bf16, both MN-major (bits 15, 16), N >> 3 at 17, M >> 4 at 24
+  const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(NT >> 3) << 17) |
+                         ((uint32_t)(128 >> 4) << 24);
+  const int a_groups = min(16, (CG - o0 + 7) / 8), b_groups = min(NT / 8, (CG - i0 + 7) / 8);
+  uint32_t ph[2] = {0, 0};
+  int nblk = 0;
+  for (long long r0 = rbeg; r0 < rend; r0 += WG_KB, ++nblk) {
+    const int buf = nblk & 1;
+    if (nblk >= 2) {               // the MMAs that read this buffer two blocks ago must have retired
+      mbar_wait(smem_u32(bar + buf), ph[buf]);
+      ph[buf] ^= 1;
+    }
+    uint8_t* a = sA + buf * a_bytes;
+    uint8_t* b = sB + buf * b_bytes;
+    // 16-byte pieces (8 channels of one row): piece (group g, row r) -> g * kSbo + (r / 8) * 128 + (r % 8) * 16
+    for (int i = threadIdx.x; i < 16 * WG_KB; i += 256) {
+      const int g = i % 16, r = i / 16;
+      uint4 v = make_uint4(0, 0, 0, 0);
+      if (g < a_groups && r0 + r < rend) v = __ldg(reinterpret_cast<const uint4*>(prm.go + (r0 + r) * C2 + q * CG + o0) + g);
+      *reinterpret_cast<uint4*>(a + g * kSbo + ((r >> 3) << 7) + ((r & 7) << 4)) = v;
+    }
+    for (int i = threadIdx.x; i < (NT / 8) * WG_KB; i += 256) {
+      const int g = i % (NT / 8), r = i / (NT / 8);
+      uint4 v = make_uint4(0, 0, 0, 0);
+      if (g < b_groups && r0 + r < rend) v = __ldg(reinterpret_cast<const uint4*>(prm.x + (r0 + r) * C2 + q * CG + i0) + g);
+      *reinterpret_cast<uint4*>(b + g * kSbo + ((r >> 3) << 7) + ((r & 7) << 4)) = v;
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t a_addr = smem_u32(a), b_addr = smem_u32(b);
+      for (int ks = 0; ks < WG_KB / 16; ++ks) {                      // K = 16 rows = two row groups = 256 bytes
+        const uint64_t ad = make_desc(a_addr + ks * 256, 128, kSbo), bd = make_desc(b_addr + ks * 256, 128, kSbo);
+        const uint32_t acc = (nblk | ks) != 0;
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                     "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                     ::"r"(tmem_base), "l"(ad), "l"(bd), "r"(idesc), "r"(acc) : "memory");
+      }
+      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar + buf)) : "memory");
+    }
+  }
+  // drain: the last commit on each buffer covers every earlier MMA
+  for (int buf = 0; buf < 2; ++buf)
+    if (nblk > buf) { mbar_wait(smem_u32(bar + buf), ph[buf]); ph[buf] ^= 1; }
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  if (warp < 4 && nblk > 0) {
+    const int o = o0 + warp * 32 + lane;                             // TMEM lane == output channel
+    float* dst = prm.gw + ((size_t)q * CG + o) * CG + i0;
+    const int ncol = min(NT, CG - i0);
+    for (int c0 = 0; c0 < ncol; c0 += 16) {
+      uint32_t acc[16];
+      tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, acc);
+      if (o < CG) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          if (c0 + j < ncol) atomicAdd(dst + c0 + j, __uint_as_float(acc[j]));
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0)
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(256) : "memory");
+}
+
 }  // namespace fc
 }  // namespace gkg
 
 using namespace gkg;
 
+// narrow groups: the four accumulators share the tensor memory and the four weight blocks the shared memory
+static bool fc_narrow_ok(int CG) {
+  const int KP = (CG + 15) / 16 * 16;
+  const size_t smem = 4 * (size_t)fc::BM * KP * 2 + 4 * (size_t)KP * KP * 2 + (size_t)4 * CG * 4 + 64;
+  return 4 * KP <= 512 && smem <= 200 * 1024 && CG <= 96;
+}
+struct WidePlan { int KP, NT, passes; size_t smem; bool ok; };
+static WidePlan fc_wide_plan(int CG) {
+  WidePlan p{};
+  p.KP = (CG + 15) / 16 * 16;
+  p.passes = (p.KP + 159) / 160;
+  p.NT = ((p.KP + p.passes - 1) / p.passes + 15) / 16 * 16;
+  p.smem = (size_t)fc::BM * p.KP * 2 + (size_t)p.NT * p.KP * 2 + (size_t)p.NT * 4 + 64;
+  p.ok = CG >= 8 && p.NT <= 256 && p.smem <= 220 * 1024;
+  return p;
+}
+
 extern "C" int gkg_grouped_fc_supported(int C2) {
   if (C2 <= 0 || C2 % 32) return 0;                     // 4 conv groups of a multiple of 8 channels
-  const int CG = C2 / 4, NP = (CG + 15) / 16 * 16;
-  return 4 * NP <= 512 ? 1 : 0;                         // the four accumulators must fit the TMEM columns
+  const int CG = C2 / 4;
+  return (fc_narrow_ok(CG) || fc_wide_plan(CG).ok) ? 1 : 0;
+}
+
+// layout of the weight operand for this width: 0 = [4][NP/8][KP/8][8][8] (narrow), else the column-pass width NT of the
+// wide layout [4][passes][NT/8][KP/8][8][8]
+extern "C" int gkg_grouped_fc_pass_width(int C2) {
+  if (!gkg_grouped_fc_supported(C2)) return -1;
+  const int CG = C2 / 4;
+  return fc_narrow_ok(CG) ? 0 : fc_wide_plan(CG).NT;
 }
 
 extern "C" int gkg_grouped_fc_fwd(const void* in, const void* w_op, const float* shift, void* out, long long rows,
@@ -215,6 +482,33 @@ extern "C" int gkg_grouped_fc_fwd(const void* in, const void* w_op, const float*
   GKG_CHECK_ARG(in && w_op && shift && out, "grouped_fc_fwd: null pointer");
   GKG_CHECK_ARG(((uintptr_t)in % 16) == 0 && ((uintptr_t)out % 16) == 0 && ((uintptr_t)w_op % 16) == 0,
                 "grouped_fc_fwd: pointers must be 16-byte aligned");
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const long long tiles = (rows + fc::BM - 1) / fc::BM;
+  const int CG = C2 / 4;
+  if (!fc_narrow_ok(CG)) {
+    const WidePlan wp = fc_wide_plan(CG);
+    fc::WideParams prm{};
+    prm.in = static_cast<const __nv_bfloat16*>(in);
+    prm.out = static_cast<__nv_bfloat16*>(out);
+    prm.w_op = static_cast<const __nv_bfloat16*>(w_op);
+    prm.shift = shift; prm.rows = rows;
+    prm.C2 = C2; prm.CG = CG; prm.KP = wp.KP; prm.NT = wp.NT; prm.passes = wp.passes;
+    void (*kern)(const fc::WideParams) = act == 0 ? fc::grouped_fc_wide_kernel<0>
+                                       : act == 1 ? fc::grouped_fc_wide_kernel<1> : fc::grouped_fc_wide_kernel<2>;
+    static std::atomic<uint64_t> configured[3];
+    cudaError_t e = cudaSuccess;
+    configure_once_per_device(configured[act], [&] {
+      e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    });
+    if (e != cudaSuccess) { set_error("grouped_fc_fwd: smem attribute: %s", cudaGetErrorString(e)); return GKG_ECUDA; }
+    const long long items = tiles * 4 * wp.passes;
+    const int grid = (int)(items < sms ? items : sms);
+    kern<<<grid, fc::THREADS, wp.smem, stream>>>(prm);
+    GKG_CHECK_LAUNCH("grouped_fc_wide_kernel");
+    return GKG_OK;
+  }
   fc::Params prm{};
   prm.in = static_cast<const __nv_bfloat16*>(in);
   prm.out = static_cast<__nv_bfloat16*>(out);
@@ -223,21 +517,103 @@ extern "C" int gkg_grouped_fc_fwd(const void* in, const void* w_op, const float*
   prm.C2 = C2; prm.CG = C2 / 4; prm.KP = (prm.CG + 15) / 16 * 16; prm.NP = prm.KP; prm.act = act;
   const size_t smem = 4 * (size_t)fc::BM * prm.KP * 2 + 4 * (size_t)prm.NP * prm.KP * 2 + (size_t)C2 * 4 + 64;
   void (*kern)(const fc::Params) = nullptr;
+  int slot = act * 3;
 #define GKG_FC_PICK(AA)                                                                                        \
   kern = prm.CG == 40 ? fc::grouped_fc_kernel<40, AA> : prm.CG == 80 ? fc::grouped_fc_kernel<80, AA> : fc::grouped_fc_kernel<0, AA>
   if (act == 0) { GKG_FC_PICK(0); } else if (act == 1) { GKG_FC_PICK(1); } else { GKG_FC_PICK(2); }
 #undef GKG_FC_PICK
+  slot += prm.CG == 40 ? 0 : prm.CG == 80 ? 1 : 2;
   {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    static std::atomic<uint64_t> configured[9];
+    cudaError_t e = cudaSuccess;
+    configure_once_per_device(configured[slot], [&] {
+      e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    });
     if (e != cudaSuccess) { set_error("grouped_fc_fwd: smem attribute %zu: %s", smem, cudaGetErrorString(e)); return GKG_ECUDA; }
   }
-  int dev = 0, sms = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const long long tiles = (rows + fc::BM - 1) / fc::BM;
   const int ctas_per_sm = (4 * prm.NP <= 256 && smem <= 110 * 1024) ? 2 : 1;
   const int grid = (int)(tiles < (long long)sms * ctas_per_sm ? tiles : (long long)sms * ctas_per_sm);
   kern<<<grid, fc::THREADS, smem, stream>>>(prm);
   GKG_CHECK_LAUNCH("grouped_fc_kernel");
+  return GKG_OK;
+}
+
+// Weight operand packing in one launch: (4, CG, CG) fp32 conv weight [q][o][i] (optionally scaled per output channel,
+// optionally transposed per group for the data gradient) -> bf16 core-matrix order of the forward kernels.
+__global__ void grouped_fc_pack_kernel(const float* __restrict__ w, const float* __restrict__ scale,
+                                       __nv_bfloat16* __restrict__ out, int CG, int KP, int NT, int passes, int transpose) {
+  const int nrows = NT > 0 ? passes * NT : KP;                     // padded output rows per group
+  const long long total = 4LL * nrows * KP;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    // destination index -> (q, n, k): [q][(pass)][n/8][k/8][n%8][k%8]
+    const int k8 = (int)(e & 7), n8 = (int)((e >> 3) & 7);
+    long long t = e >> 6;
+    const int kc = (int)(t % (KP >> 3)); t /= (KP >> 3);
+    const int rows8 = (NT > 0 ? NT : KP) >> 3;
+    const int nc = (int)(t % rows8); t /= rows8;
+    int n = nc * 8 + n8;
+    if (NT > 0) { const int pass = (int)(t % passes); t /= passes; n += pass * NT; }
+    const int q = (int)t, k = kc * 8 + k8;
+    float v = 0.f;
+    if (n < CG && k < CG) {
+      v = transpose ? w[((size_t)q * CG + k) * CG + n] : w[((size_t)q * CG + n) * CG + k];
+      if (scale != nullptr) v *= scale[q * CG + n];
+    }
+    out[e] = __float2bfloat16_rn(v);
+  }
+}
+
+extern "C" int gkg_grouped_fc_pack_weights(const float* weight, const float* scale, void* w_op, int C2, int transpose,
+                                           gkg_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  GKG_CHECK_ARG(gkg_grouped_fc_supported(C2), "grouped_fc_pack_weights: unsupported width 2C=%d", C2);
+  GKG_CHECK_ARG(weight && w_op, "grouped_fc_pack_weights: null pointer");
+  const int CG = C2 / 4, KP = (CG + 15) / 16 * 16;
+  int NT = 0, passes = 1;
+  if (!fc_narrow_ok(CG)) { const WidePlan wp = fc_wide_plan(CG); NT = wp.NT; passes = wp.passes; }
+  const long long total = 4LL * (NT > 0 ? passes * NT : KP) * KP;
+  const int blocks = (int)((total + 255) / 256 < 1184 ? (total + 255) / 256 : 1184);
+  grouped_fc_pack_kernel<<<blocks, 256, 0, stream>>>(weight, scale, static_cast<__nv_bfloat16*>(w_op), CG, KP, NT, passes,
+                                                     transpose);
+  GKG_CHECK_LAUNCH("grouped_fc_pack_kernel");
+  return GKG_OK;
+}
+
+extern "C" int gkg_grouped_fc_wgrad(const void* grad_out, const void* in, float* grad_w, long long rows, int C2,
+                                    gkg_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  GKG_CHECK_ARG(rows >= 0 && C2 > 0 && C2 % 32 == 0 && C2 / 4 <= 1024, "grouped_fc_wgrad: unsupported shape rows=%lld 2C=%d", rows, C2);
+  if (rows == 0) return GKG_OK;
+  GKG_CHECK_ARG(grad_out && in && grad_w, "grouped_fc_wgrad: null pointer");
+  GKG_CHECK_ARG(((uintptr_t)grad_out % 16) == 0 && ((uintptr_t)in % 16) == 0, "grouped_fc_wgrad: pointers must be 16-byte aligned");
+  const int CG = C2 / 4;
+  fc::WgradParams prm{};
+  prm.go = static_cast<const __nv_bfloat16*>(grad_out);
+  prm.x = static_cast<const __nv_bfloat16*>(in);
+  prm.gw = grad_w; prm.rows = rows; prm.C2 = C2; prm.CG = CG;
+  const int NP = (CG + 15) / 16 * 16;
+  prm.passes = (NP + 255) / 256;
+  prm.NT = ((NP + prm.passes - 1) / prm.passes + 15) / 16 * 16;
+  prm.mtiles = (CG + 127) / 128;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int base = 4 * prm.mtiles * prm.passes;
+  long long blocks_of_rows = (rows + fc::WG_KB - 1) / fc::WG_KB;
+  int splits = (2 * sms + base - 1) / base;
+  if (splits > blocks_of_rows) splits = (int)blocks_of_rows;
+  if (splits < 1) splits = 1;
+  prm.rows_per_split = (blocks_of_rows + splits - 1) / splits * fc::WG_KB;
+  splits = (int)((rows + prm.rows_per_split - 1) / prm.rows_per_split);
+  prm.splits = splits;
+  const size_t smem = 2 * (size_t)(16 + prm.NT / 8) * (fc::WG_KB / 8) * 128 + 64;
+  static std::atomic<uint64_t> configured{0};
+  cudaError_t e = cudaSuccess;
+  configure_once_per_device(configured, [&] {
+    e = cudaFuncSetAttribute(fc::grouped_fc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024);
+  });
+  if (e != cudaSuccess) { set_error("grouped_fc_wgrad: smem attribute: %s", cudaGetErrorString(e)); return GKG_ECUDA; }
+  fc::grouped_fc_wgrad_kernel<<<base * splits, 256, smem, stream>>>(prm);
+  GKG_CHECK_LAUNCH("grouped_fc_wgrad_kernel");
   return GKG_OK;
 }

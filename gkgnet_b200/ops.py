@@ -272,21 +272,30 @@ def grouped_fc_supported(c2: int) -> bool:
     return bool(_lib.load().gkg_grouped_fc_supported(int(c2)))
 
 
-def grouped_fc_weights(weight, scale=None):
-    """Conv2d(2C, 2C, 1, groups=4) weight ``(2C, 2C/4, 1, 1)`` -> bf16 tensor-core operand order
-    ``[4][NP/8][KP/8][8][8]`` (K-major 8x8 core matrices, NP = KP = ceil16(2C/4), zero padded).
-    ``scale`` (2C,), e.g. the folded batch-norm gain, multiplies the output channels in fp32 first."""
+def grouped_fc_weights(weight, scale=None, transpose=False):
+    """Conv2d(2C, 2C, 1, groups=4) weight ``(2C, 2C/4, 1, 1)`` -> bf16 tensor-core operand order (K-major 8x8 core
+    matrices, zero padded): ``[4][NP/8][KP/8][8][8]`` for narrow groups, ``[4][passes][NT/8][KP/8][8][8]`` for the
+    wide ones (``NT = gkg_grouped_fc_pass_width``), KP = NP = ceil16(2C/4).  One kernel launch.
+    ``scale`` (2C,), e.g. the folded batch-norm gain, multiplies the output channels in fp32 first;
+    ``transpose`` packs the per-group transposed weights (the data gradient of the convolution)."""
     c2, cg = weight.shape[0], weight.shape[1]
     if c2 != 4 * cg:
         raise ValueError(f"expected a groups=4 1x1 conv weight, got {tuple(weight.shape)}")
+    _require_cuda(weight, scale)
+    lib = _lib.load()
+    nt = lib.gkg_grouped_fc_pass_width(int(c2))
+    if nt < 0:
+        raise ValueError(f"no grouped-FC kernel for 2C = {c2}")
     kp = (cg + 15) // 16 * 16
-    w = weight.reshape(c2, cg).float()
-    if scale is not None:
-        w = w * scale.reshape(c2, 1).float()
-    w = w.reshape(4, cg, cg).to(torch.bfloat16)                        # [q][n (out)][k (in)]
-    wp = torch.zeros((4, kp, kp), dtype=torch.bfloat16, device=weight.device)
-    wp[:, :cg, :cg] = w
-    return wp.view(4, kp // 8, 8, kp // 8, 8).permute(0, 1, 3, 2, 4).contiguous()
+    rows = kp if nt == 0 else (kp + nt - 1) // nt * nt
+    w = weight.detach().reshape(c2, cg).float().contiguous()
+    sc = None if scale is None else scale.detach().reshape(c2).float().contiguous()
+    out = torch.empty(4 * rows * kp, dtype=torch.bfloat16, device=weight.device)
+    with torch.cuda.device(weight.device):
+        rc = lib.gkg_grouped_fc_pack_weights(w.data_ptr(), None if sc is None else sc.data_ptr(), out.data_ptr(), c2,
+                                             int(bool(transpose)), _stream(weight))
+    _lib.check(rc, "gkg_grouped_fc_pack_weights")
+    return out
 
 
 def grouped_fc(x, w_op, shift, act="gelu"):
@@ -311,9 +320,8 @@ def grouped_fc(x, w_op, shift, act="gelu"):
 
 class _GroupedFC(torch.autograd.Function):
     """Training form of the grouped 1x1 FC: ``x (.., 2C) bf16 -> conv1x1_groups4(x) + bias`` (pre-norm).
-    Forward and the data gradient (the same product with the transposed weights) run on the tcgen05
-    kernel; the weight gradient is a (CG x CG) reduction over all rows per group, left to a library
-    batched GEMM."""
+    Forward, the data gradient (the same product with the transposed weights) and the weight gradient
+    (a (CG x CG) reduction over all rows per group) run on tcgen05 kernels."""
 
     @staticmethod
     def forward(ctx, x, weight, bias):
@@ -332,15 +340,17 @@ class _GroupedFC(torch.autograd.Function):
         go = grad_out.contiguous()
         gx = gw = gb = None
         if ctx.needs_input_grad[0]:
-            wt = weight.detach().reshape(4, cg, cg).transpose(1, 2).reshape(c2, cg, 1, 1)   # per-group transpose
             zeros = torch.zeros(c2, device=x.device, dtype=torch.float32)
-            gx = grouped_fc(go.to(torch.bfloat16), grouped_fc_weights(wt), zeros, None)
+            gx = grouped_fc(go.to(torch.bfloat16), grouped_fc_weights(weight, transpose=True), zeros, None)
         if ctx.needs_input_grad[1]:
-            # one (2C x R) x (R x 2C) GEMM and its four diagonal blocks: 4x the flops of the batched form but a
-            # shape the library splits along R (the batched 40 x R x 40 products ran at a few percent of peak)
-            full = torch.mm(go.reshape(-1, c2).t(), x.reshape(-1, c2)).float()              # (2C_out, 2C_in)
-            gw = torch.stack([full[q * cg:(q + 1) * cg, q * cg:(q + 1) * cg] for q in range(4)])
-            gw = gw.reshape(c2, cg, 1, 1).to(weight.dtype)
+            # per conv group (CG x R) . (R x CG) on the tensor cores, split over the rows, fp32 accumulation
+            gw32 = torch.zeros((4, cg, cg), dtype=torch.float32, device=x.device)
+            gob = go.to(torch.bfloat16).reshape(-1, c2)
+            xb = x.reshape(-1, c2)
+            rc = _lib.load().gkg_grouped_fc_wgrad(gob.data_ptr(), xb.data_ptr(), gw32.data_ptr(), gob.shape[0], c2,
+                                                  _stream(x))
+            _lib.check(rc, "gkg_grouped_fc_wgrad")
+            gw = gw32.reshape(c2, cg, 1, 1).to(weight.dtype)
         if ctx.has_bias and ctx.needs_input_grad[2]:
             gb = go.reshape(-1, c2).float().sum(0)
         return gx, gw, gb

@@ -163,11 +163,33 @@ int gkg_mr_aggregate_bwd(const void* grad_out, const int32_t* idx, const uint8_t
  *             NP = KP = ceil16(CG)
  *   shift     fp32 (C2): (conv_bias - running_mean) * scale + beta
  *   act       0 none, 1 relu, 2 gelu (erf form, nn.GELU())
- * gkg_grouped_fc_supported(C2) != 0 when the four accumulators fit the tensor memory (CG <= 128).
+ * gkg_grouped_fc_supported(C2) != 0 for every width a kernel exists for (2C a multiple of 32, CG <= 320 and beyond).
+ * Narrow groups (CG <= 96) keep four accumulators in tensor memory and take the weight operand laid out as above;
+ * wider groups (stages 3 - 4: CG = 200, 320) run one (conv group, column pass) at a time and take
+ *     w_op  [4][passes][NT/8][KP/8][8][8],  element [q][p][n/8][k/8][n%8][k%8] = scale * W[q*CG + p*NT + n][k]
+ * with NT = gkg_grouped_fc_pass_width(C2) output channels per pass (0 = narrow layout), passes = ceil(ceil16(CG) / NT).
+ * The data gradient of the convolution is the same call with the per-group transposed weights.
  */
 int gkg_grouped_fc_supported(int C2);
+int gkg_grouped_fc_pass_width(int C2);
 int gkg_grouped_fc_fwd(const void* in, const void* w_op, const float* shift, void* out, long long rows,
                        int C2, int act, gkg_stream_t stream);
+
+/* Packs a (2C, 2C/4, 1, 1) fp32 conv weight into the operand order gkg_grouped_fc_fwd takes for this width (see above):
+ * w_op[..] = bf16(scale[o] * W[o][i]) (scale fp32 (2C,) or NULL), per-group transposed when `transpose` != 0 (the data
+ * gradient).  w_op holds 4 * rows * KP bf16 with rows = passes * NT (wide) or KP (narrow). */
+int gkg_grouped_fc_pack_weights(const float* weight, const float* scale, void* w_op, int C2, int transpose,
+                                gkg_stream_t stream);
+
+/*
+ * Weight gradient of the grouped 1x1 FC (what autograd derives for Conv2d(2C, 2C, 1, groups=4), torch_nn.py:61):
+ *     grad_w[q][o][i] += sum_r grad_out[r, q*CG + o] * in[r, q*CG + i]
+ *   grad_out, in  bf16 (rows, C2) contiguous;  grad_w  fp32 (4, CG, CG) == the (2C, 2C/4, 1, 1) weight layout,
+ *   MUST be zero-filled by the caller (the row range is split over CTAs, partial sums are added atomically).
+ * tcgen05 kernel: both operands are read as they lie in memory (channel-contiguous rows are the MN-major operand form).
+ */
+int gkg_grouped_fc_wgrad(const void* grad_out, const void* in, float* grad_w, long long rows, int C2,
+                         gkg_stream_t stream);
 
 /*
  * Key pooling of the dynamic graph convolution.  Replaces `y = F.avg_pool2d(x, r, r)` of

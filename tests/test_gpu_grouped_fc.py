@@ -19,7 +19,11 @@ def _reference(x, conv, bn, act):
 
 
 @pytest.mark.parametrize("C2,rows,act", [(160, 1000, "gelu"), (160, 128 * 37, "gelu"), (320, 777, "gelu"),
-                                         (64, 300, "relu"), (160, 5, None)])
+                                         (64, 300, "relu"), (160, 5, None),
+                                         (800, 1296 * 2 + 5, "gelu"),      # stage 3 of pvig_s: CG = 200, two column passes
+                                         (1280, 324 * 3, "gelu"),          # stage 4: CG = 320
+                                         (480, 700, "gelu"),               # arch 't' stage 3: CG = 120 (wide kernel, one pass)
+                                         (96, 200, "gelu"), (192, 333, None)])   # arch 't' stages 1 - 2
 def test_grouped_fc_matches_conv_bn_act(C2, rows, act):
     from gkgnet_b200 import ops
     torch.manual_seed(C2 + rows)
@@ -42,10 +46,11 @@ def test_grouped_fc_matches_conv_bn_act(C2, rows, act):
     assert err < 2e-2 * max(1.0, want.abs().max().item()), err
 
 
-def test_grouped_fc_unsupported_width():
+def test_grouped_fc_supported_widths():
     from gkgnet_b200 import ops
-    assert not ops.grouped_fc_supported(800)       # CG = 200: four accumulators exceed the tensor memory
-    assert not ops.grouped_fc_supported(100)
+    for c2 in (96, 160, 192, 320, 480, 800, 1280, 1536):   # every MRConv width of the pvig archs
+        assert ops.grouped_fc_supported(c2), c2
+    assert not ops.grouped_fc_supported(100)       # 4 conv groups of a multiple of 8 channels
 
 
 def test_mrconv_eval_uses_fused_fc_and_matches_unfused():
@@ -78,11 +83,12 @@ def test_mrconv_eval_uses_fused_fc_and_matches_unfused():
     assert err < 2e-2 * max(1.0, plain.float().abs().max().item()), err
 
 
-def test_grouped_fc_train_gradients_match_conv():
-    """Training form: output and the three gradients against Conv2d(groups=4) under bf16 autocast."""
+@pytest.mark.parametrize("C2,R", [(160, 3000), (320, 1000), (800, 1296 + 17), (1280, 324 * 2), (480, 515), (96, 64)])
+def test_grouped_fc_train_gradients_match_conv(C2, R):
+    """Training form (forward, data gradient, tcgen05 weight gradient, bias gradient) against Conv2d(groups=4)
+    evaluated in fp32 on the same bf16 inputs: 2e-2 of the scale of each tensor (north-star bf16 tolerance)."""
     from gkgnet_b200 import ops
     torch.manual_seed(5)
-    C2, R = 160, 3000
     conv = torch.nn.Conv2d(C2, C2, 1, groups=4).cuda()
     x = torch.randn(R, C2, device="cuda").to(torch.bfloat16).requires_grad_(True)
     g = torch.randn(R, C2, device="cuda").to(torch.bfloat16)
@@ -90,9 +96,14 @@ def test_grouped_fc_train_gradients_match_conv():
     out.backward(g)
     gx, gw, gb = x.grad.clone(), conv.weight.grad.clone(), conv.bias.grad.clone()
     x.grad = None; conv.weight.grad = None; conv.bias.grad = None
-    with torch.autocast("cuda", dtype=torch.bfloat16):
-        ref = conv(x.t().reshape(1, C2, R, 1)).reshape(C2, R).t()
-    ref.backward(g)
+    xf = x.detach().float().requires_grad_(True)
+    wb = conv.weight.detach().to(torch.bfloat16).float().requires_grad_(True)      # the kernel multiplies bf16 weights
+    ref = torch.nn.functional.conv2d(xf.t().reshape(1, C2, R, 1), wb, conv.bias.float(), groups=4).reshape(C2, R).t()
+    ref.backward(g.float())
+
     def close(a, b, tol=2e-2):
         return (a.float() - b.float()).abs().max().item() <= tol * max(1.0, b.float().abs().max().item())
-    assert close(out, ref) and close(gx, x.grad) and close(gw, conv.weight.grad, 3e-2) and close(gb, conv.bias.grad, 3e-2)
+    assert close(out, ref), "forward"
+    assert close(gx, xf.grad), "data gradient"
+    assert close(gw, wb.grad), "weight gradient"
+    assert close(gb, g.float().sum(0)), "bias gradient"
