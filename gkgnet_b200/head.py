@@ -1,11 +1,14 @@
-"""LabelQueryHead + its losses -- mirror of mmcls/models/heads/label_query_head.py.
-Tiny ((B, 80, 640) -> (B, 80)); plain PyTorch, listed as a 'next' row in SURVEY.md 8(f)."""
+"""LabelQueryHead + its losses -- mirror of mmcls/models/heads/label_query_head.py (SURVEY.md 8(f) rank 3).
+On CUDA tensors the scores, both losses and their gradients run on the kernels of csrc/label_head.cu
+(``ops.label_score`` / ``ops.multilabel_losses``); the PyTorch expressions below are the host-side definition the
+CPU tests (gloo data-parallel plumbing, oracle comparison) exercise."""
 from __future__ import annotations
 
 import torch
 import torch.nn.functional as F
 from torch import nn
 
+from . import ops
 from .registry import HEADS, register_into_mmcls
 
 
@@ -47,6 +50,8 @@ class LabelQueryHead(nn.Module):
 
     def get_score(self, x):
         label_emb, gap = x[0], x[1]
+        if label_emb.is_cuda:
+            return ops.label_score(label_emb, gap, self.fc1.weight, self.fc1.bias, self.fc2.weight, self.fc2.bias)
         diag = (label_emb * self.fc1.weight.unsqueeze(0)).sum(-1) + self.fc1.bias
         return diag + self.fc2(gap)
 
@@ -60,9 +65,13 @@ class LabelQueryHead(nn.Module):
     def forward_train(self, x, gt_label, **kwargs):
         score = self.get_score(x).float()
         n = score.shape[0]
-        asl = asymmetric_loss(score, gt_label, **self.loss_cfg) / n
-        smooth = gt_label.type_as(score) * 0.8 + 0.1          # LabelSmoothLoss(0.1, 'multi_label')
-        bce = F.binary_cross_entropy_with_logits(score, smooth, reduction="sum") / n
+        if score.is_cuda:
+            asl, bce = ops.multilabel_losses(score, gt_label, smooth=0.1, **self.loss_cfg)
+            asl, bce = asl / n, bce / n
+        else:
+            asl = asymmetric_loss(score, gt_label, **self.loss_cfg) / n
+            smooth = gt_label.type_as(score) * 0.8 + 0.1          # LabelSmoothLoss(0.1, 'multi_label')
+            bce = F.binary_cross_entropy_with_logits(score, smooth, reduction="sum") / n
         if self.double_loss:
             return {"bce_loss": bce, "asy_loss": asl * 10.0}
         return {"loss": asl}

@@ -360,3 +360,79 @@ def grouped_fc_train(x, weight, bias):
     """Differentiable ``conv1x1_groups4(x) + bias`` on token-major bf16 ``x (..., 2C)`` (pre-norm output)."""
     _require_cuda(x, weight)
     return _GroupedFC.apply(x, weight, bias)
+
+
+# ----------------------------------------------------------------------------------------
+# label-query head: per-label scores and the two multi-label losses
+# ----------------------------------------------------------------------------------------
+class _LabelScore(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, L, gap, W1, b1, W2, b2):
+        lib = _lib.load()
+        Lf, gf = L.float().contiguous(), gap.float().contiguous()
+        w1, w2 = W1.float().contiguous(), W2.float().contiguous()
+        B, n, C = Lf.shape
+        score = torch.empty((B, n), dtype=torch.float32, device=L.device)
+        with torch.cuda.device(L.device):
+            rc = lib.gkg_label_score_fwd(Lf.data_ptr(), gf.data_ptr(), w1.data_ptr(), b1.float().contiguous().data_ptr(),
+                                         w2.data_ptr(), b2.float().contiguous().data_ptr(), score.data_ptr(), B, n, C,
+                                         _stream(L))
+        _lib.check(rc, "gkg_label_score_fwd")
+        ctx.save_for_backward(Lf, gf, w1, w2)
+        ctx.dtypes = (L.dtype, gap.dtype, W1.dtype, b1.dtype, W2.dtype, b2.dtype)
+        return score
+
+    @staticmethod
+    def backward(ctx, ds):
+        Lf, gf, w1, w2 = ctx.saved_tensors
+        B, n, C = Lf.shape
+        dev = Lf.device
+        ds = ds.float().contiguous()
+        dL = torch.empty_like(Lf)
+        dg = torch.empty_like(gf)
+        dW1, dW2 = torch.empty_like(w1), torch.empty_like(w2)
+        db1 = torch.empty(n, dtype=torch.float32, device=dev)
+        db2 = torch.empty(n, dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            rc = _lib.load().gkg_label_score_bwd(ds.data_ptr(), Lf.data_ptr(), gf.data_ptr(), w1.data_ptr(), w2.data_ptr(),
+                                                 dL.data_ptr(), dg.data_ptr(), dW1.data_ptr(), dW2.data_ptr(), db1.data_ptr(),
+                                                 db2.data_ptr(), B, n, C, _stream(ds))
+        _lib.check(rc, "gkg_label_score_bwd")
+        dt = ctx.dtypes
+        return dL.to(dt[0]), dg.to(dt[1]), dW1.to(dt[2]), db1.to(dt[3]), dW2.to(dt[4]), db2.to(dt[5])
+
+
+def label_score(label_emb, gap, fc1_weight, fc1_bias, fc2_weight, fc2_bias):
+    """``score[b, i] = fc1.weight[i] . L[b, i] + fc1.bias[i] + fc2(gap)[b, i]`` (label_query_head.py:49-57)
+    as one row-dot kernel, fp32, differentiable."""
+    _require_cuda(label_emb, gap, fc1_weight, fc2_weight)
+    return _LabelScore.apply(label_emb, gap, fc1_weight, fc1_bias, fc2_weight, fc2_bias)
+
+
+class _MultiLabelLoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, score, target, gamma_pos, gamma_neg, clip, eps, smooth):
+        s = score.float().contiguous()
+        t = target.to(torch.float32).contiguous()
+        sums = torch.empty(2, dtype=torch.float32, device=s.device)
+        d_asl, d_bce = torch.empty_like(s), torch.empty_like(s)
+        with torch.cuda.device(s.device):
+            rc = _lib.load().gkg_multilabel_loss(s.data_ptr(), t.data_ptr(), sums.data_ptr(), d_asl.data_ptr(),
+                                                 d_bce.data_ptr(), s.numel(), float(gamma_pos), float(gamma_neg),
+                                                 float(clip or 0.0), float(eps), float(smooth), _stream(s))
+        _lib.check(rc, "gkg_multilabel_loss")
+        ctx.save_for_backward(d_asl, d_bce)
+        ctx.dtype = score.dtype
+        return sums[0], sums[1]
+
+    @staticmethod
+    def backward(ctx, g_asl, g_bce):
+        d_asl, d_bce = ctx.saved_tensors
+        return (d_asl * g_asl + d_bce * g_bce).to(ctx.dtype), None, None, None, None, None, None
+
+
+def multilabel_losses(score, target, gamma_pos=0.0, gamma_neg=2.0, clip=0.05, eps=1e-8, smooth=0.1):
+    """(sum of AsymmetricLoss terms, sum of label-smoothed BCE-with-logits terms) over all entries of ``score`` --
+    the two losses of LabelQueryHead.forward_train before the division by the batch -- in one kernel."""
+    _require_cuda(score, target)
+    return _MultiLabelLoss.apply(score, target, gamma_pos, gamma_neg, clip, eps, smooth)

@@ -206,6 +206,32 @@ int gkg_pool_keys_fwd(const void* x, int64_t x_stride_b, int64_t x_stride_n, voi
 int gkg_pool_keys_bwd(const void* grad_y, void* grad_x,
                       int B, int H, int W, int C, int r, int dtype, gkg_stream_t stream);
 
+/*
+ * Label-query head.  Replaces LabelQueryHead.get_score (mmcls/models/heads/label_query_head.py:49-57: fc1 on all
+ * label embeddings -- a (B, n, n) product -- masked to its diagonal, plus fc2(gap)):
+ *     score[b, i] = W1[i] . L[b, i] + b1[i] + W2[i] . gap[b] + b2[i]
+ *   L fp32 (B, n, C) contiguous, gap fp32 (B, C), W1 / W2 fp32 (n, C), b1 / b2 fp32 (n), score fp32 (B, n).
+ * gkg_label_score_bwd: what autograd derives for it -- dL (B, n, C), dgap (B, C), dW1 / dW2 (n, C), db1 / db2 (n) from
+ * dscore (B, n); every output is overwritten.
+ */
+int gkg_label_score_fwd(const float* L, const float* gap, const float* W1, const float* b1, const float* W2,
+                        const float* b2, float* score, int B, int n, int C, gkg_stream_t stream);
+int gkg_label_score_bwd(const float* dscore, const float* L, const float* gap, const float* W1, const float* W2,
+                        float* dL, float* dgap, float* dW1, float* dW2, float* db1, float* db2,
+                        int B, int n, int C, gkg_stream_t stream);
+
+/*
+ * The two losses of LabelQueryHead.forward_train (label_query_head.py:70-85) on `total` (score, target) entries:
+ *   sums[0] = sum of AsymmetricLoss terms (losses/asymmetric_loss.py:9-72: sigmoid, clip, gamma_pos / gamma_neg, eps)
+ *   sums[1] = sum of BCE-with-logits terms against the smoothed target t (1 - 2 smooth) + smooth
+ *             (label_smooth_loss.py:122-126, 168-175)
+ *   d_asl, d_bce  fp32 (total): derivatives of the two sums with respect to every score.
+ * The caller divides by the batch and applies the x10 weight of the reference.
+ */
+int gkg_multilabel_loss(const float* score, const float* target, float* sums, float* d_asl, float* d_bce,
+                        long long total, float gamma_pos, float gamma_neg, float clip, float eps, float smooth,
+                        gkg_stream_t stream);
+
 /* Number of kernels this library has launched since load (for bench accounting). */
 uint64_t gkg_launch_count(void);
 
