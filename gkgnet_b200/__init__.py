@@ -8,4 +8,5 @@ from .head import LabelQueryHead  # noqa: F401
 from .layers import BasicConv, act_layer, batched_index_select, norm_layer, set_norm_type  # noqa: F401
 from .registry import BACKBONES, HEADS, build_backbone, build_head  # noqa: F401
 from .vertex import (DyGraphConv2d, DyGraphConv2dMultiGroup, DyGraphLabel,  # noqa: F401
-                     DyGraphLabelMultiGroup, FFNLabel, GraphConv2d, Grapher, GrapherLabel, MRConv2d)
+                     DyGraphLabelMultiGroup, EdgeConv2d, FFNLabel, GINConv2d, GraphAtten, GraphConv2d, Grapher,
+                     GrapherLabel, GraphSAGE, MRConv2d)

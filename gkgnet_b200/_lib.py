@@ -40,6 +40,10 @@ SIGNATURES = {
     "gkg_grouped_fc_supported": (_i32, [_i32]),
     "gkg_grouped_fc_pass_width": (_i32, [_i32]),
     "gkg_grouped_fc_fwd": (_i32, [_vp, _vp, _vp, _vp, _c.c_longlong, _i32, _i32, _vp]),
+    "gkg_neighbor_gather_fwd": (_i32, [_vp, _i64, _i64, _vp, _vp] + [_i32] * 7 + [_vp]),
+    "gkg_neighbor_gather_bwd": (_i32, [_vp, _vp, _vp] + [_i32] * 7 + [_vp]),
+    "gkg_neighbor_sum_fwd": (_i32, [_vp, _i64, _i64, _vp, _vp] + [_i32] * 7 + [_vp]),
+    "gkg_neighbor_sum_bwd": (_i32, [_vp, _vp, _vp] + [_i32] * 7 + [_vp]),
     "gkg_label_score_fwd": (_i32, [_vp] * 7 + [_i32] * 3 + [_vp]),
     "gkg_label_score_bwd": (_i32, [_vp] * 11 + [_i32] * 3 + [_vp]),
     "gkg_multilabel_loss": (_i32, [_vp] * 5 + [_c.c_longlong] + [_c.c_float] * 5 + [_vp]),

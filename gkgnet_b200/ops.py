@@ -436,3 +436,63 @@ def multilabel_losses(score, target, gamma_pos=0.0, gamma_neg=2.0, clip=0.05, ep
     the two losses of LabelQueryHead.forward_train before the division by the batch -- in one kernel."""
     _require_cuda(score, target)
     return _MultiLabelLoss.apply(score, target, gamma_pos, gamma_neg, clip, eps, smooth)
+
+
+# ----------------------------------------------------------------------------------------
+# neighbour gather / neighbour sum (the graph-convolution variants other than max-relative)
+# ----------------------------------------------------------------------------------------
+class _NeighborGather(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, y, idx, groups, reduce_sum):
+        lib = _lib.load()
+        y = _token_major(y)
+        B, M, C = y.shape
+        P, N, k = idx.shape
+        D = C // groups
+        shape = (B, N, C) if reduce_sum else (B, N, k, C)
+        out = torch.empty(shape, dtype=y.dtype, device=y.device)
+        fn = lib.gkg_neighbor_sum_fwd if reduce_sum else lib.gkg_neighbor_gather_fwd
+        with torch.cuda.device(y.device):
+            rc = fn(y.data_ptr(), y.stride(0), y.stride(1), idx.data_ptr(), out.data_ptr(), B, groups, N, M, D, k,
+                    _DT[y.dtype], _stream(y))
+        _lib.check(rc, "gkg_neighbor_sum_fwd" if reduce_sum else "gkg_neighbor_gather_fwd")
+        ctx.save_for_backward(idx)
+        ctx.meta = (B, groups, N, M, D, k, y.dtype, reduce_sum)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad):
+        (idx,) = ctx.saved_tensors
+        B, G, N, M, D, k, dtype, reduce_sum = ctx.meta
+        grad = grad.contiguous().to(dtype)
+        gy = torch.zeros((B, M, G * D), dtype=torch.float32, device=grad.device)
+        lib = _lib.load()
+        fn = lib.gkg_neighbor_sum_bwd if reduce_sum else lib.gkg_neighbor_gather_bwd
+        with torch.cuda.device(grad.device):
+            rc = fn(grad.data_ptr(), idx.data_ptr(), gy.data_ptr(), B, G, N, M, D, k, _DT[dtype], _stream(grad))
+        _lib.check(rc, "gkg_neighbor_gather_bwd")
+        return gy.to(dtype), None, None, None
+
+
+def _check_gather(y, idx, groups):
+    _require_cuda(y, idx)
+    if y.dtype not in _DT:
+        raise TypeError(f"unsupported dtype {y.dtype}")
+    if idx.dtype != torch.int32:
+        idx = idx.to(torch.int32)
+    idx = idx.contiguous()
+    if y.shape[2] % groups or idx.shape[0] != y.shape[0] * groups:
+        raise ValueError(f"idx {tuple(idx.shape)} does not match B*G = {y.shape[0] * groups}")
+    return idx
+
+
+def gather_neighbors(y, idx, *, groups=1):
+    """``out[b, n, j, c] = y[b, idx[b*G + c//D, n, j], c]`` -- batched_index_select (torch_nn.py:84-105) on the
+    token-major layout: y (B, M, C), idx int32 (B*G, N, k) -> (B, N, k, C).  Differentiable w.r.t. y."""
+    return _NeighborGather.apply(y, _check_gather(y, idx, groups), groups, False)
+
+
+def sum_neighbors(y, idx, *, groups=1):
+    """``out[b, n, c] = sum_j y[b, idx[b*G + c//D, n, j], c]`` (GINConv2d, torch_vertex.py:143-149) without the
+    gathered (B, N, k, C) tensor.  Differentiable w.r.t. y."""
+    return _NeighborGather.apply(y, _check_gather(y, idx, groups), groups, True)

@@ -117,18 +117,117 @@ class MRConv2d(nn.Module):
         return self.forward_tokens(regroup(x), nn_idx, None if y is None else regroup(y), groups=G)
 
 
+class _GatherConvBase(nn.Module):
+    """Shared plumbing of the graph convolutions that work on the gathered neighbour rows.  ``forward`` takes the
+    reference layout -- x (B, C, N, 1), edge_index (2, B, N, k), y (B, C, M, 1) | None -- ``forward_tokens`` the
+    token-major one.  Like the reference's classes they only make sense un-grouped (their ``nn`` is built for the
+    full channel count: torch_vertex.py:88-101 leaves the regrouping commented out)."""
+
+    def forward(self, x, edge_index, y=None):
+        B, C, N, _ = x.shape
+        xt = x.reshape(B, C, N).transpose(1, 2)
+        yt = None if y is None else y.reshape(B, C, -1).transpose(1, 2)
+        return self.forward_tokens(xt, edge_index[0].to(torch.int32), yt)
+
+    @staticmethod
+    def _nchw(t):            # (B, N, k, C) -> (B, C, N, k) view (channels-last memory: no copy)
+        return t.permute(0, 3, 1, 2)
+
+    def _check_groups(self, groups):
+        if groups != 1:
+            raise ValueError(f"{type(self).__name__} is defined for a single channel group (got {groups})")
+
+
+class EdgeConv2d(_GatherConvBase):
+    """max_j nn(cat[x_i, x_j - x_i]) (torch_vertex.py:82-101)."""
+
+    def __init__(self, in_channels, out_channels, act="relu", norm=None, bias=True):
+        super().__init__()
+        self.in_channels = in_channels
+        self.nn = BasicConv([in_channels * 2, out_channels], act, norm, bias)
+
+    def forward_tokens(self, xt, nn_idx, yt=None, groups=1, hw=None):
+        self._check_groups(groups)
+        x_j = ops.gather_neighbors(xt if yt is None else yt, nn_idx)            # (B, N, k, C)
+        x_i = xt.unsqueeze(2).expand_as(x_j)
+        h = self.nn(self._nchw(torch.cat((x_i, x_j - x_i), dim=-1)))
+        out = h.max(dim=-1, keepdim=True).values                                # (B, C', N, 1)
+        return out if hw is None else out.reshape(out.shape[0], out.shape[1], *hw)
+
+
+class GraphSAGE(_GatherConvBase):
+    """nn2(cat[x, max_j nn1(x_j)]) (torch_vertex.py:116-131)."""
+
+    def __init__(self, in_channels, out_channels, act="relu", norm=None, bias=True):
+        super().__init__()
+        self.nn1 = BasicConv([in_channels, in_channels], act, norm, bias)
+        self.nn2 = BasicConv([in_channels * 2, out_channels], act, norm, bias)
+
+    def forward_tokens(self, xt, nn_idx, yt=None, groups=1, hw=None):
+        self._check_groups(groups)
+        x_j = ops.gather_neighbors(xt if yt is None else yt, nn_idx)
+        m = self.nn1(self._nchw(x_j)).max(dim=-1, keepdim=True).values          # (B, C, N, 1)
+        x = xt.transpose(1, 2).unsqueeze(-1)
+        out = self.nn2(torch.cat((x, m), dim=1))
+        return out if hw is None else out.reshape(out.shape[0], out.shape[1], *hw)
+
+
+class GINConv2d(_GatherConvBase):
+    """nn((1 + eps) x + sum_j x_j) (torch_vertex.py:134-150)."""
+
+    def __init__(self, in_channels, out_channels, act="relu", norm=None, bias=True):
+        super().__init__()
+        self.nn = BasicConv([in_channels, out_channels], act, norm, bias)
+        self.eps = nn.Parameter(torch.Tensor([0.0]))
+
+    def forward_tokens(self, xt, nn_idx, yt=None, groups=1, hw=None):
+        self._check_groups(groups)
+        s = ops.sum_neighbors(xt if yt is None else yt, nn_idx)                 # (B, N, C), no gathered tensor
+        h = ((1 + self.eps) * xt + s).transpose(1, 2).unsqueeze(-1)
+        out = self.nn(h)
+        return out if hw is None else out.reshape(out.shape[0], out.shape[1], *hw)
+
+
+class GraphAtten(_GatherConvBase):
+    """Attention-weighted neighbour mean interleaved with the centre features (torch_vertex.py:16-37)."""
+
+    def __init__(self, in_channels, out_channels, act="relu", norm=None, bias=True, alpha=0.1):
+        super().__init__()
+        self.in_channels = in_channels
+        self.leakyrelu = nn.LeakyReLU(alpha)
+        self.nn = BasicConv([in_channels * 2, out_channels], act, norm, bias)
+        self.a = nn.Conv2d(in_channels * 2, 1, 1, bias=bias)
+
+    def forward_tokens(self, xt, nn_idx, yt=None, groups=1, hw=None):
+        self._check_groups(groups)
+        x_j = ops.gather_neighbors(xt if yt is None else yt, nn_idx)            # (B, N, k, C)
+        x_i = xt.unsqueeze(2).expand_as(x_j)
+        e = self.a(self._nchw(torch.cat((x_i, x_j), dim=-1)))                   # (B, 1, N, k)
+        att = torch.softmax(e.reshape(e.shape[0], e.shape[2], e.shape[3]), dim=-1)
+        m = (att.unsqueeze(-1) * x_j).sum(2)                                    # (B, N, C)
+        B, N, C = xt.shape
+        h = torch.stack((xt, m), dim=-1).reshape(B, N, 2 * C)                   # channels [x_0, m_0, x_1, m_1, ...]
+        out = self.nn(h.transpose(1, 2).unsqueeze(-1))
+        return out if hw is None else out.reshape(out.shape[0], out.shape[1], *hw)
+
+
 class GraphConv2d(nn.Module):
-    """Static graph convolution selector (torch_vertex.py:153-173).  GKGNet fixes
-    ``conv='mr'`` (gkgnet.py:124,138,205,220); the other reference variants are outside the
-    accelerated path."""
+    """Static graph convolution selector (torch_vertex.py:153-173).  GKGNet fixes ``conv='mr'``
+    (gkgnet.py:124,138,205,220): the fused max-relative kernels; the other variants run on the native neighbour
+    gather / sum (csrc/gather.cu) with their 1x1 convolutions as library ops."""
 
     def __init__(self, in_channels, out_channels, conv="edge", act="relu", norm=None, bias=True):
         super().__init__()
-        if conv == "mr":
+        if conv == "edge":
+            self.gconv = EdgeConv2d(in_channels, out_channels, act, norm, bias)
+        elif conv == "gat":
+            self.gconv = GraphAtten(in_channels, out_channels, act, norm, bias)
+        elif conv == "mr":
             self.gconv = MRConv2d(in_channels, out_channels, act, norm, bias)
-        elif conv in ("edge", "gat", "sage", "gin"):
-            raise NotImplementedError(
-                f"conv:{conv} has no sm_100a kernel yet; GKGNet only instantiates conv='mr'")
+        elif conv == "sage":
+            self.gconv = GraphSAGE(in_channels, out_channels, act, norm, bias)
+        elif conv == "gin":
+            self.gconv = GINConv2d(in_channels, out_channels, act, norm, bias)
         else:
             raise NotImplementedError("conv:{} is not supported".format(conv))
 

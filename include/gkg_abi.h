@@ -207,6 +207,24 @@ int gkg_pool_keys_bwd(const void* grad_y, void* grad_x,
                       int B, int H, int W, int C, int r, int dtype, gkg_stream_t stream);
 
 /*
+ * Neighbour gather / neighbour sum for the graph-convolution variants that need the gathered rows (EdgeConv2d,
+ * GraphSAGE, GraphAtten, GINConv2d: torch_vertex.py:16-150).  Replaces batched_index_select (torch_nn.py:84-105) on
+ * the token-major layout:
+ *     gather: out[b, n, j, c] = y[b, idx[b*G + c/D, n, j], c]        out (B, N, k, G*D) contiguous, dtype
+ *     sum:    out[b, n, c]    = sum_j y[b, idx[b*G + c/D, n, j], c]  out (B, N, G*D) contiguous, dtype (fp32 accumulation)
+ * Backward (index_put_(accumulate=True) of autograd): grad_y_accum fp32 (B, M, G*D), zero-filled by the caller, receives
+ * the scattered gradients (atomic adds).
+ */
+int gkg_neighbor_gather_fwd(const void* y, int64_t y_stride_b, int64_t y_stride_n, const int32_t* idx, void* out,
+                            int B, int G, int N, int M, int D, int k, int dtype, gkg_stream_t stream);
+int gkg_neighbor_gather_bwd(const void* grad, const int32_t* idx, float* grad_y_accum,
+                            int B, int G, int N, int M, int D, int k, int dtype, gkg_stream_t stream);
+int gkg_neighbor_sum_fwd(const void* y, int64_t y_stride_b, int64_t y_stride_n, const int32_t* idx, void* out,
+                         int B, int G, int N, int M, int D, int k, int dtype, gkg_stream_t stream);
+int gkg_neighbor_sum_bwd(const void* grad, const int32_t* idx, float* grad_y_accum,
+                         int B, int G, int N, int M, int D, int k, int dtype, gkg_stream_t stream);
+
+/*
  * Label-query head.  Replaces LabelQueryHead.get_score (mmcls/models/heads/label_query_head.py:49-57: fc1 on all
  * label embeddings -- a (B, n, n) product -- masked to its diagonal, plus fc2(gap)):
  *     score[b, i] = W1[i] . L[b, i] + b1[i] + W2[i] . gap[b] + b2[i]

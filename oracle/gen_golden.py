@@ -119,6 +119,22 @@ def main():
     npz("mrconv", x=x, y=y, edge_index=ei, out=out, out_self=out_self,
         x_j=x_j, maxrel=torch.max(x_j - x_i, -1, keepdim=True)[0], **sd_arrays(sd))
 
+    # ---- 3b. the other GraphConv2d variants (torch_vertex.py:16-150), un-grouped as the reference builds them ----
+    gv = torch.Generator().manual_seed(4321)          # own stream: the fixtures below keep their inputs
+    xv = torch.randn(2, 16, 64, 1, generator=gv)
+    yv = torch.randn(2, 16, 16, 1, generator=gv)
+    ei_xy = ref.DenseDilatedKnnGraph(3, 1, False, 0.0)(xv, yv)
+    ei_self = ref.DenseDilatedKnnGraph(4, 1, False, 0.0)(xv)
+    for conv_name in ("edge", "sage", "gin", "gat"):
+        m = ref.GraphConv2d(16, 32, conv_name, "gelu", "batch", True).eval()
+        sdv = fill_state_dict(m)
+        if conv_name == "gin":
+            with torch.no_grad():
+                m.gconv.eps.fill_(0.25)
+            sdv = {k_: v_.clone() for k_, v_ in m.state_dict().items()}
+        npz("gconv_" + conv_name, x=xv, y=yv, edge_index=ei_xy, edge_index_self=ei_self, out=m(xv, ei_xy, yv),
+            out_self=m(xv, ei_self, None), **sd_arrays(sdv))
+
     # ---- 4./5. Grapher with key reduction (r=2) and without (r=1, dilation 2) --------
     for name, r, dil in (("grapher_r2", 2, 1), ("grapher_r1", 1, 2)):
         m = ref.Grapher(16, 3, dil, "mr", "gelu", "batch", True, False, 0.2, r, 64, 0.0,

@@ -142,6 +142,40 @@ def mr_conv2d(sd, prefix, x, edge_index, y, in_channels, training=False):
 # --------------------------------------------------------------------------------------
 
 
+def edge_conv2d(sd, prefix, x, edge_index, y=None, training=False):
+    """EdgeConv2d.forward (torch_vertex.py:91-101): max_k nn(cat[x_i, x_j - x_i])."""
+    x_i = gather_neighbors(x, edge_index[1])
+    x_j = gather_neighbors(x if y is None else y, edge_index[0])
+    h = basic_conv(sd, prefix + "nn.", torch.cat([x_i, x_j - x_i], dim=1), training)
+    return h.max(-1, keepdim=True).values
+
+
+def graph_sage(sd, prefix, x, edge_index, y=None, training=False):
+    """GraphSAGE.forward (torch_vertex.py:125-131): nn2(cat[x, max_k nn1(x_j)])."""
+    x_j = gather_neighbors(x if y is None else y, edge_index[0])
+    m = basic_conv(sd, prefix + "nn1.", x_j, training).max(-1, keepdim=True).values
+    return basic_conv(sd, prefix + "nn2.", torch.cat([x, m], dim=1), training)
+
+
+def gin_conv2d(sd, prefix, x, edge_index, y=None, training=False):
+    """GINConv2d.forward (torch_vertex.py:143-149): nn((1 + eps) x + sum_k x_j)."""
+    x_j = gather_neighbors(x if y is None else y, edge_index[0]).sum(-1, keepdim=True)
+    return basic_conv(sd, prefix + "nn.", (1 + sd[prefix + "eps"]) * x + x_j, training)
+
+
+def graph_atten(sd, prefix, x, edge_index, y=None, training=False):
+    """GraphAtten.forward (torch_vertex.py:26-37): softmax_k(a(cat[x_i, x_j])) weighted neighbour mean, interleaved
+    with the centre features, then nn."""
+    x_i = gather_neighbors(x, edge_index[1])
+    x_j = gather_neighbors(x if y is None else y, edge_index[0])
+    e = F.conv2d(torch.cat([x_i, x_j], dim=1), sd[prefix + "a.weight"], sd[prefix + "a.bias"]).squeeze(1)
+    att = torch.softmax(e, -1)
+    m = (att.unsqueeze(-1) * x_j.permute(0, 2, 3, 1)).sum(2).transpose(1, 2).unsqueeze(-1)
+    b, c, n, _ = x.shape
+    h = torch.cat([x.unsqueeze(2), m.unsqueeze(2)], dim=2).reshape(b, 2 * c, n, 1)
+    return basic_conv(sd, prefix + "nn.", h, training)
+
+
 def dygraph_conv(sd, prefix, x, relative_pos, k, dilation, r, num_group=1, training=False):
     """DyGraphConv2dMultiGroup.forward (torch_vertex.py:191-205); ``num_group=1``
     reproduces DyGraphConv2d.forward (:218-228).  x: (B, C, H, W) -> ((B, 2C, H, W), edge_index)."""

@@ -147,7 +147,7 @@ def load_reference(root=None):
                  "DyGraphLabel", "DyGraphLabelMultiGroup", "Grapher", "GrapherLabel",
                  "FFNLabel", "xy_dense_knn_matrix", "dense_knn_matrix",
                  "xy_pairwise_distance", "pairwise_distance", "part_pairwise_distance",
-                 "get_2d_relative_pos_embed"):
+                 "get_2d_relative_pos_embed", "GraphConv2d", "EdgeConv2d", "GraphSAGE", "GINConv2d", "GraphAtten"):
         setattr(ns, name, getattr(vig, name))
     ns.GKGNet = gkg.GKGNet
     _loaded = ns

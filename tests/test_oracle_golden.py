@@ -122,3 +122,15 @@ def test_gkgnet_s192_matches_reference():
     assert ei.shape == g["edge_index"].shape
     same = (torch.sort(ei, -1).values == torch.sort(g["edge_index"], -1).values).all(-1).float().mean()
     assert same > 0.99
+
+
+@pytest.mark.parametrize("conv", ["edge", "sage", "gin", "gat"])
+def test_graphconv_variants_match_reference(conv):
+    """The graph convolutions GKGNet does not instantiate (torch_vertex.py:16-150), un-grouped as the reference
+    builds them: oracle restatement against the reference's own output, separate keys and self keys."""
+    g = load_golden("gconv_" + conv)
+    fn = {"edge": O.edge_conv2d, "sage": O.graph_sage, "gin": O.gin_conv2d, "gat": O.graph_atten}[conv]
+    out = fn(g["sd"], "gconv.", g["x"], g["edge_index"], g["y"])
+    assert torch.allclose(out, g["out"], atol=1e-5, rtol=1e-5)
+    out = fn(g["sd"], "gconv.", g["x"], g["edge_index_self"], None)
+    assert torch.allclose(out, g["out_self"], atol=1e-5, rtol=1e-5)
