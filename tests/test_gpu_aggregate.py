@@ -93,10 +93,10 @@ def test_aggregate_backward(dtype, tol, self_keys):
     yo = None if y is None else y.float().requires_grad_(True)
     (_oracle_agg(xo, idx, yo, G) * w.float()).sum().backward()
     scale = max(1.0, float(xo.grad.abs().max()))
-    assert (xc.grad.float().cpu() - xo.grad).abs().max() <= tol * scale * (8 if dtype == torch.bfloat16 else 1)
+    assert (xc.grad.float().cpu() - xo.grad).abs().max() <= tol * scale
     if not self_keys:
         scale = max(1.0, float(yo.grad.abs().max()))
-        assert (yc.grad.float().cpu() - yo.grad).abs().max() <= tol * scale * (8 if dtype == torch.bfloat16 else 1)
+        assert (yc.grad.float().cpu() - yo.grad).abs().max() <= tol * scale
 
 
 @pytest.mark.parametrize("quantised", [False, True])
@@ -132,10 +132,10 @@ def test_aggregate_backward_large(B, G, N, M, D, k, self_keys, quantised):
     assert torch.equal(out.detach().cpu(), oo.detach().to(dtype))
     (oo * w.float()).sum().backward()
     scale = max(1.0, float(xo.grad.abs().max()))
-    assert (xc.grad.float().cpu() - xo.grad).abs().max() <= tol * scale * 8
+    assert (xc.grad.float().cpu() - xo.grad).abs().max() <= tol * scale
     if not self_keys:
         scale = max(1.0, float(yo.grad.abs().max()))
-        assert (yc.grad.float().cpu() - yo.grad).abs().max() <= tol * scale * 8
+        assert (yc.grad.float().cpu() - yo.grad).abs().max() <= tol * scale
 
 
 def test_aggregate_many_keys_fall_back():

@@ -139,23 +139,26 @@ def test_knn_errors():
     assert tuple(empty.shape) == (0, 20, 3)
 
 
-def test_knn_full_size_stage1_properties():
-    """BASELINE config 2 shape (B=32, C=80, N=20736, M=1296, G=2, k=9): too large for the CPU
-    oracle in a test, so check size-independent properties: (a) exact and auto algorithms
-    agree up to ties, (b) on sampled rows the returned neighbours are the true top-k of an
-    fp64 recomputation on the GPU, in ascending order."""
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_knn_full_size_stage1_properties(dtype):
+    """BASELINE config 2 shape (B=32, C=80, N=20736, M=1296, G=2, k=9), fp32 and the benchmarked bf16: too large
+    for the CPU oracle in a test, so check size-independent properties: (a) the tcgen05 path (with and without the
+    separable-bias hint) and the exact kernel agree up to ties, (b) on sampled rows the returned neighbours are the
+    true top-k of an fp64 recomputation on the GPU (from the same rounded features), in ascending order, ties
+    within 1e-6 relative only."""
     ops, lib = _ops()
     B, G, N, M, D, k = 32, 2, 20736, 1296, 40, 9
     g = torch.Generator(device="cuda").manual_seed(0)
     x = torch.randn(B, N, G * D, device="cuda", generator=g)
     y = torch.nn.functional.avg_pool2d(x.view(B, 144, 144, G * D).permute(0, 3, 1, 2), 4, 4)
     y = y.permute(0, 2, 3, 1).reshape(B, M, G * D).contiguous()
+    x, y = x.to(dtype), y.to(dtype)
     from gkgnet_b200.pos_embed import relative_pos_table
     rel = relative_pos_table(G * D, N, 4)[0].cuda()
     sep = ops.fit_separable_bias(rel)
     assert sep is not None and sep[2:] == (144, 9)
-    ia = ops.knn_graph(x, y, rel, groups=G, k=k, dilation=1, algo=lib.KNN_AUTO, separable=sep)
-    idn = ops.knn_graph(x, y, rel, groups=G, k=k, dilation=1, algo=lib.KNN_AUTO)
+    ia = ops.knn_graph(x, y, rel, groups=G, k=k, dilation=1, algo=lib.KNN_TCGEN05, separable=sep)
+    idn = ops.knn_graph(x, y, rel, groups=G, k=k, dilation=1, algo=lib.KNN_TCGEN05)
     assert (ia != idn).any(-1).float().mean().item() < 1e-4
     ie = ops.knn_graph(x, y, rel, groups=G, k=k, dilation=1, algo=lib.KNN_EXACT_FP32)
     differ = (ia != ie).any(-1).float().mean().item()
@@ -166,5 +169,6 @@ def test_knn_full_size_stage1_properties():
         xs = torch.nn.functional.normalize(x[b, rows, gi * D:(gi + 1) * D].double(), dim=-1)
         ys = torch.nn.functional.normalize(y[b, :, gi * D:(gi + 1) * D].double(), dim=-1)
         dist = (xs * xs).sum(-1, keepdim=True) - 2 * xs @ ys.T + (ys * ys).sum(-1)[None] + rel[rows].double()
-        rep = O.check_knn_against_distances(ia[p, rows].cpu().unsqueeze(0), dist.float().cpu().unsqueeze(0), k, 1, 2e-6)
-        assert rep["rows_bad"] == 0, rep
+        for ids in (ia, ie):
+            rep = O.check_knn_against_distances(ids[p, rows].cpu().unsqueeze(0), dist.cpu().unsqueeze(0), k, 1, 1e-6)
+            assert rep["rows_bad"] == 0, rep

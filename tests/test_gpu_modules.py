@@ -95,11 +95,40 @@ def test_gkgnet_s192_eval():
         want = O.gkgnet_forward({k: v.cpu() for k, v in net.state_dict().items()}, img, "s", 9, 9, 2, trace=trace)
     assert torch.allclose(want[1], g["gap"], atol=2e-4, rtol=1e-3)      # oracle == reference fixture
 
+    sd_cpu = {k: v.cpu() for k, v in net.state_dict().items()}
+    plan, _, _ = O.backbone_plan("s", 9)
     with torch.no_grad():
         for i, layer in enumerate(net.backbone):
-            out = layer(trace[f"backbone.{i}.in"].cuda())
+            xin = trace[f"backbone.{i}.in"]
+            out = layer(xin.cuda())
             frac = _frac_close(out.cpu(), trace[f"backbone.{i}.out"])
             assert frac > 0.99, (i, frac)
+            if plan[i][0] == "down":
+                continue
+            # WHY a position differs: the 1x1 convs and the aggregate act per node, so a node's output can only
+            # deviate when its neighbour ids do -- and every id deviation must be a distance tie within the band
+            # the GPU / CPU rounding of fc1 opens (1e-4 relative), never a wrong neighbour
+            _, C, kk, dil, r = plan[i]
+            gr, p = layer[0], f"backbone.{i}.0."
+            B, _, H, W = xin.shape
+            h = gr.fc1(xin.cuda())
+            xt = G.vertex.nchw_to_tokens(h)
+            yt = G.ops.pool_keys(xt, H, W, r) if r > 1 else None
+            ids = G.ops.knn_graph(xt, yt, gr.relative_pos, groups=2, k=kk, dilation=dil).cpu()      # (B*2, N, k)
+            h_or = O.conv1x1_bn(sd_cpu, p + "fc1.", xin)
+            y_or = torch.nn.functional.avg_pool2d(h_or, r, r) if r > 1 else None
+            D, N = C // 2, H * W
+            xr = h_or.reshape(B * 2, D, N, 1)
+            yr = None if y_or is None else y_or.reshape(B * 2, D, -1, 1)
+            dist = O.knn_distance_matrix(xr, yr, sd_cpu[p + "relative_pos"])
+            rep = O.check_knn_against_distances(ids, dist, kk, dil, 1e-4)
+            assert rep["rows_bad"] == 0, (i, rep)
+            ei_or = O.dense_dilated_knn_graph(xr, yr, kk, dil, sd_cpu[p + "relative_pos"])[0]
+            node_ids_differ = (ids != ei_or).any(-1).view(B, 2, N).any(1)                             # (B, N)
+            o, w = out.cpu(), trace[f"backbone.{i}.out"]
+            node_out_differs = ((o - w).abs() > 1e-3 + 1e-3 * w.abs()).any(1).reshape(B, N)
+            unexplained = (node_out_differs & ~node_ids_differ).sum().item()
+            assert unexplained == 0, (i, unexplained, int(node_out_differs.sum()), int(node_ids_differ.sum()))
         for j in range(4):
             feats = trace[f"backbone.{net.layer_index[j]}.out"].cuda()
             out, ei = net.gcn_label[j][0](trace[f"gcn_label.{j}.0.in"].cuda(), feats)
