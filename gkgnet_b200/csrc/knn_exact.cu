@@ -4,7 +4,7 @@
 //   topk(-dist, k*d) sorted ascending, keep ranks 0, d, 2d, ...   torch_edge.py:104,148
 // This is the always-available path (any D <= 640, any k*d <= 64) and the exactness
 // yard-stick for the tcgen05 kernel; it never materialises the N x M matrix either.
-#include "common.cuh"
+#include "knn_tc.cuh"
 
 namespace gkg {
 
@@ -125,8 +125,12 @@ int launch_knn_exact(const KnnWorkspace& w, const float* relpos, int32_t* idx_ou
                       sizeof(float) * kExactKeys;
   GKG_CHECK_ARG(smem <= 227 * 1024, "knn_exact: D=%d needs %zu B of shared memory", D, smem);
   auto kern = D <= 320 ? knn_exact_kernel<kExactRowsWide> : knn_exact_kernel<32>;
-  if (smem > 48 * 1024) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  {
+    static std::atomic<uint64_t> configured[2];
+    cudaError_t e = cudaSuccess;
+    configure_once_per_device(configured[D <= 320 ? 0 : 1], [&] {
+      e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    });
     if (e != cudaSuccess) {
       set_error("knn_exact: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
       return GKG_ECUDA;

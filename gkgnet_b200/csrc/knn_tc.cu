@@ -919,6 +919,10 @@ int launch_knn_tc(const KnnWorkspace& w, void* extra_ws, const void* x, int64_t 
   prm.a_tile_bytes = pl.a_tile_bytes; prm.b_block_bytes = pl.b_block_bytes;
   prm.force_rerank = flags;
   prm.delta = tc_delta(pl.KP);
+  // the separable form of the bias is a hint the caller verified to within kSepBiasTol of the dense table the exact
+  // re-rank reads (include/gkg_abi.h): that residual is part of the approximation error the gap test must cover
+  constexpr float kSepBiasTol = 5e-7f;
+  if (relpos != nullptr && sep.a != nullptr && sep.b != nullptr) prm.delta += kSepBiasTol;
   int ga = (M / 18 >= 3 * (T - 1)) ? 18 : (M / 6 >= 3 * (T - 1)) ? 6 : 3;
   if (dbg && (dbg->ga == 18 || dbg->ga == 6 || dbg->ga == 3)) ga = dbg->ga;
   prm.sep_a = sep.a; prm.sep_b = sep.b; prm.grid_w = sep.grid_w > 0 ? sep.grid_w : 1;

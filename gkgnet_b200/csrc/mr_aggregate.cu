@@ -12,7 +12,7 @@
 // Layout: token-major (b, n, c): one thread owns a 16-byte channel chunk of one node, so
 // x reads, idx reads, out writes are coalesced and every neighbour row is fetched with
 // 128-bit loads (served from L2: the key set of one image is <= a few hundred KB).
-#include "common.cuh"
+#include "knn_tc.cuh"
 #include <stdlib.h>
 
 namespace gkg {
@@ -563,8 +563,7 @@ extern "C" int gkg_mr_aggregate_fwd(const void* x, int64_t x_sb, int64_t x_sn, c
   } else if (vec == 8 && (k == 9 || k == 18)) {
     const int cs = agg_smem_slice(N, M, D);
     AggWarpPlan wp;
-    static const bool old_path = getenv("GKG_AGG_OLD") != nullptr;   // A/B switch for measurements
-    if (!old_path && agg_warp_plan(N, M, D, C, &wp)) {
+    if (agg_warp_plan(N, M, D, C, &wp)) {
       int dev = 0, sms = 148;
       cudaGetDevice(&dev);
       cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -578,7 +577,10 @@ extern "C" int gkg_mr_aggregate_fwd(const void* x, int64_t x_sb, int64_t x_sn, c
 #define LAUNCH_W(KK, CP, SB, AA)                                                                    \
   do {                                                                                               \
     auto kern = mr_aggregate_fwd_bf16_warp_kernel<KK, CP, SB, AA>;                                   \
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kAggWarpSmemMax); \
+    static std::atomic<uint64_t> configured{0};                                                     \
+    cudaError_t e = cudaSuccess;                                                                    \
+    configure_once_per_device(configured, [&] {                                                     \
+      e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kAggWarpSmemMax); }); \
     if (e != cudaSuccess) { set_error("mr_aggregate_fwd: smem attribute: %s", cudaGetErrorString(e)); return GKG_ECUDA; } \
     kern<<<wgrid, wp.threads, wp.smem, stream>>>(static_cast<const __nv_bfloat16*>(x), x_sb, x_sn,   \
         static_cast<const __nv_bfloat16*>(y), y_sb, y_sn, idx, static_cast<__nv_bfloat16*>(out), argmax, \
@@ -607,7 +609,10 @@ extern "C" int gkg_mr_aggregate_fwd(const void* x, int64_t x_sb, int64_t x_sn, c
 #define LAUNCH_SM(KK, AA)                                                                          \
   do {                                                                                               \
     auto kern = mr_aggregate_fwd_bf16_smem_kernel<KK, AA>;                                           \
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kAggSmemKeysMax + 16 * 1024)); \
+    static std::atomic<uint64_t> configured{0};                                                     \
+    cudaError_t e = cudaSuccess;                                                                    \
+    configure_once_per_device(configured, [&] {                                                     \
+      e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kAggSmemKeysMax + 16 * 1024)); }); \
     if (e != cudaSuccess) { set_error("mr_aggregate_fwd: smem attribute: %s", cudaGetErrorString(e)); return GKG_ECUDA; } \
     kern<<<sgrid, kAggSmemThreads, smem, stream>>>(static_cast<const __nv_bfloat16*>(x), x_sb, x_sn,  \
         static_cast<const __nv_bfloat16*>(y), y_sb, y_sn, idx, static_cast<__nv_bfloat16*>(out), argmax, \

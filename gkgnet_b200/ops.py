@@ -7,6 +7,8 @@ reference's ``(B*G, D, N, 1)`` regrouping (torch_vertex.py:197-202).
 """
 from __future__ import annotations
 
+import functools
+
 import torch
 
 from . import _lib
@@ -16,6 +18,19 @@ _DT = {torch.float32: _lib.GKG_F32, torch.bfloat16: _lib.GKG_BF16}
 
 def _stream(t: torch.Tensor) -> int:
     return torch.cuda.current_stream(t.device).cuda_stream
+
+
+def _guard(fn):
+    """Run ``fn`` with the device of its first CUDA tensor argument current: the library launches on the current
+    device (``<<<>>>``, ``cudaFuncSetAttribute``), which need not be the tensors' device in a multi-GPU process."""
+    @functools.wraps(fn)
+    def wrapper(*args, **kw):
+        dev = next((a.device for a in args if isinstance(a, torch.Tensor) and a.is_cuda), None)
+        if dev is None:
+            return fn(*args, **kw)
+        with torch.cuda.device(dev):
+            return fn(*args, **kw)
+    return wrapper
 
 
 def _token_major(t: torch.Tensor) -> torch.Tensor:
@@ -160,6 +175,7 @@ def _workspace(device, nbytes):
 
 class _MRAggregate(torch.autograd.Function):
     @staticmethod
+    @_guard
     def forward(ctx, x, y, idx, groups):
         lib = _lib.load()
         x = _token_major(x)
@@ -185,6 +201,7 @@ class _MRAggregate(torch.autograd.Function):
         return out
 
     @staticmethod
+    @_guard
     def backward(ctx, grad_out):
         idx, amax = ctx.saved_tensors
         B, G, N, M, D, k, self_keys, dtype = ctx.meta
@@ -227,6 +244,7 @@ def mr_aggregate(x, idx, y=None, *, groups=1):
 # ----------------------------------------------------------------------------------------
 class _PoolKeys(torch.autograd.Function):
     @staticmethod
+    @_guard
     def forward(ctx, x, H, W, r):
         lib = _lib.load()
         x = _token_major(x)
@@ -239,6 +257,7 @@ class _PoolKeys(torch.autograd.Function):
         return y
 
     @staticmethod
+    @_guard
     def backward(ctx, grad_y):
         B, H, W, C, r, dtype = ctx.meta
         lib = _lib.load()
@@ -298,6 +317,7 @@ def grouped_fc_weights(weight, scale=None, transpose=False):
     return out
 
 
+@_guard
 def grouped_fc(x, w_op, shift, act="gelu"):
     """``act(conv1x1_groups4(x; scale * W) + shift)`` on token-major bf16 ``x (..., 2C)``: the eval-mode
     ``BasicConv([2C, 2C])`` of the reference (torch_nn.py:57-81) in one pass.  ``w_op`` from
@@ -324,6 +344,7 @@ class _GroupedFC(torch.autograd.Function):
     (a (CG x CG) reduction over all rows per group) run on tcgen05 kernels."""
 
     @staticmethod
+    @_guard
     def forward(ctx, x, weight, bias):
         c2 = x.shape[-1]
         shift = bias.detach().float() if bias is not None else torch.zeros(c2, device=x.device)
@@ -333,6 +354,7 @@ class _GroupedFC(torch.autograd.Function):
         return out
 
     @staticmethod
+    @_guard
     def backward(ctx, grad_out):
         x, weight = ctx.saved_tensors
         c2 = x.shape[-1]

@@ -81,7 +81,8 @@ size_t gkg_knn_workspace_bytes(int B, int G, int N, int M, int D, int k, int dil
  *     relpos[n, m] == sep_a[n % sep_grid_w][m % sep_kw] + sep_b[n / sep_grid_w][m / sep_kw]
  * sep_a is fp32 (sep_grid_w, sep_kw), sep_b fp32 (N / sep_grid_w, M / sep_kw); pass NULL / 0
  * when unknown.  The analytic table of the reference (pos_embed.py:21-29 +
- * torch_vertex.py:309-315) always has this form; the caller must have verified it.
+ * torch_vertex.py:309-315) always has this form; the caller must have verified it to within 5e-7 (absolute) of
+ * `relpos` -- the residual is added to the error bound of the certified ordering.
  */
 int gkg_knn_graph(const void* x, int64_t x_stride_b, int64_t x_stride_n,
                   const void* y, int64_t y_stride_b, int64_t y_stride_n,
