@@ -35,6 +35,8 @@ SIGNATURES = {
                             + [_i32] * 9 + [_vp, _sz, _vp] + [_i32, _vp, _vp, _i32, _i32]),
     "gkg_mr_aggregate_fwd": (_i32, [_vp, _i64, _i64, _vp, _i64, _i64, _vp, _vp, _vp] + [_i32] * 7 + [_vp]),
     "gkg_mr_aggregate_bwd": (_i32, [_vp, _vp, _vp, _vp, _vp] + [_i32] * 7 + [_vp]),
+    "gkg_mr_aggregate_bwd_det": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp] + [_i32] * 7 + [_vp]),
+    "gkg_fixed_to_float": (_i32, [_vp, _vp, _vp, _c.c_longlong, _vp]),
     "gkg_pool_keys_fwd": (_i32, [_vp, _i64, _i64, _vp] + [_i32] * 6 + [_vp]),
     "gkg_pool_keys_bwd": (_i32, [_vp, _vp] + [_i32] * 6 + [_vp]),
     "gkg_grouped_fc_supported": (_i32, [_i32]),

@@ -81,12 +81,15 @@ mr_aggregate_fwd_kernel(const T* __restrict__ x, int64_t x_sb, int64_t x_sn,
   }
 }
 
-template <typename T, int VEC>
+// DET: the scattered sum runs in 64-bit fixed point (value * scale, scale a power of two read from device memory):
+// integer addition is associative, so the result does not depend on the order in which the atomics land.
+template <typename T, int VEC, bool DET>
 __global__ void __launch_bounds__(256)
 mr_aggregate_bwd_kernel(const T* __restrict__ gout, const int32_t* __restrict__ idx,
                         const uint8_t* __restrict__ argmax, T* __restrict__ gx,
-                        float* __restrict__ gy, int G, int N, int M, int D, int k,
+                        float* __restrict__ gy, const float* __restrict__ scale_ptr, int G, int N, int M, int D, int k,
                         long long total_chunks) {
+  const float scale = DET ? __ldg(scale_ptr) : 1.f;
   using P = Pack<T, VEC>;
   const int C = G * D;
   const int chunks_per_node = C / VEC;
@@ -118,12 +121,16 @@ mr_aggregate_bwd_kernel(const T* __restrict__ gout, const int32_t* __restrict__ 
     }
     const Pack<uint8_t, VEC> am = *reinterpret_cast<const Pack<uint8_t, VEC>*>(argmax + bn * C + c0);
     P o;
-    float* gyb = gy + (b * M) * (long long)C + c0;
+    float* gyb = gy + (DET ? 2 : 1) * ((b * M) * (long long)C + c0);
 #pragma unroll
     for (int e = 0; e < VEC; ++e) {
       o.v[e] = from_f32<T>(g_self[e] - g_rel[e]);
       const int m = __ldg(ip + am.v[e]);
-      atomicAdd(gyb + (long long)m * C + e, g_rel[e]);
+      if (DET)
+        atomicAdd(reinterpret_cast<unsigned long long*>(gyb) + (long long)m * C + e,
+                  (unsigned long long)__float2ll_rn(g_rel[e] * scale));
+      else
+        atomicAdd(gyb + (long long)m * C + e, g_rel[e]);
     }
     *reinterpret_cast<P*>(gx + bn * C + c0) = o;
   }
@@ -633,10 +640,9 @@ extern "C" int gkg_mr_aggregate_fwd(const void* x, int64_t x_sb, int64_t x_sn, c
   return GKG_OK;
 }
 
-extern "C" int gkg_mr_aggregate_bwd(const void* grad_out, const int32_t* idx, const uint8_t* argmax,
-                                    void* grad_x, float* grad_y_accum, int B, int G, int N, int M,
-                                    int D, int k, int dtype, gkg_stream_t stream_) {
-  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+static int mr_aggregate_bwd_impl(const void* grad_out, const int32_t* idx, const uint8_t* argmax, void* grad_x,
+                                 float* grad_y_accum, const float* scale, int B, int G, int N, int M, int D, int k,
+                                 int dtype, cudaStream_t stream) {
   GKG_CHECK_ARG(dtype == GKG_F32 || dtype == GKG_BF16, "mr_aggregate_bwd: bad dtype %d", dtype);
   GKG_CHECK_ARG(B >= 0 && G > 0 && N >= 0 && M > 0 && D > 0 && k > 0 && k <= 255,
                 "mr_aggregate_bwd: bad shape B=%d G=%d N=%d M=%d D=%d k=%d", B, G, N, M, D, k);
@@ -648,9 +654,14 @@ extern "C" int gkg_mr_aggregate_bwd(const void* grad_out, const int32_t* idx, co
   const long long chunks = (long long)B * N * (C / vec);
   const unsigned grid = grid_for(chunks, 256);
 #define LAUNCH(T, V)                                                                           \
-  mr_aggregate_bwd_kernel<T, V><<<grid, 256, 0, stream>>>(                                     \
-      static_cast<const T*>(grad_out), idx, argmax, static_cast<T*>(grad_x), grad_y_accum, G, \
-      N, M, D, k, chunks)
+  do {                                                                                         \
+    if (scale != nullptr)                                                                      \
+      mr_aggregate_bwd_kernel<T, V, true><<<grid, 256, 0, stream>>>(                           \
+          static_cast<const T*>(grad_out), idx, argmax, static_cast<T*>(grad_x), grad_y_accum, scale, G, N, M, D, k, chunks); \
+    else                                                                                       \
+      mr_aggregate_bwd_kernel<T, V, false><<<grid, 256, 0, stream>>>(                          \
+          static_cast<const T*>(grad_out), idx, argmax, static_cast<T*>(grad_x), grad_y_accum, nullptr, G, N, M, D, k, chunks); \
+  } while (0)
   if (dtype == GKG_F32) {
     if (vec == 4) LAUNCH(float, 4); else if (vec == 2) LAUNCH(float, 2); else LAUNCH(float, 1);
   } else {
@@ -659,5 +670,38 @@ extern "C" int gkg_mr_aggregate_bwd(const void* grad_out, const int32_t* idx, co
   }
 #undef LAUNCH
   GKG_CHECK_LAUNCH("mr_aggregate_bwd");
+  return GKG_OK;
+}
+
+extern "C" int gkg_mr_aggregate_bwd(const void* grad_out, const int32_t* idx, const uint8_t* argmax,
+                                    void* grad_x, float* grad_y_accum, int B, int G, int N, int M,
+                                    int D, int k, int dtype, gkg_stream_t stream) {
+  return mr_aggregate_bwd_impl(grad_out, idx, argmax, grad_x, grad_y_accum, nullptr, B, G, N, M, D, k, dtype,
+                               static_cast<cudaStream_t>(stream));
+}
+
+// Deterministic form: grad_y is accumulated in 64-bit fixed point (see the kernel) and converted afterwards.
+extern "C" int gkg_mr_aggregate_bwd_det(const void* grad_out, const int32_t* idx, const uint8_t* argmax,
+                                        void* grad_x, long long* grad_y_fixed, const float* scale, int B, int G, int N,
+                                        int M, int D, int k, int dtype, gkg_stream_t stream) {
+  GKG_CHECK_ARG(scale != nullptr, "mr_aggregate_bwd_det: null scale");
+  return mr_aggregate_bwd_impl(grad_out, idx, argmax, grad_x, reinterpret_cast<float*>(grad_y_fixed), scale, B, G, N, M,
+                               D, k, dtype, static_cast<cudaStream_t>(stream));
+}
+
+namespace gkg {
+__global__ void fixed_to_float_kernel(const long long* __restrict__ in, const float* __restrict__ scale,
+                                      float* __restrict__ out, long long n) {
+  const float inv = 1.f / __ldg(scale);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    out[i] = (float)((double)in[i] * (double)inv);
+}
+}  // namespace gkg
+
+extern "C" int gkg_fixed_to_float(const long long* in, const float* scale, float* out, long long n, gkg_stream_t stream) {
+  GKG_CHECK_ARG(n >= 0 && (n == 0 || (in && scale && out)), "fixed_to_float: bad arguments");
+  if (n == 0) return GKG_OK;
+  gkg::fixed_to_float_kernel<<<grid_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(in, scale, out, n);
+  GKG_CHECK_LAUNCH("fixed_to_float_kernel");
   return GKG_OK;
 }

@@ -203,20 +203,47 @@ class _MRAggregate(torch.autograd.Function):
     @staticmethod
     @_guard
     def backward(ctx, grad_out):
-        idx, amax = ctx.saved_tensors
+        idx, amax_plane = ctx.saved_tensors
         B, G, N, M, D, k, self_keys, dtype = ctx.meta
         lib = _lib.load()
         C = G * D
         grad_out = grad_out.contiguous()
         gx = torch.empty((B, N, C), dtype=dtype, device=grad_out.device)
-        gy = torch.zeros((B, M, C), dtype=torch.float32, device=grad_out.device)
-        rc = lib.gkg_mr_aggregate_bwd(grad_out.data_ptr(), idx.data_ptr(), amax.data_ptr(),
-                                      gx.data_ptr(), gy.data_ptr(), B, G, N, M, D, k, _DT[dtype],
-                                      _stream(grad_out))
-        _lib.check(rc, "gkg_mr_aggregate_bwd")
+        if deterministic_aggregate():
+            # 64-bit fixed-point accumulation: integer adds commute, the result is bitwise reproducible
+            amax = grad_out.detach().abs().max().float().clamp_min(1e-30)
+            scale = torch.exp2(40.0 - torch.ceil(torch.log2(amax))).reshape(1).contiguous()
+            gfix = torch.zeros((B, M, C), dtype=torch.int64, device=grad_out.device)
+            rc = lib.gkg_mr_aggregate_bwd_det(grad_out.data_ptr(), idx.data_ptr(), amax_plane.data_ptr(), gx.data_ptr(),
+                                              gfix.data_ptr(), scale.data_ptr(), B, G, N, M, D, k, _DT[dtype],
+                                              _stream(grad_out))
+            _lib.check(rc, "gkg_mr_aggregate_bwd_det")
+            gy = torch.empty((B, M, C), dtype=torch.float32, device=grad_out.device)
+            _lib.check(lib.gkg_fixed_to_float(gfix.data_ptr(), scale.data_ptr(), gy.data_ptr(), gfix.numel(),
+                                              _stream(grad_out)), "gkg_fixed_to_float")
+        else:
+            gy = torch.zeros((B, M, C), dtype=torch.float32, device=grad_out.device)
+            rc = lib.gkg_mr_aggregate_bwd(grad_out.data_ptr(), idx.data_ptr(), amax_plane.data_ptr(),
+                                          gx.data_ptr(), gy.data_ptr(), B, G, N, M, D, k, _DT[dtype],
+                                          _stream(grad_out))
+            _lib.check(rc, "gkg_mr_aggregate_bwd")
         if self_keys:
             return (gx.float() + gy).to(dtype), None, None, None
         return gx, gy.to(dtype), None, None
+
+
+_DETERMINISTIC = None
+
+
+def set_deterministic_aggregate(flag):
+    """True / False: force the deterministic (64-bit fixed-point) scatter of the aggregate backward on / off;
+    None (default): follow ``torch.are_deterministic_algorithms_enabled()``."""
+    global _DETERMINISTIC
+    _DETERMINISTIC = flag
+
+
+def deterministic_aggregate():
+    return torch.are_deterministic_algorithms_enabled() if _DETERMINISTIC is None else bool(_DETERMINISTIC)
 
 
 def mr_aggregate(x, idx, y=None, *, groups=1):

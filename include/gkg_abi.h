@@ -153,6 +153,19 @@ int gkg_mr_aggregate_bwd(const void* grad_out, const int32_t* idx, const uint8_t
                          gkg_stream_t stream);
 
 /*
+ * Deterministic form of gkg_mr_aggregate_bwd (bitwise reproducible whatever the order of the atomics): the scattered
+ * sum runs in 64-bit fixed point.
+ *   grad_y_fixed  int64 (B, M, G*D), zero-filled by the caller: sum of round(g * scale)
+ *   scale         DEVICE pointer to one fp32 power of two, e.g. 2^(40 - ceil(log2(max |grad_out|))): ~40 bits below the
+ *                 largest gradient, so the rounding is far below fp32 resolution and 2^23 terms cannot overflow
+ * gkg_fixed_to_float converts: out[i] = in[i] / scale.
+ */
+int gkg_mr_aggregate_bwd_det(const void* grad_out, const int32_t* idx, const uint8_t* argmax,
+                             void* grad_x, long long* grad_y_fixed, const float* scale,
+                             int B, int G, int N, int M, int D, int k, int dtype, gkg_stream_t stream);
+int gkg_fixed_to_float(const long long* in, const float* scale, float* out, long long n, gkg_stream_t stream);
+
+/*
  * Grouped 1x1 FC of the max-relative convolution with norm and activation folded in (inference form).
  * Replaces MRConv2d.nn = BasicConv([2C, 2C]) = Conv2d(2C, 2C, 1, groups=4, bias) -> norm -> act
  * (torch_nn.py:57-81; torch_vertex.py:45,61) in eval mode, where the batch norm is an affine map:

@@ -190,3 +190,32 @@ def test_aggregate_full_size_stage1_linearity():
     lhs = x.grad.double().sum() + y.grad.double().sum()
     rhs = go[..., 0::2].double().sum()
     assert abs(float(lhs - rhs)) < 2e-2 * float(go.double().abs().sum()) ** 0.5 + 64
+
+
+def test_aggregate_backward_deterministic_option():
+    """The 64-bit fixed-point scatter (ops.set_deterministic_aggregate / torch.use_deterministic_algorithms): two runs
+    agree bit for bit, and with the fp32-atomic path up to fp32 summation order."""
+    from gkgnet_b200 import ops
+    g = torch.Generator().manual_seed(9)
+    B, G, N, M, D, k = 2, 2, 3000, 200, 40, 9
+    C = G * D
+    x = torch.randn(B, N, C, generator=g).bfloat16().cuda().requires_grad_(True)
+    y = torch.randn(B, M, C, generator=g).bfloat16().cuda().requires_grad_(True)
+    idx = torch.randint(0, M, (B * G, N, k), generator=g, dtype=torch.int32).cuda()
+    w = torch.randn(B, N, 2 * C, generator=g).bfloat16().cuda()
+
+    def grads():
+        x.grad = y.grad = None
+        ops.mr_aggregate(x, idx, y, groups=G).backward(w)
+        return x.grad.clone(), y.grad.clone()
+
+    plain = grads()
+    ops.set_deterministic_aggregate(True)
+    try:
+        a, b = grads(), grads()
+    finally:
+        ops.set_deterministic_aggregate(None)
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
+    assert torch.equal(a[0], plain[0])
+    scale = max(1.0, plain[1].float().abs().max().item())
+    assert (a[1].float() - plain[1].float()).abs().max().item() <= 8e-3 * scale      # one bf16 ulp of the largest sum
