@@ -56,9 +56,11 @@ template <typename T, bool IS_KEY, int DT>
 __global__ void __launch_bounds__(256)
 tc_prepare_kernel(const T* __restrict__ feat, int64_t stride_b, int64_t stride_n, float* __restrict__ hat,
                   float* __restrict__ sq, __half* __restrict__ op, int G, int rows, int D_rt, int KP_rt, int KC,
-                  int tiles, int tile_rows, int tile_keys, int write_hat) {
+                  int tiles, int tile_rows, int tile_keys, int write_hat, int PA_split) {
+  // PA_split > 0: split-plane layout [hi (+ extra pair) -> PA_split | lo -> KP_rt] (knn_tc_kernel.cuh), same for
+  // queries and keys; 0: the K-concatenated fp16x3 rows.
   const int D = DT > 0 ? DT : D_rt;
-  const int KP = DT > 0 ? k_padded(DT > 0 ? DT : 1) : KP_rt;
+  const int KP = (DT > 0 && PA_split == 0) ? k_padded(DT > 0 ? DT : 1) : KP_rt;
   extern __shared__ __align__(16) float prep_s[];   // [PREP_ROWS][DS] normalised rows + [PREP_ROWS] norms
   const int DS = prep_stride(D);
   float* xs = prep_s;
@@ -133,7 +135,7 @@ tc_prepare_kernel(const T* __restrict__ feat, int64_t stride_b, int64_t stride_n
   __syncthreads();
 
   const int kcs = KC >> 3, nkb = KP / KC, rgs = tile_rows >> 3, kc_all = KP >> 3;
-  const int PA = k_prefix(D);
+  const int PA = PA_split > 0 ? PA_split : k_prefix(D);
   if ((D & 7) == 0) {
     // One thread per (row, 8-column piece of the normalised row): two LDS.128, hi / lo split once, then the three
     // 16-byte core-matrix rows that piece feeds (A = [hi | hi | lo], B = [hi | lo | hi]); the remaining chunks of a row
@@ -141,7 +143,8 @@ tc_prepare_kernel(const T* __restrict__ feat, int64_t stride_b, int64_t stride_n
     // same operand bits, as the per-chunk loop below -- at a third of its instructions.
     const int npiece = D >> 3;
     const int nmid = (PA - D) >> 3;                                 // chunks between the first segment and PA
-    const int nother = nmid + ((KP - PA - 2 * D) >> 3);
+    const int ntail0 = PA_split > 0 ? (PA + D) >> 3 : (PA + 2 * D) >> 3;   // first chunk of the zero tail
+    const int nother = nmid + (kc_all - ntail0);
     const int per_row = npiece + nother;
     const int items = PREP_ROWS * per_row;
     for (int ci = threadIdx.x; ci < items; ci += 256) {
@@ -171,11 +174,15 @@ tc_prepare_kernel(const T* __restrict__ feat, int64_t stride_b, int64_t stride_n
         }
         const uint4 H = *reinterpret_cast<const uint4*>(hi), Lo = *reinterpret_cast<const uint4*>(lo);
         store(it, H);
-        store((PA >> 3) + it, IS_KEY ? Lo : H);
-        store(((PA + D) >> 3) + it, IS_KEY ? H : Lo);
+        if (PA_split > 0) {
+          store((PA >> 3) + it, Lo);
+        } else {
+          store((PA >> 3) + it, IS_KEY ? Lo : H);
+          store(((PA + D) >> 3) + it, IS_KEY ? H : Lo);
+        }
       } else {
         const int o = it - npiece;
-        const int kcI = o < nmid ? npiece + o : ((PA + 2 * D) >> 3) + (o - nmid);
+        const int kcI = o < nmid ? npiece + o : ntail0 + (o - nmid);
         __align__(16) __half z[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) z[e] = __float2half_rn(0.f);
@@ -864,7 +871,7 @@ static int launch_prepare_typed(const KnnWorkspace& w, const TcWorkspace& t, con
     });
     auto kq = D == 200 ? tc_prepare_kernel<T, false, 200> : D == 320 ? tc_prepare_kernel<T, false, 320> : tc_prepare_kernel<T, false, 0>;
     kq<<<grid, 256, smem, stream>>>(static_cast<const T*>(x), x_sb, x_sn, nullptr, nullptr, t.a_op, G, N, D, pl.KP, pl.KC,
-                                    pl.QTP, BM, BM, 0);
+                                    pl.QTP, BM, BM, 0, pl.split ? pl.PA : 0);
     GKG_CHECK_LAUNCH("tc_prepare_kernel<query>");
   }
   {
@@ -872,7 +879,7 @@ static int launch_prepare_typed(const KnnWorkspace& w, const TcWorkspace& t, con
     const T* src = static_cast<const T*>(self_keys ? x : y);
     auto kk = D == 200 ? tc_prepare_kernel<T, true, 200> : D == 320 ? tc_prepare_kernel<T, true, 320> : tc_prepare_kernel<T, true, 0>;
     kk<<<grid, 256, smem, stream>>>(src, self_keys ? x_sb : y_sb, self_keys ? x_sn : y_sn, w.yhat, w.ysq, t.b_op, G, M, D,
-                                    pl.KP, pl.KC, pl.KT, bnp, bn, 1);
+                                    pl.KP, pl.KC, pl.KT, bnp, bn, 1, pl.split ? pl.PA : 0);
     GKG_CHECK_LAUNCH("tc_prepare_kernel<key>");
   }
   return GKG_OK;
@@ -916,9 +923,10 @@ int launch_knn_tc(const KnnWorkspace& w, void* extra_ws, const void* x, int64_t 
   prm.P = P; prm.N = N; prm.M = M; prm.D = D; prm.k = k; prm.dilation = dilation; prm.kd = k * dilation;
   prm.KP = pl.KP; prm.PA = pl.PA; prm.KC = pl.KC; prm.NKB = pl.NKB; prm.NKBA = pl.NKBA; prm.NA = pl.NA; prm.NS = pl.NS; prm.QT = pl.QT;
   prm.QI = pl.QI; prm.QTP = pl.QTP; prm.KT = pl.KT;
-  prm.a_tile_bytes = pl.a_tile_bytes; prm.b_block_bytes = pl.b_block_bytes;
+  prm.split = pl.split; prm.KS1 = pl.KS1; prm.KSL = pl.KSL;
+  prm.a_tile_bytes = pl.a_tile_bytes; prm.a_res_bytes = pl.a_res_bytes; prm.b_block_bytes = pl.b_block_bytes;
   prm.force_rerank = flags;
-  prm.delta = tc_delta(pl.KP);
+  prm.delta = pl.split ? tc_delta_steps(pl.KS1 + 2 * pl.KSL) : tc_delta(pl.KP);
   // the separable form of the bias is a hint the caller verified to within kSepBiasTol of the dense table the exact
   // re-rank reads (include/gkg_abi.h): that residual is part of the approximation error the gap test must cover
   constexpr float kSepBiasTol = 5e-7f;

@@ -19,6 +19,7 @@ constexpr float kScoreFloor = -8e6f; // initial threshold: above every padded ke
 // Bound on |approx - exact| of the fp16x3 GEMM in distance units: every K=16 accumulation step rounds
 // the fp32 accumulator (|acc| <= 1.5 S^2 -> 3.6e-7 per step), plus the 2^-21 relative split error.
 inline float tc_delta(int KP) { return 3.6e-7f * (float)(KP / 16) + 1.2e-6f; }
+inline float tc_delta_steps(int ksteps) { return 3.6e-7f * (float)ksteps + 1.2e-6f; }
 // |single-plane - fp16x3| <= S^2 * 2^-10 * sum|xh_i yh_i| <= 64 (Cauchy-Schwarz, unit rows); + fp32 accumulation
 constexpr float kSweepSlack = 66.f;
 constexpr int MAX_STAGES = 8;
@@ -34,7 +35,11 @@ struct Geom {
   static constexpr int RS = RS_, BN = BN_, BNP = BNP_, NACC = NACC_, ACC_STRIDE = ACC_STRIDE_;
   static constexpr int NCH = BN / CH;             // chunks per accumulator
   static constexpr int NEPI = 4 * RS;             // epilogue warps
-  static constexpr int NTHREADS = 32 * (1 + RS + NEPI); // warp 0 TMA, warps 1..RS MMA (one per row set), then the epilogue warps
+  // MMA issuer warps: one per row set; with a single row set, NACC of them take the key tiles (= accumulator
+  // slots) in turn -- the issue loop of ONE warp (~130 instructions per operand block: barrier wait, descriptors,
+  // commits) was what bounded the wide-group shapes, not the tensor pipe
+  static constexpr int NISS = RS == 1 ? NACC_ : RS;
+  static constexpr int NTHREADS = 32 * (1 + NISS + NEPI); // warp 0 TMA, warps 1..NISS MMA issue, then the epilogue warps
   static constexpr int ROWS = BM * RS;
   static constexpr uint32_t LOG_STRIDE = ROWS * 16;   // bytes between consecutive log slots of a row
   static constexpr int SEPW = SEPW_;              // staged floats of the separable bias table B per epilogue warp
@@ -62,15 +67,23 @@ __host__ __device__ constexpr int k_padded(int D) { return k_prefix(D) + (2 * D 
 struct Plan {
   int geom;                        // 0 = GeomA, 1 = GeomB
   int KP, PA, KC, NKB, NKBA, NA, NS, QT, QI, QTP, KT;
-  uint32_t a_tile_bytes, b_block_bytes;
+  int split, KS1, KSL;             // split-plane operands (see below): valid K steps of the first / the lo segment
+  uint32_t a_tile_bytes, a_res_bytes, b_block_bytes;
   size_t smem_bytes;
   size_t a_op_bytes, b_op_bytes;   // per launch operand buffers
   bool ok;
 };
 
-// Two operand-staging modes:
+// Three operand-staging modes:
 //   resident  (NA = 1 | 2 buffers per row set): the whole 128-row A tiles (all K) sit in shared memory
 //             for the item, B blocks (BNP keys x KC) stream through the ring;
+//   split     (wide groups, D % 8 == 0, GeomA): the fp16x3 operand rows [hi | hi | lo] / [hi | lo | hi] repeat
+//             their hi plane, so only TWO planes per row are stored, [hi (+ extra pair) -> PA | lo -> KP - PA] for
+//             queries and keys alike (each segment zero-padded to a multiple of KC).  The hi segment of the A tile
+//             stays resident; a ring stage carries one B block and, for a block of the first segment in sweep B,
+//             the matching A.lo block.  The issuer multiplies  A.hi x B.first (+ A.lo x B.first in sweep B)  for
+//             a block of the first segment and  A.hi x B.lo  for a block of the lo segment: per key tile 233 KB
+//             through the ring instead of 444 KB at D = 200;
 //   streaming (NA = 0):     A and B blocks of one K slice travel together through the ring (the A
 //             tiles would not leave room for the triplet log) -- A is re-read once per key tile.
 template <class G>
@@ -110,6 +123,45 @@ inline Plan make_plan_g(int P, int N, int M, int D, int T, bool strict) {
       }
     }
   }
+#ifndef GKG_NO_SPLIT
+  if (!pl.ok && !strict && G::RS == 1 && D % 8 == 0) {
+    // pass 0: the widest blocks of >= 32 columns with >= 4 stages and >= 64 KB in flight; pass 1: >= 3 stages and
+    // >= 48 KB; pass 2: whatever keeps the most bytes in flight.  (Measured at D = 200: 5 x 17 KB beats 3 x 26 KB
+    // and 8 x 9 KB for lists of 20; 3 x 17 KB beats 8 x 9 KB for lists of 29 -- fewer barrier round trips per tile.)
+    size_t best = 0;
+    for (int pass = 0; pass < 3 && !pl.ok; ++pass) {
+      for (int kc = 64; kc >= 16; kc -= 16) {
+#ifdef GKG_SPLIT_KC                                   // experiments only: force the block width of the split plan
+        if (kc != GKG_SPLIT_KC) continue;
+#endif
+        const int pas = (D + 2 + kc - 1) / kc * kc, pls = (D + kc - 1) / kc * kc;
+        const size_t a_res = (size_t)BM * pas * 2;
+        const size_t fixed = cand + G::kBarBytes + a_res;
+        if (fixed >= kSmemBudget) continue;
+        const size_t stage = (size_t)(G::BNP + BM) * kc * 2;
+        int ns = (int)((kSmemBudget - fixed) / stage);
+        if (ns > MAX_STAGES) ns = MAX_STAGES;
+        if (ns < 3) continue;
+        const size_t flight = (size_t)ns * stage;
+        const bool take = pass == 0 ? (kc >= 32 && ns >= 4 && flight >= 64 * 1024)
+                        : pass == 1 ? (kc >= 32 && flight >= 48 * 1024)
+                                    : flight > best;
+        if (!take) continue;
+        best = flight;
+        pl.split = 1; pl.NA = 1; pl.KC = kc; pl.NS = ns;
+        pl.PA = pas; pl.KP = pas + pls;
+        pl.b_block_bytes = (uint32_t)((size_t)G::BNP * kc * 2);
+        pl.a_tile_bytes = (uint32_t)((size_t)BM * (pas + pls) * 2);
+        if (pass < 2) { pl.ok = true; break; }
+      }
+      if (pass == 2 && best > 0) pl.ok = true;
+    }
+    if (pl.ok) {
+      pl.KS1 = (D + 2 + 15) / 16;
+      pl.KSL = (D + 15) / 16;
+    }
+  }
+#endif
   if (!pl.ok && !strict && cand + G::kBarBytes < kSmemBudget) {
     const size_t room = kSmemBudget - cand - G::kBarBytes;
     for (int kc = 64; kc >= 16 && !pl.ok; kc -= 16) {
@@ -126,9 +178,10 @@ inline Plan make_plan_g(int P, int N, int M, int D, int T, bool strict) {
   }
   if (!pl.ok) return pl;
   pl.NKB = pl.KP / pl.KC;
-  pl.NKBA = (pl.PA + pl.KC - 1) / pl.KC;
-  const size_t stage = pl.b_block_bytes + (pl.NA == 0 ? (size_t)G::ROWS * pl.KC * 2 : 0);
-  pl.smem_bytes = cand + G::kBarBytes + (size_t)pl.NA * G::RS * pl.a_tile_bytes + (size_t)pl.NS * stage;
+  pl.NKBA = (pl.PA + pl.KC - 1) / pl.KC;     // split: the blocks of the first segment
+  const size_t stage = pl.b_block_bytes + (pl.NA == 0 ? (size_t)G::ROWS * pl.KC * 2 : pl.split ? (size_t)BM * pl.KC * 2 : 0);
+  pl.a_res_bytes = pl.split ? (uint32_t)((size_t)BM * pl.PA * 2) : pl.a_tile_bytes;   // resident part of an A tile
+  pl.smem_bytes = cand + G::kBarBytes + (size_t)pl.NA * G::RS * pl.a_res_bytes + (size_t)pl.NS * stage;
   pl.a_op_bytes = (size_t)P * pl.QTP * pl.a_tile_bytes;
   pl.b_op_bytes = (size_t)P * pl.KT * (size_t)G::BNP * pl.KP * 2;
   return pl;
@@ -202,6 +255,16 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {
     if (BACKOFF) __nanosleep(32);
     if ((++spins & 1023u) == 0 && globaltimer_ns() - t0 > 4000000000ull) __trap();
+  }
+}
+// Single-lane variant for the lean producer / issuer loops below: no timer reads on the fast path, a spin bound
+// instead of a wall-clock bound (2^26 naps of >= 20 ns: more than a second).
+__device__ __forceinline__ void mbar_wait_lean(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    __nanosleep(20);
+    if (++spins > (1u << 26)) __trap();
   }
 }
 __device__ __forceinline__ void tma_bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
@@ -415,7 +478,8 @@ struct TcParams {
   float* dbg_dist;
   int P, N, M, D, k, dilation, kd;
   int KP, PA, KC, NKB, NKBA, NA, NS, QT, QI, QTP, KT;
-  uint32_t a_tile_bytes, b_block_bytes;
+  int split, KS1, KSL;
+  uint32_t a_tile_bytes, a_res_bytes, b_block_bytes;
   int force_rerank;
   float delta;                     // bound on |approx - exact| of the fp16x3 GEMM (dist units), see tc_delta()
 };
@@ -461,9 +525,9 @@ __global__ void __launch_bounds__(G::NTHREADS, 1) knn_tc_kernel(const TcParams p
   extern __shared__ __align__(1024) uint8_t smem[];
   // carve-up: [A tiles x NA x RS][ring x NS: B block (+ A slices when streaming)][triplet log][barriers + tmem ptr][staged B rows]
   const uint32_t a_blk_bytes = (uint32_t)(BM * prm.KC * 2);                    // one K slice of one A tile
-  const uint32_t stage_bytes = prm.b_block_bytes + (prm.NA == 0 ? RS * a_blk_bytes : 0u);
+  const uint32_t stage_bytes = prm.b_block_bytes + (prm.NA == 0 ? RS * a_blk_bytes : prm.split ? a_blk_bytes : 0u);
   uint8_t* sA = smem;
-  uint8_t* sB = sA + (size_t)prm.NA * RS * prm.a_tile_bytes;
+  uint8_t* sB = sA + (size_t)prm.NA * RS * prm.a_res_bytes;
   uint8_t* cand = sB + (size_t)prm.NS * stage_bytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(cand + G::cand_bytes(T));
   uint64_t* a_full = bars;                    // [2 * RS]
@@ -479,8 +543,8 @@ __global__ void __launch_bounds__(G::NTHREADS, 1) knn_tc_kernel(const TcParams p
   const int lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < 4; ++i) { mbar_init(smem_u32(a_full + i), 1); mbar_init(smem_u32(a_empty + i), 1); }
-    for (int i = 0; i < MAX_STAGES; ++i) { mbar_init(smem_u32(b_full + i), 1); mbar_init(smem_u32(b_empty + i), RS); }
+    for (int i = 0; i < 4; ++i) { mbar_init(smem_u32(a_full + i), 1); mbar_init(smem_u32(a_empty + i), RS == 1 ? G::NISS : 1); }
+    for (int i = 0; i < MAX_STAGES; ++i) { mbar_init(smem_u32(b_full + i), 1); mbar_init(smem_u32(b_empty + i), G::NISS); }
     for (int i = 0; i < 8; ++i) { mbar_init(smem_u32(t_full + i), 1); mbar_init(smem_u32(t_empty + i), 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -501,6 +565,57 @@ __global__ void __launch_bounds__(G::NTHREADS, 1) knn_tc_kernel(const TcParams p
     // ================================ TMA producer ===================================
     // The whole warp walks the loops (converged control flow); one elected lane issues the copies.
     // Per item: sweep A streams the first NKBA K blocks of every key tile, sweep B all NKB of them.
+    if (RS == 1 && prm.NA > 0) {
+      // Lean form for one row set with a resident A tile (every wide-group shape): loop invariants in registers,
+      // addresses by increments.  The generic loop below spends ~115 instructions per operand block, which (with
+      // the same weight in the issuer) bounded the D = 200 layers at ~800 cycles per 17 KB block.  The warp stays
+      // converged (a divergent single-lane loop makes the compiler wrap every UBLKCP / UTCHMMA in a 15-instruction
+      // uniformisation loop); one elected lane issues.
+      {
+        const uint32_t KT = prm.KT, NKB = prm.NKB, NKBA = prm.NKBA, NS = prm.NS, NA = prm.NA;
+        const uint32_t bblk = prm.b_block_bytes, a_res = prm.a_res_bytes;
+        const bool split = prm.split != 0;
+        const uint32_t nkbl = NKB - NKBA;
+        const uint32_t sA_u = smem_u32(sA), sB_u = smem_u32(sB);
+        const uint32_t afull_u = smem_u32(a_full), aempty_u = smem_u32(a_empty);
+        const uint32_t bfull_u = smem_u32(b_full), bempty_u = smem_u32(b_empty);
+        uint32_t ab = 0, aph = 0, bs = 0, bph = 0;
+        for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+          const int p = item / prm.QI, qi = item - p * prm.QI;
+          const uint8_t* asrc = reinterpret_cast<const uint8_t*>(prm.a_op) +
+                                ((size_t)p * prm.QTP + (size_t)qi) * prm.a_tile_bytes;
+          mbar_wait_lean(aempty_u + ab * 8, aph ^ 1);
+          if (elect_one()) {
+            mbar_expect_tx(afull_u + ab * 8, a_res);
+            tma_bulk_g2s(sA_u + ab * a_res, asrc, a_res, afull_u + ab * 8);
+          }
+          __syncwarp();
+          if (++ab == NA) { ab = 0; aph ^= 1; }
+          const uint8_t* alo = asrc + (size_t)NKBA * a_blk_bytes;       // split: the lo segment of the A tile
+          const uint8_t* bsrc = reinterpret_cast<const uint8_t*>(prm.b_op) + (size_t)p * KT * NKB * bblk;
+          for (uint32_t sweep = 0; sweep < 2; ++sweep) {
+            const uint32_t nkb = sweep == 0 ? NKBA : NKB;
+            const uint32_t nlo = (split && sweep == 1) ? nkbl : 0u;     // blocks that travel with an A.lo block
+            const uint8_t* src = bsrc;
+            for (uint32_t kt = 0; kt < KT; ++kt, src += (size_t)NKB * bblk) {
+              const uint8_t* sb = src;
+              for (uint32_t kb = 0; kb < nkb; ++kb, sb += bblk) {
+                mbar_wait_lean(bempty_u + bs * 8, bph ^ 1);
+                const uint32_t bar = bfull_u + bs * 8, dst = sB_u + bs * stage_bytes;
+                const bool with_lo = kb < nlo;
+                if (elect_one()) {
+                  mbar_expect_tx(bar, bblk + (with_lo ? a_blk_bytes : 0u));
+                  tma_bulk_g2s(dst, sb, bblk, bar);
+                  if (with_lo) tma_bulk_g2s(dst + bblk, alo + (size_t)kb * a_blk_bytes, a_blk_bytes, bar);
+                }
+                __syncwarp();
+                if (++bs == NS) { bs = 0; bph ^= 1; }
+              }
+            }
+          }
+        }
+      }
+    } else {
     int ab = 0, aph = 0, bs = 0, bph = 0;
     for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
       const int p = item / prm.QI, qi = item - p * prm.QI;
@@ -512,9 +627,9 @@ __global__ void __launch_bounds__(G::NTHREADS, 1) knn_tc_kernel(const TcParams p
           const int slot = ab * RS + r;
           mbar_wait<true>(smem_u32(a_empty + slot), aph ^ 1);
           if (elect_one()) {
-            mbar_expect_tx(smem_u32(a_full + slot), prm.a_tile_bytes);
-            tma_bulk_g2s(smem_u32(sA + (size_t)slot * prm.a_tile_bytes), asrc + (size_t)r * prm.a_tile_bytes,
-                         prm.a_tile_bytes, smem_u32(a_full + slot));
+            mbar_expect_tx(smem_u32(a_full + slot), prm.a_res_bytes);
+            tma_bulk_g2s(smem_u32(sA + (size_t)slot * prm.a_res_bytes), asrc + (size_t)r * prm.a_tile_bytes,
+                         prm.a_res_bytes, smem_u32(a_full + slot));
           }
           __syncwarp();
         }
@@ -522,13 +637,16 @@ __global__ void __launch_bounds__(G::NTHREADS, 1) knn_tc_kernel(const TcParams p
       }
       const uint8_t* bsrc = reinterpret_cast<const uint8_t*>(prm.b_op) +
                             (size_t)p * prm.KT * prm.NKB * prm.b_block_bytes;
+      const int nkbl = prm.NKB - prm.NKBA;      // split operands: blocks of the lo segment
       for (int sweep = 0; sweep < 2; ++sweep) {
         const int nkb = sweep == 0 ? prm.NKBA : prm.NKB;
         for (int kt = 0; kt < prm.KT; ++kt) {
           for (int kb = 0; kb < nkb; ++kb) {
             mbar_wait<true>(smem_u32(b_empty + bs), bph ^ 1);
             if (elect_one()) {
-              mbar_expect_tx(smem_u32(b_full + bs), stage_bytes);
+              const bool with_lo = prm.split && sweep == 1 && kb < nkbl;   // the A.lo block that meets this B block
+              mbar_expect_tx(smem_u32(b_full + bs),
+                             prm.split ? prm.b_block_bytes + (with_lo ? a_blk_bytes : 0u) : stage_bytes);
               uint8_t* dst = sB + (size_t)bs * stage_bytes;
               tma_bulk_g2s(smem_u32(dst), bsrc + (size_t)(kt * prm.NKB + kb) * prm.b_block_bytes, prm.b_block_bytes,
                            smem_u32(b_full + bs));
@@ -538,6 +656,9 @@ __global__ void __launch_bounds__(G::NTHREADS, 1) knn_tc_kernel(const TcParams p
                   tma_bulk_g2s(smem_u32(dst + prm.b_block_bytes + r * a_blk_bytes),
                                asrc + (size_t)r * prm.a_tile_bytes + (size_t)kb * a_blk_bytes, a_blk_bytes,
                                smem_u32(b_full + bs));
+              } else if (with_lo) {
+                tma_bulk_g2s(smem_u32(dst + prm.b_block_bytes), asrc + (size_t)(prm.NKBA + kb) * a_blk_bytes,
+                             a_blk_bytes, smem_u32(b_full + bs));
               }
             }
             __syncwarp();
@@ -546,27 +667,117 @@ __global__ void __launch_bounds__(G::NTHREADS, 1) knn_tc_kernel(const TcParams p
         }
       }
     }
-  } else if (warp <= RS) {
+    }
+  } else if (warp <= G::NISS) {
     // ================================ MMA issuers ====================================
-    // One warp per row set (two independent issue streams hide each other's barrier latencies).
-    // Converged warp, one elected lane issues tcgen05.mma / tcgen05.commit (the commits must come from
-    // the thread that issued the MMAs they track; elect.sync picks the same lane every time).
-    const int r = warp - 1;                      // row set of this issuer
+    // RS > 1: one warp per row set, every key tile (two independent issue streams hide each other's barrier
+    // latencies).  RS == 1: NACC warps, warp i issues the key tiles whose accumulator slot is i and skips the
+    // operand blocks of the others.  Converged warp, one elected lane issues tcgen05.mma / tcgen05.commit (the
+    // commits must come from the thread that issued the MMAs they track; elect.sync picks the same lane every time).
+    constexpr bool RR = RS == 1;                 // round-robin over the key tiles
+    const int iss = warp - 1;
+    const int r = RR ? 0 : iss;                  // row set of this issuer
     int ab = 0, aph = 0, bs = 0, bph = 0, tb = 0, tph = 0;
     // descriptor halves: hi = SBO | version, lo = start address | LBO (both in 16-byte units)
-    const uint32_t desc_hi = ((uint32_t)(prm.KC >> 3) * 128u >> 4) | (1u << 14);
+    const uint64_t desc_hi = (uint64_t)(((uint32_t)(prm.KC >> 3) * 128u >> 4) | (1u << 14)) << 32;
     const uint32_t lbo_field = (128u >> 4) << 16;
+    const int kpb = prm.KC >> 4;                 // K steps per operand block
+    if (RR && prm.NA > 0) {
+      // Lean form (see the producer): converged warp, invariants in registers, descriptors by addition.
+      {
+        const int KT = prm.KT, NKB = prm.NKB, NKBA = prm.NKBA, NS = prm.NS, NA = prm.NA;
+        const bool split = prm.split != 0;
+        const int KS1 = prm.KS1, KSL = prm.KSL, PA16 = prm.PA >> 4, KP16 = prm.KP >> 4;
+        const uint32_t sB_lo0 = ((smem_u32(sB) & 0x3FFFFu) >> 4) | lbo_field;   // descriptor low words, 16-byte units
+        const uint32_t stage_u = stage_bytes >> 4, bblk_u = prm.b_block_bytes >> 4, ablk_u = a_blk_bytes >> 4;
+        const uint32_t sA_u = smem_u32(sA), a_res = prm.a_res_bytes;
+        const uint32_t afull_u = smem_u32(a_full), aempty_u = smem_u32(a_empty);
+        const uint32_t bfull_u = smem_u32(b_full), bempty_u = smem_u32(b_empty);
+        const uint32_t tfull_u = smem_u32(t_full + iss), tempty_u = smem_u32(t_empty + iss);
+        const uint32_t d_tmem = tmem_base + (uint32_t)(iss * G::ACC_STRIDE);
+        uint32_t ab = 0, aph = 0, bs = 0, bph = 0, tph = 0;
+        int tb = 0;
+        for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+          mbar_wait_lean(afull_u + ab * 8, aph);
+          tc_fence_after();
+          const uint32_t a_lo0 = (((sA_u + ab * a_res) & 0x3FFFFu) >> 4) | lbo_field;
+          for (int sweep = 0; sweep < 2; ++sweep) {
+            const int nkb = sweep == 0 ? NKBA : NKB;
+            const int nseg1 = split ? NKBA : nkb;                       // blocks multiplied with A block kb
+            const int lim1 = split ? KS1 : (sweep == 0 ? PA16 : KP16);   // K steps of the first segment
+            const bool cross = split && sweep == 1;                     // A.lo x B.first rides on the first segment
+            for (int kt = 0; kt < KT; ++kt) {
+              if (tb != iss) {
+                // another issuer's tile: watch its blocks arrive and acknowledge them (see the generic loop)
+                for (int kb = 0; kb < nkb; ++kb) {
+                  mbar_wait_lean(bfull_u + bs * 8, bph);
+                  if (lane == 0) mbar_arrive(bempty_u + bs * 8);
+                  if (++bs == (uint32_t)NS) { bs = 0; bph ^= 1; }
+                }
+              } else {
+                mbar_wait_lean(tempty_u, tph ^ 1);
+                tc_fence_after();
+                for (int kb = 0; kb < nkb; ++kb) {
+                  mbar_wait_lean(bfull_u + bs * 8, bph);
+                  tc_fence_after();
+                  const uint32_t b_lo = sB_lo0 + bs * stage_u;
+                  const bool seg1 = kb < nseg1;
+                  const int j = seg1 ? kb : kb - nseg1;
+                  const int n1 = min(kpb, (seg1 ? lim1 : KSL) - j * kpb);
+                  const uint32_t a_lo = a_lo0 + (uint32_t)j * ablk_u;
+                  const int n2 = (cross && seg1) ? min(kpb, KSL - kb * kpb) : 0;
+                  if (elect_one()) {
+#pragma unroll 4
+                    for (int ks = 0; ks < n1; ++ks)   // one K=16 step = two core matrices = 256 bytes = 16 units
+                      umma_f16(d_tmem, desc_hi | (a_lo + (uint32_t)ks * 16u), desc_hi | (b_lo + (uint32_t)ks * 16u),
+                               G::kIdesc, (kb | ks) != 0 ? 1u : 0u);
+                    const uint32_t a2_lo = b_lo + bblk_u;
+#pragma unroll 4
+                    for (int ks = 0; ks < n2; ++ks)
+                      umma_f16(d_tmem, desc_hi | (a2_lo + (uint32_t)ks * 16u), desc_hi | (b_lo + (uint32_t)ks * 16u),
+                               G::kIdesc, 1u);
+                    umma_commit(bempty_u + bs * 8);
+                    if (kb == nkb - 1) umma_commit(tfull_u);
+                  }
+                  __syncwarp();
+                  if (++bs == (uint32_t)NS) { bs = 0; bph ^= 1; }
+                }
+                tph ^= 1;
+              }
+              if (++tb == NACC) tb = 0;
+            }
+          }
+          if (elect_one()) umma_commit(aempty_u + ab * 8);   // the A tile may be overwritten once this issuer's MMAs retire
+          __syncwarp();
+          if (++ab == (uint32_t)NA) { ab = 0; aph ^= 1; }
+        }
+      }
+    } else
     for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
       uint32_t a_base = 0;
       if (prm.NA > 0) {
         mbar_wait<true>(smem_u32(a_full + ab * RS + r), aph);
-        a_base = smem_u32(sA + (size_t)(ab * RS + r) * prm.a_tile_bytes);
+        a_base = smem_u32(sA + (size_t)(ab * RS + r) * prm.a_res_bytes);
         tc_fence_after();
       }
       for (int sweep = 0; sweep < 2; ++sweep) {
         const int nkb = sweep == 0 ? prm.NKBA : prm.NKB;
         const int kcols = sweep == 0 ? prm.PA : prm.KP;     // operand columns this sweep multiplies
         for (int kt = 0; kt < prm.KT; ++kt) {
+          if (RR && tb != iss) {
+            // Another issuer's tile: step over its operand blocks -- but WATCH every one of them arrive.  A parity
+            // wait is only meaningful within one phase of the barrier; an issuer that jumped ahead (its next tile
+            // can be more than a ring lap away) would mistake the previous lap's completion for its own block's.
+            // The skipped stage is acknowledged too (b_empty counts every issuer), so the ring can never lap an
+            // issuer: every wait below and above stays within one phase of its barrier.
+            for (int kb = 0; kb < nkb; ++kb) {
+              mbar_wait<true>(smem_u32(b_full + bs), bph);
+              if (lane == 0) mbar_arrive(smem_u32(b_empty + bs));
+              if (++bs == prm.NS) { bs = 0; bph ^= 1; }
+            }
+            if (++tb == NACC) tb = 0;
+            continue;
+          }
           mbar_wait<true>(smem_u32(t_empty + r * NACC + tb), tph ^ 1);
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + (uint32_t)((r * NACC + tb) * G::ACC_STRIDE);
@@ -574,17 +785,34 @@ __global__ void __launch_bounds__(G::NTHREADS, 1) knn_tc_kernel(const TcParams p
             mbar_wait<true>(smem_u32(b_full + bs), bph);
             tc_fence_after();
             const uint32_t b_addr = smem_u32(sB + (size_t)bs * stage_bytes);
-            const int ksteps = min(prm.KC, kcols - kb * prm.KC) >> 4;
+            // K steps of this block and the A block(s) they multiply.  Split operands: a block of the first segment
+            // meets A.hi (and, in sweep B, A.lo = the lo x hi cross term), a block of the lo segment A.hi.
+            int ksteps, ksteps2 = 0, ablk = kb;
+            if (prm.split) {
+              if (kb < prm.NKBA) {
+                ksteps = min(kpb, prm.KS1 - kb * kpb);
+                if (sweep == 1) ksteps2 = max(0, min(kpb, prm.KSL - kb * kpb));
+              } else {
+                ablk = kb - prm.NKBA;
+                ksteps = min(kpb, prm.KSL - ablk * kpb);
+              }
+            } else {
+              ksteps = min(prm.KC, kcols - kb * prm.KC) >> 4;
+            }
             if (elect_one()) {
               const uint32_t b_lo = ((b_addr & 0x3FFFFu) >> 4) | lbo_field;
-              const uint32_t a_addr = prm.NA > 0 ? a_base + (uint32_t)kb * a_blk_bytes
+              const uint32_t a_addr = prm.NA > 0 ? a_base + (uint32_t)ablk * a_blk_bytes
                                                  : b_addr + prm.b_block_bytes + r * a_blk_bytes;
               const uint32_t a_lo = ((a_addr & 0x3FFFFu) >> 4) | lbo_field;
 #pragma unroll 4
-              for (int ks = 0; ks < ksteps; ++ks) {   // one K=16 step = two core matrices = 256 bytes = 16 units
-                const uint64_t ad = ((uint64_t)desc_hi << 32) | (a_lo + (uint32_t)ks * 16u);
-                const uint64_t bd = ((uint64_t)desc_hi << 32) | (b_lo + (uint32_t)ks * 16u);
-                umma_f16(d_tmem, ad, bd, G::kIdesc, (kb | ks) != 0 ? 1u : 0u);
+              for (int ks = 0; ks < ksteps; ++ks)     // one K=16 step = two core matrices = 256 bytes = 16 units
+                umma_f16(d_tmem, desc_hi | (a_lo + (uint32_t)ks * 16u), desc_hi | (b_lo + (uint32_t)ks * 16u), G::kIdesc,
+                         (kb | ks) != 0 ? 1u : 0u);
+              if (ksteps2 > 0) {
+                const uint32_t a2_lo = (((b_addr + prm.b_block_bytes) & 0x3FFFFu) >> 4) | lbo_field;
+                for (int ks = 0; ks < ksteps2; ++ks)
+                  umma_f16(d_tmem, desc_hi | (a2_lo + (uint32_t)ks * 16u), desc_hi | (b_lo + (uint32_t)ks * 16u),
+                           G::kIdesc, 1u);
               }
               umma_commit(smem_u32(b_empty + bs));       // this row set is done with the stage when its MMAs retire
               if (kb == nkb - 1) umma_commit(smem_u32(t_full + r * NACC + tb));   // accumulator ready
@@ -592,7 +820,8 @@ __global__ void __launch_bounds__(G::NTHREADS, 1) knn_tc_kernel(const TcParams p
             __syncwarp();
             if (++bs == prm.NS) { bs = 0; bph ^= 1; }
           }
-          if (++tb == NACC) { tb = 0; tph ^= 1; }
+          if (++tb == NACC) { tb = 0; if (!RR) tph ^= 1; }
+          if (RR) tph ^= 1;                      // this issuer's own slot: every use flips its phase
         }
       }
       if (prm.NA > 0) {
@@ -603,7 +832,7 @@ __global__ void __launch_bounds__(G::NTHREADS, 1) knn_tc_kernel(const TcParams p
     }
   } else {
     // ================================ epilogue / selection ===========================
-    const int ew = warp - 1 - RS;                // epilogue warp index
+    const int ew = warp - 1 - G::NISS;           // epilogue warp index
     const int rset = ew >> 2;                    // row set this warp works on
     const int q = warp & 3;                      // TMEM lane quarter this warp may read
     const int row_t = q * 32 + lane;

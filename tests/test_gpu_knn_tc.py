@@ -27,9 +27,13 @@ def _ref_layout(t, G):
     (1, 2, 260, 140, 80, True, torch.float32),      # KP = 256 -> 4 k-blocks of 64
     (1, 2, 200, 300, 40, True, torch.bfloat16),     # bf16 features
     (1, 2, 300, 300, 80, True, torch.bfloat16),     # 256-row items
-    (1, 2, 150, 270, 200, True, torch.float32),     # KP = 608 -> 19 k-blocks of 32, single A buffer
+    (1, 2, 150, 270, 200, True, torch.float32),     # split planes: hi resident, lo streamed, 7 + 7 k-blocks of 32
     (1, 2, 150, 270, 200, True, torch.bfloat16),
-    (1, 2, 130, 330, 320, False, torch.bfloat16),   # stage-4 width, operands streamed
+    (1, 2, 130, 330, 320, False, torch.bfloat16),   # stage-4 width: split planes, k-blocks of 32 (hi padded to 352)
+    (1, 2, 140, 300, 96, True, torch.float32),      # narrowest split shape: k-blocks of 48, lo segment shorter than hi
+    (1, 2, 140, 300, 120, False, torch.bfloat16),
+    (1, 1, 130, 200, 400, False, torch.bfloat16),   # groups = 1 at stage 3: k-blocks of 16, 26 + 25 of them
+    (1, 2, 100, 150, 100, True, torch.float32),     # D % 8 != 0: no split, operands streamed (K-concatenated rows)
     (1, 8, 100, 90, 10, False, torch.float32),      # KP = 32
     (1, 1, 90, 2000, 40, False, torch.bfloat16),    # label-head like: many key tiles
 ])
@@ -80,7 +84,7 @@ def test_tc_matches_exact_bitwise_on_random_data(dtype):
     assert torch.equal(a, b)
 
 
-@pytest.mark.parametrize("D,kd", [(200, 18), (200, 27), (320, 27), (40, 18), (80, 9)])
+@pytest.mark.parametrize("D,kd", [(200, 18), (200, 27), (320, 27), (40, 18), (80, 9), (96, 18), (200, 36)])
 def test_tc_wide_groups_bf16_match_exact(D, kd):
     """Stage 3 / 4 shapes (self keys, wide groups, long lists) in bf16: ids equal the exact kernel's."""
     from gkgnet_b200 import _lib, ops
@@ -89,6 +93,21 @@ def test_tc_wide_groups_bf16_match_exact(D, kd):
     k, d = 9, kd // 9
     a = ops.knn_graph(x, None, None, groups=2, k=k, dilation=d, algo=_lib.KNN_TCGEN05)
     b = ops.knn_graph(x, None, None, groups=2, k=k, dilation=d, algo=_lib.KNN_EXACT_FP32)
+    assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("D,d", [(200, 2), (200, 3), (80, 1)])
+def test_tc_several_items_per_cta(D, d):
+    """More work items than SMs: the resident A tile is replaced between items, the operand ring and the three
+    round-robin issuers carry their phases across items (B * G * ceil(N / 128) = 352 items on 148 CTAs)."""
+    from gkgnet_b200 import _lib, ops
+    from gkgnet_b200.pos_embed import relative_pos_table
+    g = torch.Generator(device="cuda").manual_seed(23)
+    x = torch.randn(16, 1296, 2 * D, device="cuda", generator=g).to(torch.bfloat16)
+    rel = relative_pos_table(2 * D, 1296, 1).cuda()
+    sep = ops.fit_separable_bias(rel)
+    a = ops.knn_graph(x, None, rel, groups=2, k=9, dilation=d, algo=_lib.KNN_TCGEN05, separable=sep)
+    b = ops.knn_graph(x, None, rel, groups=2, k=9, dilation=d, algo=_lib.KNN_EXACT_FP32)
     assert torch.equal(a, b)
 
 

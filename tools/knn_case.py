@@ -1,5 +1,6 @@
 """Run one kNN shape through the tcgen05 path: compare with the exact kernel, time prepare / select.
-usage: python tools/knn_case.py B C side r G k d [dtype] [iters] [skip] [ga]"""
+usage: python tools/knn_case.py B C side r G k d [dtype] [iters] [skip] [ga] [flags]
+(flags = -2: the selection epilogue drains the accumulators without ranking them -- timing experiments only)"""
 import sys
 import time
 
@@ -17,6 +18,8 @@ if len(sys.argv) > 10:
     dbg["skip"] = int(sys.argv[10])
 if len(sys.argv) > 11:
     dbg["ga"] = int(sys.argv[11])
+if len(sys.argv) > 12:
+    dbg["flags"] = int(sys.argv[12])
 n = side * side
 torch.manual_seed(0)
 x4 = torch.randn(B, C, side, side, device="cuda")
