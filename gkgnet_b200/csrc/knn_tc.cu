@@ -630,7 +630,8 @@ knn_rerank_kernel(const int* __restrict__ rr_count, const int* __restrict__ rr_l
 constexpr int kFixBins = 1024;
 constexpr int kFixCand = 2048;                 // candidate slots (keys up to the selected bin)
 constexpr int kFixTile = 8192;                 // keys whose distances live in shared memory at a time
-__global__ void __launch_bounds__(256)
+constexpr int kFixThreads = 1024;              // a row's keys over 32 warps: the exact distance is a serial D-long chain of L2 loads per key
+__global__ void __launch_bounds__(kFixThreads)
 knn_fixup_kernel(const int* __restrict__ count, const int* __restrict__ rows, RawFeat xf,
                  const float* __restrict__ yhat, const float* __restrict__ ysq,
                  const float* __restrict__ relpos, int32_t* __restrict__ idx_out, float* __restrict__ dist_g,
@@ -643,7 +644,7 @@ knn_fixup_kernel(const int* __restrict__ count, const int* __restrict__ rows, Ra
   float* cand_v = dist_s + Ms;
   int* cand_i = reinterpret_cast<int*>(cand_v + cap);
   __shared__ int hist[kFixBins];
-  __shared__ float red_lo[8], red_hi[8];
+  __shared__ float red_lo[kFixThreads / 32], red_hi[kFixThreads / 32];
   __shared__ float xs_s;
   __shared__ int bin_sel, ncand, nsel_s;
   const int total = *count;
@@ -677,7 +678,7 @@ knn_fixup_kernel(const int* __restrict__ count, const int* __restrict__ rows, Ra
     if (lane == 0) { red_lo[warp] = lo; red_hi[warp] = hi; }
     __syncthreads();
 #pragma unroll
-    for (int w = 0; w < 8; ++w) { lo = fminf(lo, red_lo[w]); hi = fmaxf(hi, red_hi[w]); }
+    for (int w = 0; w < kFixThreads / 32; ++w) { lo = fminf(lo, red_lo[w]); hi = fmaxf(hi, red_hi[w]); }
     const float scale = hi > lo ? (float)kFixBins / (hi - lo) : 0.f;
     auto bin_of = [&](float v) {
       const int q = (int)((v - lo) * scale);
@@ -924,7 +925,7 @@ int launch_knn_tc(const KnnWorkspace& w, void* extra_ws, const void* x, int64_t 
   prm.KP = pl.KP; prm.PA = pl.PA; prm.KC = pl.KC; prm.NKB = pl.NKB; prm.NKBA = pl.NKBA; prm.NA = pl.NA; prm.NS = pl.NS; prm.QT = pl.QT;
   prm.QI = pl.QI; prm.QTP = pl.QTP; prm.KT = pl.KT;
   prm.split = pl.split; prm.KS1 = pl.KS1; prm.KSL = pl.KSL;
-  prm.a_tile_bytes = pl.a_tile_bytes; prm.a_res_bytes = pl.a_res_bytes; prm.b_block_bytes = pl.b_block_bytes;
+  prm.a_tile_bytes = pl.a_tile_bytes; prm.a_res_bytes = pl.a_res_bytes; prm.b_block_bytes = pl.b_block_bytes; prm.stage_bytes = pl.stage_bytes;
   prm.force_rerank = flags;
   prm.delta = pl.split ? tc_delta_steps(pl.KS1 + 2 * pl.KSL) : tc_delta(pl.KP);
   // the separable form of the bias is a hint the caller verified to within kSepBiasTol of the dense table the exact
@@ -981,7 +982,7 @@ int launch_knn_tc(const KnnWorkspace& w, void* extra_ws, const void* x, int64_t 
     configure_once_per_device(configured, [] {
       cudaFuncSetAttribute(knn_fixup_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
     });
-    knn_fixup_kernel<<<kFixBlocks, 256, fsmem, stream>>>(t.fix_count, t.fix_rows, xf, w.yhat, w.ysq, relpos, idx_out,
+    knn_fixup_kernel<<<kFixBlocks, kFixThreads, fsmem, stream>>>(t.fix_count, t.fix_rows, xf, w.yhat, w.ysq, relpos, idx_out,
                                                          t.fix_dist, N, M, D, k, dilation);
     GKG_CHECK_LAUNCH("knn_fixup_kernel");
   }

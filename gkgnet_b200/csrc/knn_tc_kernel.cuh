@@ -68,7 +68,7 @@ struct Plan {
   int geom;                        // 0 = GeomA, 1 = GeomB
   int KP, PA, KC, NKB, NKBA, NA, NS, QT, QI, QTP, KT;
   int split, KS1, KSL;             // split-plane operands (see below): valid K steps of the first / the lo segment
-  uint32_t a_tile_bytes, a_res_bytes, b_block_bytes;
+  uint32_t a_tile_bytes, a_res_bytes, b_block_bytes, stage_bytes;
   size_t smem_bytes;
   size_t a_op_bytes, b_op_bytes;   // per launch operand buffers
   bool ok;
@@ -80,8 +80,8 @@ struct Plan {
 //   split     (wide groups, D % 8 == 0, GeomA): the fp16x3 operand rows [hi | hi | lo] / [hi | lo | hi] repeat
 //             their hi plane, so only TWO planes per row are stored, [hi (+ extra pair) -> PA | lo -> KP - PA] for
 //             queries and keys alike (each segment zero-padded to a multiple of KC).  The hi segment of the A tile
-//             stays resident; a ring stage carries one B block and, for a block of the first segment in sweep B,
-//             the matching A.lo block.  The issuer multiplies  A.hi x B.first (+ A.lo x B.first in sweep B)  for
+//             stays resident; a ring stage carries one B block with the matching A.lo block (first segment in
+//             sweep B), or else TWO consecutive B blocks (they are adjacent in global memory: one bulk copy).  The issuer multiplies  A.hi x B.first (+ A.lo x B.first in sweep B)  for
 //             a block of the first segment and  A.hi x B.lo  for a block of the lo segment: per key tile 233 KB
 //             through the ring instead of 444 KB at D = 200;
 //   streaming (NA = 0):     A and B blocks of one K slice travel together through the ring (the A
@@ -138,7 +138,7 @@ inline Plan make_plan_g(int P, int N, int M, int D, int T, bool strict) {
         const size_t a_res = (size_t)BM * pas * 2;
         const size_t fixed = cand + G::kBarBytes + a_res;
         if (fixed >= kSmemBudget) continue;
-        const size_t stage = (size_t)(G::BNP + BM) * kc * 2;
+        const size_t stage = (size_t)(2 * G::BNP > G::BNP + BM ? 2 * G::BNP : G::BNP + BM) * kc * 2;   // B + A.lo | 2 B
         int ns = (int)((kSmemBudget - fixed) / stage);
         if (ns > MAX_STAGES) ns = MAX_STAGES;
         if (ns < 3) continue;
@@ -179,7 +179,9 @@ inline Plan make_plan_g(int P, int N, int M, int D, int T, bool strict) {
   if (!pl.ok) return pl;
   pl.NKB = pl.KP / pl.KC;
   pl.NKBA = (pl.PA + pl.KC - 1) / pl.KC;     // split: the blocks of the first segment
-  const size_t stage = pl.b_block_bytes + (pl.NA == 0 ? (size_t)G::ROWS * pl.KC * 2 : pl.split ? (size_t)BM * pl.KC * 2 : 0);
+  const size_t stage = pl.split ? (size_t)(2 * G::BNP > G::BNP + BM ? 2 * G::BNP : G::BNP + BM) * pl.KC * 2
+                                : pl.b_block_bytes + (pl.NA == 0 ? (size_t)G::ROWS * pl.KC * 2 : 0);
+  pl.stage_bytes = (uint32_t)stage;
   pl.a_res_bytes = pl.split ? (uint32_t)((size_t)BM * pl.PA * 2) : pl.a_tile_bytes;   // resident part of an A tile
   pl.smem_bytes = cand + G::kBarBytes + (size_t)pl.NA * G::RS * pl.a_res_bytes + (size_t)pl.NS * stage;
   pl.a_op_bytes = (size_t)P * pl.QTP * pl.a_tile_bytes;
@@ -479,7 +481,7 @@ struct TcParams {
   int P, N, M, D, k, dilation, kd;
   int KP, PA, KC, NKB, NKBA, NA, NS, QT, QI, QTP, KT;
   int split, KS1, KSL;
-  uint32_t a_tile_bytes, a_res_bytes, b_block_bytes;
+  uint32_t a_tile_bytes, a_res_bytes, b_block_bytes, stage_bytes;
   int force_rerank;
   float delta;                     // bound on |approx - exact| of the fp16x3 GEMM (dist units), see tc_delta()
 };
@@ -525,7 +527,7 @@ __global__ void __launch_bounds__(G::NTHREADS, 1) knn_tc_kernel(const TcParams p
   extern __shared__ __align__(1024) uint8_t smem[];
   // carve-up: [A tiles x NA x RS][ring x NS: B block (+ A slices when streaming)][triplet log][barriers + tmem ptr][staged B rows]
   const uint32_t a_blk_bytes = (uint32_t)(BM * prm.KC * 2);                    // one K slice of one A tile
-  const uint32_t stage_bytes = prm.b_block_bytes + (prm.NA == 0 ? RS * a_blk_bytes : prm.split ? a_blk_bytes : 0u);
+  const uint32_t stage_bytes = prm.stage_bytes;
   uint8_t* sA = smem;
   uint8_t* sB = sA + (size_t)prm.NA * RS * prm.a_res_bytes;
   uint8_t* cand = sB + (size_t)prm.NS * stage_bytes;
@@ -596,20 +598,25 @@ __global__ void __launch_bounds__(G::NTHREADS, 1) knn_tc_kernel(const TcParams p
           for (uint32_t sweep = 0; sweep < 2; ++sweep) {
             const uint32_t nkb = sweep == 0 ? NKBA : NKB;
             const uint32_t nlo = (split && sweep == 1) ? nkbl : 0u;     // blocks that travel with an A.lo block
+            const uint32_t single_end = (split && sweep == 1) ? NKBA : 0u;   // blocks [0, single_end) travel alone
             const uint8_t* src = bsrc;
             for (uint32_t kt = 0; kt < KT; ++kt, src += (size_t)NKB * bblk) {
               const uint8_t* sb = src;
-              for (uint32_t kb = 0; kb < nkb; ++kb, sb += bblk) {
+              for (uint32_t kb = 0; kb < nkb;) {
+                // blocks of this stage: one (with its A.lo block, if it has one), or two B blocks of one segment
+                const uint32_t nb = (!split || kb < single_end) ? 1u : min(2u, nkb - kb);
                 mbar_wait_lean(bempty_u + bs * 8, bph ^ 1);
                 const uint32_t bar = bfull_u + bs * 8, dst = sB_u + bs * stage_bytes;
                 const bool with_lo = kb < nlo;
                 if (elect_one()) {
-                  mbar_expect_tx(bar, bblk + (with_lo ? a_blk_bytes : 0u));
-                  tma_bulk_g2s(dst, sb, bblk, bar);
+                  mbar_expect_tx(bar, nb * bblk + (with_lo ? a_blk_bytes : 0u));
+                  tma_bulk_g2s(dst, sb, nb * bblk, bar);
                   if (with_lo) tma_bulk_g2s(dst + bblk, alo + (size_t)kb * a_blk_bytes, a_blk_bytes, bar);
                 }
                 __syncwarp();
                 if (++bs == NS) { bs = 0; bph ^= 1; }
+                kb += nb;
+                sb += (size_t)nb * bblk;
               }
             }
           }
@@ -707,9 +714,11 @@ __global__ void __launch_bounds__(G::NTHREADS, 1) knn_tc_kernel(const TcParams p
             const int lim1 = split ? KS1 : (sweep == 0 ? PA16 : KP16);   // K steps of the first segment
             const bool cross = split && sweep == 1;                     // A.lo x B.first rides on the first segment
             for (int kt = 0; kt < KT; ++kt) {
+              const int single_end = cross ? NKBA : 0;                    // blocks [0, single_end): one per stage
               if (tb != iss) {
-                // another issuer's tile: watch its blocks arrive and acknowledge them (see the generic loop)
-                for (int kb = 0; kb < nkb; ++kb) {
+                // another issuer's tile: watch its stages arrive and acknowledge them (see the generic loop)
+                for (int kb = 0; kb < nkb;) {
+                  kb += (!split || kb < single_end) ? 1 : min(2, nkb - kb);
                   mbar_wait_lean(bfull_u + bs * 8, bph);
                   if (lane == 0) mbar_arrive(bempty_u + bs * 8);
                   if (++bs == (uint32_t)NS) { bs = 0; bph ^= 1; }
@@ -717,30 +726,36 @@ __global__ void __launch_bounds__(G::NTHREADS, 1) knn_tc_kernel(const TcParams p
               } else {
                 mbar_wait_lean(tempty_u, tph ^ 1);
                 tc_fence_after();
-                for (int kb = 0; kb < nkb; ++kb) {
+                for (int kb = 0; kb < nkb;) {
+                  const int nb = (!split || kb < single_end) ? 1 : min(2, nkb - kb);   // blocks of this stage
                   mbar_wait_lean(bfull_u + bs * 8, bph);
                   tc_fence_after();
                   const uint32_t b_lo = sB_lo0 + bs * stage_u;
                   const bool seg1 = kb < nseg1;
                   const int j = seg1 ? kb : kb - nseg1;
-                  const int n1 = min(kpb, (seg1 ? lim1 : KSL) - j * kpb);
+                  const int lim = (seg1 ? lim1 : KSL) - j * kpb;        // K steps left in the segment
+                  const int n1 = min(nb * kpb, lim);                    // two adjacent blocks: one run of K steps
                   const uint32_t a_lo = a_lo0 + (uint32_t)j * ablk_u;
                   const int n2 = (cross && seg1) ? min(kpb, KSL - kb * kpb) : 0;
                   if (elect_one()) {
-#pragma unroll 4
-                    for (int ks = 0; ks < n1; ++ks)   // one K=16 step = two core matrices = 256 bytes = 16 units
-                      umma_f16(d_tmem, desc_hi | (a_lo + (uint32_t)ks * 16u), desc_hi | (b_lo + (uint32_t)ks * 16u),
+                    // K step ks of the run: block ks / kpb of the stage (B blocks bblk_u apart, A blocks ablk_u apart)
+#pragma unroll 2
+                    for (int ks = 0; ks < n1; ++ks) {   // one K=16 step = two core matrices = 256 bytes = 16 units
+                      const uint32_t u = ks >= kpb ? 1u : 0u, kk = (uint32_t)ks - u * (uint32_t)kpb;
+                      umma_f16(d_tmem, desc_hi | (a_lo + u * ablk_u + kk * 16u), desc_hi | (b_lo + u * bblk_u + kk * 16u),
                                G::kIdesc, (kb | ks) != 0 ? 1u : 0u);
+                    }
                     const uint32_t a2_lo = b_lo + bblk_u;
-#pragma unroll 4
+#pragma unroll 2
                     for (int ks = 0; ks < n2; ++ks)
                       umma_f16(d_tmem, desc_hi | (a2_lo + (uint32_t)ks * 16u), desc_hi | (b_lo + (uint32_t)ks * 16u),
                                G::kIdesc, 1u);
                     umma_commit(bempty_u + bs * 8);
-                    if (kb == nkb - 1) umma_commit(tfull_u);
+                    if (kb + nb == nkb) umma_commit(tfull_u);
                   }
                   __syncwarp();
                   if (++bs == (uint32_t)NS) { bs = 0; bph ^= 1; }
+                  kb += nb;
                 }
                 tph ^= 1;
               }
