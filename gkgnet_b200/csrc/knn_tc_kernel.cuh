@@ -644,16 +644,13 @@ __global__ void __launch_bounds__(G::NTHREADS, 1) knn_tc_kernel(const TcParams p
       }
       const uint8_t* bsrc = reinterpret_cast<const uint8_t*>(prm.b_op) +
                             (size_t)p * prm.KT * prm.NKB * prm.b_block_bytes;
-      const int nkbl = prm.NKB - prm.NKBA;      // split operands: blocks of the lo segment
       for (int sweep = 0; sweep < 2; ++sweep) {
         const int nkb = sweep == 0 ? prm.NKBA : prm.NKB;
         for (int kt = 0; kt < prm.KT; ++kt) {
           for (int kb = 0; kb < nkb; ++kb) {
             mbar_wait<true>(smem_u32(b_empty + bs), bph ^ 1);
             if (elect_one()) {
-              const bool with_lo = prm.split && sweep == 1 && kb < nkbl;   // the A.lo block that meets this B block
-              mbar_expect_tx(smem_u32(b_full + bs),
-                             prm.split ? prm.b_block_bytes + (with_lo ? a_blk_bytes : 0u) : stage_bytes);
+              mbar_expect_tx(smem_u32(b_full + bs), stage_bytes);
               uint8_t* dst = sB + (size_t)bs * stage_bytes;
               tma_bulk_g2s(smem_u32(dst), bsrc + (size_t)(kt * prm.NKB + kb) * prm.b_block_bytes, prm.b_block_bytes,
                            smem_u32(b_full + bs));
@@ -663,9 +660,6 @@ __global__ void __launch_bounds__(G::NTHREADS, 1) knn_tc_kernel(const TcParams p
                   tma_bulk_g2s(smem_u32(dst + prm.b_block_bytes + r * a_blk_bytes),
                                asrc + (size_t)r * prm.a_tile_bytes + (size_t)kb * a_blk_bytes, a_blk_bytes,
                                smem_u32(b_full + bs));
-              } else if (with_lo) {
-                tma_bulk_g2s(smem_u32(dst + prm.b_block_bytes), asrc + (size_t)(prm.NKBA + kb) * a_blk_bytes,
-                             a_blk_bytes, smem_u32(b_full + bs));
               }
             }
             __syncwarp();
@@ -800,35 +794,16 @@ __global__ void __launch_bounds__(G::NTHREADS, 1) knn_tc_kernel(const TcParams p
             mbar_wait<true>(smem_u32(b_full + bs), bph);
             tc_fence_after();
             const uint32_t b_addr = smem_u32(sB + (size_t)bs * stage_bytes);
-            // K steps of this block and the A block(s) they multiply.  Split operands: a block of the first segment
-            // meets A.hi (and, in sweep B, A.lo = the lo x hi cross term), a block of the lo segment A.hi.
-            int ksteps, ksteps2 = 0, ablk = kb;
-            if (prm.split) {
-              if (kb < prm.NKBA) {
-                ksteps = min(kpb, prm.KS1 - kb * kpb);
-                if (sweep == 1) ksteps2 = max(0, min(kpb, prm.KSL - kb * kpb));
-              } else {
-                ablk = kb - prm.NKBA;
-                ksteps = min(kpb, prm.KSL - ablk * kpb);
-              }
-            } else {
-              ksteps = min(prm.KC, kcols - kb * prm.KC) >> 4;
-            }
+            const int ksteps = min(prm.KC, kcols - kb * prm.KC) >> 4;
             if (elect_one()) {
               const uint32_t b_lo = ((b_addr & 0x3FFFFu) >> 4) | lbo_field;
-              const uint32_t a_addr = prm.NA > 0 ? a_base + (uint32_t)ablk * a_blk_bytes
+              const uint32_t a_addr = prm.NA > 0 ? a_base + (uint32_t)kb * a_blk_bytes
                                                  : b_addr + prm.b_block_bytes + r * a_blk_bytes;
               const uint32_t a_lo = ((a_addr & 0x3FFFFu) >> 4) | lbo_field;
 #pragma unroll 4
               for (int ks = 0; ks < ksteps; ++ks)     // one K=16 step = two core matrices = 256 bytes = 16 units
                 umma_f16(d_tmem, desc_hi | (a_lo + (uint32_t)ks * 16u), desc_hi | (b_lo + (uint32_t)ks * 16u), G::kIdesc,
                          (kb | ks) != 0 ? 1u : 0u);
-              if (ksteps2 > 0) {
-                const uint32_t a2_lo = (((b_addr + prm.b_block_bytes) & 0x3FFFFu) >> 4) | lbo_field;
-                for (int ks = 0; ks < ksteps2; ++ks)
-                  umma_f16(d_tmem, desc_hi | (a2_lo + (uint32_t)ks * 16u), desc_hi | (b_lo + (uint32_t)ks * 16u),
-                           G::kIdesc, 1u);
-              }
               umma_commit(smem_u32(b_empty + bs));       // this row set is done with the stage when its MMAs retire
               if (kb == nkb - 1) umma_commit(smem_u32(t_full + r * NACC + tb));   // accumulator ready
             }
