@@ -51,6 +51,9 @@ SIGNATURES = {
     "gkg_multilabel_loss": (_i32, [_vp] * 5 + [_c.c_longlong] + [_c.c_float] * 5 + [_vp]),
     "gkg_grouped_fc_pack_weights": (_i32, [_vp, _vp, _vp, _i32, _i32, _vp]),
     "gkg_grouped_fc_wgrad": (_i32, [_vp, _vp, _vp, _c.c_longlong, _i32, _vp]),
+    "gkg_bn_workspace_bytes": (_sz, [_c.c_longlong, _i32]),
+    "gkg_bn_stats": (_i32, [_vp, _c.c_longlong, _i32, _i32, _c.c_float, _c.c_float, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "gkg_bn_backward_reduce": (_i32, [_vp, _vp, _vp, _vp, _c.c_longlong, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
 }
 
 _lib = None

@@ -1,0 +1,304 @@
+// Training-mode batch-norm reductions on the token-major (rows, C) layout of this library.
+//
+// Reference: every conv -> norm pair of the graph blocks is `norm_layer('batch')` = (Sync)BatchNorm over
+// (B, C, H, W) (torch_nn.py:32-42; BasicConv torch_nn.py:61-65, Grapher.fc1 / fc2 torch_vertex.py:290-306, FFN
+// gkgnet.py:46-72): y = (x - mean_c) * rsqrt(var_c + eps) * gamma_c + beta_c with the biased batch variance, running
+// statistics updated with the unbiased one.  The forward needs per-channel (mean, invstd) BEFORE the elementwise pass,
+// the backward per-channel (sum dy, sum dy * (x - mean)) before its elementwise pass; both are pure HBM-bound
+// reductions over rows.  These kernels compute exactly the quantities of ATen's batch_norm_stats /
+// batch_norm_backward_reduce (the elementwise halves stay ATen's batch_norm_elemt / batch_norm_backward_elemt, which
+// already run near the HBM rate), at about four times the speed of ATen's channels-last reduction kernels.
+//
+// Layout of a reduction: a thread owns VEC consecutive channels (one 16-byte load per row); the block is LX column
+// threads x LY row lanes and walks a contiguous row range with LY rows per pass, several independent loads in flight
+// per thread; row lanes are combined through shared memory and every block writes ONE partial per channel
+// (no atomics: the result is deterministic).  A second, tiny kernel combines the partials.
+//
+// Numerics of the statistics: a block accumulates sums of d = x - pivot_c (pivot = the block's first row), so that
+// sum d^2 - (sum d)^2 / n does not cancel when |mean| >> std; block partials (n, mean, M2) are merged with Chan's
+// parallel-variance update in the finalize kernel.
+#include "knn_tc.cuh"
+
+namespace gkg {
+namespace {
+
+constexpr int kBnMaxThreads = 512;
+constexpr int kBnMaxBlocks = 148 * 2;      // row ranges (partials per channel)
+constexpr int kBnUnroll = 4;               // independent row loads in flight per thread
+
+template <typename T> struct BnVec;
+template <> struct BnVec<__nv_bfloat16> { static constexpr int N = 8; };
+template <> struct BnVec<float> { static constexpr int N = 4; };
+
+template <typename T, int VEC>
+struct alignas(sizeof(T) * VEC) BnPack {
+  T v[VEC];
+};
+
+// partial layout: [block][2][C] floats
+template <typename T, bool BWD>
+__global__ void __launch_bounds__(kBnMaxThreads)
+bn_reduce_kernel(const T* __restrict__ x, const T* __restrict__ dy, const float* __restrict__ mean,
+                 float* __restrict__ partial, long long rows, int C, int LX, int LY, long long rows_per_block) {
+  constexpr int VEC = BnVec<T>::N;
+  using P = BnPack<T, VEC>;
+  extern __shared__ float bn_s[];            // [LY][LX][2 * VEC]
+  const int tx = threadIdx.x % LX, ty = threadIdx.x / LX;
+  const int cchunk = blockIdx.y * LX + tx;   // 16-byte column chunk of this thread
+  const int c0 = cchunk * VEC;
+  const bool col_ok = c0 < C;
+  const long long r0 = (long long)blockIdx.x * rows_per_block;
+  const long long r1 = r0 + rows_per_block < rows ? r0 + rows_per_block : rows;
+  float a[VEC], b[VEC], piv[VEC];
+#pragma unroll
+  for (int e = 0; e < VEC; ++e) { a[e] = 0.f; b[e] = 0.f; piv[e] = 0.f; }
+  if (col_ok && r0 < r1) {
+    if (BWD) {
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) piv[e] = mean[c0 + e];
+    } else {
+      const P p = *reinterpret_cast<const P*>(x + r0 * C + c0);
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) piv[e] = to_f32<T>(p.v[e]);
+    }
+    long long r = r0 + ty;
+    for (; r + (long long)(kBnUnroll - 1) * LY < r1; r += (long long)kBnUnroll * LY) {
+      P xv[kBnUnroll], gv[kBnUnroll];
+#pragma unroll
+      for (int u = 0; u < kBnUnroll; ++u) {
+        xv[u] = *reinterpret_cast<const P*>(x + (r + (long long)u * LY) * C + c0);
+        if (BWD) gv[u] = *reinterpret_cast<const P*>(dy + (r + (long long)u * LY) * C + c0);
+      }
+#pragma unroll
+      for (int u = 0; u < kBnUnroll; ++u) {
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) {
+          const float d = to_f32<T>(xv[u].v[e]) - piv[e];
+          if (BWD) {
+            const float g = to_f32<T>(gv[u].v[e]);
+            a[e] += g;
+            b[e] = fmaf(g, d, b[e]);
+          } else {
+            a[e] += d;
+            b[e] = fmaf(d, d, b[e]);
+          }
+        }
+      }
+    }
+    for (; r < r1; r += LY) {
+      const P xv = *reinterpret_cast<const P*>(x + r * C + c0);
+      P gv;
+      if (BWD) gv = *reinterpret_cast<const P*>(dy + r * C + c0);
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) {
+        const float d = to_f32<T>(xv.v[e]) - piv[e];
+        if (BWD) {
+          const float g = to_f32<T>(gv.v[e]);
+          a[e] += g;
+          b[e] = fmaf(g, d, b[e]);
+        } else {
+          a[e] += d;
+          b[e] = fmaf(d, d, b[e]);
+        }
+      }
+    }
+  }
+  float* mine = bn_s + ((size_t)ty * LX + tx) * (2 * VEC);
+#pragma unroll
+  for (int e = 0; e < VEC; ++e) { mine[e] = a[e]; mine[VEC + e] = b[e]; }
+  __syncthreads();
+  if (ty == 0 && col_ok) {
+    for (int l = 1; l < LY; ++l) {
+      const float* o = bn_s + ((size_t)l * LX + tx) * (2 * VEC);
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) { a[e] += o[e]; b[e] += o[VEC + e]; }
+    }
+    float* out = partial + (size_t)blockIdx.x * 2 * C;
+    const float n = (float)(r1 > r0 ? r1 - r0 : 0);
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) {
+      if (BWD) {
+        out[c0 + e] = a[e];                  // sum dy
+        out[C + c0 + e] = b[e];              // sum dy * (x - mean)
+      } else {
+        // block mean and M2 = sum (x - block mean)^2 from the shifted sums
+        const float md = n > 0.f ? a[e] / n : 0.f;
+        out[c0 + e] = piv[e] + md;
+        out[C + c0 + e] = fmaxf(b[e] - a[e] * md, 0.f);
+      }
+    }
+  }
+}
+
+// Combine the block partials.  A block takes 32 channels x kFinLanes partial lanes: lane py merges partials py,
+// py + kFinLanes, ... of its channel (reads coalesced over the 32 channels; a one-thread-per-channel loop over 592
+// partials was a 100 us dependent chain of L2 loads), the lanes are merged through shared memory.
+constexpr int kFinLanes = 16;
+
+__device__ __forceinline__ void chan_merge(float& n, float& mean, float& m2, float nb, float mb, float qb) {
+  if (nb <= 0.f) return;
+  const float tot = n + nb;
+  const float delta = mb - mean;
+  mean += delta * (nb / tot);
+  m2 += qb + delta * delta * (n * nb / tot);
+  n = tot;
+}
+
+// Chan's parallel-variance merge -> mean, invstd; running statistics like nn.BatchNorm2d (momentum update, unbiased
+// variance).
+__global__ void __launch_bounds__(32 * kFinLanes)
+bn_stats_finalize_kernel(const float* __restrict__ partial, int nblocks, long long rows, long long rows_per_block,
+                         int C, float eps, float momentum, float* __restrict__ mean_out,
+                         float* __restrict__ invstd_out, float* __restrict__ running_mean,
+                         float* __restrict__ running_var) {
+  __shared__ float sn[kFinLanes][32], sm[kFinLanes][32], sq[kFinLanes][32];
+  const int cx = threadIdx.x & 31, py = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cx;
+  float n = 0.f, mean = 0.f, m2 = 0.f;
+  if (c < C) {
+    for (int bI = py; bI < nblocks; bI += kFinLanes) {
+      const long long r0 = (long long)bI * rows_per_block;
+      const long long r1 = r0 + rows_per_block < rows ? r0 + rows_per_block : rows;
+      chan_merge(n, mean, m2, (float)(r1 > r0 ? r1 - r0 : 0), partial[(size_t)bI * 2 * C + c],
+                 partial[(size_t)bI * 2 * C + C + c]);
+    }
+  }
+  sn[py][cx] = n; sm[py][cx] = mean; sq[py][cx] = m2;
+  __syncthreads();
+  if (py != 0 || c >= C) return;
+  for (int l = 1; l < kFinLanes; ++l) chan_merge(n, mean, m2, sn[l][cx], sm[l][cx], sq[l][cx]);
+  const float var = n > 0.f ? m2 / n : 0.f;
+  mean_out[c] = mean;
+  invstd_out[c] = rsqrtf(var + eps);
+  if (running_mean != nullptr) {
+    const float unbiased = n > 1.f ? m2 / (n - 1.f) : var;
+    running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mean;
+    running_var[c] = (1.f - momentum) * running_var[c] + momentum * unbiased;
+  }
+}
+
+__global__ void __launch_bounds__(32 * kFinLanes)
+bn_bwd_finalize_kernel(const float* __restrict__ partial, int nblocks, int C, const float* __restrict__ invstd,
+                       float* __restrict__ sum_dy, float* __restrict__ sum_dy_xmu, float* __restrict__ grad_weight,
+                       float* __restrict__ grad_bias) {
+  __shared__ float ss[kFinLanes][32], st[kFinLanes][32];
+  const int cx = threadIdx.x & 31, py = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cx;
+  float s = 0.f, t = 0.f;
+  if (c < C) {
+    for (int bI = py; bI < nblocks; bI += kFinLanes) {
+      s += partial[(size_t)bI * 2 * C + c];
+      t += partial[(size_t)bI * 2 * C + C + c];
+    }
+  }
+  ss[py][cx] = s; st[py][cx] = t;
+  __syncthreads();
+  if (py != 0 || c >= C) return;
+  for (int l = 1; l < kFinLanes; ++l) { s += ss[l][cx]; t += st[l][cx]; }
+  sum_dy[c] = s;
+  sum_dy_xmu[c] = t;
+  if (grad_weight != nullptr) grad_weight[c] = t * invstd[c];
+  if (grad_bias != nullptr) grad_bias[c] = s;
+}
+
+struct BnPlan {
+  int LX, LY, slabs, blocks;
+  long long rows_per_block;
+  size_t smem;
+};
+
+BnPlan bn_plan(long long rows, int C, int vec) {
+  BnPlan p;
+  const int chunks = C / vec;
+  p.slabs = (chunks + 255) / 256;            // column slabs of <= 256 chunks, evenly filled
+  p.LX = (chunks + p.slabs - 1) / p.slabs;
+  p.LY = kBnMaxThreads / p.LX;
+  if (p.LY > 64) p.LY = 64;
+  // enough row ranges to fill the GPU, not so many that a range is shorter than a few passes
+  long long want = (rows + (long long)p.LY * kBnUnroll * 2 - 1) / ((long long)p.LY * kBnUnroll * 2);
+  if (want < 1) want = 1;
+  long long cap = kBnMaxBlocks / p.slabs;
+  if (cap < 1) cap = 1;
+  p.blocks = (int)(want < cap ? want : cap);
+  p.rows_per_block = (rows + p.blocks - 1) / p.blocks;
+  p.blocks = (int)((rows + p.rows_per_block - 1) / p.rows_per_block);
+  p.smem = sizeof(float) * (size_t)p.LX * p.LY * 2 * vec;
+  return p;
+}
+
+template <typename T, bool BWD>
+int launch_bn_reduce(const void* x, const void* dy, const float* mean, float* partial, long long rows, int C,
+                     const BnPlan& p, cudaStream_t stream) {
+  static std::atomic<uint64_t> configured{0};
+  configure_once_per_device(configured, [] {
+    cudaFuncSetAttribute(bn_reduce_kernel<T, BWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+  });
+  dim3 grid(p.blocks, p.slabs);
+  bn_reduce_kernel<T, BWD><<<grid, p.LX * p.LY, p.smem, stream>>>(static_cast<const T*>(x), static_cast<const T*>(dy),
+                                                                 mean, partial, rows, C, p.LX, p.LY, p.rows_per_block);
+  GKG_CHECK_LAUNCH(BWD ? "bn_reduce_kernel<bwd>" : "bn_reduce_kernel<stats>");
+  return GKG_OK;
+}
+
+int check_bn_args(const void* x, long long rows, int C, int dtype, int* vec) {
+  GKG_CHECK_ARG(dtype == GKG_F32 || dtype == GKG_BF16, "batch_norm: dtype %d", dtype);
+  *vec = dtype == GKG_F32 ? 4 : 8;
+  GKG_CHECK_ARG(rows >= 1 && C >= *vec && C % *vec == 0, "batch_norm: rows=%lld C=%d (C must be a multiple of %d)", rows, C,
+                *vec);
+  GKG_CHECK_ARG(((uintptr_t)x % 16) == 0, "batch_norm: activation pointer not 16-byte aligned");
+  return GKG_OK;
+}
+
+}  // namespace
+}  // namespace gkg
+
+using namespace gkg;
+
+extern "C" size_t gkg_bn_workspace_bytes(long long rows, int C) {
+  (void)rows;
+  return sizeof(float) * (size_t)kBnMaxBlocks * 2 * (size_t)(C > 0 ? C : 0);
+}
+
+extern "C" int gkg_bn_stats(const void* x, long long rows, int C, int dtype, float eps, float momentum,
+                            float* mean, float* invstd, float* running_mean, float* running_var, void* ws,
+                            size_t ws_bytes, gkg_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  int vec = 0;
+  int rc = check_bn_args(x, rows, C, dtype, &vec);
+  if (rc != GKG_OK) return rc;
+  GKG_CHECK_ARG(mean != nullptr && invstd != nullptr && ws != nullptr, "gkg_bn_stats: null output / workspace");
+  GKG_CHECK_ARG((running_mean == nullptr) == (running_var == nullptr), "gkg_bn_stats: running_mean / running_var");
+  GKG_CHECK_ARG(ws_bytes >= gkg_bn_workspace_bytes(rows, C), "gkg_bn_stats: workspace too small");
+  const BnPlan p = bn_plan(rows, C, vec);
+  float* partial = static_cast<float*>(ws);
+  rc = dtype == GKG_F32 ? launch_bn_reduce<float, false>(x, nullptr, nullptr, partial, rows, C, p, stream)
+                        : launch_bn_reduce<__nv_bfloat16, false>(x, nullptr, nullptr, partial, rows, C, p, stream);
+  if (rc != GKG_OK) return rc;
+  bn_stats_finalize_kernel<<<(C + 31) / 32, 32 * kFinLanes, 0, stream>>>(partial, p.blocks, rows, p.rows_per_block, C, eps,
+                                                                momentum, mean, invstd, running_mean, running_var);
+  GKG_CHECK_LAUNCH("bn_stats_finalize_kernel");
+  return GKG_OK;
+}
+
+extern "C" int gkg_bn_backward_reduce(const void* grad_out, const void* x, const float* mean, const float* invstd,
+                                      long long rows, int C, int dtype, float* sum_dy, float* sum_dy_xmu,
+                                      float* grad_weight, float* grad_bias, void* ws, size_t ws_bytes,
+                                      gkg_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  int vec = 0;
+  int rc = check_bn_args(x, rows, C, dtype, &vec);
+  if (rc != GKG_OK) return rc;
+  GKG_CHECK_ARG(((uintptr_t)grad_out % 16) == 0, "gkg_bn_backward_reduce: gradient pointer not 16-byte aligned");
+  GKG_CHECK_ARG(mean != nullptr && invstd != nullptr && sum_dy != nullptr && sum_dy_xmu != nullptr && ws != nullptr,
+                "gkg_bn_backward_reduce: null pointer");
+  GKG_CHECK_ARG(ws_bytes >= gkg_bn_workspace_bytes(rows, C), "gkg_bn_backward_reduce: workspace too small");
+  const BnPlan p = bn_plan(rows, C, vec);
+  float* partial = static_cast<float*>(ws);
+  rc = dtype == GKG_F32 ? launch_bn_reduce<float, true>(x, grad_out, mean, partial, rows, C, p, stream)
+                        : launch_bn_reduce<__nv_bfloat16, true>(x, grad_out, mean, partial, rows, C, p, stream);
+  if (rc != GKG_OK) return rc;
+  bn_bwd_finalize_kernel<<<(C + 31) / 32, 32 * kFinLanes, 0, stream>>>(partial, p.blocks, C, invstd, sum_dy, sum_dy_xmu,
+                                                              grad_weight, grad_bias);
+  GKG_CHECK_LAUNCH("bn_bwd_finalize_kernel");
+  return GKG_OK;
+}

@@ -18,13 +18,31 @@ def set_norm_type(kind: str):
     norm_cfg["type"] = kind
 
 
+class BatchNorm2d(nn.BatchNorm2d):
+    """nn.BatchNorm2d (same parameters, buffers and state-dict keys) whose training forward on channels-last CUDA
+    activations takes its statistics and backward reductions from the native kernels (ops.batch_norm_train:
+    SURVEY 8(f) rank 1); everything else -- eval mode, CPU, NCHW-contiguous input, odd widths -- is the stock module."""
+
+    native = True      # class-wide switch (tests compare against the stock path)
+
+    def forward(self, x):
+        if (self.native and self.training and self.affine and self.track_running_stats and self.momentum is not None
+                and isinstance(x, torch.Tensor) and x.is_cuda):
+            from . import ops
+            if ops.batch_norm_native_ok(x):
+                self.num_batches_tracked.add_(1)
+                return ops.batch_norm_train(x, self.weight, self.bias, self.running_mean, self.running_var,
+                                            self.momentum, self.eps)
+        return super().forward(x)
+
+
 def build_norm_layer(cfg, num_features, postfix=""):
     """Stand-in for mmcv.cnn.build_norm_layer with the two types the reference uses."""
     kind = cfg.get("type", "SyncBN")
     if kind == "SyncBN":
         layer = nn.SyncBatchNorm(num_features)
     elif kind == "BN":
-        layer = nn.BatchNorm2d(num_features)
+        layer = BatchNorm2d(num_features)
     else:
         raise NotImplementedError(f"norm type [{kind}] is not supported")
     for p in layer.parameters():

@@ -545,3 +545,88 @@ def sum_neighbors(y, idx, *, groups=1):
     """``out[b, n, c] = sum_j y[b, idx[b*G + c//D, n, j], c]`` (GINConv2d, torch_vertex.py:143-149) without the
     gathered (B, N, k, C) tensor.  Differentiable w.r.t. y."""
     return _NeighborGather.apply(y, _check_gather(y, idx, groups), groups, True)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# training-mode batch norm: native statistics / backward reductions (csrc/batch_norm.cu), ATen elementwise halves
+# ---------------------------------------------------------------------------------------------------------
+_COUNT_CACHE = {}
+
+
+def _rows_of(x):
+    """(rows, C) contiguous view of a channels-last (B, C, H, W) or token-major (..., C) activation, or None."""
+    if x.dim() == 4:
+        t = x.permute(0, 2, 3, 1)
+        return t.reshape(-1, x.shape[1]) if t.is_contiguous() else None
+    return None
+
+
+def batch_norm_native_ok(x):
+    if not (isinstance(x, torch.Tensor) and x.is_cuda and x.dim() == 4 and x.numel() > 0):
+        return False
+    if x.dtype not in (torch.bfloat16, torch.float32):
+        return False
+    if x.shape[1] % (8 if x.dtype == torch.bfloat16 else 4) != 0 or x.shape[0] * x.shape[2] * x.shape[3] < 2:
+        return False
+    return x.permute(0, 2, 3, 1).is_contiguous() and x.data_ptr() % 16 == 0
+
+
+class _BatchNormTrain(torch.autograd.Function):
+    """y = batch_norm(x) with batch statistics (torch_nn.py:32-42 -> nn.BatchNorm2d training forward): statistics
+    and backward reductions by gkg_bn_stats / gkg_bn_backward_reduce, elementwise passes by ATen's
+    batch_norm_elemt / batch_norm_backward_elemt (the decomposition SyncBatchNorm uses)."""
+
+    @staticmethod
+    @_guard
+    def forward(ctx, x, weight, bias, running_mean, running_var, momentum, eps):
+        lib = _lib.load()
+        x2 = _rows_of(x)
+        rows, C = x2.shape
+        mean = torch.empty(C, dtype=torch.float32, device=x.device)
+        invstd = torch.empty(C, dtype=torch.float32, device=x.device)
+        ws = _workspace(x.device, lib.gkg_bn_workspace_bytes(rows, C))
+        rc = lib.gkg_bn_stats(x2.data_ptr(), rows, C, _DT[x.dtype], float(eps), float(momentum), mean.data_ptr(),
+                              invstd.data_ptr(), None if running_mean is None else running_mean.data_ptr(),
+                              None if running_var is None else running_var.data_ptr(), ws.data_ptr(), ws.numel(),
+                              _stream(x))
+        _lib.check(rc, "gkg_bn_stats")
+        y = torch.batch_norm_elemt(x, weight, bias, mean, invstd, eps)
+        ctx.save_for_backward(x, weight, mean, invstd)
+        return y
+
+    @staticmethod
+    @_guard
+    def backward(ctx, dy):
+        lib = _lib.load()
+        x, weight, mean, invstd = ctx.saved_tensors
+        if not dy.permute(0, 2, 3, 1).is_contiguous():
+            dy = dy.contiguous(memory_format=torch.channels_last)
+        dy = dy.to(x.dtype)
+        x2, g2 = _rows_of(x), _rows_of(dy)
+        rows, C = x2.shape
+        out = torch.empty(4, C, dtype=torch.float32, device=x.device)       # sum_dy, sum_dy_xmu, grad_weight, grad_bias
+        ws = _workspace(x.device, lib.gkg_bn_workspace_bytes(rows, C))
+        rc = lib.gkg_bn_backward_reduce(g2.data_ptr(), x2.data_ptr(), mean.data_ptr(), invstd.data_ptr(), rows, C,
+                                        _DT[x.dtype], out[0].data_ptr(), out[1].data_ptr(), out[2].data_ptr(),
+                                        out[3].data_ptr(), ws.data_ptr(), ws.numel(), _stream(x))
+        _lib.check(rc, "gkg_bn_backward_reduce")
+        key = (x.device.index, rows)
+        count = _COUNT_CACHE.get(key)
+        if count is None:
+            count = _COUNT_CACHE[key] = torch.full((1,), rows, dtype=torch.int32, device=x.device)
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.batch_norm_backward_elemt(dy, x, mean, invstd, weight, out[0], out[1], count)
+        gw = out[2].to(weight.dtype) if ctx.needs_input_grad[1] else None
+        gb = out[3].to(weight.dtype) if ctx.needs_input_grad[2] else None
+        return dx, gw, gb, None, None, None, None
+
+
+def batch_norm_train(x, weight, bias, running_mean, running_var, momentum, eps):
+    """Training-mode batch norm of a channels-last (B, C, H, W) CUDA activation; updates the running statistics in
+    place like nn.BatchNorm2d.  Raises on anything the kernels do not take (callers check batch_norm_native_ok)."""
+    _require_cuda(x)
+    if not batch_norm_native_ok(x):
+        raise ValueError("batch_norm_train: needs a channels-last (B, C, H, W) bf16 / fp32 CUDA tensor, C % 8 (4) == 0")
+    return _BatchNormTrain.apply(x, weight, bias, running_mean, running_var, momentum, eps)
+

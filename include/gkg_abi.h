@@ -264,6 +264,26 @@ int gkg_multilabel_loss(const float* score, const float* target, float* sums, fl
                         long long total, float gamma_pos, float gamma_neg, float clip, float eps, float smooth,
                         gkg_stream_t stream);
 
+/*
+ * Training-mode batch-norm reductions on the token-major (rows, C) layout (rows = B*H*W of a channels-last tensor).
+ * Replace the statistics / backward-reduce halves of `norm_layer('batch')` = (Sync)BatchNorm2d in training
+ * (torch_nn.py:32-42; used by BasicConv torch_nn.py:61-65, Grapher.fc1 / fc2 torch_vertex.py:290-306, FFN
+ * gkgnet.py:46-72); the elementwise halves are the caller's (ATen batch_norm_elemt / batch_norm_backward_elemt).
+ *   gkg_bn_stats:  mean[c], invstd[c] = rsqrt(biased var + eps) over the rows; when running_mean / running_var are
+ *     given they are updated like nn.BatchNorm2d (momentum, unbiased variance).  Deterministic (no atomics).
+ *   gkg_bn_backward_reduce:  sum_dy[c] = sum_r dy, sum_dy_xmu[c] = sum_r dy * (x - mean[c]); optionally
+ *     grad_weight = sum_dy_xmu * invstd and grad_bias = sum_dy.
+ *   x, grad_out  (rows, C) contiguous, dtype; C a multiple of 8 (bf16) / 4 (fp32); everything else fp32 (C).
+ *   ws: gkg_bn_workspace_bytes(rows, C) bytes of scratch (per-block partials).
+ */
+size_t gkg_bn_workspace_bytes(long long rows, int C);
+int gkg_bn_stats(const void* x, long long rows, int C, int dtype, float eps, float momentum,
+                 float* mean, float* invstd, float* running_mean, float* running_var,
+                 void* ws, size_t ws_bytes, gkg_stream_t stream);
+int gkg_bn_backward_reduce(const void* grad_out, const void* x, const float* mean, const float* invstd,
+                           long long rows, int C, int dtype, float* sum_dy, float* sum_dy_xmu,
+                           float* grad_weight, float* grad_bias, void* ws, size_t ws_bytes, gkg_stream_t stream);
+
 /* Number of kernels this library has launched since load (for bench accounting). */
 uint64_t gkg_launch_count(void);
 

@@ -1,0 +1,112 @@
+"""Training-mode batch norm: gkg_bn_stats / gkg_bn_backward_reduce behind ops.batch_norm_train
+and layers.BatchNorm2d, against ATen's F.batch_norm (what `norm_layer('batch')`, torch_nn.py:32-42, resolves to)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def _cl(t):
+    return t.contiguous(memory_format=torch.channels_last)
+
+
+@pytest.mark.parametrize("B,C,H,W,dtype", [
+    (4, 80, 36, 36, torch.bfloat16),
+    (2, 160, 20, 21, torch.bfloat16),        # ragged row count
+    (16, 2560, 18, 18, torch.bfloat16),      # 4C at stage 4: two column slabs
+    (3, 40, 7, 9, torch.bfloat16),           # stem width, few rows
+    (2, 400, 36, 36, torch.float32),
+    (5, 12, 11, 13, torch.float32),          # C % 4 == 0 only
+    (16, 160, 144, 144, torch.bfloat16),     # the stage-1 BasicConv norm of the training benchmark
+])
+def test_batch_norm_train_matches_aten(B, C, H, W, dtype):
+    from gkgnet_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(5)
+    x = _cl((torch.randn(B, C, H, W, device="cuda", generator=g) * 1.7 + 0.3).to(dtype))
+    dy = _cl(torch.randn(B, C, H, W, device="cuda", generator=g).to(dtype))
+    w = torch.rand(C, device="cuda", generator=g) + 0.5
+    b = torch.randn(C, device="cuda", generator=g)
+    res = []
+    for native in (True, False):
+        xi = x.clone().requires_grad_(True)
+        wi, bi = w.clone().requires_grad_(True), b.clone().requires_grad_(True)
+        rm, rv = torch.zeros(C, device="cuda"), torch.ones(C, device="cuda")
+        if native:
+            y = ops.batch_norm_train(xi, wi, bi, rm, rv, 0.1, 1e-5)
+        else:
+            y = F.batch_norm(xi, rm, rv, wi, bi, True, 0.1, 1e-5)
+        y.backward(dy)
+        res.append((y.detach().float(), xi.grad.float(), wi.grad, bi.grad, rm, rv))
+    (y0, dx0, dw0, db0, rm0, rv0), (y1, dx1, dw1, db1, rm1, rv1) = res
+    tol = 2e-2 if dtype == torch.bfloat16 else 2e-5
+    assert y0.shape == y1.shape and y0.dtype == y1.dtype
+    assert torch.allclose(y0, y1, atol=tol, rtol=tol)
+    assert torch.allclose(dx0, dx1, atol=tol, rtol=tol)
+    rows = B * H * W
+    # parameter gradients are sums over the rows: compare relative to their scale
+    assert (dw0 - dw1).abs().max() <= 1e-3 * max(1.0, dw1.abs().max().item()) * (10 if dtype == torch.bfloat16 else 1)
+    assert (db0 - db1).abs().max() <= 1e-3 * max(1.0, db1.abs().max().item())
+    assert torch.allclose(rm0, rm1, atol=1e-5, rtol=1e-5)
+    assert torch.allclose(rv0, rv1, atol=1e-5, rtol=1e-4)
+    assert rows > 1
+
+
+def test_batch_norm_stats_large_mean_fp64():
+    """|mean| >> std: the shifted block sums + Chan merge must not lose the variance (naive sum / sum-of-squares in
+    fp32 would: 1e4^2 * 2^-24 ~ 6 > var)."""
+    from gkgnet_b200 import _lib, ops
+    g = torch.Generator(device="cuda").manual_seed(9)
+    C = 64
+    x = _cl(torch.randn(8, C, 60, 60, device="cuda", generator=g) * 0.5 + 1.0e4)
+    rows = x.shape[0] * x.shape[2] * x.shape[3]
+    lib = _lib.load()
+    mean = torch.empty(C, device="cuda")
+    invstd = torch.empty(C, device="cuda")
+    ws = torch.empty(lib.gkg_bn_workspace_bytes(rows, C), dtype=torch.uint8, device="cuda")
+    x2 = x.permute(0, 2, 3, 1).reshape(rows, C)
+    rc = lib.gkg_bn_stats(x2.data_ptr(), rows, C, 0, 1e-5, 0.1, mean.data_ptr(), invstd.data_ptr(), None, None,
+                          ws.data_ptr(), ws.numel(), torch.cuda.current_stream().cuda_stream)
+    assert rc == 0
+    xd = x2.double()
+    want_mean = xd.mean(0)
+    want_invstd = (xd.var(0, unbiased=False) + 1e-5).rsqrt()
+    assert torch.allclose(mean.double(), want_mean, rtol=5e-7, atol=0)      # a few fp32 ulps at 1e4
+    assert torch.allclose(invstd.double(), want_invstd, rtol=2e-3)
+
+
+def test_batch_norm_is_deterministic():
+    from gkgnet_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(2)
+    x = _cl(torch.randn(8, 320, 72, 72, device="cuda", generator=g).to(torch.bfloat16))
+    dy = _cl(torch.randn(8, 320, 72, 72, device="cuda", generator=g).to(torch.bfloat16))
+    outs = []
+    for _ in range(2):
+        xi = x.clone().requires_grad_(True)
+        w = torch.ones(320, device="cuda", requires_grad=True)
+        b = torch.zeros(320, device="cuda", requires_grad=True)
+        y = ops.batch_norm_train(xi, w, b, None, None, 0.1, 1e-5)
+        y.backward(dy)
+        outs.append((y.detach(), xi.grad, w.grad, b.grad))
+    for a, c in zip(*outs):
+        assert torch.equal(a, c)
+
+
+def test_batch_norm_module_keeps_state_dict_and_falls_back():
+    from gkgnet_b200.layers import BatchNorm2d
+    torch.manual_seed(0)
+    ours, ref = BatchNorm2d(80).cuda(), torch.nn.BatchNorm2d(80).cuda()
+    ref.load_state_dict(ours.state_dict())
+    assert list(ours.state_dict().keys()) == list(ref.state_dict().keys())
+    x = torch.randn(4, 80, 24, 24, device="cuda")
+    for inp in (_cl(x), x.contiguous()):            # channels-last -> native kernels; NCHW -> stock module
+        ya, yb = ours(inp), ref(inp)
+        assert torch.allclose(ya, yb, atol=2e-5, rtol=2e-5)
+    assert int(ours.num_batches_tracked) == int(ref.num_batches_tracked) == 2
+    assert torch.allclose(ours.running_mean, ref.running_mean, atol=1e-6)
+    assert torch.allclose(ours.running_var, ref.running_var, rtol=1e-5)
+    ours.eval(), ref.eval()
+    assert torch.allclose(ours(_cl(x)), ref(_cl(x)), atol=1e-6)
+    with pytest.raises(ValueError):
+        from gkgnet_b200 import ops
+        ops.batch_norm_train(x.contiguous(), ours.weight, ours.bias, None, None, 0.1, 1e-5)   # not channels-last
