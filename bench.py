@@ -665,15 +665,21 @@ def run_model(args):
     model = Model().to(dev)
     model.train(train)
     params = [p for p in model.parameters() if p.requires_grad]
-    opt = torch.optim.AdamW(params, lr=1e-4, weight_decay=0.05) if train else None
-    ddp = P.data_parallel(model, dev) if train else model
+    graphed = train and not args.no_graph and not args.syncbn      # SyncBN keeps the eager DDP path
+    opt = torch.optim.AdamW(params, lr=1e-4, weight_decay=0.05, fused=True, capturable=graphed) if train else None
+    ddp = P.data_parallel(model, dev) if train and not graphed else model
     g = torch.Generator().manual_seed(100 + rank)
     img_h = torch.randn(B, 3, 576, 576, generator=g).pin_memory()
     tgt_h = (torch.rand(B, 80, generator=g) < 0.04).float().pin_memory()
     img, tgt = img_h.to(dev), tgt_h.to(dev)
     stream = torch.cuda.current_stream(dev)
+    # the whole step (fwd, loss, bwd, gradient all-reduce over NCCL, clip, AdamW) as ONE CUDA graph: issued from Python
+    # the ~3000 launches of a 16-image step take longer than the kernels run (tools/host_bound.py)
+    gstep = P.GraphedTrainStep(model, opt, params, img, tgt, clip_norm=5.0, warmup=3) if graphed else None
 
     def step(from_host=False):
+        if gstep is not None:
+            return gstep(img_h, tgt_h) if from_host else gstep()
         x, t = (img_h.to(dev, non_blocking=True), tgt_h.to(dev, non_blocking=True)) if from_host else (img, tgt)
         with torch.autocast("cuda", dtype=torch.bfloat16):
             if train:
@@ -706,6 +712,8 @@ def run_model(args):
     l0 = _lib.launch_count()
     ms = timed(args.steps, False)
     launches = _lib.launch_count() - l0
+    if gstep is not None:
+        launches = args.steps * gstep.launches_per_replay       # replayed from the graph: counted at capture
     clocks = sampler.stop()
     e2e_ms = timed(max(3, min(args.steps, 5)), True)
     coll = None
@@ -742,7 +750,9 @@ def run_model(args):
         "metric": METRIC, "value": world * B / (ms * 1e-3), "unit": "images/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": train_config(world, args.syncbn, B) if train else {
+        "config": dict(train_config(world, args.syncbn, B),
+                       launch=("one CUDA graph per step (fwd + loss + bwd + NCCL gradient all-reduce + clip + AdamW)"
+                               if graphed else "eager launches through DistributedDataParallel")) if train else {
             "workload": "BASELINE configs[2]: GKGNet-576 inference, bf16 autocast, replicas only",
             "images_per_gpu": B, "global_batch": B * world, "parallelism": f"dp{world} (replicas)",
             "norm": "SyncBN" if args.syncbn else "per-GPU BN",
@@ -820,7 +830,7 @@ def eager_train_baseline(model, img, tgt, dev):
     out = {}
     try:
         sd, params = _oracle_state(dev)
-        opt = torch.optim.AdamW(params, lr=1e-4, weight_decay=0.05)
+        opt = torch.optim.AdamW(params, lr=1e-4, weight_decay=0.05, fused=True)     # same optimizer kernel as our arm
         for name, ctx in (("fp32", None), ("bf16_autocast", torch.bfloat16)):
             def one():
                 if ctx is None:
@@ -890,6 +900,9 @@ def main():
                     help="full = training step (headline) + stage-1 layer microbench in one line; or one part alone")
     ap.add_argument("--batch", type=int, default=0, help="images per GPU for --workload train / infer")
     ap.add_argument("--syncbn", action="store_true", help="keep the reference's SyncBN (default: per-GPU BN)")
+    ap.add_argument("--no-graph", action="store_true",
+                    help="training: issue the step from Python through DistributedDataParallel instead of replaying "
+                         "the captured CUDA graph")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

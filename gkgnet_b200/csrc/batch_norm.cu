@@ -36,11 +36,13 @@ struct alignas(sizeof(T) * VEC) BnPack {
 };
 
 // partial layout: [block][2][C] floats
-template <typename T, bool BWD>
+// MODE 0: statistics (shifted sum, sum of squares); 1: backward reduce (sum dy, sum dy * (x - mean)); 2: column sum of x
+template <typename T, int MODE>
 __global__ void __launch_bounds__(kBnMaxThreads)
 bn_reduce_kernel(const T* __restrict__ x, const T* __restrict__ dy, const float* __restrict__ mean,
                  float* __restrict__ partial, long long rows, int C, int LX, int LY, long long rows_per_block) {
   constexpr int VEC = BnVec<T>::N;
+  constexpr bool BWD = MODE == 1, SUM = MODE == 2;
   using P = BnPack<T, VEC>;
   extern __shared__ float bn_s[];            // [LY][LX][2 * VEC]
   const int tx = threadIdx.x % LX, ty = threadIdx.x / LX;
@@ -56,7 +58,7 @@ bn_reduce_kernel(const T* __restrict__ x, const T* __restrict__ dy, const float*
     if (BWD) {
 #pragma unroll
       for (int e = 0; e < VEC; ++e) piv[e] = mean[c0 + e];
-    } else {
+    } else if (!SUM) {
       const P p = *reinterpret_cast<const P*>(x + r0 * C + c0);
 #pragma unroll
       for (int e = 0; e < VEC; ++e) piv[e] = to_f32<T>(p.v[e]);
@@ -80,7 +82,7 @@ bn_reduce_kernel(const T* __restrict__ x, const T* __restrict__ dy, const float*
             b[e] = fmaf(g, d, b[e]);
           } else {
             a[e] += d;
-            b[e] = fmaf(d, d, b[e]);
+            if (!SUM) b[e] = fmaf(d, d, b[e]);
           }
         }
       }
@@ -98,7 +100,7 @@ bn_reduce_kernel(const T* __restrict__ x, const T* __restrict__ dy, const float*
           b[e] = fmaf(g, d, b[e]);
         } else {
           a[e] += d;
-          b[e] = fmaf(d, d, b[e]);
+          if (!SUM) b[e] = fmaf(d, d, b[e]);
         }
       }
     }
@@ -117,8 +119,8 @@ bn_reduce_kernel(const T* __restrict__ x, const T* __restrict__ dy, const float*
     const float n = (float)(r1 > r0 ? r1 - r0 : 0);
 #pragma unroll
     for (int e = 0; e < VEC; ++e) {
-      if (BWD) {
-        out[c0 + e] = a[e];                  // sum dy
+      if (BWD || SUM) {
+        out[c0 + e] = a[e];                  // sum dy | column sum
         out[C + c0 + e] = b[e];              // sum dy * (x - mean)
       } else {
         // block mean and M2 = sum (x - block mean)^2 from the shifted sums
@@ -196,7 +198,7 @@ bn_bwd_finalize_kernel(const float* __restrict__ partial, int nblocks, int C, co
   if (py != 0 || c >= C) return;
   for (int l = 1; l < kFinLanes; ++l) { s += ss[l][cx]; t += st[l][cx]; }
   sum_dy[c] = s;
-  sum_dy_xmu[c] = t;
+  if (sum_dy_xmu != nullptr) sum_dy_xmu[c] = t;
   if (grad_weight != nullptr) grad_weight[c] = t * invstd[c];
   if (grad_bias != nullptr) grad_bias[c] = s;
 }
@@ -226,17 +228,17 @@ BnPlan bn_plan(long long rows, int C, int vec) {
   return p;
 }
 
-template <typename T, bool BWD>
+template <typename T, int MODE>
 int launch_bn_reduce(const void* x, const void* dy, const float* mean, float* partial, long long rows, int C,
                      const BnPlan& p, cudaStream_t stream) {
   static std::atomic<uint64_t> configured{0};
   configure_once_per_device(configured, [] {
-    cudaFuncSetAttribute(bn_reduce_kernel<T, BWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    cudaFuncSetAttribute(bn_reduce_kernel<T, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
   });
   dim3 grid(p.blocks, p.slabs);
-  bn_reduce_kernel<T, BWD><<<grid, p.LX * p.LY, p.smem, stream>>>(static_cast<const T*>(x), static_cast<const T*>(dy),
+  bn_reduce_kernel<T, MODE><<<grid, p.LX * p.LY, p.smem, stream>>>(static_cast<const T*>(x), static_cast<const T*>(dy),
                                                                  mean, partial, rows, C, p.LX, p.LY, p.rows_per_block);
-  GKG_CHECK_LAUNCH(BWD ? "bn_reduce_kernel<bwd>" : "bn_reduce_kernel<stats>");
+  GKG_CHECK_LAUNCH(MODE == 1 ? "bn_reduce_kernel<bwd>" : MODE == 2 ? "bn_reduce_kernel<colsum>" : "bn_reduce_kernel<stats>");
   return GKG_OK;
 }
 
@@ -271,8 +273,8 @@ extern "C" int gkg_bn_stats(const void* x, long long rows, int C, int dtype, flo
   GKG_CHECK_ARG(ws_bytes >= gkg_bn_workspace_bytes(rows, C), "gkg_bn_stats: workspace too small");
   const BnPlan p = bn_plan(rows, C, vec);
   float* partial = static_cast<float*>(ws);
-  rc = dtype == GKG_F32 ? launch_bn_reduce<float, false>(x, nullptr, nullptr, partial, rows, C, p, stream)
-                        : launch_bn_reduce<__nv_bfloat16, false>(x, nullptr, nullptr, partial, rows, C, p, stream);
+  rc = dtype == GKG_F32 ? launch_bn_reduce<float, 0>(x, nullptr, nullptr, partial, rows, C, p, stream)
+                        : launch_bn_reduce<__nv_bfloat16, 0>(x, nullptr, nullptr, partial, rows, C, p, stream);
   if (rc != GKG_OK) return rc;
   bn_stats_finalize_kernel<<<(C + 31) / 32, 32 * kFinLanes, 0, stream>>>(partial, p.blocks, rows, p.rows_per_block, C, eps,
                                                                 momentum, mean, invstd, running_mean, running_var);
@@ -294,11 +296,32 @@ extern "C" int gkg_bn_backward_reduce(const void* grad_out, const void* x, const
   GKG_CHECK_ARG(ws_bytes >= gkg_bn_workspace_bytes(rows, C), "gkg_bn_backward_reduce: workspace too small");
   const BnPlan p = bn_plan(rows, C, vec);
   float* partial = static_cast<float*>(ws);
-  rc = dtype == GKG_F32 ? launch_bn_reduce<float, true>(x, grad_out, mean, partial, rows, C, p, stream)
-                        : launch_bn_reduce<__nv_bfloat16, true>(x, grad_out, mean, partial, rows, C, p, stream);
+  rc = dtype == GKG_F32 ? launch_bn_reduce<float, 1>(x, grad_out, mean, partial, rows, C, p, stream)
+                        : launch_bn_reduce<__nv_bfloat16, 1>(x, grad_out, mean, partial, rows, C, p, stream);
   if (rc != GKG_OK) return rc;
   bn_bwd_finalize_kernel<<<(C + 31) / 32, 32 * kFinLanes, 0, stream>>>(partial, p.blocks, C, invstd, sum_dy, sum_dy_xmu,
                                                               grad_weight, grad_bias);
   GKG_CHECK_LAUNCH("bn_bwd_finalize_kernel");
+  return GKG_OK;
+}
+
+// Column sums of a (rows, C) activation: the bias gradient of a token-major 1x1 convolution / linear layer
+// (what autograd derives for Conv2d(.., 1).bias in Grapher.fc1 / fc2, FFN: torch_vertex.py:290-306, gkgnet.py:46-72).
+extern "C" int gkg_column_sum(const void* x, long long rows, int C, int dtype, float* out, void* ws, size_t ws_bytes,
+                              gkg_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  int vec = 0;
+  int rc = check_bn_args(x, rows, C, dtype, &vec);
+  if (rc != GKG_OK) return rc;
+  GKG_CHECK_ARG(out != nullptr && ws != nullptr, "gkg_column_sum: null output / workspace");
+  GKG_CHECK_ARG(ws_bytes >= gkg_bn_workspace_bytes(rows, C), "gkg_column_sum: workspace too small");
+  const BnPlan p = bn_plan(rows, C, vec);
+  float* partial = static_cast<float*>(ws);
+  rc = dtype == GKG_F32 ? launch_bn_reduce<float, 2>(x, nullptr, nullptr, partial, rows, C, p, stream)
+                        : launch_bn_reduce<__nv_bfloat16, 2>(x, nullptr, nullptr, partial, rows, C, p, stream);
+  if (rc != GKG_OK) return rc;
+  bn_bwd_finalize_kernel<<<(C + 31) / 32, 32 * kFinLanes, 0, stream>>>(partial, p.blocks, C, nullptr, out, nullptr,
+                                                                      nullptr, nullptr);
+  GKG_CHECK_LAUNCH("bn_bwd_finalize_kernel<colsum>");
   return GKG_OK;
 }

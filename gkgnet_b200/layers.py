@@ -89,8 +89,10 @@ class FoldedSequential(nn.Sequential):
                 if (isinstance(m, nn.Conv2d) and m.kernel_size == (1, 1) and m.stride == (1, 1) and m.padding == (0, 0)
                         and m.groups == 1 and x.dim() == 4 and x.is_contiguous(memory_format=torch.channels_last)
                         and x.is_cuda):
-                    x = torch.nn.functional.linear(x.permute(0, 2, 3, 1), m.weight.view(m.out_channels, -1),
-                                                   m.bias).permute(0, 3, 1, 2)
+                    if torch.is_autocast_enabled():
+                        x = x.to(torch.get_autocast_dtype("cuda"))
+                    from . import ops
+                    x = ops.conv1x1(x, m.weight, m.bias)
                 else:
                     x = m(x)
             return x

@@ -284,6 +284,14 @@ int gkg_bn_backward_reduce(const void* grad_out, const void* x, const float* mea
                            long long rows, int C, int dtype, float* sum_dy, float* sum_dy_xmu,
                            float* grad_weight, float* grad_bias, void* ws, size_t ws_bytes, gkg_stream_t stream);
 
+/*
+ * Column sums of a (rows, C) contiguous activation into fp32 out (C): the bias gradient autograd derives for a
+ * token-major 1x1 convolution (Grapher.fc1 / fc2 torch_vertex.py:290-306, FFN gkgnet.py:46-72).  Same row-range
+ * partials as the batch-norm reductions (deterministic); ws: gkg_bn_workspace_bytes(rows, C).
+ */
+int gkg_column_sum(const void* x, long long rows, int C, int dtype, float* out, void* ws, size_t ws_bytes,
+                   gkg_stream_t stream);
+
 /* Number of kernels this library has launched since load (for bench accounting). */
 uint64_t gkg_launch_count(void);
 

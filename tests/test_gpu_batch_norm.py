@@ -110,3 +110,39 @@ def test_batch_norm_module_keeps_state_dict_and_falls_back():
     with pytest.raises(ValueError):
         from gkgnet_b200 import ops
         ops.batch_norm_train(x.contiguous(), ours.weight, ours.bias, None, None, 0.1, 1e-5)   # not channels-last
+
+
+@pytest.mark.parametrize("rows,C,dtype", [(20736, 160, torch.bfloat16), (1001, 2560, torch.bfloat16), (777, 12, torch.float32)])
+def test_column_sum(rows, C, dtype):
+    from gkgnet_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(3)
+    x = torch.randn(rows, C, device="cuda", generator=g).to(dtype)
+    got = ops.column_sum(x)
+    want = x.double().sum(0)
+    assert got.dtype == torch.float32
+    assert torch.allclose(got.double(), want, rtol=1e-5, atol=1e-3)
+    assert torch.equal(got, ops.column_sum(x))          # deterministic
+
+
+def test_conv1x1_matches_conv2d_with_autograd():
+    """layers.FoldedSequential routes 1x1 convolutions on channels-last activations through ops.conv1x1."""
+    from gkgnet_b200 import ops
+    torch.manual_seed(1)
+    conv = torch.nn.Conv2d(80, 160, 1).cuda()
+    x = _cl(torch.randn(4, 80, 20, 20, device="cuda"))
+    dy = _cl(torch.randn(4, 160, 20, 20, device="cuda"))
+    xa = x.clone().requires_grad_(True)
+    ya = ops.conv1x1(xa, conv.weight, conv.bias)
+    ya.backward(dy)
+    ga = (xa.grad.clone(), conv.weight.grad.clone(), conv.bias.grad.clone())
+    conv.zero_grad()
+    xb = x.clone().requires_grad_(True)
+    yb = conv(xb)
+    yb.backward(dy)
+    assert torch.allclose(ya, yb, atol=1e-4, rtol=1e-4)
+    for a, b in zip(ga, (xb.grad, conv.weight.grad, conv.bias.grad)):
+        assert a.shape == b.shape and a.dtype == b.dtype
+        assert torch.allclose(a, b, atol=2e-3, rtol=1e-3)
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        yc = ops.conv1x1(x.to(torch.bfloat16), conv.weight, conv.bias)
+    assert yc.dtype == torch.bfloat16 and torch.allclose(yc.float(), yb, atol=5e-2, rtol=5e-2)

@@ -52,7 +52,20 @@ def _worker(rank, world, port, out_dir):
     loss = ddp(full_lab[lo:hi], full_gap[lo:hi], tgt[lo:hi])
     loss.backward()
     grads = {k: p.grad.clone() for k, p in head.named_parameters()}
-    torch.save({"grads": grads, "range": (lo, hi)}, os.path.join(out_dir, f"rank{rank}.pt"))
+
+    # the same exchange without DDP: gradients as views of one flat buffer, averaged with bucketed all-reduces
+    # (parallel.FlatGradients -- what the captured training step of bench.py uses)
+    torch.manual_seed(0)
+    head2 = G.LabelQueryHead(num_classes=6, in_channels=16)
+    fg = P.FlatGradients(list(head2.parameters()), bucket_bytes=256)        # several buckets, ragged last one
+    assert all(p.grad.data_ptr() >= fg.flat.data_ptr() for p in fg.params)
+    for _ in range(2):                                                      # zero() makes the step repeatable
+        fg.zero()
+        out = _Loss(head2)(full_lab[lo:hi], full_gap[lo:hi], tgt[lo:hi])
+        out.backward()
+        fg.all_reduce_mean()
+    flat = {k: p.grad.clone() for k, p in head2.named_parameters()}
+    torch.save({"grads": grads, "flat": flat, "range": (lo, hi)}, os.path.join(out_dir, f"rank{rank}.pt"))
     torch.distributed.destroy_process_group()
 
 
@@ -91,6 +104,9 @@ def test_world2_gloo_gradient_allreduce(tmp_path):
     total.backward()
     for k, p in head.named_parameters():
         assert torch.allclose(p.grad, r0["grads"][k], atol=1e-6, rtol=1e-5), k
+        # FlatGradients: the same mean over ranks, on both ranks
+        assert torch.allclose(p.grad, r0["flat"][k], atol=1e-6, rtol=1e-5), k
+        assert torch.equal(r0["flat"][k], r1["flat"][k]), k
 
 
 def test_pin_host_cores_partitions_the_affinity_mask():
