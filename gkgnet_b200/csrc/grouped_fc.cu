@@ -65,10 +65,27 @@ __device__ __forceinline__ float fast_erf(float x) {
   const float e = 1.f - p * t * __expf(-ax * ax);
   return copysignf(e, x);
 }
+// nn.GELU() (erf form) = v * Phi(v) with the same 7.1.26 polynomial arranged for the fewest instructions:
+//   Phi(-|v|) = 0.5 erfc(|v| / sqrt 2) = (0.5 (a1 t + .. + a5 t^5)) * 2^(-(|v| sqrt(log2(e) / 2))^2),  t = 1 / (1 + (p / sqrt 2) |v|)
+// 13 FMA-pipe operations + a compare + 2 MUFU per element (the 0.5 v (1 + erf(v / sqrt 2)) form took ~20: the epilogue of the
+// fused FC is issue bound).  |error of Phi| <= 7.5e-8.
+__device__ __forceinline__ float gelu_erf(float v) {
+  const float a = fabsf(v);
+  float t, e;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.231641888f, a, 1.f)));
+  float p = fmaf(0.5307027145f, t, -0.7265760135f);
+  p = fmaf(p, t, 0.7107068705f);
+  p = fmaf(p, t, -0.142248368f);
+  p = fmaf(p, t, 0.127414796f);
+  const float sq = a * 0.849321800f;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-sq * sq));
+  const float h = p * t * e;
+  return v * (v >= 0.f ? 1.f - h : h);
+}
 template <int ACT>
 __device__ __forceinline__ float activate(float v) {
   if (ACT == 1) return fmaxf(v, 0.f);
-  if (ACT == 2) return 0.5f * v * (1.f + fast_erf(v * 0.70710678118654752f));    // nn.GELU() (erf form)
+  if (ACT == 2) return gelu_erf(v);
   return v;
 }
 
@@ -193,6 +210,182 @@ __global__ void __launch_bounds__(THREADS, 2) grouped_fc_kernel(const Params prm
 
   if (warp == 0)
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
+}
+
+
+// ------------------------------------------------------------------------------------
+// narrow groups, software pipelined (round 2)
+// ------------------------------------------------------------------------------------
+// Same arithmetic and shared-memory formats as grouped_fc_kernel, ONE persistent CTA per SM with two A buffers and (when
+// eight accumulators fit: CG <= 64) two sets of TMEM accumulators.  Iteration i:
+//     wait for the cp.async copies of tile i+1  ->  barrier  ->  issue the MMAs of tile i+1  ->  wait for the MMAs of
+//     tile i  ->  start the copies of tile i+2 into the buffer tile i just left  ->  epilogue of tile i
+// so the global loads of a tile have a whole iteration to land and the MMA + commit round trip of the next tile runs
+// under the epilogue of this one.  With one accumulator set (CG = 80) the MMAs of tile i+1 are issued after the
+// epilogue of tile i instead (its loads still overlap).  The synchronous kernel above spent half its time waiting
+// for the copy-in and the MMA round trip (0.19 ms at the bench shape against 65 us of HBM time).
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+
+template <int CGT, int ACT>
+__global__ void __launch_bounds__(THREADS, 1) grouped_fc_pipe_kernel(const Params prm) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int CG = CGT > 0 ? CGT : prm.CG;
+  const int KP = (CG + 15) / 16 * 16, NP = KP, C2 = 4 * CG;
+  const bool two_acc = 8 * NP <= 512;
+  const uint32_t a_group_bytes = (uint32_t)BM * KP * 2;
+  const uint32_t b_group_bytes = (uint32_t)NP * KP * 2;
+  uint8_t* sA = smem;                                   // 2 x 4 x [BM/8][KP/8][8][8]
+  uint8_t* sB = sA + 8 * a_group_bytes;                 // 4 x [NP/8][KP/8][8][8]
+  float* s_shift = reinterpret_cast<float*>(sB + 4 * b_group_bytes);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(s_shift + C2);      // [2]: MMAs of the tile in accumulator set 0 / 1
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 2);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  for (uint32_t i = threadIdx.x; i < 4 * b_group_bytes / 16; i += THREADS)
+    reinterpret_cast<uint4*>(sB)[i] = __ldg(reinterpret_cast<const uint4*>(prm.w_op) + i);
+  for (int i = threadIdx.x; i < C2; i += THREADS) s_shift[i] = prm.shift[i];
+  for (uint32_t i = threadIdx.x; i < 8 * a_group_bytes / 16; i += THREADS)      // K padding of both buffers stays zero
+    reinterpret_cast<uint4*>(sA)[i] = make_uint4(0, 0, 0, 0);
+  if (threadIdx.x == 0) {
+    mbar_init(smem_u32(bar), 1);
+    mbar_init(smem_u32(bar + 1), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+
+  const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NP >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+  const uint32_t sbo = (uint32_t)(KP >> 3) * 128u;
+  const int chunks_per_row = C2 >> 3, cg_chunks = CG >> 3;
+  const long long tiles = (prm.rows + BM - 1) / BM;
+  const long long first = blockIdx.x, stride = gridDim.x;
+  const long long mine = first < tiles ? (tiles - first + stride - 1) / stride : 0;     // tiles of this CTA
+
+  // copy-in: thread t owns the 16-byte piece cc = t % chunks_per_row of the rows rl, rl + rpp, ... (rpp rows per pass):
+  // the piece's conv group and position inside the core-matrix layout are fixed per thread
+  const int rpp = THREADS / chunks_per_row;
+  const int ld_rl = threadIdx.x / chunks_per_row, ld_cc = threadIdx.x - ld_rl * chunks_per_row;
+  const bool ld_on = ld_rl < rpp;
+  const uint32_t ld_col = (uint32_t)(ld_cc / cg_chunks) * a_group_bytes + ((uint32_t)(ld_cc % cg_chunks) << 7);
+  auto load_tile = [&](long long j) {                   // j-th tile of this CTA -> A buffer j & 1 (asynchronous)
+    const long long r0 = (first + j * stride) * BM;
+    const uint32_t base = smem_u32(sA) + (uint32_t)(j & 1) * 4 * a_group_bytes + ld_col;
+    if (ld_on) {
+      const __nv_bfloat16* src = prm.in + (r0 + ld_rl) * C2 + ld_cc * 8;
+      const long long step = (long long)rpp * C2;
+      if (r0 + BM <= prm.rows) {                        // every tile but (possibly) the last: no row checks
+#pragma unroll 2
+        for (int r = ld_rl; r < BM; r += rpp, src += step)
+          cp_async16(base + ((uint32_t)((r >> 3) * (KP >> 3)) << 7) + ((r & 7) << 4), src, 16u);
+      } else {
+        for (int r = ld_rl; r < BM; r += rpp, src += step) {
+          const bool ok = r0 + r < prm.rows;
+          cp_async16(base + ((uint32_t)((r >> 3) * (KP >> 3)) << 7) + ((r & 7) << 4), ok ? src : prm.in, ok ? 16u : 0u);
+        }
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  auto issue_mma = [&](long long j) {                   // one thread; tile j: A buffer j & 1 -> accumulator set
+    const uint32_t acc_set = two_acc ? (uint32_t)(j & 1) : 0u;
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    for (int q = 0; q < 4; ++q) {
+      const uint32_t a_addr = smem_u32(sA) + (uint32_t)(j & 1) * 4 * a_group_bytes + q * a_group_bytes;
+      const uint32_t b_addr = smem_u32(sB + q * b_group_bytes);
+      for (int ks = 0; ks < (KP >> 4); ++ks) {
+        const uint64_t ad = make_desc(a_addr + ks * 256, 128, sbo), bd = make_desc(b_addr + ks * 256, 128, sbo);
+        const uint32_t acc = ks != 0;
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                     "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                     ::"r"(tmem_base + acc_set * 4 * NP + (uint32_t)(q * NP)), "l"(ad), "l"(bd), "r"(idesc), "r"(acc) : "memory");
+      }
+    }
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar + acc_set)) : "memory");
+  };
+  auto epilogue = [&](long long j) {
+    const long long r0 = (first + j * stride) * BM;
+    const uint32_t acc_set = two_acc ? (uint32_t)(j & 1) : 0u;
+    const int row = (warp & 3) * 32 + lane;
+    const bool row_ok = r0 + row < prm.rows;
+    __nv_bfloat16* orow = prm.out + (r0 + row) * C2;
+    const int q = warp >> 2;
+    for (int c0 = 0; c0 < CG; c0 += 16) {
+      uint32_t acc[16];
+      tmem_ld16(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + acc_set * 4 * NP + (uint32_t)(q * NP + c0), acc);
+      __align__(16) __nv_bfloat162 o[8];
+#pragma unroll
+      for (int j4 = 0; j4 < 16; j4 += 4) {
+        float v[4] = {0.f, 0.f, 0.f, 0.f};
+        if (c0 + j4 < CG) {
+          const float4 sh = *reinterpret_cast<const float4*>(s_shift + q * CG + c0 + j4);
+          v[0] = activate<ACT>(__uint_as_float(acc[j4]) + sh.x);
+          v[1] = activate<ACT>(__uint_as_float(acc[j4 + 1]) + sh.y);
+          v[2] = activate<ACT>(__uint_as_float(acc[j4 + 2]) + sh.z);
+          v[3] = activate<ACT>(__uint_as_float(acc[j4 + 3]) + sh.w);
+        }
+        o[j4 >> 1] = __floats2bfloat162_rn(v[0], v[1]);
+        o[(j4 >> 1) + 1] = __floats2bfloat162_rn(v[2], v[3]);
+      }
+      if (row_ok) {
+        *reinterpret_cast<uint4*>(orow + q * CG + c0) = *reinterpret_cast<const uint4*>(o);
+        if (c0 + 8 < CG) *reinterpret_cast<uint4*>(orow + q * CG + c0 + 8) = *reinterpret_cast<const uint4*>(o + 4);
+      }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  };
+
+  uint32_t ph[2] = {0, 0};
+  auto wait_mma = [&](long long j) {
+    const uint32_t acc_set = two_acc ? (uint32_t)(j & 1) : 0u;
+    mbar_wait(smem_u32(bar + acc_set), ph[acc_set]);
+    ph[acc_set] ^= 1;
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  };
+  // every thread's copies of the OLDER tile done and visible to the MMA (newer: one more group may stay in flight)
+  auto loads_landed = [&](bool newer_in_flight) {
+    if (newer_in_flight) asm volatile("cp.async.wait_group 1;" ::: "memory");
+    else asm volatile("cp.async.wait_group 0;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+  };
+
+  if (mine > 0) {
+    load_tile(0);
+    loads_landed(false);
+    if (threadIdx.x == 0) issue_mma(0);
+    if (mine > 1) load_tile(1);
+    for (long long j = 0; j < mine; ++j) {
+      if (two_acc) {
+        if (j + 1 < mine) {
+          loads_landed(false);                           // tile j+1 in its buffer; every warp is past the epilogue of j-1
+          if (threadIdx.x == 0) issue_mma(j + 1);
+        }
+        wait_mma(j);                                     // buffer j & 1 has been read: refill it
+        if (j + 2 < mine) load_tile(j + 2);
+        epilogue(j);
+      } else {
+        wait_mma(j);
+        if (j + 2 < mine) load_tile(j + 2);              // (buffer j & 1 is free; tile j+1 was started an iteration ago)
+        epilogue(j);
+        if (j + 1 < mine) {
+          loads_landed(j + 2 < mine);                    // also: every warp has drained the accumulators of tile j
+          if (threadIdx.x == 0) issue_mma(j + 1);
+        }
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0)
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512) : "memory");
 }
 
 
@@ -516,6 +709,26 @@ extern "C" int gkg_grouped_fc_fwd(const void* in, const void* w_op, const float*
   prm.shift = shift; prm.rows = rows;
   prm.C2 = C2; prm.CG = C2 / 4; prm.KP = (prm.CG + 15) / 16 * 16; prm.NP = prm.KP; prm.act = act;
   const size_t smem = 4 * (size_t)fc::BM * prm.KP * 2 + 4 * (size_t)prm.NP * prm.KP * 2 + (size_t)C2 * 4 + 64;
+  const size_t smem_pipe = smem + 4 * (size_t)fc::BM * prm.KP * 2;          // second A buffer
+  if (smem_pipe <= 220 * 1024 && tiles >= 2LL * sms) {
+    // software-pipelined kernel: one persistent CTA per SM (worth it once every SM has a few tiles)
+    void (*pk)(const fc::Params) = nullptr;
+#define GKG_FC_PICK(AA)                                                                                        \
+    pk = prm.CG == 40 ? fc::grouped_fc_pipe_kernel<40, AA> : prm.CG == 80 ? fc::grouped_fc_pipe_kernel<80, AA> : fc::grouped_fc_pipe_kernel<0, AA>
+    if (act == 0) { GKG_FC_PICK(0); } else if (act == 1) { GKG_FC_PICK(1); } else { GKG_FC_PICK(2); }
+#undef GKG_FC_PICK
+    const int pslot = act * 3 + (prm.CG == 40 ? 0 : prm.CG == 80 ? 1 : 2);
+    static std::atomic<uint64_t> pconfigured[9];
+    cudaError_t e = cudaSuccess;
+    configure_once_per_device(pconfigured[pslot], [&] {
+      e = cudaFuncSetAttribute(pk, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    });
+    if (e != cudaSuccess) { set_error("grouped_fc_fwd: smem attribute %zu: %s", smem_pipe, cudaGetErrorString(e)); return GKG_ECUDA; }
+    const int pgrid = (int)(tiles < sms ? tiles : sms);
+    pk<<<pgrid, fc::THREADS, smem_pipe, stream>>>(prm);
+    GKG_CHECK_LAUNCH("grouped_fc_pipe_kernel");
+    return GKG_OK;
+  }
   void (*kern)(const fc::Params) = nullptr;
   int slot = act * 3;
 #define GKG_FC_PICK(AA)                                                                                        \
