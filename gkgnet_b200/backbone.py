@@ -12,7 +12,7 @@ from __future__ import annotations
 import torch
 from torch import nn
 
-from .layers import DropPath, FoldedSequential, act_layer, build_norm_layer, norm_cfg
+from .layers import DropPath, FoldedSequential, act_layer, build_norm_layer, norm_cfg, run_modules
 from .registry import BACKBONES, register_into_mmcls
 from .vertex import Grapher, GrapherLabel
 
@@ -35,7 +35,11 @@ class FFN(nn.Module):
         self.drop_path = DropPath(drop_path) if drop_path > 0.0 else nn.Identity()
 
     def forward(self, x):
-        return self.drop_path(self.fc2(self.act(self.fc1(x)))) + x
+        if self.training or torch.is_grad_enabled():
+            h = run_modules(list(self.fc1) + [self.act], x)          # norm + GELU of fc1 in one pass
+        else:
+            h = self.act(self.fc1(x))
+        return self.drop_path(self.fc2(h)) + x
 
 
 class Stem(nn.Module):

@@ -37,12 +37,44 @@ struct alignas(sizeof(T) * VEC) BnPack {
 
 // partial layout: [block][2][C] floats
 // MODE 0: statistics (shifted sum, sum of squares); 1: backward reduce (sum dy, sum dy * (x - mean)); 2: column sum of x
+// nn.GELU() (erf form) and its derivative from one evaluation of the Abramowitz-Stegun 7.1.26 polynomial (the
+// arrangement of grouped_fc.cu: Phi(-|z|) = (0.5 poly(t)) 2^(-(|z| sqrt(log2(e)/2))^2), |error of Phi| <= 7.5e-8):
+//   gelu(z) = z Phi(z),   gelu'(z) = Phi(z) + z phi(z),   phi(z) = exp(-z^2 / 2) / sqrt(2 pi)
+__device__ __forceinline__ void gelu_parts(float z, float& phi_cdf, float& pdf) {
+  const float a = fabsf(z);
+  float t, e;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.231641888f, a, 1.f)));
+  float p = fmaf(0.5307027145f, t, -0.7265760135f);
+  p = fmaf(p, t, 0.7107068705f);
+  p = fmaf(p, t, -0.142248368f);
+  p = fmaf(p, t, 0.127414796f);
+  const float sq = a * 0.849321800f;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-sq * sq));
+  const float h = p * t * e;
+  phi_cdf = z >= 0.f ? 1.f - h : h;
+  pdf = e * 0.3989422804f;
+}
+__device__ __forceinline__ float gelu_fwd(float z) {
+  float c, d;
+  gelu_parts(z, c, d);
+  return z * c;
+}
+__device__ __forceinline__ float gelu_grad(float z) {
+  float c, d;
+  gelu_parts(z, c, d);
+  return fmaf(z, d, c);
+}
+
+// MODE 3: backward reduce THROUGH the activation: g = dy * gelu'(z), z = (x - mean) * (invstd * gamma) + beta
+// (MODE 3 only: invstd, gamma, beta)
 template <typename T, int MODE>
 __global__ void __launch_bounds__(kBnMaxThreads)
 bn_reduce_kernel(const T* __restrict__ x, const T* __restrict__ dy, const float* __restrict__ mean,
-                 float* __restrict__ partial, long long rows, int C, int LX, int LY, long long rows_per_block) {
+                 float* __restrict__ partial, long long rows, int C, int LX, int LY, long long rows_per_block,
+                 const float* __restrict__ invstd = nullptr, const float* __restrict__ gamma = nullptr,
+                 const float* __restrict__ beta = nullptr) {
   constexpr int VEC = BnVec<T>::N;
-  constexpr bool BWD = MODE == 1, SUM = MODE == 2;
+  constexpr bool BWD = MODE == 1 || MODE == 3, SUM = MODE == 2, ACTG = MODE == 3;
   using P = BnPack<T, VEC>;
   extern __shared__ float bn_s[];            // [LY][LX][2 * VEC]
   const int tx = threadIdx.x % LX, ty = threadIdx.x / LX;
@@ -51,9 +83,13 @@ bn_reduce_kernel(const T* __restrict__ x, const T* __restrict__ dy, const float*
   const bool col_ok = c0 < C;
   const long long r0 = (long long)blockIdx.x * rows_per_block;
   const long long r1 = r0 + rows_per_block < rows ? r0 + rows_per_block : rows;
-  float a[VEC], b[VEC], piv[VEC];
+  float a[VEC], b[VEC], piv[VEC], asc[ACTG ? VEC : 1], ash[ACTG ? VEC : 1];
 #pragma unroll
   for (int e = 0; e < VEC; ++e) { a[e] = 0.f; b[e] = 0.f; piv[e] = 0.f; }
+  if (ACTG && col_ok) {
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) { asc[ACTG ? e : 0] = invstd[c0 + e] * gamma[c0 + e]; ash[ACTG ? e : 0] = beta[c0 + e]; }
+  }
   if (col_ok && r0 < r1) {
     if (BWD) {
 #pragma unroll
@@ -77,7 +113,8 @@ bn_reduce_kernel(const T* __restrict__ x, const T* __restrict__ dy, const float*
         for (int e = 0; e < VEC; ++e) {
           const float d = to_f32<T>(xv[u].v[e]) - piv[e];
           if (BWD) {
-            const float g = to_f32<T>(gv[u].v[e]);
+            float g = to_f32<T>(gv[u].v[e]);
+            if (ACTG) g *= gelu_grad(fmaf(d, asc[ACTG ? e : 0], ash[ACTG ? e : 0]));
             a[e] += g;
             b[e] = fmaf(g, d, b[e]);
           } else {
@@ -95,7 +132,8 @@ bn_reduce_kernel(const T* __restrict__ x, const T* __restrict__ dy, const float*
       for (int e = 0; e < VEC; ++e) {
         const float d = to_f32<T>(xv.v[e]) - piv[e];
         if (BWD) {
-          const float g = to_f32<T>(gv.v[e]);
+          float g = to_f32<T>(gv.v[e]);
+          if (ACTG) g *= gelu_grad(fmaf(d, asc[ACTG ? e : 0], ash[ACTG ? e : 0]));
           a[e] += g;
           b[e] = fmaf(g, d, b[e]);
         } else {
@@ -129,6 +167,82 @@ bn_reduce_kernel(const T* __restrict__ x, const T* __restrict__ dy, const float*
         out[C + c0 + e] = fmaxf(b[e] - a[e] * md, 0.f);
       }
     }
+  }
+}
+
+// Elementwise halves for the norm -> GELU pairs (BasicConv torch_nn.py:61-65, FFN.fc1 gkgnet.py:52-58, Stem): the
+// activation is applied in the same pass as the normalisation, and undone (g = dy * gelu'(z), z recomputed from x) in
+// the two backward passes -- the stand-alone GELU forward / backward passes and the saved norm output disappear.
+// Same thread layout as the reductions: a thread keeps its 8 channels' coefficients in registers.
+// FWD:  y = gelu((x - mean) * sc + beta),  sc = invstd * gamma
+// BWD:  dx = (g - sum_g / N - (x - mean) * invstd^2 * sum_g_xmu / N) * sc
+template <typename T, bool BWD>
+__global__ void __launch_bounds__(kBnMaxThreads)
+bn_act_elemt_kernel(const T* __restrict__ x, const T* __restrict__ dy, T* __restrict__ out,
+                    const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ gamma,
+                    const float* __restrict__ beta, const float* __restrict__ sum_g, const float* __restrict__ sum_g_xmu,
+                    long long rows, int C, int LX, int LY, long long rows_per_block) {
+  constexpr int VEC = BnVec<T>::N;
+  using P = BnPack<T, VEC>;
+  const int tx = threadIdx.x % LX, ty = threadIdx.x / LX;
+  const int c0 = (blockIdx.y * LX + tx) * VEC;
+  if (c0 >= C) return;
+  const long long r0 = (long long)blockIdx.x * rows_per_block;
+  const long long r1 = r0 + rows_per_block < rows ? r0 + rows_per_block : rows;
+  float mu[VEC], sc[VEC], sh[VEC], k1[BWD ? VEC : 1], k2[BWD ? VEC : 1];
+  const float inv_n = 1.f / (float)rows;
+#pragma unroll
+  for (int e = 0; e < VEC; ++e) {
+    const float is = invstd[c0 + e];
+    mu[e] = mean[c0 + e];
+    sc[e] = is * gamma[c0 + e];
+    sh[e] = beta[c0 + e];
+    if (BWD) {
+      k1[BWD ? e : 0] = sum_g[c0 + e] * inv_n;
+      k2[BWD ? e : 0] = is * is * sum_g_xmu[c0 + e] * inv_n;
+    }
+  }
+  long long r = r0 + ty;
+  for (; r + (long long)(kBnUnroll - 1) * LY < r1; r += (long long)kBnUnroll * LY) {
+    P xv[kBnUnroll], gv[kBnUnroll];
+#pragma unroll
+    for (int u = 0; u < kBnUnroll; ++u) {
+      xv[u] = *reinterpret_cast<const P*>(x + (r + (long long)u * LY) * C + c0);
+      if (BWD) gv[u] = *reinterpret_cast<const P*>(dy + (r + (long long)u * LY) * C + c0);
+    }
+#pragma unroll
+    for (int u = 0; u < kBnUnroll; ++u) {
+      P o;
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) {
+        const float d = to_f32<T>(xv[u].v[e]) - mu[e];
+        const float z = fmaf(d, sc[e], sh[e]);
+        if (BWD) {
+          const float g = to_f32<T>(gv[u].v[e]) * gelu_grad(z);
+          o.v[e] = from_f32<T>((g - k1[BWD ? e : 0] - d * k2[BWD ? e : 0]) * sc[e]);
+        } else {
+          o.v[e] = from_f32<T>(gelu_fwd(z));
+        }
+      }
+      *reinterpret_cast<P*>(out + (r + (long long)u * LY) * C + c0) = o;
+    }
+  }
+  for (; r < r1; r += LY) {
+    const P xv = *reinterpret_cast<const P*>(x + r * C + c0);
+    P gv, o;
+    if (BWD) gv = *reinterpret_cast<const P*>(dy + r * C + c0);
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) {
+      const float d = to_f32<T>(xv.v[e]) - mu[e];
+      const float z = fmaf(d, sc[e], sh[e]);
+      if (BWD) {
+        const float g = to_f32<T>(gv.v[e]) * gelu_grad(z);
+        o.v[e] = from_f32<T>((g - k1[BWD ? e : 0] - d * k2[BWD ? e : 0]) * sc[e]);
+      } else {
+        o.v[e] = from_f32<T>(gelu_fwd(z));
+      }
+    }
+    *reinterpret_cast<P*>(out + r * C + c0) = o;
   }
 }
 
@@ -230,15 +344,17 @@ BnPlan bn_plan(long long rows, int C, int vec) {
 
 template <typename T, int MODE>
 int launch_bn_reduce(const void* x, const void* dy, const float* mean, float* partial, long long rows, int C,
-                     const BnPlan& p, cudaStream_t stream) {
+                     const BnPlan& p, cudaStream_t stream, const float* invstd = nullptr, const float* gamma = nullptr,
+                     const float* beta = nullptr) {
   static std::atomic<uint64_t> configured{0};
   configure_once_per_device(configured, [] {
     cudaFuncSetAttribute(bn_reduce_kernel<T, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
   });
   dim3 grid(p.blocks, p.slabs);
   bn_reduce_kernel<T, MODE><<<grid, p.LX * p.LY, p.smem, stream>>>(static_cast<const T*>(x), static_cast<const T*>(dy),
-                                                                 mean, partial, rows, C, p.LX, p.LY, p.rows_per_block);
-  GKG_CHECK_LAUNCH(MODE == 1 ? "bn_reduce_kernel<bwd>" : MODE == 2 ? "bn_reduce_kernel<colsum>" : "bn_reduce_kernel<stats>");
+                                                                 mean, partial, rows, C, p.LX, p.LY, p.rows_per_block,
+                                                                 invstd, gamma, beta);
+  GKG_CHECK_LAUNCH(MODE == 3 ? "bn_reduce_kernel<bwd, gelu>" : MODE == 1 ? "bn_reduce_kernel<bwd>" : MODE == 2 ? "bn_reduce_kernel<colsum>" : "bn_reduce_kernel<stats>");
   return GKG_OK;
 }
 
@@ -257,8 +373,8 @@ int check_bn_args(const void* x, long long rows, int C, int dtype, int* vec) {
 using namespace gkg;
 
 extern "C" size_t gkg_bn_workspace_bytes(long long rows, int C) {
-  (void)rows;
-  return sizeof(float) * (size_t)kBnMaxBlocks * 2 * (size_t)(C > 0 ? C : 0);
+  (void)rows;                                           // per-block partials + the two sums of the fused backward
+  return sizeof(float) * ((size_t)kBnMaxBlocks + 1) * 2 * (size_t)(C > 0 ? C : 0);
 }
 
 extern "C" int gkg_bn_stats(const void* x, long long rows, int C, int dtype, float eps, float momentum,
@@ -323,5 +439,66 @@ extern "C" int gkg_column_sum(const void* x, long long rows, int C, int dtype, f
   bn_bwd_finalize_kernel<<<(C + 31) / 32, 32 * kFinLanes, 0, stream>>>(partial, p.blocks, C, nullptr, out, nullptr,
                                                                       nullptr, nullptr);
   GKG_CHECK_LAUNCH("bn_bwd_finalize_kernel<colsum>");
+  return GKG_OK;
+}
+
+// norm -> GELU in one pass and its backward (see bn_act_elemt_kernel); act: 2 = GELU (erf form) -- the only pairing the
+// reference's stacks contain.
+extern "C" int gkg_bn_act_forward(const void* x, const float* mean, const float* invstd, const float* gamma,
+                                  const float* beta, long long rows, int C, int dtype, int act, void* y,
+                                  gkg_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  int vec = 0;
+  int rc = check_bn_args(x, rows, C, dtype, &vec);
+  if (rc != GKG_OK) return rc;
+  GKG_CHECK_ARG(act == 2, "gkg_bn_act_forward: activation %d (only 2 = GELU)", act);
+  GKG_CHECK_ARG(mean && invstd && gamma && beta && y && ((uintptr_t)y % 16) == 0, "gkg_bn_act_forward: null / unaligned pointer");
+  const BnPlan p = bn_plan(rows, C, vec);
+  dim3 grid(p.blocks, p.slabs);
+  if (dtype == GKG_F32)
+    bn_act_elemt_kernel<float, false><<<grid, p.LX * p.LY, 0, stream>>>(
+        static_cast<const float*>(x), nullptr, static_cast<float*>(y), mean, invstd, gamma, beta, nullptr, nullptr, rows, C,
+        p.LX, p.LY, p.rows_per_block);
+  else
+    bn_act_elemt_kernel<__nv_bfloat16, false><<<grid, p.LX * p.LY, 0, stream>>>(
+        static_cast<const __nv_bfloat16*>(x), nullptr, static_cast<__nv_bfloat16*>(y), mean, invstd, gamma, beta, nullptr,
+        nullptr, rows, C, p.LX, p.LY, p.rows_per_block);
+  GKG_CHECK_LAUNCH("bn_act_elemt_kernel<fwd>");
+  return GKG_OK;
+}
+
+extern "C" int gkg_bn_act_backward(const void* grad_out, const void* x, const float* mean, const float* invstd,
+                                   const float* gamma, const float* beta, long long rows, int C, int dtype, int act,
+                                   void* grad_x, float* grad_weight, float* grad_bias, void* ws, size_t ws_bytes,
+                                   gkg_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  int vec = 0;
+  int rc = check_bn_args(x, rows, C, dtype, &vec);
+  if (rc != GKG_OK) return rc;
+  GKG_CHECK_ARG(act == 2, "gkg_bn_act_backward: activation %d (only 2 = GELU)", act);
+  GKG_CHECK_ARG(grad_out && mean && invstd && gamma && beta && grad_x && ws, "gkg_bn_act_backward: null pointer");
+  GKG_CHECK_ARG(((uintptr_t)grad_out % 16) == 0 && ((uintptr_t)grad_x % 16) == 0, "gkg_bn_act_backward: unaligned pointer");
+  GKG_CHECK_ARG(ws_bytes >= gkg_bn_workspace_bytes(rows, C), "gkg_bn_act_backward: workspace too small");
+  const BnPlan p = bn_plan(rows, C, vec);
+  float* partial = static_cast<float*>(ws);
+  float* sums = partial + (size_t)kBnMaxBlocks * 2 * C;          // [2][C]: sum g, sum g (x - mean)
+  rc = dtype == GKG_F32
+           ? launch_bn_reduce<float, 3>(x, grad_out, mean, partial, rows, C, p, stream, invstd, gamma, beta)
+           : launch_bn_reduce<__nv_bfloat16, 3>(x, grad_out, mean, partial, rows, C, p, stream, invstd, gamma, beta);
+  if (rc != GKG_OK) return rc;
+  bn_bwd_finalize_kernel<<<(C + 31) / 32, 32 * kFinLanes, 0, stream>>>(partial, p.blocks, C, invstd, sums, sums + C,
+                                                                      grad_weight, grad_bias);
+  GKG_CHECK_LAUNCH("bn_bwd_finalize_kernel");
+  dim3 grid(p.blocks, p.slabs);
+  if (dtype == GKG_F32)
+    bn_act_elemt_kernel<float, true><<<grid, p.LX * p.LY, 0, stream>>>(
+        static_cast<const float*>(x), static_cast<const float*>(grad_out), static_cast<float*>(grad_x), mean, invstd, gamma,
+        beta, sums, sums + C, rows, C, p.LX, p.LY, p.rows_per_block);
+  else
+    bn_act_elemt_kernel<__nv_bfloat16, true><<<grid, p.LX * p.LY, 0, stream>>>(
+        static_cast<const __nv_bfloat16*>(x), static_cast<const __nv_bfloat16*>(grad_out),
+        static_cast<__nv_bfloat16*>(grad_x), mean, invstd, gamma, beta, sums, sums + C, rows, C, p.LX, p.LY,
+        p.rows_per_block);
+  GKG_CHECK_LAUNCH("bn_act_elemt_kernel<bwd>");
   return GKG_OK;
 }

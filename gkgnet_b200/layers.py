@@ -25,15 +25,49 @@ class BatchNorm2d(nn.BatchNorm2d):
 
     native = True      # class-wide switch (tests compare against the stock path)
 
-    def forward(self, x):
-        if (self.native and self.training and self.affine and self.track_running_stats and self.momentum is not None
+    def takes_native(self, x):
+        if not (self.native and self.training and self.affine and self.track_running_stats and self.momentum is not None
                 and isinstance(x, torch.Tensor) and x.is_cuda):
+            return False
+        from . import ops
+        return ops.batch_norm_native_ok(x)
+
+    def forward(self, x, act=None):
+        """act="gelu": the exact GELU that follows this norm in the stack, applied in the same pass (native path only;
+        callers check takes_native first)."""
+        if self.takes_native(x):
             from . import ops
-            if ops.batch_norm_native_ok(x):
-                self.num_batches_tracked.add_(1)
-                return ops.batch_norm_train(x, self.weight, self.bias, self.running_mean, self.running_var,
-                                            self.momentum, self.eps)
+            self.num_batches_tracked.add_(1)
+            return ops.batch_norm_train(x, self.weight, self.bias, self.running_mean, self.running_var,
+                                        self.momentum, self.eps, act)
+        if act is not None:
+            raise ValueError("fused activation needs the native path")
         return super().forward(x)
+
+
+def run_modules(mods, x):
+    """Run a conv -> norm -> act stack as written (training / gradient passes), with two substitutions that keep the
+    arithmetic: a 1x1 convolution on channels-last CUDA activations is the token-major GEMM it is (ops.conv1x1), and a
+    native batch norm followed by the exact nn.GELU runs as one pass (ops.batch_norm_train(act="gelu"))."""
+    mods = list(mods)
+    i = 0
+    while i < len(mods):
+        m = mods[i]
+        nxt = mods[i + 1] if i + 1 < len(mods) else None
+        if (isinstance(m, nn.Conv2d) and m.kernel_size == (1, 1) and m.stride == (1, 1) and m.padding == (0, 0)
+                and m.groups == 1 and x.dim() == 4 and x.is_contiguous(memory_format=torch.channels_last) and x.is_cuda):
+            if torch.is_autocast_enabled():
+                x = x.to(torch.get_autocast_dtype("cuda"))
+            from . import ops
+            x = ops.conv1x1(x, m.weight, m.bias)
+        elif (isinstance(m, BatchNorm2d) and isinstance(nxt, nn.GELU) and getattr(nxt, "approximate", "none") == "none"
+              and m.weight is not None and m.weight.dtype == torch.float32 and m.takes_native(x)):
+            x = m(x, act="gelu")
+            i += 1
+        else:
+            x = m(x)
+        i += 1
+    return x
 
 
 def build_norm_layer(cfg, num_features, postfix=""):
@@ -83,19 +117,7 @@ class FoldedSequential(nn.Sequential):
 
     def forward(self, x):
         if self.training or torch.is_grad_enabled():
-            # modules as written, except that a 1x1 convolution on channels-last activations is the GEMM it is
-            # (bias in the epilogue, GEMM backward) instead of a cuDNN convolution plus a bias pass
-            for m in self:
-                if (isinstance(m, nn.Conv2d) and m.kernel_size == (1, 1) and m.stride == (1, 1) and m.padding == (0, 0)
-                        and m.groups == 1 and x.dim() == 4 and x.is_contiguous(memory_format=torch.channels_last)
-                        and x.is_cuda):
-                    if torch.is_autocast_enabled():
-                        x = x.to(torch.get_autocast_dtype("cuda"))
-                    from . import ops
-                    x = ops.conv1x1(x, m.weight, m.bias)
-                else:
-                    x = m(x)
-            return x
+            return run_modules(self, x)
         mods = list(self)
         i = 0
         while i < len(mods):

@@ -401,7 +401,11 @@ class _GroupedFC(torch.autograd.Function):
             _lib.check(rc, "gkg_grouped_fc_wgrad")
             gw = gw32.reshape(c2, cg, 1, 1).to(weight.dtype)
         if ctx.has_bias and ctx.needs_input_grad[2]:
-            gb = go.reshape(-1, c2).float().sum(0)
+            go2 = go.reshape(-1, c2)
+            if go2.dtype in _DT and go2.data_ptr() % 16 == 0:
+                gb = column_sum(go2)                  # one pass, fp32 accumulation (was: an fp32 copy + ATen's reduction)
+            else:
+                gb = go2.float().sum(0)
         return gx, gw, gb
 
 
@@ -572,13 +576,15 @@ def batch_norm_native_ok(x):
 
 
 class _BatchNormTrain(torch.autograd.Function):
-    """y = batch_norm(x) with batch statistics (torch_nn.py:32-42 -> nn.BatchNorm2d training forward): statistics
-    and backward reductions by gkg_bn_stats / gkg_bn_backward_reduce, elementwise passes by ATen's
-    batch_norm_elemt / batch_norm_backward_elemt (the decomposition SyncBatchNorm uses)."""
+    """y = act(batch_norm(x)) with batch statistics (torch_nn.py:32-42 -> nn.BatchNorm2d training forward, optionally
+    followed by the stack's nn.GELU): statistics and backward reductions by gkg_bn_stats / gkg_bn_backward_reduce.
+    act None: elementwise passes by ATen's batch_norm_elemt / batch_norm_backward_elemt (the decomposition
+    SyncBatchNorm uses).  act "gelu": gkg_bn_act_forward / gkg_bn_act_backward -- the activation rides on the
+    normalisation pass, and its derivative on the two backward passes (the norm output is recomputed, not saved)."""
 
     @staticmethod
     @_guard
-    def forward(ctx, x, weight, bias, running_mean, running_var, momentum, eps):
+    def forward(ctx, x, weight, bias, running_mean, running_var, momentum, eps, act):
         lib = _lib.load()
         x2 = _rows_of(x)
         rows, C = x2.shape
@@ -590,15 +596,23 @@ class _BatchNormTrain(torch.autograd.Function):
                               None if running_var is None else running_var.data_ptr(), ws.data_ptr(), ws.numel(),
                               _stream(x))
         _lib.check(rc, "gkg_bn_stats")
-        y = torch.batch_norm_elemt(x, weight, bias, mean, invstd, eps)
-        ctx.save_for_backward(x, weight, mean, invstd)
+        ctx.act = act
+        if act is None:
+            y = torch.batch_norm_elemt(x, weight, bias, mean, invstd, eps)
+            ctx.save_for_backward(x, weight, mean, invstd)
+            return y
+        y = torch.empty_like(x)                                   # same (channels-last) strides
+        rc = lib.gkg_bn_act_forward(x2.data_ptr(), mean.data_ptr(), invstd.data_ptr(), weight.data_ptr(),
+                                    bias.data_ptr(), rows, C, _DT[x.dtype], 2, y.data_ptr(), _stream(x))
+        _lib.check(rc, "gkg_bn_act_forward")
+        ctx.save_for_backward(x, weight, mean, invstd, bias)
         return y
 
     @staticmethod
     @_guard
     def backward(ctx, dy):
         lib = _lib.load()
-        x, weight, mean, invstd = ctx.saved_tensors
+        x, weight, mean, invstd = ctx.saved_tensors[:4]
         if not dy.permute(0, 2, 3, 1).is_contiguous():
             dy = dy.contiguous(memory_format=torch.channels_last)
         dy = dy.to(x.dtype)
@@ -606,29 +620,42 @@ class _BatchNormTrain(torch.autograd.Function):
         rows, C = x2.shape
         out = torch.empty(4, C, dtype=torch.float32, device=x.device)       # sum_dy, sum_dy_xmu, grad_weight, grad_bias
         ws = _workspace(x.device, lib.gkg_bn_workspace_bytes(rows, C))
-        rc = lib.gkg_bn_backward_reduce(g2.data_ptr(), x2.data_ptr(), mean.data_ptr(), invstd.data_ptr(), rows, C,
-                                        _DT[x.dtype], out[0].data_ptr(), out[1].data_ptr(), out[2].data_ptr(),
-                                        out[3].data_ptr(), ws.data_ptr(), ws.numel(), _stream(x))
-        _lib.check(rc, "gkg_bn_backward_reduce")
-        key = (x.device.index, rows)
-        count = _COUNT_CACHE.get(key)
-        if count is None:
-            count = _COUNT_CACHE[key] = torch.full((1,), rows, dtype=torch.int32, device=x.device)
-        dx = None
-        if ctx.needs_input_grad[0]:
-            dx = torch.batch_norm_backward_elemt(dy, x, mean, invstd, weight, out[0], out[1], count)
+        if ctx.act is not None:
+            bias = ctx.saved_tensors[4]
+            dx = torch.empty_like(x)
+            rc = lib.gkg_bn_act_backward(g2.data_ptr(), x2.data_ptr(), mean.data_ptr(), invstd.data_ptr(),
+                                         weight.data_ptr(), bias.data_ptr(), rows, C, _DT[x.dtype], 2, dx.data_ptr(),
+                                         out[2].data_ptr(), out[3].data_ptr(), ws.data_ptr(), ws.numel(), _stream(x))
+            _lib.check(rc, "gkg_bn_act_backward")
+        else:
+            rc = lib.gkg_bn_backward_reduce(g2.data_ptr(), x2.data_ptr(), mean.data_ptr(), invstd.data_ptr(), rows, C,
+                                            _DT[x.dtype], out[0].data_ptr(), out[1].data_ptr(), out[2].data_ptr(),
+                                            out[3].data_ptr(), ws.data_ptr(), ws.numel(), _stream(x))
+            _lib.check(rc, "gkg_bn_backward_reduce")
+            key = (x.device.index, rows)
+            count = _COUNT_CACHE.get(key)
+            if count is None:
+                count = _COUNT_CACHE[key] = torch.full((1,), rows, dtype=torch.int32, device=x.device)
+            dx = None
+            if ctx.needs_input_grad[0]:
+                dx = torch.batch_norm_backward_elemt(dy, x, mean, invstd, weight, out[0], out[1], count)
         gw = out[2].to(weight.dtype) if ctx.needs_input_grad[1] else None
         gb = out[3].to(weight.dtype) if ctx.needs_input_grad[2] else None
-        return dx, gw, gb, None, None, None, None
+        return dx, gw, gb, None, None, None, None, None
 
 
-def batch_norm_train(x, weight, bias, running_mean, running_var, momentum, eps):
-    """Training-mode batch norm of a channels-last (B, C, H, W) CUDA activation; updates the running statistics in
-    place like nn.BatchNorm2d.  Raises on anything the kernels do not take (callers check batch_norm_native_ok)."""
+def batch_norm_train(x, weight, bias, running_mean, running_var, momentum, eps, act=None):
+    """Training-mode batch norm of a channels-last (B, C, H, W) CUDA activation, optionally fused with the GELU that
+    follows it (act="gelu"); updates the running statistics in place like nn.BatchNorm2d.  Raises on anything the
+    kernels do not take (callers check batch_norm_native_ok)."""
     _require_cuda(x)
     if not batch_norm_native_ok(x):
         raise ValueError("batch_norm_train: needs a channels-last (B, C, H, W) bf16 / fp32 CUDA tensor, C % 8 (4) == 0")
-    return _BatchNormTrain.apply(x, weight, bias, running_mean, running_var, momentum, eps)
+    if act not in (None, "gelu"):
+        raise ValueError(f"batch_norm_train: activation {act!r} (None or 'gelu')")
+    if act is not None and (weight is None or bias is None or weight.dtype != torch.float32):
+        raise ValueError("batch_norm_train: the fused activation needs fp32 affine parameters")
+    return _BatchNormTrain.apply(x, weight, bias, running_mean, running_var, momentum, eps, act)
 
 
 # ---------------------------------------------------------------------------------------------------------

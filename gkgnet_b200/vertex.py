@@ -15,7 +15,7 @@ from torch import nn
 
 from . import ops
 from .graph import DenseDilatedKnnGraph, edge_index_from_neighbors
-from .layers import BasicConv, DropPath, FoldedSequential, act_layer, build_norm_layer, norm_cfg
+from .layers import BasicConv, DropPath, FoldedSequential, act_layer, build_norm_layer, norm_cfg, run_modules
 from .pos_embed import relative_pos_table
 
 
@@ -58,9 +58,7 @@ class MRConv2d(nn.Module):
                 and ops.grouped_fc_supported(conv.out_channels)):
             # training: the FC and its data gradient on the tensor-core kernel, norm / act stay modules
             h = tokens_to_nchw(ops.grouped_fc_train(agg, conv.weight, conv.bias), H, W)
-            for mod in list(self.nn)[1:]:
-                h = mod(h)
-            return h
+            return run_modules(list(self.nn)[1:], h)                 # norm + GELU in one pass
         return self.nn(tokens_to_nchw(agg, H, W))
 
     def _fused_fc(self, agg):

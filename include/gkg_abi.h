@@ -285,6 +285,20 @@ int gkg_bn_backward_reduce(const void* grad_out, const void* x, const float* mea
                            float* grad_weight, float* grad_bias, void* ws, size_t ws_bytes, gkg_stream_t stream);
 
 /*
+ * norm -> GELU pairs (BasicConv torch_nn.py:61-65, FFN.fc1 gkgnet.py:52-58, Stem gkgnet.py:82-90) in training:
+ *   gkg_bn_act_forward:   y = gelu((x - mean) * invstd * gamma + beta)  with the statistics of gkg_bn_stats
+ *   gkg_bn_act_backward:  everything autograd derives for that pair from grad_out = dL/dy: grad_x (rows, C),
+ *                         grad_weight = dL/dgamma, grad_bias = dL/dbeta (the norm output is recomputed from x, not saved)
+ * act: 2 = GELU (erf form); x, y, grad_out, grad_x (rows, C) contiguous, dtype; ws as above.
+ */
+int gkg_bn_act_forward(const void* x, const float* mean, const float* invstd, const float* gamma, const float* beta,
+                       long long rows, int C, int dtype, int act, void* y, gkg_stream_t stream);
+int gkg_bn_act_backward(const void* grad_out, const void* x, const float* mean, const float* invstd,
+                        const float* gamma, const float* beta, long long rows, int C, int dtype, int act,
+                        void* grad_x, float* grad_weight, float* grad_bias, void* ws, size_t ws_bytes,
+                        gkg_stream_t stream);
+
+/*
  * Column sums of a (rows, C) contiguous activation into fp32 out (C): the bias gradient autograd derives for a
  * token-major 1x1 convolution (Grapher.fc1 / fc2 torch_vertex.py:290-306, FFN gkgnet.py:46-72).  Same row-range
  * partials as the batch-norm reductions (deterministic); ws: gkg_bn_workspace_bytes(rows, C).

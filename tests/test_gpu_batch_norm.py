@@ -146,3 +146,69 @@ def test_conv1x1_matches_conv2d_with_autograd():
     with torch.autocast("cuda", dtype=torch.bfloat16):
         yc = ops.conv1x1(x.to(torch.bfloat16), conv.weight, conv.bias)
     assert yc.dtype == torch.bfloat16 and torch.allclose(yc.float(), yb, atol=5e-2, rtol=5e-2)
+
+
+@pytest.mark.parametrize("B,C,H,W,dtype", [
+    (4, 160, 36, 36, torch.bfloat16),
+    (2, 320, 20, 21, torch.bfloat16),
+    (3, 40, 17, 9, torch.bfloat16),
+    (2, 400, 18, 18, torch.float32),
+])
+def test_batch_norm_gelu_fused_matches_aten(B, C, H, W, dtype):
+    """norm -> nn.GELU() as one forward pass and two backward passes (gkg_bn_act_forward / _backward)."""
+    from gkgnet_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(6)
+    x = _cl((torch.randn(B, C, H, W, device="cuda", generator=g) * 1.3 - 0.2).to(dtype))
+    dy = _cl(torch.randn(B, C, H, W, device="cuda", generator=g).to(dtype))
+    w = torch.rand(C, device="cuda", generator=g) + 0.5
+    b = torch.randn(C, device="cuda", generator=g) * 0.5
+    res = []
+    for native in (True, False):
+        xi = x.clone().requires_grad_(True)
+        wi, bi = w.clone().requires_grad_(True), b.clone().requires_grad_(True)
+        rm, rv = torch.zeros(C, device="cuda"), torch.ones(C, device="cuda")
+        if native:
+            y = ops.batch_norm_train(xi, wi, bi, rm, rv, 0.1, 1e-5, act="gelu")
+        else:
+            y = F.gelu(F.batch_norm(xi, rm, rv, wi, bi, True, 0.1, 1e-5))
+        y.backward(dy)
+        res.append((y.detach().float(), xi.grad.float(), wi.grad, bi.grad, rm, rv))
+    (y0, dx0, dw0, db0, rm0, rv0), (y1, dx1, dw1, db1, rm1, rv1) = res
+    tol = 2e-2 if dtype == torch.bfloat16 else 3e-5
+    assert torch.allclose(y0, y1, atol=tol, rtol=tol)
+    assert torch.allclose(dx0, dx1, atol=tol, rtol=tol)
+    scale = 10 if dtype == torch.bfloat16 else 1       # the unfused bf16 path rounds the norm output and dgelu to bf16
+    assert (dw0 - dw1).abs().max() <= 2e-3 * scale * max(1.0, dw1.abs().max().item())
+    assert (db0 - db1).abs().max() <= 2e-3 * scale * max(1.0, db1.abs().max().item())
+    assert torch.allclose(rm0, rm1, atol=1e-5, rtol=1e-5) and torch.allclose(rv0, rv1, atol=1e-5, rtol=1e-4)
+    if dtype == torch.float32:
+        # against float64: the fused kernels must be at least as accurate as the two-kernel fp32 path
+        xd = x.double().requires_grad_(True)
+        yd = F.gelu(F.batch_norm(xd, None, None, w.double(), b.double(), True, 0.1, 1e-5))
+        yd.backward(dy.double())
+        assert (y0.double() - yd).abs().max() < 1e-5
+        assert (dx0.double() - xd.grad).abs().max() < 1e-4
+
+
+def test_run_modules_fuses_norm_and_gelu():
+    """layers.run_modules: conv1x1 -> native norm + GELU == the stack as written (stock modules)."""
+    from gkgnet_b200 import layers
+    torch.manual_seed(3)
+    conv = torch.nn.Conv2d(80, 160, 1).cuda()
+    bn = layers.BatchNorm2d(160).cuda()
+    act = torch.nn.GELU()
+    x = _cl(torch.randn(4, 80, 24, 24, device="cuda"))
+    ref_bn = torch.nn.BatchNorm2d(160).cuda()
+    ref_bn.load_state_dict(bn.state_dict())
+    xa = x.clone().requires_grad_(True)
+    ya = layers.run_modules([conv, bn, act], xa)
+    ya.sum().backward()
+    ga = (xa.grad.clone(), conv.weight.grad.clone(), bn.weight.grad.clone(), bn.bias.grad.clone())
+    conv.zero_grad()
+    xb = x.clone().requires_grad_(True)
+    yb = act(ref_bn(conv(xb)))
+    yb.sum().backward()
+    assert torch.allclose(ya, yb, atol=1e-4, rtol=1e-4)
+    for a, b in zip(ga, (xb.grad, conv.weight.grad, ref_bn.weight.grad, ref_bn.bias.grad)):
+        assert torch.allclose(a, b, atol=5e-3, rtol=2e-3)
+    assert torch.allclose(bn.running_var, ref_bn.running_var, rtol=1e-5)
