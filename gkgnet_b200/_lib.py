@@ -53,8 +53,8 @@ SIGNATURES = {
     "gkg_grouped_fc_wgrad": (_i32, [_vp, _vp, _vp, _c.c_longlong, _i32, _vp]),
     "gkg_bn_workspace_bytes": (_sz, [_c.c_longlong, _i32]),
     "gkg_bn_stats": (_i32, [_vp, _c.c_longlong, _i32, _i32, _c.c_float, _c.c_float, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
-    "gkg_bn_act_forward": (_i32, [_vp] * 5 + [_c.c_longlong, _i32, _i32, _i32, _vp, _vp]),
-    "gkg_bn_act_backward": (_i32, [_vp] * 6 + [_c.c_longlong, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "gkg_bn_act_forward": (_i32, [_vp] * 5 + [_c.c_longlong, _i32, _i32, _i32, _vp, _vp, _vp]),
+    "gkg_bn_act_backward": (_i32, [_vp] * 7 + [_c.c_longlong, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _sz, _vp]),
     "gkg_column_sum": (_i32, [_vp, _c.c_longlong, _i32, _i32, _vp, _vp, _sz, _vp]),
     "gkg_bn_backward_reduce": (_i32, [_vp, _vp, _vp, _vp, _c.c_longlong, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
 }

@@ -72,9 +72,9 @@ __global__ void __launch_bounds__(kBnMaxThreads)
 bn_reduce_kernel(const T* __restrict__ x, const T* __restrict__ dy, const float* __restrict__ mean,
                  float* __restrict__ partial, long long rows, int C, int LX, int LY, long long rows_per_block,
                  const float* __restrict__ invstd = nullptr, const float* __restrict__ gamma = nullptr,
-                 const float* __restrict__ beta = nullptr) {
+                 const float* __restrict__ beta = nullptr, const T* __restrict__ dact = nullptr) {
   constexpr int VEC = BnVec<T>::N;
-  constexpr bool BWD = MODE == 1 || MODE == 3, SUM = MODE == 2, ACTG = MODE == 3;
+  constexpr bool BWD = MODE == 1 || MODE == 3 || MODE == 4, SUM = MODE == 2, ACTG = MODE == 3, SAVED = MODE == 4;
   using P = BnPack<T, VEC>;
   extern __shared__ float bn_s[];            // [LY][LX][2 * VEC]
   const int tx = threadIdx.x % LX, ty = threadIdx.x / LX;
@@ -101,11 +101,12 @@ bn_reduce_kernel(const T* __restrict__ x, const T* __restrict__ dy, const float*
     }
     long long r = r0 + ty;
     for (; r + (long long)(kBnUnroll - 1) * LY < r1; r += (long long)kBnUnroll * LY) {
-      P xv[kBnUnroll], gv[kBnUnroll];
+      P xv[kBnUnroll], gv[kBnUnroll], av[SAVED ? kBnUnroll : 1];
 #pragma unroll
       for (int u = 0; u < kBnUnroll; ++u) {
         xv[u] = *reinterpret_cast<const P*>(x + (r + (long long)u * LY) * C + c0);
         if (BWD) gv[u] = *reinterpret_cast<const P*>(dy + (r + (long long)u * LY) * C + c0);
+        if (SAVED) av[SAVED ? u : 0] = *reinterpret_cast<const P*>(dact + (r + (long long)u * LY) * C + c0);
       }
 #pragma unroll
       for (int u = 0; u < kBnUnroll; ++u) {
@@ -115,6 +116,7 @@ bn_reduce_kernel(const T* __restrict__ x, const T* __restrict__ dy, const float*
           if (BWD) {
             float g = to_f32<T>(gv[u].v[e]);
             if (ACTG) g *= gelu_grad(fmaf(d, asc[ACTG ? e : 0], ash[ACTG ? e : 0]));
+            if (SAVED) g *= to_f32<T>(av[SAVED ? u : 0].v[e]);
             a[e] += g;
             b[e] = fmaf(g, d, b[e]);
           } else {
@@ -126,14 +128,16 @@ bn_reduce_kernel(const T* __restrict__ x, const T* __restrict__ dy, const float*
     }
     for (; r < r1; r += LY) {
       const P xv = *reinterpret_cast<const P*>(x + r * C + c0);
-      P gv;
+      P gv, av;
       if (BWD) gv = *reinterpret_cast<const P*>(dy + r * C + c0);
+      if (SAVED) av = *reinterpret_cast<const P*>(dact + r * C + c0);
 #pragma unroll
       for (int e = 0; e < VEC; ++e) {
         const float d = to_f32<T>(xv.v[e]) - piv[e];
         if (BWD) {
           float g = to_f32<T>(gv.v[e]);
           if (ACTG) g *= gelu_grad(fmaf(d, asc[ACTG ? e : 0], ash[ACTG ? e : 0]));
+          if (SAVED) g *= to_f32<T>(av.v[e]);
           a[e] += g;
           b[e] = fmaf(g, d, b[e]);
         } else {
@@ -176,9 +180,11 @@ bn_reduce_kernel(const T* __restrict__ x, const T* __restrict__ dy, const float*
 // Same thread layout as the reductions: a thread keeps its 8 channels' coefficients in registers.
 // FWD:  y = gelu((x - mean) * sc + beta),  sc = invstd * gamma
 // BWD:  dx = (g - sum_g / N - (x - mean) * invstd^2 * sum_g_xmu / N) * sc
-template <typename T, bool BWD>
+// SAVED: the forward also writes gelu'(z) (dact, feature dtype) and the backward passes multiply by it instead of
+// re-evaluating the derivative -- with it the two backward passes are pure streaming kernels (no MUFU work at all).
+template <typename T, bool BWD, bool SAVED>
 __global__ void __launch_bounds__(kBnMaxThreads)
-bn_act_elemt_kernel(const T* __restrict__ x, const T* __restrict__ dy, T* __restrict__ out,
+bn_act_elemt_kernel(const T* __restrict__ x, const T* __restrict__ dy, T* __restrict__ out, T* __restrict__ dact,
                     const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ gamma,
                     const float* __restrict__ beta, const float* __restrict__ sum_g, const float* __restrict__ sum_g_xmu,
                     long long rows, int C, int LX, int LY, long long rows_per_block) {
@@ -204,45 +210,55 @@ bn_act_elemt_kernel(const T* __restrict__ x, const T* __restrict__ dy, T* __rest
   }
   long long r = r0 + ty;
   for (; r + (long long)(kBnUnroll - 1) * LY < r1; r += (long long)kBnUnroll * LY) {
-    P xv[kBnUnroll], gv[kBnUnroll];
+    P xv[kBnUnroll], gv[kBnUnroll], av[(BWD && SAVED) ? kBnUnroll : 1];
 #pragma unroll
     for (int u = 0; u < kBnUnroll; ++u) {
       xv[u] = *reinterpret_cast<const P*>(x + (r + (long long)u * LY) * C + c0);
       if (BWD) gv[u] = *reinterpret_cast<const P*>(dy + (r + (long long)u * LY) * C + c0);
+      if (BWD && SAVED) av[(BWD && SAVED) ? u : 0] = *reinterpret_cast<const P*>(dact + (r + (long long)u * LY) * C + c0);
     }
 #pragma unroll
     for (int u = 0; u < kBnUnroll; ++u) {
-      P o;
+      P o, da;
 #pragma unroll
       for (int e = 0; e < VEC; ++e) {
         const float d = to_f32<T>(xv[u].v[e]) - mu[e];
         const float z = fmaf(d, sc[e], sh[e]);
         if (BWD) {
-          const float g = to_f32<T>(gv[u].v[e]) * gelu_grad(z);
+          const float g = to_f32<T>(gv[u].v[e]) * (SAVED ? to_f32<T>(av[(BWD && SAVED) ? u : 0].v[e]) : gelu_grad(z));
           o.v[e] = from_f32<T>((g - k1[BWD ? e : 0] - d * k2[BWD ? e : 0]) * sc[e]);
         } else {
-          o.v[e] = from_f32<T>(gelu_fwd(z));
+          float cdf, pdf;
+          gelu_parts(z, cdf, pdf);
+          o.v[e] = from_f32<T>(z * cdf);
+          if (SAVED) da.v[e] = from_f32<T>(fmaf(z, pdf, cdf));
         }
       }
       *reinterpret_cast<P*>(out + (r + (long long)u * LY) * C + c0) = o;
+      if (!BWD && SAVED) *reinterpret_cast<P*>(dact + (r + (long long)u * LY) * C + c0) = da;
     }
   }
   for (; r < r1; r += LY) {
     const P xv = *reinterpret_cast<const P*>(x + r * C + c0);
-    P gv, o;
+    P gv, av, o, da;
     if (BWD) gv = *reinterpret_cast<const P*>(dy + r * C + c0);
+    if (BWD && SAVED) av = *reinterpret_cast<const P*>(dact + r * C + c0);
 #pragma unroll
     for (int e = 0; e < VEC; ++e) {
       const float d = to_f32<T>(xv.v[e]) - mu[e];
       const float z = fmaf(d, sc[e], sh[e]);
       if (BWD) {
-        const float g = to_f32<T>(gv.v[e]) * gelu_grad(z);
+        const float g = to_f32<T>(gv.v[e]) * (SAVED ? to_f32<T>(av.v[e]) : gelu_grad(z));
         o.v[e] = from_f32<T>((g - k1[BWD ? e : 0] - d * k2[BWD ? e : 0]) * sc[e]);
       } else {
-        o.v[e] = from_f32<T>(gelu_fwd(z));
+        float cdf, pdf;
+        gelu_parts(z, cdf, pdf);
+        o.v[e] = from_f32<T>(z * cdf);
+        if (SAVED) da.v[e] = from_f32<T>(fmaf(z, pdf, cdf));
       }
     }
     *reinterpret_cast<P*>(out + r * C + c0) = o;
+    if (!BWD && SAVED) *reinterpret_cast<P*>(dact + r * C + c0) = da;
   }
 }
 
@@ -345,7 +361,7 @@ BnPlan bn_plan(long long rows, int C, int vec) {
 template <typename T, int MODE>
 int launch_bn_reduce(const void* x, const void* dy, const float* mean, float* partial, long long rows, int C,
                      const BnPlan& p, cudaStream_t stream, const float* invstd = nullptr, const float* gamma = nullptr,
-                     const float* beta = nullptr) {
+                     const float* beta = nullptr, const void* dact = nullptr) {
   static std::atomic<uint64_t> configured{0};
   configure_once_per_device(configured, [] {
     cudaFuncSetAttribute(bn_reduce_kernel<T, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
@@ -353,8 +369,8 @@ int launch_bn_reduce(const void* x, const void* dy, const float* mean, float* pa
   dim3 grid(p.blocks, p.slabs);
   bn_reduce_kernel<T, MODE><<<grid, p.LX * p.LY, p.smem, stream>>>(static_cast<const T*>(x), static_cast<const T*>(dy),
                                                                  mean, partial, rows, C, p.LX, p.LY, p.rows_per_block,
-                                                                 invstd, gamma, beta);
-  GKG_CHECK_LAUNCH(MODE == 3 ? "bn_reduce_kernel<bwd, gelu>" : MODE == 1 ? "bn_reduce_kernel<bwd>" : MODE == 2 ? "bn_reduce_kernel<colsum>" : "bn_reduce_kernel<stats>");
+                                                                 invstd, gamma, beta, static_cast<const T*>(dact));
+  GKG_CHECK_LAUNCH(MODE == 4 ? "bn_reduce_kernel<bwd, saved gelu'>" : MODE == 3 ? "bn_reduce_kernel<bwd, gelu>" : MODE == 1 ? "bn_reduce_kernel<bwd>" : MODE == 2 ? "bn_reduce_kernel<colsum>" : "bn_reduce_kernel<stats>");
   return GKG_OK;
 }
 
@@ -445,60 +461,65 @@ extern "C" int gkg_column_sum(const void* x, long long rows, int C, int dtype, f
 // norm -> GELU in one pass and its backward (see bn_act_elemt_kernel); act: 2 = GELU (erf form) -- the only pairing the
 // reference's stacks contain.
 extern "C" int gkg_bn_act_forward(const void* x, const float* mean, const float* invstd, const float* gamma,
-                                  const float* beta, long long rows, int C, int dtype, int act, void* y,
+                                  const float* beta, long long rows, int C, int dtype, int act, void* y, void* dact,
                                   gkg_stream_t stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   int vec = 0;
   int rc = check_bn_args(x, rows, C, dtype, &vec);
   if (rc != GKG_OK) return rc;
   GKG_CHECK_ARG(act == 2, "gkg_bn_act_forward: activation %d (only 2 = GELU)", act);
-  GKG_CHECK_ARG(mean && invstd && gamma && beta && y && ((uintptr_t)y % 16) == 0, "gkg_bn_act_forward: null / unaligned pointer");
+  GKG_CHECK_ARG(mean && invstd && gamma && beta && y && ((uintptr_t)y % 16) == 0 && ((uintptr_t)dact % 16) == 0,
+                "gkg_bn_act_forward: null / unaligned pointer");
   const BnPlan p = bn_plan(rows, C, vec);
   dim3 grid(p.blocks, p.slabs);
-  if (dtype == GKG_F32)
-    bn_act_elemt_kernel<float, false><<<grid, p.LX * p.LY, 0, stream>>>(
-        static_cast<const float*>(x), nullptr, static_cast<float*>(y), mean, invstd, gamma, beta, nullptr, nullptr, rows, C,
-        p.LX, p.LY, p.rows_per_block);
-  else
-    bn_act_elemt_kernel<__nv_bfloat16, false><<<grid, p.LX * p.LY, 0, stream>>>(
-        static_cast<const __nv_bfloat16*>(x), nullptr, static_cast<__nv_bfloat16*>(y), mean, invstd, gamma, beta, nullptr,
-        nullptr, rows, C, p.LX, p.LY, p.rows_per_block);
+#define GKG_BN_FWD(TT, SV)                                                                                         \
+  bn_act_elemt_kernel<TT, false, SV><<<grid, p.LX * p.LY, 0, stream>>>(                                            \
+      static_cast<const TT*>(x), nullptr, static_cast<TT*>(y), static_cast<TT*>(dact), mean, invstd, gamma, beta,  \
+      nullptr, nullptr, rows, C, p.LX, p.LY, p.rows_per_block)
+  if (dtype == GKG_F32) { if (dact) GKG_BN_FWD(float, true); else GKG_BN_FWD(float, false); }
+  else { if (dact) GKG_BN_FWD(__nv_bfloat16, true); else GKG_BN_FWD(__nv_bfloat16, false); }
+#undef GKG_BN_FWD
   GKG_CHECK_LAUNCH("bn_act_elemt_kernel<fwd>");
   return GKG_OK;
 }
 
-extern "C" int gkg_bn_act_backward(const void* grad_out, const void* x, const float* mean, const float* invstd,
-                                   const float* gamma, const float* beta, long long rows, int C, int dtype, int act,
-                                   void* grad_x, float* grad_weight, float* grad_bias, void* ws, size_t ws_bytes,
-                                   gkg_stream_t stream_) {
+extern "C" int gkg_bn_act_backward(const void* grad_out, const void* x, const void* dact, const float* mean,
+                                   const float* invstd, const float* gamma, const float* beta, long long rows, int C,
+                                   int dtype, int act, void* grad_x, float* grad_weight, float* grad_bias, void* ws,
+                                   size_t ws_bytes, gkg_stream_t stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   int vec = 0;
   int rc = check_bn_args(x, rows, C, dtype, &vec);
   if (rc != GKG_OK) return rc;
   GKG_CHECK_ARG(act == 2, "gkg_bn_act_backward: activation %d (only 2 = GELU)", act);
   GKG_CHECK_ARG(grad_out && mean && invstd && gamma && beta && grad_x && ws, "gkg_bn_act_backward: null pointer");
-  GKG_CHECK_ARG(((uintptr_t)grad_out % 16) == 0 && ((uintptr_t)grad_x % 16) == 0, "gkg_bn_act_backward: unaligned pointer");
+  GKG_CHECK_ARG(((uintptr_t)grad_out % 16) == 0 && ((uintptr_t)grad_x % 16) == 0 && ((uintptr_t)dact % 16) == 0,
+                "gkg_bn_act_backward: unaligned pointer");
   GKG_CHECK_ARG(ws_bytes >= gkg_bn_workspace_bytes(rows, C), "gkg_bn_act_backward: workspace too small");
   const BnPlan p = bn_plan(rows, C, vec);
   float* partial = static_cast<float*>(ws);
   float* sums = partial + (size_t)kBnMaxBlocks * 2 * C;          // [2][C]: sum g, sum g (x - mean)
-  rc = dtype == GKG_F32
-           ? launch_bn_reduce<float, 3>(x, grad_out, mean, partial, rows, C, p, stream, invstd, gamma, beta)
-           : launch_bn_reduce<__nv_bfloat16, 3>(x, grad_out, mean, partial, rows, C, p, stream, invstd, gamma, beta);
+  if (dact != nullptr)
+    rc = dtype == GKG_F32
+             ? launch_bn_reduce<float, 4>(x, grad_out, mean, partial, rows, C, p, stream, invstd, gamma, beta, dact)
+             : launch_bn_reduce<__nv_bfloat16, 4>(x, grad_out, mean, partial, rows, C, p, stream, invstd, gamma, beta, dact);
+  else
+    rc = dtype == GKG_F32
+             ? launch_bn_reduce<float, 3>(x, grad_out, mean, partial, rows, C, p, stream, invstd, gamma, beta)
+             : launch_bn_reduce<__nv_bfloat16, 3>(x, grad_out, mean, partial, rows, C, p, stream, invstd, gamma, beta);
   if (rc != GKG_OK) return rc;
   bn_bwd_finalize_kernel<<<(C + 31) / 32, 32 * kFinLanes, 0, stream>>>(partial, p.blocks, C, invstd, sums, sums + C,
                                                                       grad_weight, grad_bias);
   GKG_CHECK_LAUNCH("bn_bwd_finalize_kernel");
   dim3 grid(p.blocks, p.slabs);
-  if (dtype == GKG_F32)
-    bn_act_elemt_kernel<float, true><<<grid, p.LX * p.LY, 0, stream>>>(
-        static_cast<const float*>(x), static_cast<const float*>(grad_out), static_cast<float*>(grad_x), mean, invstd, gamma,
-        beta, sums, sums + C, rows, C, p.LX, p.LY, p.rows_per_block);
-  else
-    bn_act_elemt_kernel<__nv_bfloat16, true><<<grid, p.LX * p.LY, 0, stream>>>(
-        static_cast<const __nv_bfloat16*>(x), static_cast<const __nv_bfloat16*>(grad_out),
-        static_cast<__nv_bfloat16*>(grad_x), mean, invstd, gamma, beta, sums, sums + C, rows, C, p.LX, p.LY,
-        p.rows_per_block);
+#define GKG_BN_BWD(TT, SV)                                                                                          \
+  bn_act_elemt_kernel<TT, true, SV><<<grid, p.LX * p.LY, 0, stream>>>(                                              \
+      static_cast<const TT*>(x), static_cast<const TT*>(grad_out), static_cast<TT*>(grad_x),                        \
+      const_cast<TT*>(static_cast<const TT*>(dact)), mean, invstd, gamma, beta, sums, sums + C, rows, C, p.LX, p.LY,  \
+      p.rows_per_block)
+  if (dtype == GKG_F32) { if (dact) GKG_BN_BWD(float, true); else GKG_BN_BWD(float, false); }
+  else { if (dact) GKG_BN_BWD(__nv_bfloat16, true); else GKG_BN_BWD(__nv_bfloat16, false); }
+#undef GKG_BN_BWD
   GKG_CHECK_LAUNCH("bn_act_elemt_kernel<bwd>");
   return GKG_OK;
 }

@@ -523,6 +523,7 @@ __global__ void __launch_bounds__(THREADS, 1) grouped_fc_wide_kernel(const WideP
 // walks its rows in blocks of 64 (K = 64 per block, 4 MMAs of M = 128, N = NT), accumulates in TMEM and adds its
 // partial (fp32) into gw with atomics at the end (split-R reduction; gw must be zero-filled by the caller).
 constexpr int WG_KB = 64;
+constexpr int WG_STAGES = 3;
 struct WgradParams {
   const __nv_bfloat16* go;       // (rows, C2)
   const __nv_bfloat16* x;        // (rows, C2)
@@ -537,10 +538,10 @@ __global__ void __launch_bounds__(256, 2) grouped_fc_wgrad_kernel(const WgradPar
   const int CG = prm.CG, NT = prm.NT, C2 = prm.C2;
   constexpr uint32_t kSbo = (WG_KB / 8) * 128;                       // bytes between groups of 8 channels
   const uint32_t a_bytes = 16 * kSbo, b_bytes = (uint32_t)(NT / 8) * kSbo;
-  uint8_t* sA = smem;                                               // 2 x [16 channel groups][8 row groups][8 rows][8 channels]
-  uint8_t* sB = sA + 2 * a_bytes;                                   // 2 x [NT/8 channel groups][...]
-  uint64_t* bar = reinterpret_cast<uint64_t*>(sB + 2 * b_bytes);    // [2]: MMAs of a buffer retired
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 2);
+  uint8_t* sA = smem;                                               // WG_STAGES x [16 channel groups][8 row groups][8 rows][8 channels]
+  uint8_t* sB = sA + WG_STAGES * a_bytes;                           // WG_STAGES x [NT/8 channel groups][...]
+  uint64_t* bar = reinterpret_cast<uint64_t*>(sB + WG_STAGES * b_bytes);   // [WG_STAGES]: MMAs of a buffer retired
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + WG_STAGES);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   int it = blockIdx.x;
@@ -553,7 +554,7 @@ __global__ void __launch_bounds__(256, 2) grouped_fc_wgrad_kernel(const WgradPar
   const long long rend = min(prm.rows, rbeg + prm.rows_per_split);
 
   if (threadIdx.x == 0) {
-    mbar_init(smem_u32(bar), 1); mbar_init(smem_u32(bar + 1), 1);
+    for (int i = 0; i < WG_STAGES; ++i) mbar_init(smem_u32(bar + i), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
@@ -568,47 +569,67 @@ __global__ void __launch_bounds__(256, 2) grouped_fc_wgrad_kernel(const WgradPar
   const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(NT >> 3) << 17) |
                          ((uint32_t)(128 >> 4) << 24);
   const int a_groups = min(16, (CG - o0 + 7) / 8), b_groups = min(NT / 8, (CG - i0 + 7) / 8);
-  uint32_t ph[2] = {0, 0};
-  int nblk = 0;
-  for (long long r0 = rbeg; r0 < rend; r0 += WG_KB, ++nblk) {
-    const int buf = nblk & 1;
-    if (nblk >= 2) {               // the MMAs that read this buffer two blocks ago must have retired
-      mbar_wait(smem_u32(bar + buf), ph[buf]);
-      ph[buf] ^= 1;
+  // Three-stage cp.async ring over blocks of WG_KB rows: block i+2 is in flight while block i is multiplied (the
+  // synchronous version paid one DRAM round trip per 64-row block: ~100 us per call whatever the layer).
+  uint32_t ph[WG_STAGES] = {0, 0, 0};
+  const long long nblocks = rend > rbeg ? (rend - rbeg + WG_KB - 1) / WG_KB : 0;
+  const int nblk = (int)nblocks;
+  auto load_block = [&](long long blk) {            // asynchronous; one commit group per call, empty past the end
+    if (blk < nblocks) {
+      const long long r0 = rbeg + blk * WG_KB;
+      const uint32_t a = smem_u32(sA) + (uint32_t)(blk % WG_STAGES) * a_bytes;
+      const uint32_t b = smem_u32(sB) + (uint32_t)(blk % WG_STAGES) * b_bytes;
+      // 16-byte pieces (8 channels of one row): piece (group g, row r) -> g * kSbo + (r / 8) * 128 + (r % 8) * 16
+      for (int i = threadIdx.x; i < 16 * WG_KB; i += 256) {
+        const int g = i % 16, r = i / 16;
+        const bool ok = g < a_groups && r0 + r < rend;
+        cp_async16(a + g * kSbo + ((r >> 3) << 7) + ((r & 7) << 4),
+                   ok ? reinterpret_cast<const uint4*>(prm.go + (r0 + r) * C2 + q * CG + o0) + g
+                      : reinterpret_cast<const uint4*>(prm.go), ok ? 16u : 0u);
+      }
+      for (int i = threadIdx.x; i < (NT / 8) * WG_KB; i += 256) {
+        const int g = i % (NT / 8), r = i / (NT / 8);
+        const bool ok = g < b_groups && r0 + r < rend;
+        cp_async16(b + g * kSbo + ((r >> 3) << 7) + ((r & 7) << 4),
+                   ok ? reinterpret_cast<const uint4*>(prm.x + (r0 + r) * C2 + q * CG + i0) + g
+                      : reinterpret_cast<const uint4*>(prm.x), ok ? 16u : 0u);
+      }
     }
-    uint8_t* a = sA + buf * a_bytes;
-    uint8_t* b = sB + buf * b_bytes;
-    // 16-byte pieces (8 channels of one row): piece (group g, row r) -> g * kSbo + (r / 8) * 128 + (r % 8) * 16
-    for (int i = threadIdx.x; i < 16 * WG_KB; i += 256) {
-      const int g = i % 16, r = i / 16;
-      uint4 v = make_uint4(0, 0, 0, 0);
-      if (g < a_groups && r0 + r < rend) v = __ldg(reinterpret_cast<const uint4*>(prm.go + (r0 + r) * C2 + q * CG + o0) + g);
-      *reinterpret_cast<uint4*>(a + g * kSbo + ((r >> 3) << 7) + ((r & 7) << 4)) = v;
-    }
-    for (int i = threadIdx.x; i < (NT / 8) * WG_KB; i += 256) {
-      const int g = i % (NT / 8), r = i / (NT / 8);
-      uint4 v = make_uint4(0, 0, 0, 0);
-      if (g < b_groups && r0 + r < rend) v = __ldg(reinterpret_cast<const uint4*>(prm.x + (r0 + r) * C2 + q * CG + i0) + g);
-      *reinterpret_cast<uint4*>(b + g * kSbo + ((r >> 3) << 7) + ((r & 7) << 4)) = v;
-    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  load_block(0);
+  load_block(1);
+  for (long long blk = 0; blk < nblocks; ++blk) {
+    const int buf = (int)(blk % WG_STAGES);
+    asm volatile("cp.async.wait_group 1;" ::: "memory");           // block blk has landed (blk + 1 may still be in flight)
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncthreads();
     if (threadIdx.x == 0) {
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint32_t a_addr = smem_u32(a), b_addr = smem_u32(b);
+      const uint32_t a_addr = smem_u32(sA) + buf * a_bytes, b_addr = smem_u32(sB) + buf * b_bytes;
       for (int ks = 0; ks < WG_KB / 16; ++ks) {                      // K = 16 rows = two row groups = 256 bytes
         const uint64_t ad = make_desc(a_addr + ks * 256, 128, kSbo), bd = make_desc(b_addr + ks * 256, 128, kSbo);
-        const uint32_t acc = (nblk | ks) != 0;
+        const uint32_t acc = (blk | ks) != 0;
         asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
                      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
                      ::"r"(tmem_base), "l"(ad), "l"(bd), "r"(idesc), "r"(acc) : "memory");
       }
       asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar + buf)) : "memory");
     }
+    // block blk + 2 goes into the buffer block blk - 1 used: its MMAs (issued an iteration ago) must have retired
+    if (blk >= 1) {
+      const int pb = (int)((blk - 1) % WG_STAGES);
+      mbar_wait(smem_u32(bar + pb), ph[pb]);
+      ph[pb] ^= 1;
+    }
+    load_block(blk + 2);
   }
-  // drain: the last commit on each buffer covers every earlier MMA
-  for (int buf = 0; buf < 2; ++buf)
-    if (nblk > buf) { mbar_wait(smem_u32(bar + buf), ph[buf]); ph[buf] ^= 1; }
+  // drain: the commit of the last block covers every earlier MMA
+  if (nblk > 0) {
+    const int lb = (int)((nblocks - 1) % WG_STAGES);
+    mbar_wait(smem_u32(bar + lb), ph[lb]);
+    ph[lb] ^= 1;
+  }
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   if (warp < 4 && nblk > 0) {
     const int o = o0 + warp * 32 + lane;                             // TMEM lane == output channel
@@ -819,11 +840,11 @@ extern "C" int gkg_grouped_fc_wgrad(const void* grad_out, const void* in, float*
   prm.rows_per_split = (blocks_of_rows + splits - 1) / splits * fc::WG_KB;
   splits = (int)((rows + prm.rows_per_split - 1) / prm.rows_per_split);
   prm.splits = splits;
-  const size_t smem = 2 * (size_t)(16 + prm.NT / 8) * (fc::WG_KB / 8) * 128 + 64;
+  const size_t smem = fc::WG_STAGES * (size_t)(16 + prm.NT / 8) * (fc::WG_KB / 8) * 128 + 64;
   static std::atomic<uint64_t> configured{0};
   cudaError_t e = cudaSuccess;
   configure_once_per_device(configured, [&] {
-    e = cudaFuncSetAttribute(fc::grouped_fc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024);
+    e = cudaFuncSetAttribute(fc::grouped_fc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   });
   if (e != cudaSuccess) { set_error("grouped_fc_wgrad: smem attribute: %s", cudaGetErrorString(e)); return GKG_ECUDA; }
   fc::grouped_fc_wgrad_kernel<<<base * splits, 256, smem, stream>>>(prm);

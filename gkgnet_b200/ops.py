@@ -602,10 +602,14 @@ class _BatchNormTrain(torch.autograd.Function):
             ctx.save_for_backward(x, weight, mean, invstd)
             return y
         y = torch.empty_like(x)                                   # same (channels-last) strides
+        # gelu'(z) saved in the feature dtype (what the unfused path keeps is the norm output, same size): the
+        # backward passes then stream dy, x and this tensor without evaluating the derivative again
+        dact = torch.empty_like(x) if x.requires_grad or weight.requires_grad else None
         rc = lib.gkg_bn_act_forward(x2.data_ptr(), mean.data_ptr(), invstd.data_ptr(), weight.data_ptr(),
-                                    bias.data_ptr(), rows, C, _DT[x.dtype], 2, y.data_ptr(), _stream(x))
+                                    bias.data_ptr(), rows, C, _DT[x.dtype], 2, y.data_ptr(),
+                                    None if dact is None else dact.data_ptr(), _stream(x))
         _lib.check(rc, "gkg_bn_act_forward")
-        ctx.save_for_backward(x, weight, mean, invstd, bias)
+        ctx.save_for_backward(x, weight, mean, invstd, bias, dact)
         return y
 
     @staticmethod
@@ -621,9 +625,10 @@ class _BatchNormTrain(torch.autograd.Function):
         out = torch.empty(4, C, dtype=torch.float32, device=x.device)       # sum_dy, sum_dy_xmu, grad_weight, grad_bias
         ws = _workspace(x.device, lib.gkg_bn_workspace_bytes(rows, C))
         if ctx.act is not None:
-            bias = ctx.saved_tensors[4]
+            bias, dact = ctx.saved_tensors[4], ctx.saved_tensors[5]
             dx = torch.empty_like(x)
-            rc = lib.gkg_bn_act_backward(g2.data_ptr(), x2.data_ptr(), mean.data_ptr(), invstd.data_ptr(),
+            rc = lib.gkg_bn_act_backward(g2.data_ptr(), x2.data_ptr(), None if dact is None else dact.data_ptr(),
+                                         mean.data_ptr(), invstd.data_ptr(),
                                          weight.data_ptr(), bias.data_ptr(), rows, C, _DT[x.dtype], 2, dx.data_ptr(),
                                          out[2].data_ptr(), out[3].data_ptr(), ws.data_ptr(), ws.numel(), _stream(x))
             _lib.check(rc, "gkg_bn_act_backward")

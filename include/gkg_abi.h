@@ -286,14 +286,16 @@ int gkg_bn_backward_reduce(const void* grad_out, const void* x, const float* mea
 
 /*
  * norm -> GELU pairs (BasicConv torch_nn.py:61-65, FFN.fc1 gkgnet.py:52-58, Stem gkgnet.py:82-90) in training:
- *   gkg_bn_act_forward:   y = gelu((x - mean) * invstd * gamma + beta)  with the statistics of gkg_bn_stats
+ *   gkg_bn_act_forward:   y = gelu(z), z = (x - mean) * invstd * gamma + beta, with the statistics of gkg_bn_stats;
+ *                         dact (nullable, (rows, C), dtype) receives gelu'(z) for the backward
  *   gkg_bn_act_backward:  everything autograd derives for that pair from grad_out = dL/dy: grad_x (rows, C),
- *                         grad_weight = dL/dgamma, grad_bias = dL/dbeta (the norm output is recomputed from x, not saved)
+ *                         grad_weight = dL/dgamma, grad_bias = dL/dbeta.  With dact the two passes are pure streaming
+ *                         kernels; without it the derivative is re-evaluated from x (nothing but x is saved).
  * act: 2 = GELU (erf form); x, y, grad_out, grad_x (rows, C) contiguous, dtype; ws as above.
  */
 int gkg_bn_act_forward(const void* x, const float* mean, const float* invstd, const float* gamma, const float* beta,
-                       long long rows, int C, int dtype, int act, void* y, gkg_stream_t stream);
-int gkg_bn_act_backward(const void* grad_out, const void* x, const float* mean, const float* invstd,
+                       long long rows, int C, int dtype, int act, void* y, void* dact, gkg_stream_t stream);
+int gkg_bn_act_backward(const void* grad_out, const void* x, const void* dact, const float* mean, const float* invstd,
                         const float* gamma, const float* beta, long long rows, int C, int dtype, int act,
                         void* grad_x, float* grad_weight, float* grad_bias, void* ws, size_t ws_bytes,
                         gkg_stream_t stream);
