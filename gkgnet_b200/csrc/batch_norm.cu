@@ -15,8 +15,8 @@
 // (no atomics: the result is deterministic).  A second, tiny kernel combines the partials.
 //
 // Numerics of the statistics: a block accumulates sums of d = x - pivot_c (pivot = the block's first row), so that
-// sum d^2 - (sum d)^2 / n does not cancel when |mean| >> std; block partials (n, mean, M2) are merged with Chan's
-// parallel-variance update in the finalize kernel.
+// sum d^2 - (sum d)^2 / n does not cancel when |mean| >> std; block partials (n, mean, M2) are merged in the finalize
+// kernel as mean = sum n_b mean_b / N, M2 = sum [M2_b + n_b (mean_b - mean)^2] (Chan's parallel variance, all at once).
 #include "knn_tc.cuh"
 
 namespace gkg {
@@ -267,39 +267,51 @@ bn_act_elemt_kernel(const T* __restrict__ x, const T* __restrict__ dy, T* __rest
 // partials was a 100 us dependent chain of L2 loads), the lanes are merged through shared memory.
 constexpr int kFinLanes = 16;
 
-__device__ __forceinline__ void chan_merge(float& n, float& mean, float& m2, float nb, float mb, float qb) {
-  if (nb <= 0.f) return;
-  const float tot = n + nb;
-  const float delta = mb - mean;
-  mean += delta * (nb / tot);
-  m2 += qb + delta * delta * (n * nb / tot);
-  n = tot;
-}
-
-// Chan's parallel-variance merge -> mean, invstd; running statistics like nn.BatchNorm2d (momentum update, unbiased
-// variance).
+// Merge of the block partials (n_b, mean_b, M2_b) -> mean, invstd; running statistics like nn.BatchNorm2d (momentum
+// update, unbiased variance).  Two passes over the (L2-resident) partials instead of a chain of Chan updates with two
+// divisions each:  mean = sum n_b mean_b / N,  M2 = sum [M2_b + n_b (mean_b - mean)^2]  -- the same quantity, every term
+// non-negative (no cancellation), one division per channel.
 __global__ void __launch_bounds__(32 * kFinLanes)
 bn_stats_finalize_kernel(const float* __restrict__ partial, int nblocks, long long rows, long long rows_per_block,
                          int C, float eps, float momentum, float* __restrict__ mean_out,
                          float* __restrict__ invstd_out, float* __restrict__ running_mean,
                          float* __restrict__ running_var) {
-  __shared__ float sn[kFinLanes][32], sm[kFinLanes][32], sq[kFinLanes][32];
+  __shared__ float sm[kFinLanes][32];
+  __shared__ float s_mean[32];
   const int cx = threadIdx.x & 31, py = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + cx;
-  float n = 0.f, mean = 0.f, m2 = 0.f;
-  if (c < C) {
-    for (int bI = py; bI < nblocks; bI += kFinLanes) {
-      const long long r0 = (long long)bI * rows_per_block;
-      const long long r1 = r0 + rows_per_block < rows ? r0 + rows_per_block : rows;
-      chan_merge(n, mean, m2, (float)(r1 > r0 ? r1 - r0 : 0), partial[(size_t)bI * 2 * C + c],
-                 partial[(size_t)bI * 2 * C + C + c]);
-    }
-  }
-  sn[py][cx] = n; sm[py][cx] = mean; sq[py][cx] = m2;
+  const bool ok = c < C;
+  const float n_full = (float)rows_per_block;
+  const float n_last = (float)(rows - (long long)(nblocks - 1) * rows_per_block);     // the last range may be shorter
+  const float inv_n = 1.f / (float)rows;
+  // pass 1: weighted mean, relative to the first block's mean (keeps the sum small when |mean| >> std)
+  const float pivot = ok ? partial[c] : 0.f;
+  float acc = 0.f;
+  if (ok)
+    for (int bI = py; bI < nblocks; bI += kFinLanes)
+      acc = fmaf(bI == nblocks - 1 ? n_last : n_full, partial[(size_t)bI * 2 * C + c] - pivot, acc);
+  sm[py][cx] = acc;
   __syncthreads();
-  if (py != 0 || c >= C) return;
-  for (int l = 1; l < kFinLanes; ++l) chan_merge(n, mean, m2, sn[l][cx], sm[l][cx], sq[l][cx]);
-  const float var = n > 0.f ? m2 / n : 0.f;
+  if (py == 0) {
+    for (int l = 1; l < kFinLanes; ++l) acc += sm[l][cx];
+    s_mean[cx] = pivot + acc * inv_n;
+  }
+  __syncthreads();
+  const float mean = s_mean[cx];
+  // pass 2: within-block + between-block sums of squares
+  float m2 = 0.f;
+  if (ok)
+    for (int bI = py; bI < nblocks; bI += kFinLanes) {
+      const float dm = partial[(size_t)bI * 2 * C + c] - mean;
+      m2 += fmaf(bI == nblocks - 1 ? n_last : n_full, dm * dm, partial[(size_t)bI * 2 * C + C + c]);
+    }
+  __syncthreads();
+  sm[py][cx] = m2;
+  __syncthreads();
+  if (py != 0 || !ok) return;
+  for (int l = 1; l < kFinLanes; ++l) m2 += sm[l][cx];
+  const float n = (float)rows;
+  const float var = m2 * inv_n;
   mean_out[c] = mean;
   invstd_out[c] = rsqrtf(var + eps);
   if (running_mean != nullptr) {

@@ -140,7 +140,9 @@ class GraphedTrainStep:
         if not img.is_cuda:
             raise ValueError("GraphedTrainStep needs CUDA tensors (there is no CPU path)")
         self.img, self.tgt = img.clone(), tgt.clone()
-        self.grads = FlatGradients(params)
+        # one all-reduce over the whole flat buffer: nothing overlaps it inside the graph, so a single large message
+        # (best bus bandwidth) beats DDP-sized buckets (8 GPUs: 0.82 ms for six 25 MB buckets)
+        self.grads = FlatGradients(params, bucket_bytes=1 << 40)
         params = self.grads.params
 
         def body():
