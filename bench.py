@@ -722,7 +722,8 @@ def run_model(args):
         # back to back on the NCCL stream -- what the step would pay if none of it overlapped the backward pass
         import torch.distributed as dist
         nbytes = sum(p.numel() * 4 for p in params)
-        bucket = torch.zeros(25 * 1024 * 1024 // 4, device=dev)
+        # the captured step reduces the flat gradient buffer in one message, the eager DDP path in 25 MB buckets
+        bucket = torch.zeros((nbytes if graphed else 25 * 1024 * 1024) // 4, device=dev)
         nb = max(1, (nbytes + bucket.numel() * 4 - 1) // (bucket.numel() * 4))
         for _ in range(2):
             for _ in range(nb):
@@ -736,7 +737,8 @@ def run_model(args):
         c.record()
         torch.cuda.synchronize()
         coll_ms = P.max_over_ranks(a.elapsed_time(c) / 3, dev)
-        coll = {"name": "NCCL all_reduce of the fp32 gradients (DDP buckets of 25 MB)", "bytes_per_step": nbytes,
+        coll = {"name": "NCCL all_reduce of the fp32 gradients (" + ("one message over the flat gradient buffer, as inside "
+                        "the captured step" if graphed else "DDP buckets of 25 MB") + ")", "bytes_per_step": nbytes,
                 "buckets": int(nb), "ms_alone": coll_ms, "share_of_step_if_exposed": coll_ms / ms,
                 "bus_gbs": 2.0 * (world - 1) / world * nbytes / (coll_ms * 1e-3) / 1e9}
         del bucket
