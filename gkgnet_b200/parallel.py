@@ -178,3 +178,29 @@ class GraphedTrainStep:
         self.graph.replay()
         return self.loss
 
+    # ---- input pipeline: the next batch crosses PCIe on a copy stream while the current step runs -------------------
+    def prefetch(self, img_host, tgt_host):
+        """Start the host -> device copy of the NEXT batch (pinned host tensors) into staging buffers on a copy stream."""
+        dev = self.img.device
+        if getattr(self, "_copy_stream", None) is None:
+            self._copy_stream = torch.cuda.Stream(device=dev)
+            self._stage = (torch.empty_like(self.img), torch.empty_like(self.tgt))
+            self._ready, self._consumed = torch.cuda.Event(), torch.cuda.Event()
+            self._consumed.record(torch.cuda.current_stream(dev))
+        cs = self._copy_stream
+        cs.wait_event(self._consumed)                      # the previous batch has left the staging buffers
+        with torch.cuda.stream(cs):
+            self._stage[0].copy_(img_host, non_blocking=True)
+            self._stage[1].copy_(tgt_host, non_blocking=True)
+            self._ready.record(cs)
+
+    def step_prefetched(self):
+        """Run one step on the batch handed to prefetch(): device -> device copy into the graph's static inputs, replay."""
+        cur = torch.cuda.current_stream(self.img.device)
+        cur.wait_event(self._ready)
+        self.img.copy_(self._stage[0])
+        self.tgt.copy_(self._stage[1])
+        self._consumed.record(cur)
+        self.graph.replay()
+        return self.loss
+

@@ -63,3 +63,30 @@ def test_graphed_step_matches_eager_training():
     img2 = torch.randn(4, 3, 192, 192, device=dev, generator=g)
     l2 = step(img2, tgt).item()
     assert l2 == l2
+
+
+def test_prefetched_inputs_reach_the_graph():
+    """prefetch() / step_prefetched(): the batch uploaded on the copy stream is the one the replay consumes."""
+    import gkgnet_b200 as G
+    from gkgnet_b200 import parallel as P
+    G.set_norm_type("BN")
+    torch.manual_seed(0)
+    dev = torch.device("cuda")
+    model = _Model(G).to(dev).train()
+    pm = [p for p in model.parameters() if p.requires_grad]
+    om = torch.optim.AdamW(pm, lr=0.0, weight_decay=0.0, fused=True, capturable=True)
+    g = torch.Generator().manual_seed(4)
+    batches = [(torch.randn(4, 3, 192, 192, generator=g).pin_memory(),
+                (torch.rand(4, 80, generator=g) < 0.1).float().pin_memory()) for _ in range(3)]
+    step = P.GraphedTrainStep(model, om, pm, batches[0][0].to(dev), batches[0][1].to(dev), clip_norm=5.0, warmup=1)
+    direct = [step(i.to(dev), t.to(dev)).item() for i, t in batches]           # lr = 0: the loss depends on the batch only
+    piped = []
+    step.prefetch(*batches[0])
+    for j in range(3):
+        out = step.step_prefetched()
+        if j + 1 < 3:
+            step.prefetch(*batches[j + 1])
+        piped.append(out.item())
+    assert len(set(round(v, 3) for v in direct)) == 3                          # three different batches, three different losses
+    for a, b in zip(direct, piped):
+        assert abs(a - b) <= 5e-3 * abs(a), (direct, piped)
