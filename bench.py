@@ -665,7 +665,7 @@ def run_model(args):
     model = Model().to(dev)
     model.train(train)
     params = [p for p in model.parameters() if p.requires_grad]
-    graphed = train and not args.no_graph and not args.syncbn      # SyncBN keeps the eager DDP path
+    graphed = train and not args.no_graph
     opt = torch.optim.AdamW(params, lr=1e-4, weight_decay=0.05, fused=True, capturable=graphed) if train else None
     ddp = P.data_parallel(model, dev) if train and not graphed else model
     g = torch.Generator().manual_seed(100 + rank)

@@ -55,6 +55,8 @@ SIGNATURES = {
     "gkg_bn_stats": (_i32, [_vp, _c.c_longlong, _i32, _i32, _c.c_float, _c.c_float, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "gkg_bn_act_forward": (_i32, [_vp] * 5 + [_c.c_longlong, _i32, _i32, _i32, _vp, _vp, _vp]),
     "gkg_bn_act_backward": (_i32, [_vp] * 7 + [_c.c_longlong, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "gkg_bn_act_backward_reduce": (_i32, [_vp] * 7 + [_c.c_longlong, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "gkg_bn_act_backward_elemt": (_i32, [_vp] * 8 + [_c.c_longlong, _c.c_longlong, _i32, _i32, _i32, _vp, _vp]),
     "gkg_column_sum": (_i32, [_vp, _c.c_longlong, _i32, _i32, _vp, _vp, _sz, _vp]),
     "gkg_bn_backward_reduce": (_i32, [_vp, _vp, _vp, _vp, _c.c_longlong, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
 }

@@ -187,7 +187,7 @@ __global__ void __launch_bounds__(kBnMaxThreads)
 bn_act_elemt_kernel(const T* __restrict__ x, const T* __restrict__ dy, T* __restrict__ out, T* __restrict__ dact,
                     const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ gamma,
                     const float* __restrict__ beta, const float* __restrict__ sum_g, const float* __restrict__ sum_g_xmu,
-                    long long rows, int C, int LX, int LY, long long rows_per_block) {
+                    long long rows, int C, int LX, int LY, long long rows_per_block, float inv_n) {
   constexpr int VEC = BnVec<T>::N;
   using P = BnPack<T, VEC>;
   const int tx = threadIdx.x % LX, ty = threadIdx.x / LX;
@@ -196,7 +196,6 @@ bn_act_elemt_kernel(const T* __restrict__ x, const T* __restrict__ dy, T* __rest
   const long long r0 = (long long)blockIdx.x * rows_per_block;
   const long long r1 = r0 + rows_per_block < rows ? r0 + rows_per_block : rows;
   float mu[VEC], sc[VEC], sh[VEC], k1[BWD ? VEC : 1], k2[BWD ? VEC : 1];
-  const float inv_n = 1.f / (float)rows;
 #pragma unroll
   for (int e = 0; e < VEC; ++e) {
     const float is = invstd[c0 + e];
@@ -487,7 +486,7 @@ extern "C" int gkg_bn_act_forward(const void* x, const float* mean, const float*
 #define GKG_BN_FWD(TT, SV)                                                                                         \
   bn_act_elemt_kernel<TT, false, SV><<<grid, p.LX * p.LY, 0, stream>>>(                                            \
       static_cast<const TT*>(x), nullptr, static_cast<TT*>(y), static_cast<TT*>(dact), mean, invstd, gamma, beta,  \
-      nullptr, nullptr, rows, C, p.LX, p.LY, p.rows_per_block)
+      nullptr, nullptr, rows, C, p.LX, p.LY, p.rows_per_block, 0.f)
   if (dtype == GKG_F32) { if (dact) GKG_BN_FWD(float, true); else GKG_BN_FWD(float, false); }
   else { if (dact) GKG_BN_FWD(__nv_bfloat16, true); else GKG_BN_FWD(__nv_bfloat16, false); }
 #undef GKG_BN_FWD
@@ -495,22 +494,24 @@ extern "C" int gkg_bn_act_forward(const void* x, const float* mean, const float*
   return GKG_OK;
 }
 
-extern "C" int gkg_bn_act_backward(const void* grad_out, const void* x, const void* dact, const float* mean,
-                                   const float* invstd, const float* gamma, const float* beta, long long rows, int C,
-                                   int dtype, int act, void* grad_x, float* grad_weight, float* grad_bias, void* ws,
-                                   size_t ws_bytes, gkg_stream_t stream_) {
+// The fused backward in its two halves (a data-parallel SyncBN all-reduces `sums` between them):
+//   reduce: sums[0..C) = sum g, sums[C..2C) = sum g (x - mean), g = dy * gelu'(z); grad_weight / grad_bias from the
+//           LOCAL sums (they are parameter gradients: the gradient all-reduce averages them like every other one)
+//   elemt:  dx from the (possibly all-reduced) sums and the total row count they cover
+extern "C" int gkg_bn_act_backward_reduce(const void* grad_out, const void* x, const void* dact, const float* mean,
+                                          const float* invstd, const float* gamma, const float* beta, long long rows,
+                                          int C, int dtype, int act, float* sums, float* grad_weight, float* grad_bias,
+                                          void* ws, size_t ws_bytes, gkg_stream_t stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   int vec = 0;
   int rc = check_bn_args(x, rows, C, dtype, &vec);
   if (rc != GKG_OK) return rc;
-  GKG_CHECK_ARG(act == 2, "gkg_bn_act_backward: activation %d (only 2 = GELU)", act);
-  GKG_CHECK_ARG(grad_out && mean && invstd && gamma && beta && grad_x && ws, "gkg_bn_act_backward: null pointer");
-  GKG_CHECK_ARG(((uintptr_t)grad_out % 16) == 0 && ((uintptr_t)grad_x % 16) == 0 && ((uintptr_t)dact % 16) == 0,
-                "gkg_bn_act_backward: unaligned pointer");
-  GKG_CHECK_ARG(ws_bytes >= gkg_bn_workspace_bytes(rows, C), "gkg_bn_act_backward: workspace too small");
+  GKG_CHECK_ARG(act == 2, "gkg_bn_act_backward_reduce: activation %d (only 2 = GELU)", act);
+  GKG_CHECK_ARG(grad_out && mean && invstd && gamma && beta && sums && ws, "gkg_bn_act_backward_reduce: null pointer");
+  GKG_CHECK_ARG(((uintptr_t)grad_out % 16) == 0 && ((uintptr_t)dact % 16) == 0, "gkg_bn_act_backward_reduce: unaligned pointer");
+  GKG_CHECK_ARG(ws_bytes >= gkg_bn_workspace_bytes(rows, C), "gkg_bn_act_backward_reduce: workspace too small");
   const BnPlan p = bn_plan(rows, C, vec);
   float* partial = static_cast<float*>(ws);
-  float* sums = partial + (size_t)kBnMaxBlocks * 2 * C;          // [2][C]: sum g, sum g (x - mean)
   if (dact != nullptr)
     rc = dtype == GKG_F32
              ? launch_bn_reduce<float, 4>(x, grad_out, mean, partial, rows, C, p, stream, invstd, gamma, beta, dact)
@@ -523,15 +524,45 @@ extern "C" int gkg_bn_act_backward(const void* grad_out, const void* x, const vo
   bn_bwd_finalize_kernel<<<(C + 31) / 32, 32 * kFinLanes, 0, stream>>>(partial, p.blocks, C, invstd, sums, sums + C,
                                                                       grad_weight, grad_bias);
   GKG_CHECK_LAUNCH("bn_bwd_finalize_kernel");
+  return GKG_OK;
+}
+
+extern "C" int gkg_bn_act_backward_elemt(const void* grad_out, const void* x, const void* dact, const float* mean,
+                                         const float* invstd, const float* gamma, const float* beta, const float* sums,
+                                         long long rows, long long total_rows, int C, int dtype, int act, void* grad_x,
+                                         gkg_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  int vec = 0;
+  int rc = check_bn_args(x, rows, C, dtype, &vec);
+  if (rc != GKG_OK) return rc;
+  GKG_CHECK_ARG(act == 2 && total_rows >= rows, "gkg_bn_act_backward_elemt: activation %d / total rows %lld", act, total_rows);
+  GKG_CHECK_ARG(grad_out && mean && invstd && gamma && beta && sums && grad_x, "gkg_bn_act_backward_elemt: null pointer");
+  GKG_CHECK_ARG(((uintptr_t)grad_out % 16) == 0 && ((uintptr_t)grad_x % 16) == 0 && ((uintptr_t)dact % 16) == 0,
+                "gkg_bn_act_backward_elemt: unaligned pointer");
+  const BnPlan p = bn_plan(rows, C, vec);
+  const float inv_n = 1.f / (float)total_rows;
   dim3 grid(p.blocks, p.slabs);
 #define GKG_BN_BWD(TT, SV)                                                                                          \
   bn_act_elemt_kernel<TT, true, SV><<<grid, p.LX * p.LY, 0, stream>>>(                                              \
       static_cast<const TT*>(x), static_cast<const TT*>(grad_out), static_cast<TT*>(grad_x),                        \
       const_cast<TT*>(static_cast<const TT*>(dact)), mean, invstd, gamma, beta, sums, sums + C, rows, C, p.LX, p.LY,  \
-      p.rows_per_block)
+      p.rows_per_block, inv_n)
   if (dtype == GKG_F32) { if (dact) GKG_BN_BWD(float, true); else GKG_BN_BWD(float, false); }
   else { if (dact) GKG_BN_BWD(__nv_bfloat16, true); else GKG_BN_BWD(__nv_bfloat16, false); }
 #undef GKG_BN_BWD
   GKG_CHECK_LAUNCH("bn_act_elemt_kernel<bwd>");
   return GKG_OK;
+}
+
+extern "C" int gkg_bn_act_backward(const void* grad_out, const void* x, const void* dact, const float* mean,
+                                   const float* invstd, const float* gamma, const float* beta, long long rows, int C,
+                                   int dtype, int act, void* grad_x, float* grad_weight, float* grad_bias, void* ws,
+                                   size_t ws_bytes, gkg_stream_t stream_) {
+  GKG_CHECK_ARG(ws != nullptr && ws_bytes >= gkg_bn_workspace_bytes(rows, C), "gkg_bn_act_backward: workspace too small");
+  float* sums = static_cast<float*>(ws) + (size_t)kBnMaxBlocks * 2 * (size_t)(C > 0 ? C : 0);   // [2][C] behind the partials
+  int rc = gkg_bn_act_backward_reduce(grad_out, x, dact, mean, invstd, gamma, beta, rows, C, dtype, act, sums,
+                                      grad_weight, grad_bias, ws, ws_bytes, stream_);
+  if (rc != GKG_OK) return rc;
+  return gkg_bn_act_backward_elemt(grad_out, x, dact, mean, invstd, gamma, beta, sums, rows, rows, C, dtype, act,
+                                   grad_x, stream_);
 }

@@ -45,6 +45,32 @@ class BatchNorm2d(nn.BatchNorm2d):
         return super().forward(x)
 
 
+class SyncBatchNorm(nn.SyncBatchNorm):
+    """nn.SyncBatchNorm (the reference's norm: torch_nn.py:8, gkgnet.py:23; same parameters, buffers, state-dict keys)
+    whose training forward on channels-last CUDA activations runs the native kernels with the statistics exchanged by
+    one all-gather (forward) and one all-reduce (backward) of per-channel vectors.  Every rank must hold the same number
+    of rows (the benchmark's fixed per-GPU batch; the stock module also handles ragged batches and is used otherwise)."""
+
+    native = True
+
+    def takes_native(self, x):
+        if not (self.native and self.training and self.affine and self.track_running_stats and self.momentum is not None
+                and isinstance(x, torch.Tensor) and x.is_cuda):
+            return False
+        from . import ops
+        return ops.batch_norm_native_ok(x)
+
+    def forward(self, x, act=None):
+        if self.takes_native(x):
+            from . import ops
+            self.num_batches_tracked.add_(1)
+            return ops.batch_norm_train(x, self.weight, self.bias, self.running_mean, self.running_var,
+                                        self.momentum, self.eps, act, sync=True, group=self.process_group)
+        if act is not None:
+            raise ValueError("fused activation needs the native path")
+        return super().forward(x)
+
+
 def run_modules(mods, x):
     """Run a conv -> norm -> act stack as written (training / gradient passes), with two substitutions that keep the
     arithmetic: a 1x1 convolution on channels-last CUDA activations is the token-major GEMM it is (ops.conv1x1), and a
@@ -60,7 +86,7 @@ def run_modules(mods, x):
                 x = x.to(torch.get_autocast_dtype("cuda"))
             from . import ops
             x = ops.conv1x1(x, m.weight, m.bias)
-        elif (isinstance(m, BatchNorm2d) and isinstance(nxt, nn.GELU) and getattr(nxt, "approximate", "none") == "none"
+        elif (isinstance(m, (BatchNorm2d, SyncBatchNorm)) and isinstance(nxt, nn.GELU) and getattr(nxt, "approximate", "none") == "none"
               and m.weight is not None and m.weight.dtype == torch.float32 and m.takes_native(x)):
             x = m(x, act="gelu")
             i += 1
@@ -74,7 +100,7 @@ def build_norm_layer(cfg, num_features, postfix=""):
     """Stand-in for mmcv.cnn.build_norm_layer with the two types the reference uses."""
     kind = cfg.get("type", "SyncBN")
     if kind == "SyncBN":
-        layer = nn.SyncBatchNorm(num_features)
+        layer = SyncBatchNorm(num_features)
     elif kind == "BN":
         layer = BatchNorm2d(num_features)
     else:

@@ -575,28 +575,55 @@ def batch_norm_native_ok(x):
     return x.permute(0, 2, 3, 1).is_contiguous() and x.data_ptr() % 16 == 0
 
 
+def _sync_world(group):
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()):
+        return 1
+    return dist.get_world_size(group)
+
+
 class _BatchNormTrain(torch.autograd.Function):
-    """y = act(batch_norm(x)) with batch statistics (torch_nn.py:32-42 -> nn.BatchNorm2d training forward, optionally
-    followed by the stack's nn.GELU): statistics and backward reductions by gkg_bn_stats / gkg_bn_backward_reduce.
+    """y = act(batch_norm(x)) with batch statistics (torch_nn.py:32-42 -> nn.BatchNorm2d / nn.SyncBatchNorm training
+    forward, optionally followed by the stack's nn.GELU): statistics and backward reductions by gkg_bn_stats /
+    gkg_bn_backward_reduce.
     act None: elementwise passes by ATen's batch_norm_elemt / batch_norm_backward_elemt (the decomposition
     SyncBatchNorm uses).  act "gelu": gkg_bn_act_forward / gkg_bn_act_backward -- the activation rides on the
-    normalisation pass, and its derivative on the two backward passes (the norm output is recomputed, not saved)."""
+    normalisation pass, its derivative is saved in the feature dtype and the backward passes stream it.
+    sync: statistics over all data-parallel ranks (the reference's SyncBN, torch_nn.py:8): one all-gather of the
+    per-rank (mean, var) in the forward (equal row counts per rank: Chan's merge with equal weights), one all-reduce
+    of (sum g, sum g (x - mean)) in the backward -- two small collectives per norm, both capturable."""
 
     @staticmethod
     @_guard
-    def forward(ctx, x, weight, bias, running_mean, running_var, momentum, eps, act):
+    def forward(ctx, x, weight, bias, running_mean, running_var, momentum, eps, act, group_sync):
         lib = _lib.load()
         x2 = _rows_of(x)
         rows, C = x2.shape
+        sync, group = group_sync
+        world = _sync_world(group) if sync else 1
         mean = torch.empty(C, dtype=torch.float32, device=x.device)
         invstd = torch.empty(C, dtype=torch.float32, device=x.device)
         ws = _workspace(x.device, lib.gkg_bn_workspace_bytes(rows, C))
+        local_running = world == 1
         rc = lib.gkg_bn_stats(x2.data_ptr(), rows, C, _DT[x.dtype], float(eps), float(momentum), mean.data_ptr(),
-                              invstd.data_ptr(), None if running_mean is None else running_mean.data_ptr(),
-                              None if running_var is None else running_var.data_ptr(), ws.data_ptr(), ws.numel(),
-                              _stream(x))
+                              invstd.data_ptr(),
+                              None if (running_mean is None or not local_running) else running_mean.data_ptr(),
+                              None if (running_var is None or not local_running) else running_var.data_ptr(),
+                              ws.data_ptr(), ws.numel(), _stream(x))
         _lib.check(rc, "gkg_bn_stats")
-        ctx.act = act
+        if world > 1:
+            import torch.distributed as dist
+            local = torch.stack((mean, invstd.pow(-2) - eps))                  # (2, C): mean, biased variance of this rank
+            allst = torch.empty((world, 2, C), dtype=torch.float32, device=x.device)
+            dist.all_gather_into_tensor(allst, local, group=group)
+            mean = allst[:, 0].mean(0)
+            var = allst[:, 1].mean(0) + (allst[:, 0] - mean).square().mean(0)
+            invstd = torch.rsqrt(var + eps)
+            if running_mean is not None:
+                n = rows * world
+                running_mean.mul_(1.0 - momentum).add_(mean, alpha=momentum)
+                running_var.mul_(1.0 - momentum).add_(var, alpha=momentum * n / max(n - 1, 1))
+        ctx.act, ctx.world, ctx.group = act, world, group
         if act is None:
             y = torch.batch_norm_elemt(x, weight, bias, mean, invstd, eps)
             ctx.save_for_backward(x, weight, mean, invstd)
@@ -622,37 +649,55 @@ class _BatchNormTrain(torch.autograd.Function):
         dy = dy.to(x.dtype)
         x2, g2 = _rows_of(x), _rows_of(dy)
         rows, C = x2.shape
+        world = ctx.world
         out = torch.empty(4, C, dtype=torch.float32, device=x.device)       # sum_dy, sum_dy_xmu, grad_weight, grad_bias
         ws = _workspace(x.device, lib.gkg_bn_workspace_bytes(rows, C))
         if ctx.act is not None:
             bias, dact = ctx.saved_tensors[4], ctx.saved_tensors[5]
             dx = torch.empty_like(x)
-            rc = lib.gkg_bn_act_backward(g2.data_ptr(), x2.data_ptr(), None if dact is None else dact.data_ptr(),
-                                         mean.data_ptr(), invstd.data_ptr(),
-                                         weight.data_ptr(), bias.data_ptr(), rows, C, _DT[x.dtype], 2, dx.data_ptr(),
-                                         out[2].data_ptr(), out[3].data_ptr(), ws.data_ptr(), ws.numel(), _stream(x))
-            _lib.check(rc, "gkg_bn_act_backward")
+            dptr = None if dact is None else dact.data_ptr()
+            if world == 1:
+                rc = lib.gkg_bn_act_backward(g2.data_ptr(), x2.data_ptr(), dptr, mean.data_ptr(), invstd.data_ptr(),
+                                             weight.data_ptr(), bias.data_ptr(), rows, C, _DT[x.dtype], 2, dx.data_ptr(),
+                                             out[2].data_ptr(), out[3].data_ptr(), ws.data_ptr(), ws.numel(), _stream(x))
+                _lib.check(rc, "gkg_bn_act_backward")
+            else:
+                import torch.distributed as dist
+                rc = lib.gkg_bn_act_backward_reduce(g2.data_ptr(), x2.data_ptr(), dptr, mean.data_ptr(), invstd.data_ptr(),
+                                                    weight.data_ptr(), bias.data_ptr(), rows, C, _DT[x.dtype], 2,
+                                                    out[0].data_ptr(), out[2].data_ptr(), out[3].data_ptr(),
+                                                    ws.data_ptr(), ws.numel(), _stream(x))
+                _lib.check(rc, "gkg_bn_act_backward_reduce")
+                dist.all_reduce(out[:2], group=ctx.group)                     # (sum g, sum g (x - mean)) over all ranks
+                rc = lib.gkg_bn_act_backward_elemt(g2.data_ptr(), x2.data_ptr(), dptr, mean.data_ptr(), invstd.data_ptr(),
+                                                   weight.data_ptr(), bias.data_ptr(), out[0].data_ptr(), rows,
+                                                   rows * world, C, _DT[x.dtype], 2, dx.data_ptr(), _stream(x))
+                _lib.check(rc, "gkg_bn_act_backward_elemt")
         else:
             rc = lib.gkg_bn_backward_reduce(g2.data_ptr(), x2.data_ptr(), mean.data_ptr(), invstd.data_ptr(), rows, C,
                                             _DT[x.dtype], out[0].data_ptr(), out[1].data_ptr(), out[2].data_ptr(),
                                             out[3].data_ptr(), ws.data_ptr(), ws.numel(), _stream(x))
             _lib.check(rc, "gkg_bn_backward_reduce")
-            key = (x.device.index, rows)
+            if world > 1:
+                import torch.distributed as dist
+                dist.all_reduce(out[:2], group=ctx.group)
+            key = (x.device.index, rows, world)
             count = _COUNT_CACHE.get(key)
             if count is None:
-                count = _COUNT_CACHE[key] = torch.full((1,), rows, dtype=torch.int32, device=x.device)
+                count = _COUNT_CACHE[key] = torch.full((world,), rows, dtype=torch.int32, device=x.device)
             dx = None
             if ctx.needs_input_grad[0]:
                 dx = torch.batch_norm_backward_elemt(dy, x, mean, invstd, weight, out[0], out[1], count)
         gw = out[2].to(weight.dtype) if ctx.needs_input_grad[1] else None
         gb = out[3].to(weight.dtype) if ctx.needs_input_grad[2] else None
-        return dx, gw, gb, None, None, None, None, None
+        return dx, gw, gb, None, None, None, None, None, None
 
 
-def batch_norm_train(x, weight, bias, running_mean, running_var, momentum, eps, act=None):
+def batch_norm_train(x, weight, bias, running_mean, running_var, momentum, eps, act=None, sync=False, group=None):
     """Training-mode batch norm of a channels-last (B, C, H, W) CUDA activation, optionally fused with the GELU that
-    follows it (act="gelu"); updates the running statistics in place like nn.BatchNorm2d.  Raises on anything the
-    kernels do not take (callers check batch_norm_native_ok)."""
+    follows it (act="gelu"); updates the running statistics in place like nn.BatchNorm2d.  sync=True: statistics over
+    all ranks of ``group`` (nn.SyncBatchNorm semantics; every rank must hold the same number of rows).  Raises on
+    anything the kernels do not take (callers check batch_norm_native_ok)."""
     _require_cuda(x)
     if not batch_norm_native_ok(x):
         raise ValueError("batch_norm_train: needs a channels-last (B, C, H, W) bf16 / fp32 CUDA tensor, C % 8 (4) == 0")
@@ -660,7 +705,7 @@ def batch_norm_train(x, weight, bias, running_mean, running_var, momentum, eps, 
         raise ValueError(f"batch_norm_train: activation {act!r} (None or 'gelu')")
     if act is not None and (weight is None or bias is None or weight.dtype != torch.float32):
         raise ValueError("batch_norm_train: the fused activation needs fp32 affine parameters")
-    return _BatchNormTrain.apply(x, weight, bias, running_mean, running_var, momentum, eps, act)
+    return _BatchNormTrain.apply(x, weight, bias, running_mean, running_var, momentum, eps, act, (bool(sync), group))
 
 
 # ---------------------------------------------------------------------------------------------------------

@@ -299,6 +299,17 @@ int gkg_bn_act_backward(const void* grad_out, const void* x, const void* dact, c
                         const float* gamma, const float* beta, long long rows, int C, int dtype, int act,
                         void* grad_x, float* grad_weight, float* grad_bias, void* ws, size_t ws_bytes,
                         gkg_stream_t stream);
+/* The same backward in its two halves, for synchronised statistics (SyncBatchNorm, the reference's default norm,
+ * torch_nn.py:8): the caller all-reduces `sums` (fp32 [2][C]: sum g, sum g (x - mean)) over the data-parallel ranks
+ * between the calls and passes the total row count they cover. */
+int gkg_bn_act_backward_reduce(const void* grad_out, const void* x, const void* dact, const float* mean,
+                               const float* invstd, const float* gamma, const float* beta, long long rows, int C,
+                               int dtype, int act, float* sums, float* grad_weight, float* grad_bias,
+                               void* ws, size_t ws_bytes, gkg_stream_t stream);
+int gkg_bn_act_backward_elemt(const void* grad_out, const void* x, const void* dact, const float* mean,
+                              const float* invstd, const float* gamma, const float* beta, const float* sums,
+                              long long rows, long long total_rows, int C, int dtype, int act, void* grad_x,
+                              gkg_stream_t stream);
 
 /*
  * Column sums of a (rows, C) contiguous activation into fp32 out (C): the bias gradient autograd derives for a

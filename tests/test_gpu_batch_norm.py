@@ -212,3 +212,20 @@ def test_run_modules_fuses_norm_and_gelu():
     for a, b in zip(ga, (xb.grad, conv.weight.grad, ref_bn.weight.grad, ref_bn.bias.grad)):
         assert torch.allclose(a, b, atol=5e-3, rtol=2e-3)
     assert torch.allclose(bn.running_var, ref_bn.running_var, rtol=1e-5)
+
+
+def test_sync_batch_norm_single_process_is_batch_norm():
+    """layers.SyncBatchNorm (the reference's default norm type) without a process group == layers.BatchNorm2d."""
+    from gkgnet_b200 import layers
+    torch.manual_seed(2)
+    a, b = layers.SyncBatchNorm(160).cuda(), layers.BatchNorm2d(160).cuda()
+    b.load_state_dict(a.state_dict())
+    x = _cl(torch.randn(4, 160, 20, 20, device="cuda").to(torch.bfloat16))
+    gelu = torch.nn.GELU()
+    for mods in ((a,), (a, gelu)):
+        other = tuple(b if m is a else m for m in mods)
+        xa, xb = x.clone().requires_grad_(True), x.clone().requires_grad_(True)
+        ya, yb = layers.run_modules(mods, xa), layers.run_modules(other, xb)
+        ya.float().sum().backward(); yb.float().sum().backward()
+        assert torch.equal(ya, yb) and torch.equal(xa.grad, xb.grad)
+    assert torch.equal(a.running_var, b.running_var) and int(a.num_batches_tracked) == 2
