@@ -55,7 +55,8 @@ mr_aggregate_fwd_kernel(const T* __restrict__ x, int64_t x_sb, int64_t x_sn,
 #pragma unroll
       for (int e = 0; e < VEC; ++e) {
         const float f = to_f32<T>(yv.v[e]);
-        if (f > best[e]) { best[e] = f; arg[e] = j; }
+        // strictly greater: the first maximum wins ties; a NaN neighbour is taken once and then kept (torch.max propagates NaN)
+        if (f > best[e] || (f != f && best[e] == best[e])) { best[e] = f; arg[e] = j; }
       }
     }
     Pack<T, 2 * VEC> o;  // 2*VEC interleaved outputs [x_c, m_c, ...]
@@ -142,7 +143,8 @@ mr_aggregate_bwd_kernel(const T* __restrict__ gout, const int32_t* __restrict__ 
 // per-element convert / compare / select chain of the generic kernel disappears.  m = max - x is formed
 // in fp32 and rounded once, exactly as the generic kernel (and the reference under autocast) does.
 __device__ __forceinline__ uint32_t bf2_max(uint32_t a, uint32_t b) {
-  __nv_bfloat162 r = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&a), *reinterpret_cast<__nv_bfloat162*>(&b));
+  // HMNMX2.NAN: a NaN neighbour propagates into the maximum, as torch.max does
+  __nv_bfloat162 r = __hmax2_nan(*reinterpret_cast<__nv_bfloat162*>(&a), *reinterpret_cast<__nv_bfloat162*>(&b));
   return *reinterpret_cast<uint32_t*>(&r);
 }
 __device__ __forceinline__ uint32_t bf2_eq_mask(uint32_t a, uint32_t b) {

@@ -219,3 +219,28 @@ def test_aggregate_backward_deterministic_option():
     assert torch.equal(a[0], plain[0])
     scale = max(1.0, plain[1].float().abs().max().item())
     assert (a[1].float() - plain[1].float()).abs().max().item() <= 8e-3 * scale      # one bf16 ulp of the largest sum
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("B,G,N,M,D,k", [
+    (2, 2, 300, 70, 40, 9),       # generic / CTA-tiled kernels
+    (2, 2, 1500, 400, 40, 9),     # bf16: warp-autonomous shared-memory kernel
+    (1, 1, 33, 17, 7, 3),         # scalar path
+])
+def test_aggregate_propagates_nan_like_torch_max(dtype, B, G, N, M, D, k):
+    """torch.max(x_j - x_i, -1) propagates NaN (torch_vertex.py:53): a NaN key must poison exactly the (node, channel)
+    outputs whose neighbour list contains it, in every kernel variant (the kernels used to drop NaNs)."""
+    from gkgnet_b200 import ops
+    g = torch.Generator().manual_seed(4)
+    C = G * D
+    x = torch.randn(B, N, C, generator=g).to(dtype)
+    y = torch.randn(B, M, C, generator=g).to(dtype)
+    y[0, 3, 1] = float("nan")
+    y[B - 1, M - 1, C - 1] = float("nan")
+    idx = torch.randint(0, M, (B * G, N, k), generator=g, dtype=torch.int32)
+    out = ops.mr_aggregate(x.cuda(), idx.cuda(), y.cuda(), groups=G).cpu()
+    want = _oracle_agg(x.float(), idx, y.float(), G).to(dtype)
+    assert torch.isnan(want).any()
+    assert torch.equal(torch.isnan(out), torch.isnan(want))
+    ok = ~torch.isnan(want)
+    assert torch.equal(out[ok], want[ok])
