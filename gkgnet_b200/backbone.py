@@ -39,7 +39,8 @@ class FFN(nn.Module):
             h = run_modules(list(self.fc1) + [self.act], x)          # norm + GELU of fc1 in one pass
         else:
             h = self.act(self.fc1(x))
-        return self.drop_path(self.fc2(h)) + x
+        out = self.fc2(h)
+        return self.drop_path.add_residual(out, x) if isinstance(self.drop_path, DropPath) else self.drop_path(out) + x
 
 
 class Stem(nn.Module):

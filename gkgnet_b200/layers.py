@@ -225,6 +225,15 @@ class DropPath(nn.Module):
         shape = (x.shape[0],) + (1,) * (x.dim() - 1)
         return x * x.new_empty(shape).bernoulli_(keep).div_(keep)
 
+    def add_residual(self, x, shortcut):
+        """``self(x) + shortcut`` in one elementwise pass (the per-sample keep / scale mask rides on the residual add)."""
+        if self.drop_prob == 0.0 or not self.training:
+            return x + shortcut
+        keep = 1.0 - self.drop_prob
+        shape = (x.shape[0],) + (1,) * (x.dim() - 1)
+        mask = torch.empty(shape, dtype=torch.promote_types(x.dtype, shortcut.dtype), device=x.device)
+        return torch.addcmul(shortcut, x, mask.bernoulli_(keep).div_(keep))
+
     def extra_repr(self):
         return f"drop_prob={self.drop_prob}"
 

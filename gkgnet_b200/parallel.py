@@ -145,11 +145,21 @@ class GraphedTrainStep:
         self.grads = FlatGradients(params, bucket_bytes=1 << 40)
         params = self.grads.params
 
+        views = [p.grad for p in params]                 # the flat buffer, parameter by parameter
+
         def body():
-            self.grads.zero()
+            # autograd writes fresh gradient tensors (p.grad is None: no accumulate kernel per parameter, no memset);
+            # one multi-tensor copy then gathers them into the flat buffer, whose views become the gradients again
+            for p in params:
+                p.grad = None
             with torch.autocast("cuda", dtype=amp_dtype, enabled=amp_dtype is not None):
                 loss = model(self.img, self.tgt)
             loss.backward()
+            fresh = [p.grad if p.grad is not None else torch.zeros_like(p) for p in params]
+            torch._foreach_copy_(views, fresh)
+            for p, v in zip(params, views):
+                p.grad = v
+            del fresh
             self.grads.all_reduce_mean()
             if clip_norm is not None:
                 torch.nn.utils.clip_grad_norm_(params, clip_norm)

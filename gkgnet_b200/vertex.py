@@ -374,7 +374,7 @@ class Grapher(nn.Module):
         rel = self._get_relative_pos(self.relative_pos, H, W)
         x, _ = self.graph_conv(x, rel, self._separable(rel))
         x = self.fc2(x)
-        return self.drop_path(x) + shortcut
+        return self.drop_path.add_residual(x, shortcut) if isinstance(self.drop_path, DropPath) else self.drop_path(x) + shortcut
 
 
 class FFNLabel(nn.Module):
@@ -425,5 +425,5 @@ class GrapherLabel(nn.Module):
         B, C, N, _ = x.shape
         x, edge_index = self.graph_conv.forward_tokens(x.permute(0, 2, 3, 1).reshape(B, N, C), feats)
         x = self.fc2(x)
-        x = self.drop_path(x) + shortcut
+        x = self.drop_path.add_residual(x, shortcut) if isinstance(self.drop_path, DropPath) else self.drop_path(x) + shortcut
         return self.ffn(x), edge_index

@@ -132,3 +132,26 @@ def test_folded_sequential_matches_plain_modules_in_eval():
     assert torch.allclose(folded, plain, atol=1e-5, rtol=1e-5)
     seq.train()
     assert seq(x).requires_grad
+
+
+def test_drop_path_residual_form_equals_the_two_step_form():
+    """layers.DropPath.add_residual(x, s) == DropPath(x) + s (timm semantics: per-sample keep mask scaled by 1 / keep),
+    same random draws; identity in eval mode and for rate 0."""
+    import torch
+    from gkgnet_b200.layers import DropPath
+    dp = DropPath(0.3).train()
+    x, s = torch.randn(64, 5, 3, 3), torch.randn(64, 5, 3, 3)
+    torch.manual_seed(7)
+    a = dp.add_residual(x, s)
+    torch.manual_seed(7)
+    b = dp(x) + s
+    assert torch.allclose(a, b, atol=1e-6)
+    dropped = (a == s).flatten(1).all(1)
+    assert 0 < int(dropped.sum()) < 64                      # some samples dropped, some kept
+    kept = ~dropped
+    assert torch.allclose(a[kept], s[kept] + x[kept] / 0.7, atol=1e-6)
+    dp.eval()
+    assert torch.equal(dp.add_residual(x, s), x + s)
+    assert torch.equal(DropPath(0.0).train().add_residual(x, s), x + s)
+    mixed = DropPath(0.3).train().add_residual(x.to(torch.bfloat16), s)      # bf16 branch onto an fp32 residual stream
+    assert mixed.dtype == torch.float32
