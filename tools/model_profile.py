@@ -15,7 +15,7 @@ net = G.GKGNet(choice="s", n_classes=80, size=576, drop_path=0.1 if mode == "tra
 head = G.LabelQueryHead(80, 640).to(dev)
 net.train(mode == "train"); head.train(mode == "train")
 params = [p for p in list(net.parameters()) + list(head.parameters()) if p.requires_grad]
-opt = torch.optim.AdamW(params, lr=1e-4, weight_decay=0.05)
+opt = torch.optim.AdamW(params, lr=1e-4, weight_decay=0.05, fused=True)
 img = torch.randn(B, 3, 576, 576, device=dev)
 tgt = (torch.rand(B, 80, device=dev) < 0.04).float()
 
