@@ -675,7 +675,18 @@ def run_model(args):
     stream = torch.cuda.current_stream(dev)
     # the whole step (fwd, loss, bwd, gradient all-reduce over NCCL, clip, AdamW) as ONE CUDA graph: issued from Python
     # the ~3000 launches of a 16-image step take longer than the kernels run (tools/host_bound.py)
-    gstep = P.GraphedTrainStep(model, opt, params, img, tgt, clip_norm=5.0, warmup=3) if graphed else None
+    gstep, graph_note = None, None
+    if graphed:
+        try:
+            gstep = P.GraphedTrainStep(model, opt, params, img, tgt, clip_norm=5.0, warmup=3)
+        except Exception as exc:      # capture refused (driver / allocator state): measure the eager path, and say so
+            graph_note = f"{type(exc).__name__}: {str(exc)[:160]}"
+            graphed, gstep = False, None
+            torch.cuda.synchronize(dev)
+            for p_ in params:
+                p_.grad = None
+            opt = torch.optim.AdamW(params, lr=1e-4, weight_decay=0.05, fused=True)
+            ddp = P.data_parallel(model, dev)
 
     def step(from_host=False):
         if gstep is not None:
@@ -765,7 +776,8 @@ def run_model(args):
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": dict(train_config(world, args.syncbn, B),
                        launch=("one CUDA graph per step (fwd + loss + bwd + NCCL gradient all-reduce + clip + AdamW)"
-                               if graphed else "eager launches through DistributedDataParallel")) if train else {
+                               if graphed else "eager launches through DistributedDataParallel"
+                               + (f" (graph capture failed: {graph_note})" if graph_note else ""))) if train else {
             "workload": "BASELINE configs[2]: GKGNet-576 inference, bf16 autocast, replicas only",
             "images_per_gpu": B, "global_batch": B * world, "parallelism": f"dp{world} (replicas)",
             "norm": "SyncBN" if args.syncbn else "per-GPU BN",
