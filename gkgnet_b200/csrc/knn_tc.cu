@@ -10,9 +10,13 @@
 //         A = [x_hi | S  S | 0.. | x_hi | x_lo],   B = [y_hi | c_hi c_lo | 0.. | y_lo | y_hi],   c = -0.5*|yh|^2*S,
 //     so ONE fp16 GEMM with fp32 accumulation yields S^2 (xh.yh - |yh|^2/2) to ~2^-21 relative (the "fp16x3" split),
 //     and its first PA columns alone the single-plane product the threshold sweep uses.  Rows are stored in the UMMA
-//     no-swizzle K-major core-matrix order, tile by tile, so an operand block is one contiguous TMA bulk copy;
+//     no-swizzle K-major core-matrix order, tile by tile, so an operand block is one contiguous TMA bulk copy.  Wide
+//     groups (D > 80, D % 8 == 0) store TWO planes per row instead, [hi (+ extras) | lo] for queries and keys alike --
+//     the hi plane of the concatenated row is a repeat -- and the issuer forms hi.hi + lo.hi + hi.lo from them
+//     (knn_tc_kernel.cuh: "split" plans);
 //   * knn_tc_kernel (persistent, warp specialised, see knn_tc_kernel.cuh): warp 0 streams operand blocks, one warp per
-//     row set issues tcgen05.mma into TMEM accumulators, the epilogue warps drain them with tcgen05.ld (thread ==
+//     row set (256-row items) or three warps taking the key tiles in turn (128-row items) issue tcgen05.mma into TMEM
+//     accumulators, the epilogue warps drain them with tcgen05.ld (thread ==
 //     query row), add the position bias and select in two sweeps over the keys of an item: a threshold sweep (sorted
 //     register list of group maxima) and a logging sweep (predicated 16-byte shared-memory stores of the key triplets
 //     that beat the threshold); the logged keys that reach the threshold go to global memory;
