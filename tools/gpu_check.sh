@@ -15,7 +15,7 @@ timeout 900 python bench.py --impl reference 2>&1 | tail -1 | tee gpurun_out/${T
 echo "== bench --workload infer"
 timeout 600 python bench.py --workload infer --no-cpu 2>&1 | tail -1 | tee gpurun_out/${TAG}_bench_infer.json
 echo "== ncu launch list of the default bench command (our kernels only)"
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:'gkg|knn|mr_aggregate|tc_prepare|grouped_fc|pool_keys|label_|multilabel|neighbor' -c 1500 --csv \
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:'gkg|knn|mr_aggregate|tc_prepare|grouped_fc|pool_keys|label_|multilabel|neighbor|bn_' -c 2500 --csv \
     --log-file gpurun_out/${TAG}_launches.csv python bench.py --steps 2 --warmup 3 --no-cpu > gpurun_out/${TAG}_ncu_bench.log 2>&1
 tail -1 gpurun_out/${TAG}_ncu_bench.log | cut -c1-300
 echo "== ncu full (layer microbench kernels)"
