@@ -834,7 +834,9 @@ extern "C" int gkg_grouped_fc_wgrad(const void* grad_out, const void* in, float*
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int base = 4 * prm.mtiles * prm.passes;
   long long blocks_of_rows = (rows + fc::WG_KB - 1) / fc::WG_KB;
-  int splits = (2 * sms + base - 1) / base;
+  // row splits: every split ends in CG x CG fp32 atomics, so the wide groups (160 k addresses, tens of atomics each)
+  // take one CTA per SM; the narrow ones two (their epilogue is small, their copy-in latency needs the overlap)
+  int splits = ((CG > 96 ? 1 : 2) * sms + base - 1) / base;
   if (splits > blocks_of_rows) splits = (int)blocks_of_rows;
   if (splits < 1) splits = 1;
   prm.rows_per_split = (blocks_of_rows + splits - 1) / splits * fc::WG_KB;
