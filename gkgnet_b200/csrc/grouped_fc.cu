@@ -407,7 +407,7 @@ struct WideParams {
 };
 
 template <int ACT>
-__global__ void __launch_bounds__(THREADS, 1) grouped_fc_wide_kernel(const WideParams prm) {
+__global__ void __launch_bounds__(THREADS, 2) grouped_fc_wide_kernel(const WideParams prm) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const int CG = prm.CG, KP = prm.KP, NT = prm.NT, C2 = prm.C2;
   const uint32_t a_bytes = (uint32_t)BM * KP * 2, b_bytes = (uint32_t)NT * KP * 2;
@@ -718,7 +718,10 @@ extern "C" int gkg_grouped_fc_fwd(const void* in, const void* w_op, const float*
     });
     if (e != cudaSuccess) { set_error("grouped_fc_fwd: smem attribute: %s", cudaGetErrorString(e)); return GKG_ECUDA; }
     const long long items = tiles * 4 * wp.passes;
-    const int grid = (int)(items < sms ? items : sms);
+    // two co-resident CTAs per SM when their shared memory allows (CG = 120, 200): one copies rows in while the
+    // other is in its MMA / epilogue (the kernel itself is synchronous)
+    const long long ctas = (long long)sms * (wp.smem <= 110 * 1024 ? 2 : 1);
+    const int grid = (int)(items < ctas ? items : ctas);
     kern<<<grid, fc::THREADS, wp.smem, stream>>>(prm);
     GKG_CHECK_LAUNCH("grouped_fc_wide_kernel");
     return GKG_OK;
