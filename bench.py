@@ -765,7 +765,9 @@ def run_model(args):
     elif igraph is not None:
         launches = args.steps * igraph_launches
     clocks = sampler.stop()
-    e2e_ms = timed(max(3, min(args.steps, 5)), True)
+    # end to end: as many steps as the device-timed run when the input pipeline is one batch deep (its first upload is
+    # not hidden; over 5 steps it would weigh 20 % of a copy per step), 3-5 steps otherwise
+    e2e_ms = timed(max(3, args.steps if gstep is not None else min(args.steps, 5)), True)
     coll = None
     if train and world > 1:
         # the one collective of the step, timed alone: an all-reduce of the gradient bytes in DDP-sized buckets (25 MB),
