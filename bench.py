@@ -767,6 +767,7 @@ def run_model(args):
     clocks = sampler.stop()
     # end to end: as many steps as the device-timed run when the input pipeline is one batch deep (its first upload is
     # not hidden; over 5 steps it would weigh 20 % of a copy per step), 3-5 steps otherwise
+    timed(2, True)          # untimed warm-up of the host -> device path (first touch of the pinned batch, copy stream)
     e2e_ms = timed(max(3, args.steps if gstep is not None else min(args.steps, 5)), True)
     coll = None
     if train and world > 1:
