@@ -211,6 +211,27 @@ class BasicConv(FoldedSequential):
                 nn.init.zeros_(m.bias)
 
 
+class _ScaledResidual(torch.autograd.Function):
+    """shortcut + x * scale (scale: per-sample, broadcast) in one pass; the gradient of the low-precision branch is
+    written in its own dtype by the same kernel that scales it (autograd's addcmul backward multiplies in the residual
+    stream's fp32 and casts in a second pass)."""
+
+    @staticmethod
+    def forward(ctx, x, shortcut, scale):
+        ctx.save_for_backward(scale)
+        ctx.xdtype = x.dtype
+        return torch.addcmul(shortcut, x, scale)
+
+    @staticmethod
+    def backward(ctx, g):
+        (scale,) = ctx.saved_tensors
+        gx = None
+        if ctx.needs_input_grad[0]:
+            gx = torch.empty_like(g, dtype=ctx.xdtype)
+            torch.mul(g, scale, out=gx)
+        return gx, (g if ctx.needs_input_grad[1] else None), None
+
+
 class DropPath(nn.Module):
     """Stochastic depth per sample (timm.models.layers.DropPath semantics)."""
 
@@ -232,7 +253,7 @@ class DropPath(nn.Module):
         keep = 1.0 - self.drop_prob
         shape = (x.shape[0],) + (1,) * (x.dim() - 1)
         mask = torch.empty(shape, dtype=torch.promote_types(x.dtype, shortcut.dtype), device=x.device)
-        return torch.addcmul(shortcut, x, mask.bernoulli_(keep).div_(keep))
+        return _ScaledResidual.apply(x, shortcut, mask.bernoulli_(keep).div_(keep))
 
     def extra_repr(self):
         return f"drop_prob={self.drop_prob}"

@@ -155,3 +155,25 @@ def test_drop_path_residual_form_equals_the_two_step_form():
     assert torch.equal(DropPath(0.0).train().add_residual(x, s), x + s)
     mixed = DropPath(0.3).train().add_residual(x.to(torch.bfloat16), s)      # bf16 branch onto an fp32 residual stream
     assert mixed.dtype == torch.float32
+
+
+def test_drop_path_residual_gradients():
+    """The fused residual form routes gradients like the two-step form: g * mask / keep to the branch (in the branch's
+    dtype), g to the shortcut."""
+    import torch
+    from gkgnet_b200.layers import DropPath
+    dp = DropPath(0.4).train()
+    x = torch.randn(32, 4, 2, 2, requires_grad=True)
+    s = torch.randn(32, 4, 2, 2, requires_grad=True)
+    w = torch.randn(32, 4, 2, 2)
+    torch.manual_seed(3)
+    (dp.add_residual(x, s) * w).sum().backward()
+    ga, gs = x.grad.clone(), s.grad.clone()
+    x.grad = s.grad = None
+    torch.manual_seed(3)
+    ((dp(x) + s) * w).sum().backward()
+    assert torch.allclose(ga, x.grad, atol=1e-6) and torch.allclose(gs, s.grad, atol=1e-6)
+    xb = torch.randn(8, 4, 2, 2).to(torch.bfloat16).requires_grad_(True)
+    sb = torch.randn(8, 4, 2, 2, requires_grad=True)
+    dp.add_residual(xb, sb).sum().backward()
+    assert xb.grad.dtype == torch.bfloat16 and sb.grad.dtype == torch.float32
