@@ -9,8 +9,11 @@ BASELINE.json's metric has two clauses and the default run measures both, in one
 
   * "GKGNet-576 images/sec (fwd+bwd, 1/2/4/8 B200)" -- the headline `value` / `ms_per_step` / `e2e`: one training
     step of GKGNet-576 (BASELINE configs[3]: pvig_s backbone + label-query head, random init, bf16 autocast,
-    fwd + loss + bwd + grad clip + AdamW, 16 images per GPU).  N GPUs shard by image (DDP): the only collective is
-    the NCCL gradient all-reduce, inside the timed region; value = images of all ranks / max-over-ranks device time.
+    fwd + loss + bwd + grad clip + AdamW, 16 images per GPU).  N GPUs shard by image: the only collective is the NCCL
+    gradient all-reduce (mean over ranks, what DDP computes), inside the timed region; value = images of all ranks /
+    max-over-ranks device time.  The step is captured once in a CUDA graph and replayed (parallel.GraphedTrainStep;
+    --no-graph issues it eagerly through DistributedDataParallel); `e2e` uploads every batch from pinned host memory one
+    batch ahead on a copy stream and reads every step's loss back.
   * "Grapher kNN+agg us/layer, % roofline" -- keys `layer`, `phase_ms`, `roofline*`: the stage-1 Grapher layer hot
     path (BASELINE configs[1]: B=32 images per GPU, C=80, N=144x144 patches, M=1296 pooled keys, G=2, k=9): kNN-graph
     construction (normalise + distance + top-k), max-relative aggregation forward and backward through the C ABI,
