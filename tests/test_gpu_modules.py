@@ -162,6 +162,36 @@ def test_gkgnet_576_bf16_smoke():
     assert not missing, missing[:5]
 
 
+def test_gkgnet_t_bf16_train_and_eval():
+    """Arch 't' (channels 48 / 96 / 240 / 384: grouped-FC widths 2C/4 = 24, 48, 120, 192; group widths D = 24, 48, 120,
+    192 -- none of them the 's' widths the kernels were tuned on; ADVICE r1: C2 = 480 used to pass the support check and
+    fail at launch): training step and eval forward under bf16 autocast, every parameter gets a gradient, the eval fast
+    paths agree with the module stack run with autograd on."""
+    import gkgnet_b200 as G
+    G.set_norm_type("BN")
+    try:
+        torch.manual_seed(0)
+        net = G.GKGNet(choice="t", n_classes=80, size=192, drop_path=0.1).cuda().train()
+        head = G.LabelQueryHead(80, 384).cuda()
+    finally:
+        G.set_norm_type("SyncBN")
+    img = torch.randn(2, 3, 192, 192, device="cuda")
+    tgt = (torch.rand(2, 80, device="cuda") < 0.1).float()
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        loss = sum(head.forward_train(net(img), tgt).values())
+    loss.backward()
+    assert torch.isfinite(loss)
+    missing = [n for n, p in net.named_parameters() if p.requires_grad and p.grad is None]
+    assert not missing, missing[:5]
+    net.eval()
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        with torch.no_grad():
+            fast = net(img)[1].float()                      # folded norms, fused grouped FC
+        slow = net(img)[1].float()                          # modules as written (autograd on)
+    cos = torch.nn.functional.cosine_similarity(fast.flatten(), slow.flatten(), dim=0).item()
+    assert cos > 0.98, cos
+
+
 @pytest.mark.parametrize("name", ["grapher_r2"])   # (the r = 1 fixture has 8-dim groups: bf16 ties flip too many neighbours)
 def test_grapher_eval_bf16_fast_paths_agree_with_module_stack(name):
     """Inference fast paths (Conv -> BN folding, 1x1 convs as GEMMs, tcgen05 grouped FC with folded norm +
