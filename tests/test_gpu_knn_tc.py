@@ -221,6 +221,8 @@ def test_tc_smooth_key_field_compacts_instead_of_fixup():
     (1, 2, 96, 128, 8, 9, 2, "grid"),           # coarse grid: piles of exactly equal distances
     (1, 1, 48, 300, 16, 9, 2, "constant"),      # every distance ties: one bin, all keys are candidates
     (1, 1, 32, 2500, 16, 9, 1, "constant"),     # ... and more of them than candidate slots: count over all keys
+    (1, 1, 40, 5184, 16, 9, 2, "few_unique"),   # fewer than k*d distinct near keys, thousands tied in the last
+                                                # (clamped) histogram bin that holds the k*d-th neighbour
 ])
 def test_tc_fixup_kernel_matches_exact_kernel(B, G, N, M, D, k, d, keys):
     """Debug hook 3 routes every row to the brute-force fix-up kernel (histogram select + rank by counting):
@@ -234,6 +236,9 @@ def test_tc_fixup_kernel_matches_exact_kernel(B, G, N, M, D, k, d, keys):
         x, y = (x * 2).round() / 2, (y * 2).round() / 2
     elif keys == "constant":
         y = y[:, :1].expand(B, M, C).contiguous()
+    elif keys == "few_unique":
+        far = -x.mean(1, keepdim=True)                             # one far point, repeated
+        y = torch.cat((y[:, :5], far.expand(B, M - 5, C)), 1).contiguous()
     x, y = x.cuda(), y.cuda()
     info = {"flags": 3}
     got = ops.knn_graph(x, y, None, groups=G, k=k, dilation=d, algo=_lib.KNN_TCGEN05, debug=info)
