@@ -221,6 +221,9 @@ def test_tc_smooth_key_field_compacts_instead_of_fixup():
     (1, 2, 96, 128, 8, 9, 2, "grid"),           # coarse grid: piles of exactly equal distances
     (1, 1, 48, 300, 16, 9, 2, "constant"),      # every distance ties: one bin, all keys are candidates
     (1, 1, 32, 2500, 16, 9, 1, "constant"),     # ... and more of them than candidate slots: count over all keys
+    (1, 1, 24, 20736, 40, 9, 1, "random"),      # stage-1 label head: more keys than the shared-memory distance tile
+                                                # (8192): distances in the global scratch row (M > 47104 limit)
+    (1, 1, 8, 50176, 40, 9, 1, "random"),       # the 896-pixel label head the old kernel refused
     (1, 1, 40, 5184, 16, 9, 2, "few_unique"),   # fewer than k*d distinct near keys, thousands tied in the last
                                                 # (clamped) histogram bin that holds the k*d-th neighbour
 ])
