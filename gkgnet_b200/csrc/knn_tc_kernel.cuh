@@ -49,8 +49,9 @@ struct Geom {
   static_assert(BN % CH == 0 && BNP % 16 == 0 && BNP >= BN && RS * NACC * ACC_STRIDE <= 512 && ACC_STRIDE >= BNP, "geometry");
   // Triplet log of a row: log_valid(T) entries can be kept (the second sweep logs ~T + 1 on average, see
   // the kernel); behind them log_slack(T) slots absorb the triplets logged between two capacity checks
-  // (6 per half chunk).
-  __host__ __device__ static constexpr int log_valid(int T) { return T + (T / 2 > 8 ? T / 2 : 8); }
+  // (6 per half chunk).  T + 8 for every list length (it was T + T / 2 for the long lists: the 12 KB that frees at
+  // T = 29 buy the wide-group plans a fourth operand stage, -4 % at D = 200, k*d = 27; a row that logs more compacts).
+  __host__ __device__ static constexpr int log_valid(int T) { return T + 8; }
   __host__ __device__ static constexpr int log_slack(int T) { return 6; }
   __host__ __device__ static constexpr size_t cand_bytes(int T) {
     return (size_t)ROWS * (log_valid(T) + log_slack(T)) * 16;
