@@ -16,6 +16,8 @@
 // bf16.  The weights sit in shared memory for the CTA's lifetime in the same core-matrix order (built by
 // the caller, see gkgnet_b200/ops.py:grouped_fc_weights).  Memory bound: 2 * rows * 2C * 2 bytes.
 #include "knn_tc.cuh"
+#include <cuda.h>
+#include <cudaTypedefs.h>
 
 namespace gkg {
 namespace fc {
@@ -96,6 +98,8 @@ struct Params {
   const float* shift;            // (C2); the per-channel scale is folded into w_op by the caller
   long long rows;
   int C2, CG, KP, NP, act;
+  int stages;                    // TMA kernel: depth of the A-tile ring
+  int stage_out;                 // TMA kernel: output tiles leave through the consumed stage + one bulk store each
 };
 
 // CGT: channels per conv group at compile time (the two wide layers), 0 = run-time value
@@ -379,6 +383,189 @@ __global__ void __launch_bounds__(THREADS, 1) grouped_fc_pipe_kernel(const Param
           loads_landed(j + 2 < mine);                    // also: every warp has drained the accumulators of tile j
           if (threadIdx.x == 0) issue_mma(j + 1);
         }
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0)
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512) : "memory");
+}
+
+// ------------------------------------------------------------------------------------
+// the same pipeline with the copy-in on the TMA: a 3-D tensor map over the input, (8 channels, rows, C2 / 8) with box
+// (8, BM, C2 / 8), lands a tile as [C2 / 8][BM][16 bytes].  That IS a no-swizzle K-major operand: the 8 rows of a core
+// matrix are 128 contiguous bytes, 8-row groups are 128 bytes apart (SBO), K-adjacent core matrices BM * 16 bytes (LBO).
+// One instruction per tile instead of BM * C2 / 8 per-thread cp.async: the per-thread 16-byte path saturates near
+// 4 TB/s chip-wide.  The K padding of a group (CG = 40: 40 -> 48) reads the first 8 channels of the NEXT
+// group against zero weight rows (finite x 0; the last group reads the 2 KB zero tail behind the ring... of the last
+// stage only -- the other stages are followed by the next stage's tile, also finite), rows past the end are zero-filled
+// by the TMA.  NST stages: tiles j+1 .. j+NST-1 are in flight during the epilogue of tile j.
+template <int CGT, int ACT>
+__global__ void __launch_bounds__(THREADS + 32, 1) grouped_fc_tma_kernel(const Params prm, const __grid_constant__ CUtensorMap tmap) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int CG = CGT > 0 ? CGT : prm.CG;
+  const int KP = (CG + 15) / 16 * 16, NP = KP, C2 = 4 * CG;
+  const bool two_acc = 8 * NP <= 512;
+  const int NST = prm.stages;
+  const uint32_t tile_bytes = (uint32_t)BM * C2 * 2;
+  const uint32_t b_group_bytes = (uint32_t)NP * KP * 2;
+  uint8_t* sA = smem;                                   // NST x [C2/8][BM][8] + 2 KB of zeros
+  uint8_t* sB = sA + (uint32_t)NST * tile_bytes + 2048; // 4 x [NP/8][KP/8][8][8]
+  float* s_shift = reinterpret_cast<float*>(sB + 4 * b_group_bytes);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(s_shift + C2);      // [2]: MMAs of the tile in accumulator set 0 / 1
+  uint64_t* full = bar + 2;                                       // [NST]: tile landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(full + 4);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // warp 16 (one thread) is the control thread: TMA loads, MMA issue, bulk stores; warps 0-15 only wait for the MMAs and run
+  // the epilogue.  stage_out: the output tile is written into the A stage the MMA has just consumed (same size, row-major
+  // like the output itself) and leaves as ONE bulk store; the stage is refilled once the store has read it.
+  const bool ctl = threadIdx.x == THREADS;
+  const bool stage_out = two_acc && NST >= 3 && prm.stage_out != 0;
+
+  for (uint32_t i = threadIdx.x; i < 4 * b_group_bytes / 16; i += THREADS + 32)
+    reinterpret_cast<uint4*>(sB)[i] = __ldg(reinterpret_cast<const uint4*>(prm.w_op) + i);
+  for (int i = threadIdx.x; i < C2; i += THREADS + 32) s_shift[i] = prm.shift[i];
+  // every stage starts finite (the K padding of the last group reads the head of the NEXT stage, loaded or not) + the tail
+  for (uint32_t i = threadIdx.x; i < ((uint32_t)NST * tile_bytes + 2048) / 16; i += THREADS + 32)
+    reinterpret_cast<uint4*>(sA)[i] = make_uint4(0, 0, 0, 0);
+  if (threadIdx.x == 0) {
+    mbar_init(smem_u32(bar), 1);
+    mbar_init(smem_u32(bar + 1), 1);
+    for (int i = 0; i < NST; ++i) mbar_init(smem_u32(full + i), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // zero tail / weights written by this proxy, read by the MMA
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+
+  const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NP >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+  const uint32_t sbo_b = (uint32_t)(KP >> 3) * 128u;
+  const int cg_chunks = CG >> 3;
+  const long long tiles = (prm.rows + BM - 1) / BM;
+  const long long first = blockIdx.x, stride = gridDim.x;
+  const long long mine = first < tiles ? (tiles - first + stride - 1) / stride : 0;     // tiles of this CTA
+
+  auto load_tile = [&](long long j) {                   // one thread; j-th tile of this CTA -> stage j % NST
+    const int s = (int)(j % NST);
+    const int r0 = (int)((first + j * stride) * BM);
+    const uint32_t fb = smem_u32(full + s);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(fb), "r"(tile_bytes) : "memory");
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                 ::"r"(smem_u32(sA) + (uint32_t)s * tile_bytes), "l"(reinterpret_cast<uint64_t>(&tmap)), "r"(0), "r"(r0), "r"(0),
+                   "r"(fb) : "memory");
+  };
+  auto issue_mma = [&](long long j) {                   // one thread; tile j: stage j % NST -> accumulator set
+    const uint32_t acc_set = two_acc ? (uint32_t)(j & 1) : 0u;
+    mbar_wait(smem_u32(full + (int)(j % NST)), (uint32_t)((j / NST) & 1));
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t a_tile = smem_u32(sA) + (uint32_t)(j % NST) * tile_bytes;
+    for (int q = 0; q < 4; ++q) {
+      const uint32_t a_addr = a_tile + (uint32_t)(q * cg_chunks) * (BM * 16);
+      const uint32_t b_addr = smem_u32(sB + q * b_group_bytes);
+      for (int ks = 0; ks < (KP >> 4); ++ks) {
+        const uint64_t ad = make_desc(a_addr + ks * 2 * (BM * 16), BM * 16, 128), bd = make_desc(b_addr + ks * 256, 128, sbo_b);
+        const uint32_t acc = ks != 0;
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                     "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                     ::"r"(tmem_base + acc_set * 4 * NP + (uint32_t)(q * NP)), "l"(ad), "l"(bd), "r"(idesc), "r"(acc) : "memory");
+      }
+    }
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar + acc_set)) : "memory");
+  };
+  auto epilogue = [&](long long j) {
+    const long long r0 = (first + j * stride) * BM;
+    const uint32_t acc_set = two_acc ? (uint32_t)(j & 1) : 0u;
+    const int row = (warp & 3) * 32 + lane;
+    const bool row_ok = r0 + row < prm.rows;
+    __nv_bfloat16* orow = prm.out + (r0 + row) * C2;
+    const int q = warp >> 2;
+    for (int c0 = 0; c0 < CG; c0 += 16) {
+      uint32_t acc[16];
+      tmem_ld16(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + acc_set * 4 * NP + (uint32_t)(q * NP + c0), acc);
+      __align__(16) __nv_bfloat162 o[8];
+#pragma unroll
+      for (int j4 = 0; j4 < 16; j4 += 4) {
+        float v[4] = {0.f, 0.f, 0.f, 0.f};
+        if (c0 + j4 < CG) {
+          const float4 sh = *reinterpret_cast<const float4*>(s_shift + q * CG + c0 + j4);
+          v[0] = activate<ACT>(__uint_as_float(acc[j4]) + sh.x);
+          v[1] = activate<ACT>(__uint_as_float(acc[j4 + 1]) + sh.y);
+          v[2] = activate<ACT>(__uint_as_float(acc[j4 + 2]) + sh.z);
+          v[3] = activate<ACT>(__uint_as_float(acc[j4 + 3]) + sh.w);
+        }
+        o[j4 >> 1] = __floats2bfloat162_rn(v[0], v[1]);
+        o[(j4 >> 1) + 1] = __floats2bfloat162_rn(v[2], v[3]);
+      }
+      if (stage_out) {
+        uint4* dst = reinterpret_cast<uint4*>(sA + (uint32_t)(j % NST) * tile_bytes + ((uint32_t)row * C2 + q * CG + c0) * 2);
+        dst[0] = *reinterpret_cast<const uint4*>(o);
+        if (c0 + 8 < CG) dst[1] = *reinterpret_cast<const uint4*>(o + 4);
+      } else if (row_ok) {
+        *reinterpret_cast<uint4*>(orow + q * CG + c0) = *reinterpret_cast<const uint4*>(o);
+        if (c0 + 8 < CG) *reinterpret_cast<uint4*>(orow + q * CG + c0 + 8) = *reinterpret_cast<const uint4*>(o + 4);
+      }
+    }
+    if (stage_out) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // staged rows -> visible to the bulk store
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  };
+  auto store_tile = [&](long long j) {                  // control thread, after a barrier behind epilogue(j)
+    const long long r0 = (first + j * stride) * BM;
+    const long long nrows = prm.rows - r0 < BM ? prm.rows - r0 : BM;
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                 ::"l"(prm.out + r0 * C2), "r"(smem_u32(sA) + (uint32_t)(j % NST) * tile_bytes), "r"((uint32_t)(nrows * C2 * 2))
+                 : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+  };
+  uint32_t ph[2] = {0, 0};
+  auto wait_mma = [&](long long j) {
+    const uint32_t acc_set = two_acc ? (uint32_t)(j & 1) : 0u;
+    mbar_wait(smem_u32(bar + acc_set), ph[acc_set]);
+    ph[acc_set] ^= 1;
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  };
+
+  if (mine > 0) {
+    if (ctl) {
+      for (long long t = 0; t < mine && t < NST; ++t) load_tile(t);
+      issue_mma(0);
+    }
+    for (long long j = 0; j < mine; ++j) {
+      if (two_acc) {
+        if (stage_out || j + 1 < mine) __syncthreads();  // every warp is past the epilogue of j-1: its accumulators are free
+        if (ctl) {
+          if (j + 1 < mine) issue_mma(j + 1);
+          if (stage_out && j >= 1) {
+            store_tile(j - 1);
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");      // the stage has been read: refill it
+            if (j - 1 + NST < mine) load_tile(j - 1 + NST);
+          }
+        }
+        if (!stage_out || !ctl) wait_mma(j);             // stage j % NST has been read by the MMAs
+        if (!stage_out && ctl && j + NST < mine) load_tile(j + NST);
+        if (warp < 16) epilogue(j);
+      } else {
+        wait_mma(j);
+        if (ctl && j + NST < mine) load_tile(j + NST);
+        if (warp < 16) epilogue(j);
+        if (j + 1 < mine) {
+          __syncthreads();                               // every warp has drained the accumulators of tile j
+          if (ctl) issue_mma(j + 1);
+        }
+      }
+    }
+    if (stage_out) {
+      __syncthreads();
+      if (ctl) {
+        store_tile(mine - 1);
+        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
       }
     }
   }
@@ -687,6 +874,27 @@ extern "C" int gkg_grouped_fc_pass_width(int C2) {
   return fc_narrow_ok(CG) ? 0 : fc_wide_plan(CG).NT;
 }
 
+// 3-D tensor map over a (rows, C2) bf16 activation: (8 channels, rows, C2 / 8), box (8, BM, C2 / 8); rows past the end read as
+// zeros.  false when the driver entry point is missing or rejects the shape (the caller then takes the cp.async kernel).
+static bool fc_input_map(CUtensorMap* map, const void* in, long long rows, int C2) {
+  static const PFN_cuTensorMapEncodeTiled_v12000 encode = [] {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult st;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &st) != cudaSuccess ||
+        st != cudaDriverEntryPointSuccess)
+      fn = nullptr;
+    return reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
+  }();
+  if (encode == nullptr || C2 / 8 > 256) return false;
+  const cuuint64_t gdim[3] = {8, (cuuint64_t)rows, (cuuint64_t)(C2 / 8)};
+  const cuuint64_t gstr[2] = {(cuuint64_t)C2 * 2, 16};
+  const cuuint32_t box[3] = {8, (cuuint32_t)fc::BM, (cuuint32_t)(C2 / 8)};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  return encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(in), gdim, gstr, box, estr,
+                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 extern "C" int gkg_grouped_fc_fwd(const void* in, const void* w_op, const float* shift, void* out, long long rows,
                                   int C2, int act, gkg_stream_t stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
@@ -733,6 +941,34 @@ extern "C" int gkg_grouped_fc_fwd(const void* in, const void* w_op, const float*
   prm.shift = shift; prm.rows = rows;
   prm.C2 = C2; prm.CG = C2 / 4; prm.KP = (prm.CG + 15) / 16 * 16; prm.NP = prm.KP; prm.act = act;
   const size_t smem = 4 * (size_t)fc::BM * prm.KP * 2 + 4 * (size_t)prm.NP * prm.KP * 2 + (size_t)C2 * 4 + 64;
+  // TMA copy-in (grouped_fc_tma_kernel) when the driver encodes the 3-D map and at least two stages fit
+  if (tiles >= 2LL * sms && rows < (1LL << 31)) {
+    const size_t tile_bytes = (size_t)fc::BM * C2 * 2;
+    const size_t fixed = 2048 + 4 * (size_t)prm.NP * prm.KP * 2 + (size_t)C2 * 4 + 8 * 6 + 16;
+    int nst = 4;
+    while (nst >= 2 && nst * tile_bytes + fixed > 220 * 1024) --nst;
+    CUtensorMap tmap;
+    if (nst >= 2 && fc_input_map(&tmap, in, rows, C2)) {
+      prm.stages = nst;
+      prm.stage_out = (8 * prm.NP <= 512 && nst >= 3) ? 1 : 0;
+      void (*tk)(const fc::Params, const CUtensorMap) = nullptr;
+#define GKG_FC_PICK(AA)                                                                                        \
+      tk = prm.CG == 40 ? fc::grouped_fc_tma_kernel<40, AA> : prm.CG == 80 ? fc::grouped_fc_tma_kernel<80, AA> : fc::grouped_fc_tma_kernel<0, AA>
+      if (act == 0) { GKG_FC_PICK(0); } else if (act == 1) { GKG_FC_PICK(1); } else { GKG_FC_PICK(2); }
+#undef GKG_FC_PICK
+      const int tslot = act * 3 + (prm.CG == 40 ? 0 : prm.CG == 80 ? 1 : 2);
+      static std::atomic<uint64_t> tconfigured[9];
+      cudaError_t e = cudaSuccess;
+      configure_once_per_device(tconfigured[tslot], [&] {
+        e = cudaFuncSetAttribute(tk, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+      });
+      if (e != cudaSuccess) { set_error("grouped_fc_fwd: smem attribute: %s", cudaGetErrorString(e)); return GKG_ECUDA; }
+      const int tgrid = (int)(tiles < sms ? tiles : sms);
+      tk<<<tgrid, fc::THREADS + 32, nst * tile_bytes + fixed, stream>>>(prm, tmap);
+      GKG_CHECK_LAUNCH("grouped_fc_tma_kernel");
+      return GKG_OK;
+    }
+  }
   const size_t smem_pipe = smem + 4 * (size_t)fc::BM * prm.KP * 2;          // second A buffer
   if (smem_pipe <= 220 * 1024 && tiles >= 2LL * sms) {
     // software-pipelined kernel: one persistent CTA per SM (worth it once every SM has a few tiles)
