@@ -451,10 +451,11 @@ __global__ void __launch_bounds__(THREADS + 32, 1) grouped_fc_tma_kernel(const P
   const int cg_chunks = CG >> 3;
   const long long tiles = (prm.rows + BM - 1) / BM;
   const long long first = blockIdx.x, stride = gridDim.x;
-  const long long mine = first < tiles ? (tiles - first + stride - 1) / stride : 0;     // tiles of this CTA
+  const int mine = first < tiles ? (int)((tiles - first + stride - 1) / stride) : 0;     // tiles of this CTA (32-bit loop
+  // counters: `j % NST` on a long long is a 64-bit division routine, and it sat in the epilogue's inner loop)
 
-  auto load_tile = [&](long long j) {                   // one thread; j-th tile of this CTA -> stage j % NST
-    const int s = (int)(j % NST);
+  auto load_tile = [&](int j) {                   // one thread; j-th tile of this CTA -> stage j % NST
+    const int s = j % NST;
     const int r0 = (int)((first + j * stride) * BM);
     const uint32_t fb = smem_u32(full + s);
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(fb), "r"(tile_bytes) : "memory");
@@ -462,11 +463,12 @@ __global__ void __launch_bounds__(THREADS + 32, 1) grouped_fc_tma_kernel(const P
                  ::"r"(smem_u32(sA) + (uint32_t)s * tile_bytes), "l"(reinterpret_cast<uint64_t>(&tmap)), "r"(0), "r"(r0), "r"(0),
                    "r"(fb) : "memory");
   };
-  auto issue_mma = [&](long long j) {                   // one thread; tile j: stage j % NST -> accumulator set
+  auto issue_mma = [&](int j) {                   // one thread; tile j: stage j % NST -> accumulator set
     const uint32_t acc_set = two_acc ? (uint32_t)(j & 1) : 0u;
-    mbar_wait(smem_u32(full + (int)(j % NST)), (uint32_t)((j / NST) & 1));
+    const int sj = j % NST;
+    mbar_wait(smem_u32(full + sj), (uint32_t)((j / NST) & 1));
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const uint32_t a_tile = smem_u32(sA) + (uint32_t)(j % NST) * tile_bytes;
+    const uint32_t a_tile = smem_u32(sA) + (uint32_t)sj * tile_bytes;
     for (int q = 0; q < 4; ++q) {
       const uint32_t a_addr = a_tile + (uint32_t)(q * cg_chunks) * (BM * 16);
       const uint32_t b_addr = smem_u32(sB + q * b_group_bytes);
@@ -480,13 +482,14 @@ __global__ void __launch_bounds__(THREADS + 32, 1) grouped_fc_tma_kernel(const P
     }
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar + acc_set)) : "memory");
   };
-  auto epilogue = [&](long long j) {
+  auto epilogue = [&](int j) {
     const long long r0 = (first + j * stride) * BM;
     const uint32_t acc_set = two_acc ? (uint32_t)(j & 1) : 0u;
     const int row = (warp & 3) * 32 + lane;
     const bool row_ok = r0 + row < prm.rows;
     __nv_bfloat16* orow = prm.out + (r0 + row) * C2;
     const int q = warp >> 2;
+    uint8_t* srow = sA + (uint32_t)(j % NST) * tile_bytes + ((uint32_t)row * C2 + q * CG) * 2;   // stage_out
     for (int c0 = 0; c0 < CG; c0 += 16) {
       uint32_t acc[16];
       tmem_ld16(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + acc_set * 4 * NP + (uint32_t)(q * NP + c0), acc);
@@ -505,7 +508,7 @@ __global__ void __launch_bounds__(THREADS + 32, 1) grouped_fc_tma_kernel(const P
         o[(j4 >> 1) + 1] = __floats2bfloat162_rn(v[2], v[3]);
       }
       if (stage_out) {
-        uint4* dst = reinterpret_cast<uint4*>(sA + (uint32_t)(j % NST) * tile_bytes + ((uint32_t)row * C2 + q * CG + c0) * 2);
+        uint4* dst = reinterpret_cast<uint4*>(srow + c0 * 2);
         dst[0] = *reinterpret_cast<const uint4*>(o);
         if (c0 + 8 < CG) dst[1] = *reinterpret_cast<const uint4*>(o + 4);
       } else if (row_ok) {
@@ -516,7 +519,7 @@ __global__ void __launch_bounds__(THREADS + 32, 1) grouped_fc_tma_kernel(const P
     if (stage_out) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // staged rows -> visible to the bulk store
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   };
-  auto store_tile = [&](long long j) {                  // control thread, after a barrier behind epilogue(j)
+  auto store_tile = [&](int j) {                  // control thread, after a barrier behind epilogue(j)
     const long long r0 = (first + j * stride) * BM;
     const long long nrows = prm.rows - r0 < BM ? prm.rows - r0 : BM;
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
@@ -525,7 +528,7 @@ __global__ void __launch_bounds__(THREADS + 32, 1) grouped_fc_tma_kernel(const P
     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
   };
   uint32_t ph[2] = {0, 0};
-  auto wait_mma = [&](long long j) {
+  auto wait_mma = [&](int j) {
     const uint32_t acc_set = two_acc ? (uint32_t)(j & 1) : 0u;
     mbar_wait(smem_u32(bar + acc_set), ph[acc_set]);
     ph[acc_set] ^= 1;
@@ -534,10 +537,10 @@ __global__ void __launch_bounds__(THREADS + 32, 1) grouped_fc_tma_kernel(const P
 
   if (mine > 0) {
     if (ctl) {
-      for (long long t = 0; t < mine && t < NST; ++t) load_tile(t);
+      for (int t = 0; t < mine && t < NST; ++t) load_tile(t);
       issue_mma(0);
     }
-    for (long long j = 0; j < mine; ++j) {
+    for (int j = 0; j < mine; ++j) {
       if (two_acc) {
         if (stage_out || j + 1 < mine) __syncthreads();  // every warp is past the epilogue of j-1: its accumulators are free
         if (ctl) {
