@@ -23,7 +23,13 @@ def _reference(x, conv, bn, act):
                                          (800, 1296 * 2 + 5, "gelu"),      # stage 3 of pvig_s: CG = 200, two column passes
                                          (1280, 324 * 3, "gelu"),          # stage 4: CG = 320
                                          (480, 700, "gelu"),               # arch 't' stage 3: CG = 120 (wide kernel, one pass)
-                                         (96, 200, "gelu"), (192, 333, None)])   # arch 't' stages 1 - 2
+                                         (96, 200, "gelu"), (192, 333, None),    # arch 't' stages 1 - 2
+                                         # >= 2 tiles per SM: the TMA kernel (3-D tensor map copy-in, bulk-store staging)
+                                         (160, 128 * 300 + 77, "gelu"),    # ragged last tile, 2 - 3 tiles per CTA, CG = 40
+                                         (160, 128 * 148 * 7 + 1, None),   # 7 - 8 tiles per CTA: every stage reused
+                                         (320, 128 * 297 + 5, "gelu"),     # CG = 80: one accumulator set, two stages
+                                         (96, 40000, "gelu"),              # CG = 24: K padded 24 -> 32 (reads the next group)
+                                         (192, 38000, "relu"), (64, 38001, None)])
 def test_grouped_fc_matches_conv_bn_act(C2, rows, act):
     from gkgnet_b200 import ops
     torch.manual_seed(C2 + rows)
@@ -44,6 +50,23 @@ def test_grouped_fc_matches_conv_bn_act(C2, rows, act):
     want = _reference(x, conv, bn, act)
     err = (got.float() - want).abs().max().item()
     assert err < 2e-2 * max(1.0, want.abs().max().item()), err
+
+
+@pytest.mark.parametrize("C2,rows", [(160, 128 * 300 + 77), (320, 128 * 297 + 5), (96, 40000), (192, 128 * 296)])
+def test_grouped_fc_tma_kernel_is_bit_identical_to_the_small_launch_kernels(C2, rows):
+    """>= 2 tiles per SM take the TMA kernel (tensor-map copy-in, staged bulk stores); slices of the same rows take the
+    cp.async kernels.  Same MMAs in the same K order, same epilogue: the bf16 outputs must be equal bit for bit."""
+    from gkgnet_b200 import ops
+    torch.manual_seed(C2 * 7 + rows)
+    w = torch.randn(C2, C2 // 4, 1, 1, device="cuda") * 0.2
+    scale = torch.rand(C2, device="cuda") + 0.5
+    shift = torch.randn(C2, device="cuda") * 0.3
+    x = (torch.randn(rows, C2, device="cuda") * 2).to(torch.bfloat16)
+    w_op = ops.grouped_fc_weights(w, scale)
+    for act in ("gelu", None):
+        big = ops.grouped_fc(x, w_op, shift, act)
+        small = torch.cat([ops.grouped_fc(x[i:i + 4096].contiguous(), w_op, shift, act) for i in range(0, rows, 4096)])
+        assert torch.equal(big.view(torch.int16), small.view(torch.int16)), (act, (big.float() - small.float()).abs().max().item())
 
 
 def test_grouped_fc_supported_widths():
@@ -83,7 +106,8 @@ def test_mrconv_eval_uses_fused_fc_and_matches_unfused():
     assert err < 2e-2 * max(1.0, plain.float().abs().max().item()), err
 
 
-@pytest.mark.parametrize("C2,R", [(160, 3000), (320, 1000), (800, 1296 + 17), (1280, 324 * 2), (480, 515), (96, 64)])
+@pytest.mark.parametrize("C2,R", [(160, 3000), (320, 1000), (800, 1296 + 17), (1280, 324 * 2), (480, 515), (96, 64),
+                                  (160, 128 * 300 + 9), (320, 128 * 296 + 64)])    # TMA kernel (forward and data gradient)
 def test_grouped_fc_train_gradients_match_conv(C2, R):
     """Training form (forward, data gradient, tcgen05 weight gradient, bias gradient) against Conv2d(groups=4)
     evaluated in fp32 on the same bf16 inputs: 2e-2 of the scale of each tensor (north-star bf16 tolerance)."""
