@@ -15,6 +15,9 @@
 // their accumulator rows back with tcgen05.ld (thread == row, one conv group per warp), apply scale / shift / activation and store
 // bf16.  The weights sit in shared memory for the CTA's lifetime in the same core-matrix order (built by
 // the caller, see gkgnet_b200/ops.py:grouped_fc_weights).  Memory bound: 2 * rows * 2C * 2 bytes.
+// Three generations of the narrow kernel live here: grouped_fc_kernel (synchronous, small launches), grouped_fc_pipe_kernel
+// (cp.async double buffering; fallback when the tensor map cannot be encoded) and grouped_fc_tma_kernel (TMA copy-in, control
+// warp, bulk-store copy-out: >= 2 tiles per SM); grouped_fc_wide_kernel covers CG > 96, grouped_fc_wgrad_kernel the weight gradient.
 #include "knn_tc.cuh"
 #include <cuda.h>
 #include <cudaTypedefs.h>

@@ -183,6 +183,12 @@ int gkg_fixed_to_float(const long long* in, const float* scale, float* out, long
  *     w_op  [4][passes][NT/8][KP/8][8][8],  element [q][p][n/8][k/8][n%8][k%8] = scale * W[q*CG + p*NT + n][k]
  * with NT = gkg_grouped_fc_pass_width(C2) output channels per pass (0 = narrow layout), passes = ceil(ceil16(CG) / NT).
  * The data gradient of the convolution is the same call with the per-group transposed weights.
+ * Launches with at least two 128-row tiles per SM and CG <= 80 copy the rows in through a 3-D TMA tensor map
+ * (cuTensorMapEncodeTiled, resolved with cudaGetDriverEntryPoint: no link-time libcuda dependency; if the driver does not
+ * provide it the per-thread cp.async kernel runs instead -- same results bit for bit).  The map is built from `in`, `rows`
+ * and C2 at call time and baked into the launch, so a captured CUDA graph must be replayed with the same buffers (as for
+ * every other pointer argument).  When CG is not a multiple of 16 the K padding of conv group q multiplies the first 8
+ * channels of group q+1 of the same row by zero weights: non-finite values there reach group q of that row.
  */
 int gkg_grouped_fc_supported(int C2);
 int gkg_grouped_fc_pass_width(int C2);
