@@ -383,6 +383,10 @@ tc_prepare_rows_kernel(const T* __restrict__ feat, int64_t stride_b, int64_t str
   const int kcs = KC >> 3, nkb = KP / KC, rgs = tile_rows >> 3;
   const int rg = slot >> 3, r = slot & 7;
   uint4* base = reinterpret_cast<uint4*>(op) + ((p * tiles + tile) * nkb * (long long)rgs) * kcs * 8;
+  // queries: the block IS one operand tile (tile_rows == PREP_THREADS), contiguous in the operand buffer -> it is assembled in
+  // shared memory and leaves as ONE bulk store instead of KP / 8 16-byte stores per thread
+  extern __shared__ __align__(128) uint4 prep_stage[];
+  uint4* dst = IS_KEY ? base : prep_stage;
 #pragma unroll
   for (int kcI = 0; kcI < KP / 8; ++kcI) {
     __align__(16) __half out[8];
@@ -405,7 +409,17 @@ tc_prepare_rows_kernel(const T* __restrict__ feat, int64_t stride_b, int64_t str
       out[e] = __float2half_rn(val);
     }
     const int kb = kcI / kcs, kc = kcI - kb * kcs;
-    base[(((long long)kb * rgs + rg) * kcs + kc) * 8 + r] = *reinterpret_cast<const uint4*>(out);
+    dst[(((long long)kb * rgs + rg) * kcs + kc) * 8 + r] = *reinterpret_cast<const uint4*>(out);
+  }
+  if (!IS_KEY) {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                   ::"l"(base), "r"((uint32_t)__cvta_generic_to_shared(prep_stage)), "r"((uint32_t)(tile_rows * KP * 2)) : "memory");
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    }
   }
 }
 
@@ -826,9 +840,15 @@ static int launch_prepare_rows(const KnnWorkspace& w, const TcWorkspace& t, cons
                                bool self_keys, cudaStream_t stream) {
   const int bn = pl.geom == 1 ? GeomB::BN : GeomA::BN, bnp = pl.geom == 1 ? GeomB::BNP : GeomA::BNP;
   {
+    static_assert(BM == PREP_THREADS, "a block of the query kernel assembles exactly one operand tile");
     dim3 grid((pl.QTP * BM + PREP_THREADS - 1) / PREP_THREADS, P);
-    tc_prepare_rows_kernel<T, D, false><<<grid, PREP_THREADS, 0, stream>>>(x, x_sb, x_sn, nullptr, nullptr, t.a_op, G, N,
-                                                                           pl.KC, pl.QTP, BM, BM, 0);
+    const size_t stage_bytes = (size_t)BM * k_padded(D) * 2;
+    static std::atomic<uint64_t> configured{0};
+    configure_once_per_device(configured, [] {
+      cudaFuncSetAttribute(tc_prepare_rows_kernel<T, D, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+    });
+    tc_prepare_rows_kernel<T, D, false><<<grid, PREP_THREADS, stage_bytes, stream>>>(x, x_sb, x_sn, nullptr, nullptr, t.a_op,
+                                                                                     G, N, pl.KC, pl.QTP, BM, BM, 0);
     GKG_CHECK_LAUNCH("tc_prepare_rows_kernel<query>");
   }
   {
