@@ -772,24 +772,56 @@ __global__ void __launch_bounds__(256, 2) grouped_fc_wgrad_kernel(const WgradPar
       const long long r0 = rbeg + blk * WG_KB;
       const uint32_t a = smem_u32(sA) + (uint32_t)(blk % WG_STAGES) * a_bytes;
       const uint32_t b = smem_u32(sB) + (uint32_t)(blk % WG_STAGES) * b_bytes;
-      // 16-byte pieces (8 channels of one row): piece (group g, row r) -> g * kSbo + (r / 8) * 128 + (r % 8) * 16
-      for (int i = threadIdx.x; i < 16 * WG_KB; i += 256) {
-        const int g = i % 16, r = i / 16;
-        const bool ok = g < a_groups && r0 + r < rend;
-        cp_async16(a + g * kSbo + ((r >> 3) << 7) + ((r & 7) << 4),
-                   ok ? reinterpret_cast<const uint4*>(prm.go + (r0 + r) * C2 + q * CG + o0) + g
-                      : reinterpret_cast<const uint4*>(prm.go), ok ? 16u : 0u);
+      // 16-byte pieces (8 channels of one row): piece (group g, row r) -> g * kSbo + (r / 8) * 128 + (r % 8) * 16.
+      // Narrow operands (<= 8 channel groups): only the groups that exist are copied (CG = 40 fills 5 of the 16 groups of the
+      // M = 128 operand: the padding groups are zeroed once, below) and 8 consecutive lanes take the 8 rows of one core matrix (128 contiguous
+      // bytes of shared memory: lanes walking the groups of ONE row all hit the same banks, 1 KB apart).
+      if (a_groups <= 8) {
+        for (int i = threadIdx.x; i < a_groups * WG_KB; i += 256) {
+          const int r8 = i & 7, t = i >> 3, g = t % a_groups, r = (t / a_groups) * 8 + r8;
+          const bool ok = r0 + r < rend;
+          cp_async16(a + g * kSbo + ((r >> 3) << 7) + (r8 << 4),
+                     ok ? reinterpret_cast<const uint4*>(prm.go + (r0 + r) * C2 + q * CG + o0) + g
+                        : reinterpret_cast<const uint4*>(prm.go), ok ? 16u : 0u);
+        }
+      } else {                                      // wide slabs: 256 contiguous bytes per row (measured faster there)
+        for (int i = threadIdx.x; i < 16 * WG_KB; i += 256) {
+          const int g = i % 16, r = i / 16;
+          const bool ok = g < a_groups && r0 + r < rend;
+          cp_async16(a + g * kSbo + ((r >> 3) << 7) + ((r & 7) << 4),
+                     ok ? reinterpret_cast<const uint4*>(prm.go + (r0 + r) * C2 + q * CG + o0) + g
+                        : reinterpret_cast<const uint4*>(prm.go), ok ? 16u : 0u);
+        }
       }
-      for (int i = threadIdx.x; i < (NT / 8) * WG_KB; i += 256) {
-        const int g = i % (NT / 8), r = i / (NT / 8);
-        const bool ok = g < b_groups && r0 + r < rend;
-        cp_async16(b + g * kSbo + ((r >> 3) << 7) + ((r & 7) << 4),
-                   ok ? reinterpret_cast<const uint4*>(prm.x + (r0 + r) * C2 + q * CG + i0) + g
-                      : reinterpret_cast<const uint4*>(prm.x), ok ? 16u : 0u);
+      if (b_groups <= 8) {
+        for (int i = threadIdx.x; i < b_groups * WG_KB; i += 256) {
+          const int r8 = i & 7, t = i >> 3, g = t % b_groups, r = (t / b_groups) * 8 + r8;
+          const bool ok = r0 + r < rend;
+          cp_async16(b + g * kSbo + ((r >> 3) << 7) + (r8 << 4),
+                     ok ? reinterpret_cast<const uint4*>(prm.x + (r0 + r) * C2 + q * CG + i0) + g
+                        : reinterpret_cast<const uint4*>(prm.x), ok ? 16u : 0u);
+        }
+      } else {
+        for (int i = threadIdx.x; i < (NT / 8) * WG_KB; i += 256) {
+          const int g = i % (NT / 8), r = i / (NT / 8);
+          const bool ok = g < b_groups && r0 + r < rend;
+          cp_async16(b + g * kSbo + ((r >> 3) << 7) + ((r & 7) << 4),
+                     ok ? reinterpret_cast<const uint4*>(prm.x + (r0 + r) * C2 + q * CG + i0) + g
+                        : reinterpret_cast<const uint4*>(prm.x), ok ? 16u : 0u);
+        }
       }
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
+  // channel groups past the end of the conv group stay zero in every stage
+  {
+    const uint32_t a_pad = (uint32_t)(16 - a_groups) * kSbo / 16, b_pad = (uint32_t)(NT / 8 - b_groups) * kSbo / 16;   // uint4 per stage
+    for (uint32_t i = threadIdx.x; i < WG_STAGES * a_pad; i += 256)
+      reinterpret_cast<uint4*>(sA + (i / a_pad) * a_bytes + (uint32_t)a_groups * kSbo)[i % a_pad] = make_uint4(0, 0, 0, 0);
+    for (uint32_t i = threadIdx.x; i < WG_STAGES * b_pad; i += 256)
+      reinterpret_cast<uint4*>(sB + (i / b_pad) * b_bytes + (uint32_t)b_groups * kSbo)[i % b_pad] = make_uint4(0, 0, 0, 0);
+    __syncthreads();
+  }
   load_block(0);
   load_block(1);
   for (long long blk = 0; blk < nblocks; ++blk) {
