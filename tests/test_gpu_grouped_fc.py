@@ -52,7 +52,8 @@ def test_grouped_fc_matches_conv_bn_act(C2, rows, act):
     assert err < 2e-2 * max(1.0, want.abs().max().item()), err
 
 
-@pytest.mark.parametrize("C2,rows", [(160, 128 * 300 + 77), (320, 128 * 297 + 5), (96, 40000), (192, 128 * 296)])
+@pytest.mark.parametrize("C2,rows", [(160, 128 * 300 + 77), (320, 128 * 297 + 5), (96, 40000), (192, 128 * 296),
+                                     (256, 128 * 296 + 3)])     # CG = 64: two accumulator sets, two stages, direct stores
 def test_grouped_fc_tma_kernel_is_bit_identical_to_the_small_launch_kernels(C2, rows):
     """>= 2 tiles per SM take the TMA kernel (tensor-map copy-in, staged bulk stores); slices of the same rows take the
     cp.async kernels.  Same MMAs in the same K order, same epilogue: the bf16 outputs must be equal bit for bit."""
